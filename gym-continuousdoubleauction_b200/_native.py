@@ -1,0 +1,129 @@
+"""ctypes binding of the C-ABI in include/cda_b200.h (libcda_b200.so, built in-tree by nvcc).
+
+There is NO CPU fallback: if the shared library is missing or was not built for this machine
+the import of the env fails loudly.  `build()` cross-compiles on a box without a GPU.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libcda_b200.so")
+SOURCES = ("cda_b200.cu", "cda_kernels.cuh", "cda_zig_tables.cuh")
+HEADER = os.path.join(_ROOT, "include", "cda_b200.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
+    "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class CdaConfig(ctypes.Structure):
+    _fields_ = [
+        ("num_agents", ctypes.c_int32), ("n_hist", ctypes.c_int32), ("max_step", ctypes.c_int32),
+        ("tick_size", ctypes.c_int32), ("init_cash", ctypes.c_int64), ("min_size", ctypes.c_int32),
+        ("mkt_max_size", ctypes.c_int32), ("limit_size_multiple", ctypes.c_int32),
+        ("initial_price_min", ctypes.c_int32), ("initial_price_max", ctypes.c_int32),
+        ("order_capacity", ctypes.c_int32), ("fill_capacity", ctypes.c_int32),
+        ("order_penalty", ctypes.c_double), ("trade_penalty", ctypes.c_double),
+        ("drawdown_penalty", ctypes.c_double), ("passive_bonus", ctypes.c_double),
+        ("loss_multiplier", ctypes.c_double),
+    ]
+
+
+INFO_FIELDS = (
+    "cash", "cash_on_hold", "cost_basis", "nav", "prev_nav", "max_nav", "net_position",
+    "position_val", "num_trades", "num_trades_step", "num_passive_fills_step",
+    "order_step_placed", "num_rejected_step", "is_pass_action", "market",
+)
+INFO_MARKET_COLS = ("last_price", "best_bid", "best_ask", "time", "next_order_id", "t_step",
+                    "done_mask", "status")
+
+EXPORTS = (
+    "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_rollout_random",
+    "cda_get_info", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
+    "cda_load_state", "cda_num_markets", "cda_obs_dim", "cda_order_capacity",
+    "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
+    "cda_seed_to_pcg64",
+)
+
+
+def needs_build():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """nvcc -> csrc/libcda_b200.so (sm_100a).  Works without a GPU (cross-compile)."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libcda_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", CSRC,
+                                 "-o", SO_PATH, os.path.join(CSRC, "cda_b200.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (fails loudly when it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the env step)")
+    L = ctypes.CDLL(SO_PATH)
+    vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+    L.cda_create.argtypes = [ctypes.POINTER(CdaConfig), i32, i32, ctypes.POINTER(vp)]
+    L.cda_destroy.argtypes = [vp]
+    L.cda_reset.argtypes = [vp, vp, vp, vp, vp]
+    L.cda_step.argtypes = [vp] * 11
+    L.cda_step_host.argtypes = [vp] * 11
+    L.cda_rollout_random.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp]
+    L.cda_get_info.argtypes = [vp, i32, vp, vp]
+    L.cda_get_fills.argtypes = [vp, vp, vp, vp]
+    L.cda_dump_market.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]
+    L.cda_state_bytes.argtypes = [vp]
+    L.cda_state_bytes.restype = ctypes.c_size_t
+    L.cda_save_state.argtypes = [vp, vp, vp]
+    L.cda_load_state.argtypes = [vp, vp, vp]
+    for name in ("cda_num_markets", "cda_obs_dim", "cda_order_capacity"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = i32
+    L.cda_kernel_launches.argtypes = [vp]
+    L.cda_kernel_launches.restype = i64
+    for name in ("cda_strerror", "cda_last_cuda_error", "cda_build_info"):
+        getattr(L, name).restype = ctypes.c_char_p
+    L.cda_strerror.argtypes = [i32]
+    L.cda_seed_to_pcg64.argtypes = [u64, ctypes.POINTER(u64)]
+    _lib = L
+    return L
+
+
+class CdaError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        L = lib()
+        msg = L.cda_strerror(rc).decode()
+        if rc == -2:
+            msg += ": " + L.cda_last_cuda_error().decode()
+        if rc == -1:
+            raise ValueError("cda_b200: " + msg)
+        raise CdaError("cda_b200: " + msg)

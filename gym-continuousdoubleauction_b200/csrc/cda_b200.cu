@@ -1,0 +1,308 @@
+// cda_b200.cu — C-ABI (include/cda_b200.h) over the sm_100a kernels in cda_kernels.cuh.
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared ...
+// (-fmad=false: the reference computes loc + scale*z, the reward sum and the ziggurat wedge
+//  test with separately rounded multiplies and adds; contracting them into FMAs would change
+//  results in the last bit.)
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "cda_kernels.cuh"
+
+#ifndef CDA_WARPS_PER_CTA
+#define CDA_WARPS_PER_CTA 4
+#endif
+
+static thread_local char g_cuda_err[256] = "";
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+            return CDA_ECUDA;                                                                   \
+        }                                                                                       \
+    } while (0)
+
+struct CdaEnv {
+    CdaConfig cfg;
+    CdaDevCfg dev;
+    int M, device;
+    unsigned char *state;      // M * stride bytes
+    size_t state_bytes;
+    int *fills; int *fill_counts;
+    // device staging for cda_step_host
+    int *s_cat; float *s_mean; float *s_sigma; int *s_pcode; int *s_poff;
+    float *s_obs; double *s_reward; unsigned char *s_term; unsigned char *s_trunc;
+    bool was_reset;
+    long long launches;
+    size_t smem_bytes;
+};
+
+static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
+
+template <int CAP>
+static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {
+    const int grid = (e->M + CDA_WARPS_PER_CTA - 1) / CDA_WARPS_PER_CTA;
+    const size_t smem = sizeof(CdaWarpSmem<CAP>) * CDA_WARPS_PER_CTA;
+    static bool attr_set[16] = {false};
+    if (!attr_set[e->device & 15]) {
+        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set[e->device & 15] = true;
+    }
+    cda_step_kernel<CAP, CDA_WARPS_PER_CTA><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {
+    switch (e->dev.cap) {
+        case 64: return launch_step<64>(e, p, st);
+        case 128: return launch_step<128>(e, p, st);
+        default: return launch_step<256>(e, p, st);
+    }
+}
+
+extern "C" {
+
+const char *cda_strerror(int code) {
+    switch (code) {
+        case CDA_OK: return "ok";
+        case CDA_EINVAL: return "invalid argument or configuration";
+        case CDA_ECUDA: return "CUDA runtime error (see cda_last_cuda_error)";
+        case CDA_ENOMEM: return "out of memory";
+        case CDA_ESTATE: return "environment used before reset";
+        default: return "unknown error";
+    }
+}
+const char *cda_last_cuda_error(void) { return g_cuda_err; }
+const char *cda_build_info(void) {
+    return "cda_b200 sm_100a; warp-per-market fused step; cp.async.bulk staged order pool; nvcc " __DATE__;
+}
+void cda_seed_to_pcg64(uint64_t seed, uint64_t out[4]) {
+    unsigned long long s[4];
+    seedseq_words(seed, s);
+    // same arithmetic as rng_seed, on the host with 128-bit integers
+    unsigned __int128 mult = (((unsigned __int128)2549297995355413924ULL) << 64) | 4865540595714422341ULL;
+    unsigned __int128 initstate = (((unsigned __int128)s[0]) << 64) | s[1];
+    unsigned __int128 initseq = (((unsigned __int128)s[2]) << 64) | s[3];
+    unsigned __int128 inc = (initseq << 1) | 1u, state = 0;
+    state = state * mult + inc;
+    state += initstate;
+    state = state * mult + inc;
+    out[0] = (uint64_t)(state >> 64); out[1] = (uint64_t)state; out[2] = (uint64_t)(inc >> 64); out[3] = (uint64_t)inc;
+}
+
+int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv **out) {
+    if (!cfg || !out || num_markets < 1) return CDA_EINVAL;
+    if (cfg->num_agents < 1 || cfg->num_agents > CDA_MAX_AGENTS) return CDA_EINVAL;
+    if (cfg->n_hist < 1 || cfg->n_hist > CDA_MAX_HIST) return CDA_EINVAL;
+    if (cfg->tick_size < 1 || cfg->init_cash <= 0 || cfg->max_step < 1) return CDA_EINVAL;
+    if (cfg->initial_price_min < 1 || cfg->initial_price_max < cfg->initial_price_min) return CDA_EINVAL;
+    if (cfg->min_size < 0 || cfg->mkt_max_size < 1 || cfg->limit_size_multiple < 1) return CDA_EINVAL;
+    int cap = cfg->order_capacity;
+    if (cap == 0) cap = cfg->num_agents <= 4 ? 128 : 256;
+    if (cap != 64 && cap != 128 && cap != 256) return CDA_EINVAL;
+    if (cfg->fill_capacity < 0 || cfg->fill_capacity > 1024) return CDA_EINVAL;
+    CUDA_TRY(cudaSetDevice(device));
+    CdaEnv *e = new (std::nothrow) CdaEnv();
+    if (!e) return CDA_ENOMEM;
+    memset(e, 0, sizeof(*e));
+    e->cfg = *cfg; e->cfg.order_capacity = cap;
+    e->M = num_markets; e->device = device;
+    CdaDevCfg &d = e->dev;
+    d.A = cfg->num_agents; d.n_hist = cfg->n_hist; d.max_step = cfg->max_step; d.tick = cfg->tick_size;
+    d.init_cash = cfg->init_cash; d.min_size = cfg->min_size;
+    // action_helper.py:46-47 — python floats, then weak-scalar cast to f32 when multiplied with the f32 mean
+    d.mkt_mul = (float)((cfg->mkt_max_size - cfg->min_size) / 2.0);
+    d.lim_mul = (float)(((double)cfg->mkt_max_size * cfg->limit_size_multiple - cfg->min_size) / 2.0);
+    d.price_lo = cfg->initial_price_min; d.price_hi = cfg->initial_price_max;
+    d.cap = cap; d.fill_cap = cfg->fill_capacity;
+    d.c_order = cfg->order_penalty; d.c_trade = cfg->trade_penalty; d.c_dd = cfg->drawdown_penalty;
+    d.c_passive = cfg->passive_bonus; d.c_loss = cfg->loss_multiplier;
+    d.W = cfg->n_hist * CDA_SNAPSHOT_DIM;
+    d.off_acct = CDA_HDR_BYTES;
+    d.off_hist = align_up(d.off_acct + (unsigned)d.A * 60u, 16);
+    d.off_pool = align_up(d.off_hist + (unsigned)d.W * 4u, 16);
+    d.stride = align_up(d.off_pool + 2u * CDA_POOL_FIELDS * (unsigned)cap * 4u, 128);
+    e->state_bytes = (size_t)d.stride * (size_t)num_markets;
+    const size_t MA = (size_t)num_markets * d.A;
+    cudaError_t err = cudaMalloc(&e->state, e->state_bytes);
+    if (err == cudaSuccess && d.fill_cap > 0) {
+        err = cudaMalloc(&e->fills, (size_t)num_markets * d.fill_cap * CDA_FILL_WORDS * sizeof(int));
+        if (err == cudaSuccess) err = cudaMalloc(&e->fill_counts, (size_t)num_markets * sizeof(int));
+    }
+    if (err == cudaSuccess) err = cudaMalloc(&e->s_cat, MA * 4 * 5);
+    if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&e->s_reward, MA * 8);
+    if (err == cudaSuccess) err = cudaMalloc(&e->s_term, (size_t)num_markets * 2);
+    if (err != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc failed: %s", cudaGetErrorString(err));
+        cda_destroy(e);
+        return err == cudaErrorMemoryAllocation ? CDA_ENOMEM : CDA_ECUDA;
+    }
+    e->s_mean = reinterpret_cast<float *>(e->s_cat + MA);
+    e->s_sigma = reinterpret_cast<float *>(e->s_cat + 2 * MA);
+    e->s_pcode = e->s_cat + 3 * MA;
+    e->s_poff = e->s_cat + 4 * MA;
+    e->s_trunc = e->s_term + num_markets;
+    CUDA_TRY(cudaMemset(e->state, 0, e->state_bytes));
+    *out = e;
+    return CDA_OK;
+}
+
+int cda_destroy(CdaEnv *e) {
+    if (!e) return CDA_OK;
+    cudaSetDevice(e->device);
+    cudaFree(e->state); cudaFree(e->fills); cudaFree(e->fill_counts);
+    cudaFree(e->s_cat); cudaFree(e->s_obs); cudaFree(e->s_reward); cudaFree(e->s_term);
+    delete e;
+    return CDA_OK;
+}
+
+int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *d_obs, void *stream) {
+    if (!e) return CDA_EINVAL;
+    if (!d_seeds && !e->was_reset) return CDA_ESTATE;   // reset(seed=None) needs an existing stream
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 128, grid = (e->M + threads - 1) / threads;
+    cda_reset_kernel<<<grid, threads, 0, st>>>(e->dev, e->state, e->M, (const unsigned long long *)d_seeds, d_mask, d_obs);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    if (!d_mask) e->was_reset = true;
+    else e->was_reset = true;   // partial first reset: unselected markets keep zeroed (inert) state
+    return CDA_OK;
+}
+
+static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st) {
+    p.cfg = e->dev; p.state = e->state; p.M = e->M;
+    p.fills = e->fills; p.fill_counts = e->fill_counts;
+    CUDA_TRY(launch_step_any(e, p, st));
+    e->launches++;
+    return CDA_OK;
+}
+
+int cda_step(CdaEnv *e, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
+             const int32_t *d_price, const int32_t *d_price_offset, float *d_obs, double *d_reward,
+             uint8_t *d_terminated, uint8_t *d_truncated, void *stream) {
+    if (!e || !d_category || !d_size_mean || !d_size_sigma || !d_price || !d_price_offset) return CDA_EINVAL;
+    if (!e->was_reset) return CDA_ESTATE;
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cat = d_category; p.mean = d_size_mean; p.sigma = d_size_sigma; p.pcode = d_price; p.poff = d_price_offset;
+    p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated;
+    return step_common(e, p, (cudaStream_t)stream);
+}
+
+int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                  const int32_t *h_price, const int32_t *h_price_offset, float *h_obs, double *h_reward,
+                  uint8_t *h_terminated, uint8_t *h_truncated, void *stream) {
+    if (!e || !h_category || !h_size_mean || !h_size_sigma || !h_price || !h_price_offset) return CDA_EINVAL;
+    if (!e->was_reset) return CDA_ESTATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t MA = (size_t)e->M * e->dev.A;
+    CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_category, MA * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->s_mean, h_size_mean, MA * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->s_sigma, h_size_sigma, MA * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->s_pcode, h_price, MA * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->s_poff, h_price_offset, MA * 4, cudaMemcpyHostToDevice, st));
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cat = e->s_cat; p.mean = e->s_mean; p.sigma = e->s_sigma; p.pcode = e->s_pcode; p.poff = e->s_poff;
+    p.obs = e->s_obs; p.reward = e->s_reward; p.term = e->s_term; p.trunc = e->s_trunc;
+    int rc = step_common(e, p, st);
+    if (rc) return rc;
+    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, e->s_obs, (size_t)e->M * e->dev.W * 4, cudaMemcpyDeviceToHost, st));
+    if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, e->s_reward, MA * 8, cudaMemcpyDeviceToHost, st));
+    if (h_terminated) CUDA_TRY(cudaMemcpyAsync(h_terminated, e->s_term, e->M, cudaMemcpyDeviceToHost, st));
+    if (h_truncated) CUDA_TRY(cudaMemcpyAsync(h_truncated, e->s_trunc, e->M, cudaMemcpyDeviceToHost, st));
+    return CDA_OK;
+}
+
+int cda_rollout_random(CdaEnv *e, int32_t num_steps, uint64_t policy_seed, float *d_obs, double *d_reward,
+                       uint8_t *d_terminated, uint8_t *d_truncated, void *stream) {
+    if (!e || num_steps < 1) return CDA_EINVAL;
+    if (!e->was_reset) return CDA_ESTATE;
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated;
+    p.num_steps = num_steps; p.policy_seed = policy_seed;
+    return step_common(e, p, (cudaStream_t)stream);
+}
+
+int cda_get_info(CdaEnv *e, int32_t field, int64_t *d_out, void *stream) {
+    if (!e || !d_out || field < 0 || field >= CDA_INFO__COUNT) return CDA_EINVAL;
+    const int n = field == CDA_INFO_MARKET ? e->M : e->M * e->dev.A;
+    const int threads = 256, grid = (n + threads - 1) / threads;
+    cda_info_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, field, (long long *)d_out);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return CDA_OK;
+}
+
+int cda_get_fills(CdaEnv *e, int32_t *d_fills, int32_t *d_counts, void *stream) {
+    if (!e || !e->fills) return CDA_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_fills) CUDA_TRY(cudaMemcpyAsync(d_fills, e->fills, (size_t)e->M * e->dev.fill_cap * CDA_FILL_WORDS * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_counts) CUDA_TRY(cudaMemcpyAsync(d_counts, e->fill_counts, (size_t)e->M * 4, cudaMemcpyDeviceToDevice, st));
+    return CDA_OK;
+}
+
+int cda_dump_market(CdaEnv *e, int32_t market, int64_t *h_bids, int64_t *h_asks, int64_t *h_bids_map,
+                    int64_t *h_asks_map, int32_t max_rows, int32_t *h_counts, uint64_t *h_rng6) {
+    if (!e || market < 0 || market >= e->M || !h_counts) return CDA_EINVAL;
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<unsigned char> blk(e->dev.stride);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(blk.data(), e->state + (size_t)market * e->dev.stride, e->dev.stride, cudaMemcpyDeviceToHost));
+    const unsigned *hdr = reinterpret_cast<const unsigned *>(blk.data());
+    const unsigned *pool = reinterpret_cast<const unsigned *>(blk.data() + e->dev.off_pool);
+    const int cap = e->dev.cap;
+    for (int side = 0; side < 2; ++side) {
+        const int n = (int)hdr[8 + side];
+        const unsigned *f = pool + (size_t)side * CDA_POOL_FIELDS * cap;
+        std::vector<int> idx(n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+            unsigned pa = f[a] & CDA_PRICE_MASK, pb = f[b] & CDA_PRICE_MASK;
+            if (pa != pb) return side == 0 ? pa > pb : pa < pb;
+            return f[4 * cap + a] < f[4 * cap + b];
+        });
+        int64_t *rows = side == 0 ? h_bids : h_asks;
+        if (rows)
+            for (int k = 0; k < n && k < max_rows; ++k) {
+                int i = idx[k];
+                rows[k * 5 + 0] = f[i] & CDA_PRICE_MASK; rows[k * 5 + 1] = f[cap + i]; rows[k * 5 + 2] = f[i] >> 24;
+                rows[k * 5 + 3] = f[2 * cap + i]; rows[k * 5 + 4] = f[3 * cap + i];
+            }
+        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return f[4 * cap + a] < f[4 * cap + b]; });
+        int64_t *mp = side == 0 ? h_bids_map : h_asks_map;
+        if (mp) for (int k = 0; k < n && k < max_rows; ++k) mp[k] = f[2 * cap + idx[k]];
+        h_counts[side] = n;
+    }
+    if (h_rng6) {
+        const unsigned long long *r = reinterpret_cast<const unsigned long long *>(hdr + 12);
+        h_rng6[0] = r[0]; h_rng6[1] = r[1]; h_rng6[2] = r[2]; h_rng6[3] = r[3]; h_rng6[4] = hdr[10]; h_rng6[5] = hdr[11];
+    }
+    return CDA_OK;
+}
+
+size_t cda_state_bytes(const CdaEnv *e) { return e ? e->state_bytes : 0; }
+int cda_save_state(CdaEnv *e, void *h_dst, void *stream) {
+    if (!e || !h_dst) return CDA_EINVAL;
+    CUDA_TRY(cudaMemcpyAsync(h_dst, e->state, e->state_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return CDA_OK;
+}
+int cda_load_state(CdaEnv *e, const void *h_src, void *stream) {
+    if (!e || !h_src) return CDA_EINVAL;
+    CUDA_TRY(cudaMemcpyAsync(e->state, h_src, e->state_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    e->was_reset = true;
+    return CDA_OK;
+}
+int32_t cda_num_markets(const CdaEnv *e) { return e ? e->M : 0; }
+int32_t cda_obs_dim(const CdaEnv *e) { return e ? e->dev.W : 0; }
+int32_t cda_order_capacity(const CdaEnv *e) { return e ? e->dev.cap : 0; }
+int64_t cda_kernel_launches(const CdaEnv *e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,826 @@
+// cda_kernels.cuh — sm_100a device code of the vectorised continuous-double-auction env.
+//
+// One WARP steps one MARKET.  The market's resting orders live in a flat, dense, unsorted
+// order pool per side (structure-of-arrays: price|trader, qty, order_id, timestamp, seq),
+// staged global->shared with cp.async.bulk (TMA bulk copy, SASS UBLKCP) behind an mbarrier;
+// the sorted-tree / FIFO-list / order-map machinery of the reference is replaced by
+// warp-wide reductions over that pool (redux.sync min/max/add + ballot):
+//     best price            = redux min/max over price
+//     head of a price level = redux min over `seq` among orders at that price
+//     a trader's order      = redux min over `seq` (limit/cancel) or `timestamp` (modify)
+// `seq` is a per-market insertion counter: in the reference an order is appended to its level's
+// FIFO list and to the side's order_map dict at the same moment (ordertree.py:44-55) and both
+// positions are kept by an in-place quantity update (orderbook.py:245-248), so one key encodes
+// both the time priority inside a level and the order_map iteration order that
+// Trader._get_order_ID depends on (trader.py:254-287).
+// The A accounts of the market live in the registers of lanes 0..A-1 for the whole step; the
+// RNG (numpy's PCG64 + ziggurat, so reset(seed) reproduces the reference's stream) is
+// evaluated redundantly by all lanes (warp-uniform, no broadcast needed).
+//
+// Reference call stack mirrored by market_step():  continuousDoubleAuction_env.py:265-309.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cda_b200.h"
+#include "cda_zig_tables.cuh"
+
+#define CDA_FULL 0xffffffffu
+#define CDA_HDR_BYTES 192
+#define CDA_POOL_FIELDS 5 /* 0 pt (trader<<24|price), 1 qty, 2 order_id, 3 timestamp, 4 seq */
+#define CDA_PRICE_MASK 0x00ffffffu
+#define CDA_FLAG_TAPE 1u
+
+// ------------------------------------------------------------------------------------------
+// Per-market block in HBM (stride bytes, 128-B aligned), see DESIGN.md "Data layout":
+//   [0,192)            header words (below)
+//   [off_acct, ...)    accounts, SoA inside the market: cash[A] hold[A] cost[A] nav[A] prev_nav[A]
+//                      max_nav[A] (i64), pos[A] (i32), num_trades[A] (u32), stepctr[A] (u32)
+//   [off_hist, ...)    snapshot ring  f32[n_hist][42]
+//   [off_pool, ...)    order pool     u32[2 sides][5 fields][cap]
+// Header words (u32 index):
+//   0 time  1 next_order_id  2 seqctr  3 t_step  4 last_price  5 flags  6 done_mask  7 status
+//   8 n_bid 9 n_ask 10 rng_has_uint32 11 rng_uinteger 12..19 rng state_hi,state_lo,inc_hi,inc_lo (u64)
+//   20..39 pre-step raw top-K prices (bid[10], ask[10]; 0 = empty)  40 best_bid 41 best_ask 42..47 pad
+// ------------------------------------------------------------------------------------------
+struct CdaDevCfg {
+    int A, n_hist, max_step, tick;
+    long long init_cash;
+    int min_size;
+    float mkt_mul, lim_mul;   // action_helper.py:46-47 (cast to f32 like numpy's weak python float)
+    int price_lo, price_hi;
+    int cap, fill_cap;
+    double c_order, c_trade, c_dd, c_passive, c_loss;
+    unsigned off_acct, off_hist, off_pool, stride;
+    int W;                    // n_hist * 42
+};
+
+struct CdaStepParams {
+    CdaDevCfg cfg;
+    unsigned char *state;
+    int M;
+    const int *cat; const float *mean; const float *sigma; const int *pcode; const int *poff;
+    float *obs; double *reward; unsigned char *term; unsigned char *trunc;
+    int *fills; int *fill_counts;
+    // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
+    int num_steps; unsigned long long policy_seed;
+};
+
+// ------------------------------------ numpy-exact RNG --------------------------------------
+// PCG64 (pcg_setseq_128_xsl_rr_64) + numpy's buffered next_uint32 + ziggurat normal +
+// masked-rejection interval + Lemire bounded ints.  Restated from the published algorithms
+// (numpy is a third-party dependency of the reference); call sites in the reference:
+// continuousDoubleAuction_env.py:221, action_helper.py:331-333, action_helper.py:198-199.
+struct CdaRng {
+    unsigned long long shi, slo, ihi, ilo;
+    unsigned has32, u32;
+};
+__device__ __forceinline__ void rng_step(CdaRng &r) {
+    const unsigned long long MH = 2549297995355413924ULL, ML = 4865540595714422341ULL;
+    unsigned long long lo = r.slo * ML;
+    unsigned long long hi = __umul64hi(r.slo, ML) + r.shi * ML + r.slo * MH;
+    unsigned long long nlo = lo + r.ilo;
+    unsigned long long carry = nlo < lo ? 1ULL : 0ULL;
+    r.slo = nlo;
+    r.shi = hi + r.ihi + carry;
+}
+__device__ __forceinline__ unsigned long long rng_u64(CdaRng &r) {
+    rng_step(r);
+    unsigned long long x = r.shi ^ r.slo;
+    unsigned rot = (unsigned)(r.shi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+__device__ __forceinline__ unsigned rng_u32(CdaRng &r) {
+    if (r.has32) { r.has32 = 0; return r.u32; }
+    unsigned long long n = rng_u64(r);
+    r.has32 = 1; r.u32 = (unsigned)(n >> 32);
+    return (unsigned)n;
+}
+__device__ __forceinline__ double rng_double(CdaRng &r) {
+    return (double)(rng_u64(r) >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ __noinline__ double rng_normal_slow(CdaRng &g, int idx, unsigned long long rabs, double x) {
+    // wedge / tail of the ziggurat (~1.2 % of draws); may recurse into fresh draws
+    for (;;) {
+        if (idx == 0) {
+            for (;;) {
+                double xx = -CDA_ZIG_NOR_INV_R * log1p(-rng_double(g));
+                double yy = -log1p(-rng_double(g));
+                if (yy + yy > xx * xx)
+                    return ((rabs >> 8) & 1ULL) ? -(CDA_ZIG_NOR_R + xx) : CDA_ZIG_NOR_R + xx;
+            }
+        } else {
+            double u = rng_double(g);
+            if (((cda_zig_fi[idx - 1] - cda_zig_fi[idx]) * u + cda_zig_fi[idx]) < exp(-0.5 * x * x)) return x;
+        }
+        unsigned long long r = rng_u64(g);
+        idx = (int)(r & 0xff);
+        r >>= 8;
+        int sign = (int)(r & 1ULL);
+        rabs = (r >> 1) & 0x000fffffffffffffULL;
+        x = (double)rabs * cda_zig_wi[idx];
+        if (sign) x = -x;
+        if (rabs < cda_zig_ki[idx]) return x;
+    }
+}
+__device__ __forceinline__ double rng_normal(CdaRng &g) {
+    unsigned long long r = rng_u64(g);
+    int idx = (int)(r & 0xff);
+    r >>= 8;
+    int sign = (int)(r & 1ULL);
+    unsigned long long rabs = (r >> 1) & 0x000fffffffffffffULL;
+    double x = (double)rabs * cda_zig_wi[idx];
+    if (sign) x = -x;
+    if (rabs < cda_zig_ki[idx]) return x;
+    return rng_normal_slow(g, idx, rabs, x);
+}
+__device__ __forceinline__ unsigned rng_interval(CdaRng &r, unsigned max) {
+    if (max == 0) return 0;
+    unsigned mask = max;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    unsigned v;
+    while ((v = (rng_u32(r) & mask)) > max) {}
+    return v;
+}
+__device__ __forceinline__ long long rng_integers(CdaRng &r, long long lo, long long hi_excl) {
+    unsigned long long rng = (unsigned long long)(hi_excl - 1 - lo);
+    if (rng == 0) return lo;
+    unsigned rng32 = (unsigned)rng, rng_excl = rng32 + 1u;
+    unsigned long long m = (unsigned long long)rng_u32(r) * rng_excl;
+    unsigned leftover = (unsigned)m;
+    if (leftover < rng_excl) {
+        unsigned threshold = (0xffffffffu - rng32) % rng_excl;
+        while (leftover < threshold) {
+            m = (unsigned long long)rng_u32(r) * rng_excl;
+            leftover = (unsigned)m;
+        }
+    }
+    return lo + (long long)(m >> 32);
+}
+// SeedSequence(seed).generate_state(4, uint64) -> PCG64 seeding (bit_generator.pyx, pcg64.c)
+__host__ __device__ inline unsigned ss_hashmix(unsigned value, unsigned &hc) {
+    value ^= hc; hc *= 0x931e8875u; value *= hc; value ^= value >> 16; return value;
+}
+__host__ __device__ inline unsigned ss_mix(unsigned x, unsigned y) {
+    unsigned r = 0xca01f9ddu * x - 0x4973f715u * y; r ^= r >> 16; return r;
+}
+__host__ __device__ inline void seedseq_words(unsigned long long seed, unsigned long long out[4]) {
+    unsigned ent[2] = {(unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32)};
+    int n_ent = ent[1] ? 2 : 1;
+    unsigned pool[4], hc = 0x43b0d7e5u;
+    for (int i = 0; i < 4; ++i) pool[i] = ss_hashmix(i < n_ent ? ent[i] : 0u, hc);
+    for (int s = 0; s < 4; ++s)
+        for (int d = 0; d < 4; ++d)
+            if (s != d) pool[d] = ss_mix(pool[d], ss_hashmix(pool[s], hc));
+    unsigned hb = 0x8b51f9ddu, w[8];
+    for (int i = 0; i < 8; ++i) {
+        unsigned v = pool[i & 3];
+        v ^= hb; hb *= 0x58f38dedu; v *= hb; v ^= v >> 16;
+        w[i] = v;
+    }
+    for (int i = 0; i < 4; ++i) out[i] = (unsigned long long)w[2 * i] | ((unsigned long long)w[2 * i + 1] << 32);
+}
+__device__ __forceinline__ void rng_seed(CdaRng &r, unsigned long long seed) {
+    unsigned long long s[4];
+    seedseq_words(seed, s);
+    // inc = (initseq << 1) | 1 ; state = 0; step; state += initstate; step
+    r.ihi = (s[2] << 1) | (s[3] >> 63);
+    r.ilo = (s[3] << 1) | 1ULL;
+    r.shi = 0; r.slo = 0;
+    rng_step(r);
+    unsigned long long nlo = r.slo + s[1];
+    r.shi = r.shi + s[0] + (nlo < r.slo ? 1ULL : 0ULL);
+    r.slo = nlo;
+    rng_step(r);
+    r.has32 = 0; r.u32 = 0;
+}
+
+// ----------------------------------- async-copy helpers ------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, non-tensor form); bytes % 16 == 0, both addresses 16-B aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// --------------------------------------- accounts ------------------------------------------
+struct CdaAcct {
+    long long cash, hold, cost, nav, prev_nav, max_nav, pos;
+    unsigned ntr, tr_step, pas_step, placed, rejected, is_pass;
+};
+// account.py:215-231 process_acc with the ledger restated on integers (cost = |pos|*VWAP):
+//   open/increase: cost += q*p (account.py:124-133, :173-176); decrease: cost -= q*p (:151-157);
+//   cover: cash += position_val - mkt_val, which is 0 for a long and 2*cost - 2*mkt for a short
+//   (:135-149 with calculate.py:24-33); flip: cover |pos| then open (q-|pos|) at p (:163-171).
+// party: 0 init_party, 1 counter_party; cash moves per cash_processor.py:31-53.
+__device__ __forceinline__ void acct_fill(CdaAcct &a, int party, int side /*0 bid,1 ask*/, long long q, long long p) {
+    a.ntr++; a.tr_step++;
+    if (party) a.pas_step++;
+    const long long tv = q * p;
+    long long inc = 0, dec = 0;      // value moved by size_increase / size_decrease transfers
+    const long long ap = a.pos < 0 ? -a.pos : a.pos;
+    if (a.pos == 0) { a.cost = tv; inc = tv; }
+    else if ((a.pos > 0) == (side == 0)) { a.cost += tv; inc = tv; }
+    else if (ap > q) { a.cost -= tv; dec = tv; }
+    else {
+        const long long mkt = ap * p;
+        if (a.pos < 0) a.cash += 2 * a.cost - 2 * mkt;   // size_zero_cash_transfer, short side
+        a.cost = 0;
+        if (ap == q) dec = tv;
+        else { dec = mkt; inc = (q - ap) * p; a.cost = inc; }
+    }
+    if (party == 0) { a.cash += dec; a.cash -= inc; }
+    else { a.cash += 2 * dec; a.hold -= dec; a.hold -= inc; }
+    a.pos += side == 0 ? q : -q;
+}
+
+// ------------------------------------- market context --------------------------------------
+template <int CAP>
+struct CdaCtx {
+    unsigned *pool[2];   // shared memory, [5][CAP] per side (0 bid, 1 ask)
+    int n[2];
+    unsigned time, next_id, seqctr, status;
+    int tape_nonempty, tape_px;
+    int lane;
+    CdaAcct ac;          // this lane's account (valid for lane < A)
+    int *fills; int fill_cap, n_fills;
+};
+
+template <int CAP> __device__ __forceinline__ int pool_best(const CdaCtx<CAP> &c, int side) {
+    const unsigned *pt = c.pool[side];
+    const int n = c.n[side];
+    if (n == 0) return -1;
+    unsigned loc = side == 0 ? 0u : 0xffffffffu;
+    for (int i = c.lane; i < n; i += 32) {
+        unsigned p = pt[i] & CDA_PRICE_MASK;
+        loc = side == 0 ? max(loc, p) : min(loc, p);
+    }
+    return (int)(side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc));
+}
+// index of the entry with the smallest key[field] among entries whose pt matches (pt & mask) == want
+template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaCtx<CAP> &c, int side, unsigned mask, unsigned want, int field) {
+    const unsigned *pt = c.pool[side];
+    const unsigned *key = c.pool[side] + field * CAP;
+    const int n = c.n[side];
+    unsigned bk = 0xffffffffu; int bi = -1;
+    for (int i = c.lane; i < n; i += 32) {
+        if ((pt[i] & mask) == want) { unsigned k = key[i]; if (k < bk) { bk = k; bi = i; } }
+    }
+    unsigned mk = __reduce_min_sync(CDA_FULL, bk);
+    if (mk == 0xffffffffu) return -1;
+    unsigned b = __ballot_sync(CDA_FULL, bk == mk);
+    return __shfl_sync(CDA_FULL, bi, __ffs(b) - 1);
+}
+// ordertree.py:70-77 remove_order_by_id: dense pool => move the last entry into the hole
+template <int CAP> __device__ __forceinline__ void pool_remove(CdaCtx<CAP> &c, int side, int idx) {
+    const int last = c.n[side] - 1;
+    __syncwarp();
+    if (idx != last && c.lane < CDA_POOL_FIELDS) {
+        unsigned *f = c.pool[side] + c.lane * CAP;
+        f[idx] = f[last];
+    }
+    c.n[side] = last;
+    __syncwarp();
+}
+// ordertree.py:44-55 insert_order: append with a fresh seq (tail of the level's FIFO and of order_map)
+template <int CAP> __device__ __forceinline__ bool pool_append(CdaCtx<CAP> &c, int side, unsigned price, unsigned qty, int trader, unsigned oid, unsigned ts) {
+    const int n = c.n[side];
+    if (n >= CAP) { c.status |= CDA_ST_POOL_OVERFLOW; return false; }
+    const unsigned seq = c.seqctr++;
+    __syncwarp();
+    if (c.lane < CDA_POOL_FIELDS) {
+        unsigned v = c.lane == 0 ? (((unsigned)trader << 24) | price) : c.lane == 1 ? qty : c.lane == 2 ? oid : c.lane == 3 ? ts : seq;
+        c.pool[side][c.lane * CAP + n] = v;
+    }
+    c.n[side] = n + 1;
+    __syncwarp();
+    return true;
+}
+
+// orderbook.py:61-142 process_order_list + :144-194 loops, with settlement applied per fill
+// (trader.py:303-328 settles after the match; matching never reads accounts, so the order of
+// ledger updates is identical).  limit < 0 => market order.  Returns the unfilled quantity.
+template <int CAP> __device__ __forceinline__ unsigned match_incoming(CdaCtx<CAP> &c, int side, unsigned qty, int limit, int taker) {
+    const int opp = 1 - side;
+    while (qty > 0) {
+        const int P = pool_best(c, opp);
+        if (P < 0) break;
+        if (limit >= 0 && (side == 0 ? limit < P : limit > P)) break;
+        const int idx = pool_argmin(c, opp, CDA_PRICE_MASK, (unsigned)P, 4);
+        unsigned *pl = c.pool[opp];
+        const unsigned hq = pl[1 * CAP + idx];
+        const int maker = (int)(pl[idx] >> 24);
+        const unsigned oid = pl[2 * CAP + idx];
+        unsigned traded; int left = -1;
+        if (qty < hq) {            // :73-85 partial fill: resting order shrinks in place
+            traded = qty; left = (int)(hq - qty);
+            __syncwarp();
+            if (c.lane == 0) pl[1 * CAP + idx] = hq - qty;
+            __syncwarp();
+            qty = 0;
+        } else {                   // :86-100 resting order consumed
+            traded = hq;
+            pool_remove(c, opp, idx);
+            qty -= traded;
+        }
+        // trade record (:109-141): price = resting price
+        c.tape_nonempty = 1; c.tape_px = P;
+        if (c.fills) {
+            if (c.n_fills < c.fill_cap) {
+                if (c.lane < CDA_FILL_WORDS) {
+                    int v = c.lane == 0 ? (int)c.time : c.lane == 1 ? P : c.lane == 2 ? (int)traded : c.lane == 3 ? maker
+                          : c.lane == 4 ? (int)oid : c.lane == 5 ? left : c.lane == 6 ? taker : side;
+                    c.fills[c.n_fills * CDA_FILL_WORDS + c.lane] = v;
+                }
+            } else c.status |= CDA_ST_FILL_OVERFLOW;
+        }
+        c.n_fills++;
+        // settlement: counter party (passive) and initiator (trader.py:311-322)
+        if (maker != taker) {
+            if (c.lane == maker) acct_fill(c.ac, 1, opp, traded, P);
+            else if (c.lane == taker) acct_fill(c.ac, 0, side, traded, P);
+        } else if (c.lane == taker) {   // cash_processor.py:55-62 init_is_counter_cash_transfer
+            const long long tv = (long long)traded * P;
+            c.ac.hold -= tv; c.ac.cash += tv;
+        }
+    }
+    return qty;
+}
+
+// cash_processor.py:15-29 order_in_book_passive_party on the initiator's lane
+template <int CAP> __device__ __forceinline__ void escrow(CdaCtx<CAP> &c, int t, long long price, long long qty) {
+    if (c.lane == t) { const long long v = price * qty; c.ac.cash -= v; c.ac.hold += v; }
+}
+// orderbook.py:210-266 modify_order, preceded by trader.py:219-235 (release the old escrow)
+template <int CAP> __device__ __forceinline__ void modify_resting(CdaCtx<CAP> &c, int side, int idx, int t, int new_price, unsigned new_qty) {
+    unsigned *pl = c.pool[side];
+    const unsigned op = pl[idx] & CDA_PRICE_MASK, oq = pl[1 * CAP + idx], oid = pl[2 * CAP + idx];
+    if (c.lane == t) { const long long ov = (long long)op * oq; c.ac.hold -= ov; c.ac.cash += ov; }
+    c.time++;
+    if ((unsigned)new_price == op && new_qty <= oq) {   // :245-248 in place: priority kept, timestamp refreshed
+        __syncwarp();
+        if (c.lane == 0) { pl[1 * CAP + idx] = new_qty; pl[3 * CAP + idx] = c.time; }
+        __syncwarp();
+        escrow(c, t, new_price, new_qty);
+        return;
+    }
+    pool_remove(c, side, idx);                          // :250-266 remove and re-process, same order_id
+    const unsigned rem = match_incoming(c, side, new_qty, new_price, t);
+    if (rem > 0 && pool_append(c, side, (unsigned)new_price, rem, t, oid, c.time)) escrow(c, t, new_price, rem);
+}
+
+// trader.py:49-106 place_order.  All arguments are warp-uniform.  type: 0 market 1 limit 2 modify 3 cancel
+template <int CAP> __device__ __forceinline__ void place_order(CdaCtx<CAP> &c, int t, int type, int side, long long size, int price) {
+    const int opp = 1 - side;
+    // ---- trader.py:108-151 _order_approved, evaluated on the trader's lane
+    int best_opp = -1;
+    if (type == 0) best_opp = pool_best(c, opp);
+    int ok_l = 0;
+    if (c.lane == t) {
+        if (c.ac.nav > 0) {
+            long long opening;
+            if ((side == 0 && c.ac.pos >= 0) || (side == 1 && c.ac.pos <= 0)) opening = size;
+            else { long long ap = c.ac.pos < 0 ? -c.ac.pos : c.ac.pos; opening = size - ap; if (opening < 0) opening = 0; }
+            if (opening <= 0) ok_l = 1;
+            else {
+                long long est = type == 0 ? (best_opp > 0 ? best_opp : (c.tape_nonempty ? c.tape_px : 1)) : price;
+                ok_l = c.ac.cash >= opening * est;
+            }
+        }
+    }
+    const int ok = __shfl_sync(CDA_FULL, ok_l, t);
+    if (!ok) { if (c.lane == t) c.ac.rejected++; return; }
+    if (type <= 1 && c.lane == t) c.ac.placed = 1;      // trader.py:75-76
+    if (size <= 0 && type <= 1) { c.status |= CDA_ST_BAD_SIZE; return; }
+    if (type == 0) {                                     // orderbook.py:33-46, :144-160
+        c.time++; c.next_id++;
+        match_incoming(c, side, (unsigned)size, -1, t);  // unfilled remainder is dropped
+    } else if (type == 1) {                              // trader.py:189-203
+        const int idx = pool_argmin(c, side, 0xffffffffu, ((unsigned)t << 24) | (unsigned)price, 4);
+        if (idx < 0) {
+            c.time++; c.next_id++;
+            const unsigned rem = match_incoming(c, side, (unsigned)size, price, t);
+            if (rem > 0 && pool_append(c, side, (unsigned)price, rem, t, c.next_id, c.time)) escrow(c, t, price, rem);
+        } else modify_resting(c, side, idx, t, price, (unsigned)size);
+    } else if (type == 2) {                              // trader.py:205-217: oldest timestamp, any price
+        const int idx = pool_argmin(c, side, 0xff000000u, (unsigned)t << 24, 3);
+        if (idx >= 0) modify_resting(c, side, idx, t, price, (unsigned)size);
+    } else {                                             // trader.py:237-252
+        const int idx = pool_argmin(c, side, 0xffffffffu, ((unsigned)t << 24) | (unsigned)price, 4);
+        if (idx >= 0) {
+            const unsigned *pl = c.pool[side];
+            const long long ov = (long long)(pl[idx] & CDA_PRICE_MASK) * pl[1 * CAP + idx];
+            c.time++;                                    // orderbook.py:196-208
+            pool_remove(c, side, idx);
+            if (c.lane == t) { c.ac.hold -= ov; c.ac.cash += ov; }
+        }
+    }
+}
+
+// counter-based generator for the fused random-policy rollout (NOT the env stream)
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+// ------------------------------------------------------------------------------------------
+// The fused step kernel: load -> decode -> shuffle -> match/settle -> MTM -> snapshot -> reward
+// -> store, one warp per market.  WARPS warps per CTA share nothing but the CTA's shared memory
+// carve-up, so there is no __syncthreads anywhere.
+// ------------------------------------------------------------------------------------------
+template <int CAP>
+struct CdaWarpSmem {
+    unsigned pool[2][CDA_POOL_FIELDS][CAP];
+    float snap[44];
+    int topk[2 * CDA_K_ROWS];        // frozen pre-step raw top-K prices (agg_LOB_raw price rows)
+    unsigned long long bar;
+    unsigned char order[32];
+    unsigned pad[2];
+};
+static_assert(sizeof(CdaWarpSmem<64>) % 16 == 0 && sizeof(CdaWarpSmem<128>) % 16 == 0 && sizeof(CdaWarpSmem<256>) % 16 == 0, "smem tile must keep 16-B alignment");
+
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * WARPS + warp;
+    if (m >= p.M) return;
+    const CdaDevCfg &cfg = p.cfg;
+    const int A = cfg.A;
+    CdaWarpSmem<CAP> &S = reinterpret_cast<CdaWarpSmem<CAP> *>(smem_raw)[warp];
+    unsigned char *blk = p.state + (size_t)m * cfg.stride;
+    unsigned *hdr = reinterpret_cast<unsigned *>(blk);
+
+    if (lane == 0) mbar_init(&S.bar, 1);
+    if (lane < 2 * CDA_K_ROWS) S.topk[lane] = (int)hdr[20 + lane];
+    __syncwarp();
+
+    // ---- header (warp-uniform 128-bit loads: one request each, value in every lane)
+    const uint4 h0 = *reinterpret_cast<const uint4 *>(hdr + 0);
+    const uint4 h1 = *reinterpret_cast<const uint4 *>(hdr + 4);
+    const uint4 h2 = *reinterpret_cast<const uint4 *>(hdr + 8);
+    const ulonglong2 r0 = *reinterpret_cast<const ulonglong2 *>(hdr + 12);
+    const ulonglong2 r1 = *reinterpret_cast<const ulonglong2 *>(hdr + 16);
+
+    CdaCtx<CAP> c;
+    c.lane = lane;
+    c.pool[0] = &S.pool[0][0][0]; c.pool[1] = &S.pool[1][0][0];
+    c.time = h0.x; c.next_id = h0.y; c.seqctr = h0.z;
+    unsigned t_step = h0.w;
+    int last_price = (int)h1.x;
+    c.tape_nonempty = (h1.y & CDA_FLAG_TAPE) ? 1 : 0;
+    unsigned done_mask = h1.z;
+    c.status = h1.w;
+    c.n[0] = (int)h2.x; c.n[1] = (int)h2.y;
+    CdaRng rng;
+    rng.has32 = h2.z; rng.u32 = h2.w;
+    rng.shi = r0.x; rng.slo = r0.y; rng.ihi = r1.x; rng.ilo = r1.y;
+    c.tape_px = last_price;
+    c.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
+    c.fill_cap = cfg.fill_cap;
+
+    // ---- order pool: TMA bulk copies of the live prefix of each field array
+    unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
+    const unsigned bytes_b = ((unsigned)c.n[0] * 4u + 15u) & ~15u, bytes_a = ((unsigned)c.n[1] * 4u + 15u) & ~15u;
+    const bool have_pool = (bytes_b | bytes_a) != 0;
+    if (have_pool && lane == 0) {
+        mbar_expect_tx(&S.bar, CDA_POOL_FIELDS * (bytes_b + bytes_a));
+#pragma unroll
+        for (int f = 0; f < CDA_POOL_FIELDS; ++f) {
+            if (bytes_b) bulk_g2s(&S.pool[0][f][0], gpool + (0 * CDA_POOL_FIELDS + f) * CAP, bytes_b, &S.bar);
+            if (bytes_a) bulk_g2s(&S.pool[1][f][0], gpool + (1 * CDA_POOL_FIELDS + f) * CAP, bytes_a, &S.bar);
+        }
+    }
+
+    // ---- accounts into lanes 0..A-1
+    long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct);
+    long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A;
+    int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
+    unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
+    c.ac = CdaAcct{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane < A) {
+        c.ac.cash = g_cash[lane]; c.ac.hold = g_hold[lane]; c.ac.cost = g_cost[lane]; c.ac.nav = g_nav[lane];
+        c.ac.prev_nav = g_prev[lane]; c.ac.max_nav = g_max[lane]; c.ac.pos = g_pos[lane]; c.ac.ntr = g_ntr[lane];
+    }
+    float *g_hist = reinterpret_cast<float *>(blk + cfg.off_hist);
+
+    bool waited = !have_pool;
+    const int n_iter = p.num_steps > 0 ? p.num_steps : 1;
+    for (int it = 0; it < n_iter; ++it) {
+        // ================= set_actions: action_helper.py:145-172, :241-397 =================
+        int a_cat = -1, a_pcode = 0, a_poff = 1; float a_mean = 0.f, a_sigma = 0.f;
+        if (lane < A) {
+            if (p.num_steps > 0) {   // fused uniform random policy (model_handler.py:38-78)
+                unsigned long long h = splitmix64(p.policy_seed ^ splitmix64(((unsigned long long)m << 32) ^ ((unsigned long long)(t_step) * 64ULL + lane)));
+                a_cat = (int)(((h & 0xffffu) * 9u) >> 16);
+                a_pcode = (int)((((h >> 16) & 0xffffu) * 10u) >> 16);
+                a_poff = (int)((((h >> 32) & 0xffffu) * 3u) >> 16);
+                unsigned long long h2 = splitmix64(h);
+                a_mean = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
+                a_sigma = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
+            } else {
+                const size_t o = (size_t)m * A + lane;
+                a_cat = p.cat[o]; a_mean = p.mean[o]; a_sigma = p.sigma[o]; a_pcode = p.pcode[o]; a_poff = p.poff[o];
+            }
+        }
+        c.n_fills = 0;
+        c.ac.tr_step = c.ac.pas_step = c.ac.placed = c.ac.rejected = c.ac.is_pass = 0;
+        bool bad = lane < A && (a_cat > 8 || (a_cat > 0 && ((a_cat - 1) & 3) != 0 && (a_pcode < 0 || a_pcode >= CDA_K_ROWS || a_poff < 0 || a_poff > 2)));
+        if (__any_sync(CDA_FULL, bad)) c.status |= CDA_ST_BAD_ACTION;
+        if (a_cat > 8) a_cat = 0;
+        if (a_pcode < 0 || a_pcode >= CDA_K_ROWS) a_pcode = 0;
+        if (a_poff < 0 || a_poff > 2) a_poff = 1;
+        const unsigned present = __ballot_sync(CDA_FULL, lane < A && a_cat >= 0);
+        // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339)
+        double z = 0.0;
+        for (unsigned pm = present; pm; pm &= pm - 1) {
+            const int a = __ffs(pm) - 1;
+            const double za = rng_normal(rng);
+            if (lane == a) z = za;
+        }
+        const int a_side = a_cat <= 0 ? -1 : (a_cat <= 4 ? 0 : 1);
+        const int a_type = a_cat <= 0 ? 0 : ((a_cat - 1) & 3);
+        long long a_size = 0; int a_price = -1;
+        if (lane < A && a_cat >= 0) {
+            const float loc = __fmul_rn(a_type == 0 ? cfg.mkt_mul : cfg.lim_mul, a_mean);  // f32 product (NEP 50)
+            const double x = (double)loc + (double)a_sigma * z;                              // numpy: loc + scale*z
+            a_size = __double2ll_rn(fabs(x)) + cfg.min_size;                                 // rint half-even, :339, :276
+            if (a_cat == 0) c.ac.is_pass = 1;
+            if (a_side >= 0 && a_type != 0) {            // _set_price :341-397 on the frozen pre-step top-K
+                const int raw = S.topk[a_side * CDA_K_ROWS + a_pcode];
+                const int off = a_poff - 1;
+                int base, pr;
+                if (a_side == 0) { base = raw == 0 ? last_price - (a_pcode + 1) * cfg.tick : raw; pr = base + off * cfg.tick; }
+                else             { base = raw == 0 ? last_price + (a_pcode + 1) * cfg.tick : raw; pr = base - off * cfg.tick; }
+                if (pr < cfg.tick) pr = cfg.tick;
+                a_price = pr;
+            }
+        }
+        if (__any_sync(CDA_FULL, a_price >= (int)CDA_PRICE_MASK)) { c.status |= CDA_ST_PRICE_RANGE; if (a_price >= (int)CDA_PRICE_MASK) a_price = CDA_PRICE_MASK - 1; }
+
+        // ================= rand_exec_seq: action_helper.py:174-199 ==========================
+        const unsigned active = __ballot_sync(CDA_FULL, lane < A && a_side >= 0);
+        const int n_act = __popc(active);
+        if (lane == 0) { int k = 0; for (unsigned am = active; am; am &= am - 1) S.order[k++] = (unsigned char)(__ffs(am) - 1); }
+        for (int i = n_act - 1; i >= 1; --i) {           // Generator.permutation: Fisher-Yates from the top
+            const unsigned j = rng_interval(rng, (unsigned)i);
+            if (lane == 0) { unsigned char tmp = S.order[i]; S.order[i] = S.order[j]; S.order[j] = tmp; }
+        }
+        __syncwarp();
+
+        if (!waited) { mbar_wait(&S.bar, 0); waited = true; }
+
+        // ================= do_actions: action_helper.py:201-239 =============================
+        for (int k = 0; k < n_act; ++k) {
+            const int t = S.order[k];
+            const int type = __shfl_sync(CDA_FULL, a_type, t);
+            const int side = __shfl_sync(CDA_FULL, a_side, t);
+            const long long size = __shfl_sync(CDA_FULL, a_size, t);
+            const int price = __shfl_sync(CDA_FULL, a_price, t);
+            place_order(c, t, type, side, size, price);
+        }
+
+        // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
+        if (c.tape_nonempty) {
+            last_price = c.tape_px;
+            if (lane < A) {
+                const long long ap = c.ac.pos < 0 ? -c.ac.pos : c.ac.pos;
+                const long long pv = c.ac.pos >= 0 ? ap * last_price : 2 * c.ac.cost - ap * last_price;
+                c.ac.prev_nav = c.ac.nav;
+                c.ac.nav = c.ac.cash + c.ac.hold + pv;
+                if (c.ac.nav > c.ac.max_nav) c.ac.max_nav = c.ac.nav;
+            }
+        }
+
+        // ================= set_agg_LOB: state_helper.py:113-214 =============================
+        int myP = 0; unsigned myV = 0;     // lane l<10: bid level l; 10<=l<20: ask level l-10
+        __syncwarp();
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const unsigned *pt = c.pool[side], *qy = c.pool[side] + CAP;
+            const int n = c.n[side];
+            unsigned prev = side == 0 ? 0x7fffffffu : 0u;
+            for (int k = 0; k < CDA_K_ROWS; ++k) {
+                unsigned loc = side == 0 ? 0u : 0xffffffffu;
+                for (int i = lane; i < n; i += 32) {
+                    unsigned pp = pt[i] & CDA_PRICE_MASK;
+                    if (side == 0 ? pp < prev : pp > prev) loc = side == 0 ? max(loc, pp) : min(loc, pp);
+                }
+                const unsigned P = side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc);
+                if (P == (side == 0 ? 0u : 0xffffffffu)) break;
+                unsigned s = 0;
+                for (int i = lane; i < n; i += 32) if ((pt[i] & CDA_PRICE_MASK) == P) s += qy[i];
+                const unsigned V = __reduce_add_sync(CDA_FULL, s);
+                if (lane == side * CDA_K_ROWS + k) { myP = (int)P; myV = V; }
+                prev = P;
+            }
+        }
+        const int best_bid = __shfl_sync(CDA_FULL, myP, 0), best_ask = __shfl_sync(CDA_FULL, myP, CDA_K_ROWS);
+        double Mid;
+        if (best_bid > 0 && best_ask > 0) Mid = ((double)best_bid + (double)best_ask) / 2.0;
+        else if (best_bid > 0) Mid = (double)best_bid;
+        else if (best_ask > 0) Mid = (double)best_ask;
+        else { Mid = (double)last_price; if (Mid <= 0) Mid = 100.0; }
+        if (lane < 2 * CDA_K_ROWS) {
+            const double pz = (double)myP, vz = (double)myV;
+            double pn, sn;
+            if (lane < CDA_K_ROWS) { pn = myP > 0 ? (Mid - pz) / Mid : 0.0; sn = myV > 0 ? sqrt(vz) : 0.0; }
+            else                   { pn = myP > 0 ? -((pz - Mid) / Mid) : 0.0; sn = myV > 0 ? -sqrt(vz) : 0.0; }
+            const int l = lane < CDA_K_ROWS ? lane : lane - CDA_K_ROWS;
+            const int b = lane < CDA_K_ROWS ? 0 : 2 * CDA_K_ROWS;
+            S.snap[b + l] = (float)pn;
+            S.snap[b + CDA_K_ROWS + l] = (float)sn;
+            S.topk[lane] = myP;                          // frozen raw top-K for the next step's _set_price
+            hdr[20 + lane] = (unsigned)myP;
+        } else if (lane == 20) {
+            S.snap[40] = (float)log(Mid);
+        } else if (lane == 21) {
+            float v = 0.0f;
+            if (best_bid > 0 && best_ask > 0) { double st = ((double)best_ask - (double)best_bid) / (double)cfg.tick; v = (float)log1p(st > 0.0 ? st : 0.0); }
+            S.snap[41] = v;
+        }
+        __syncwarp();
+
+        // ================= prep_next_state: state_helper.py:80-92 (ring + stacked obs) ======
+        const int slot_new = (int)(t_step % (unsigned)cfg.n_hist);
+        const bool last_it = it == n_iter - 1;
+        if (p.obs && last_it) {
+            float *o = p.obs + (size_t)m * cfg.W;
+            for (int e = lane; e < cfg.W; e += 32) {
+                const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+                int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
+                o[e] = (j == cfg.n_hist - 1) ? S.snap[cc] : g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+            }
+        }
+        __syncwarp();
+        for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = S.snap[cc];
+
+        // ================= set_reward / set_done: reward_helper.py:35-103, done_helper.py ===
+        bool broke = false;
+        if (lane < A) {
+            const double nav_change = (double)(c.ac.nav - c.ac.prev_nav);
+            const double nav_term = nav_change * (nav_change < 0 ? cfg.c_loss : 1.0);
+            long long ddi = c.ac.max_nav - c.ac.nav; if (ddi < 0) ddi = 0;
+            double r = 0.0;
+            r = r + nav_term;
+            r = r + -(cfg.c_order * (double)c.ac.placed);
+            r = r + -(cfg.c_trade * (double)c.ac.tr_step);
+            r = r + -(cfg.c_dd * (double)ddi);
+            r = r + cfg.c_passive * (double)c.ac.pas_step;
+            if (p.reward && last_it) p.reward[(size_t)m * A + lane] = r;
+            broke = c.ac.nav <= 0;
+        }
+        done_mask |= __ballot_sync(CDA_FULL, broke);
+        const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
+        if (lane == 0 && last_it) {
+            if (p.term) p.term[m] = (done_mask & all) == all;
+            if (p.trunc) p.trunc[m] = (t_step + 1 >= (unsigned)cfg.max_step);
+            if (p.fill_counts) p.fill_counts[m] = c.n_fills;
+        }
+        t_step++;
+        if (lane == 0) { hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask; }
+        __syncwarp();
+    }
+    if (!waited) mbar_wait(&S.bar, 0);   // (only when n_iter == 0; keeps the barrier phase consistent)
+
+    // ---- store: header, accounts, pool prefix
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(c.time, c.next_id, c.seqctr, t_step);
+        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)last_price, c.tape_nonempty ? CDA_FLAG_TAPE : 0u, done_mask, c.status);
+        *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)c.n[0], (unsigned)c.n[1], rng.has32, rng.u32);
+        *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(rng.shi, rng.slo);
+        *reinterpret_cast<ulonglong2 *>(hdr + 16) = make_ulonglong2(rng.ihi, rng.ilo);
+    }
+    if (lane < A) {
+        g_cash[lane] = c.ac.cash; g_hold[lane] = c.ac.hold; g_cost[lane] = c.ac.cost; g_nav[lane] = c.ac.nav;
+        g_prev[lane] = c.ac.prev_nav; g_max[lane] = c.ac.max_nav; g_pos[lane] = (int)c.ac.pos; g_ntr[lane] = c.ac.ntr;
+        g_ctr[lane] = (c.ac.tr_step & 0xfffu) | ((c.ac.pas_step & 0xfffu) << 12) | ((c.ac.placed & 1u) << 24) |
+                      ((c.ac.rejected & 1u) << 25) | ((c.ac.is_pass & 1u) << 26);
+    }
+    fence_proxy_async();   // every lane: its generic-proxy smem writes become visible to the async proxy
+    __syncwarp();
+    const unsigned ob = ((unsigned)c.n[0] * 4u + 15u) & ~15u, oa = ((unsigned)c.n[1] * 4u + 15u) & ~15u;
+    if (lane == 0 && (ob | oa)) {
+#pragma unroll
+        for (int f = 0; f < CDA_POOL_FIELDS; ++f) {
+            if (ob) bulk_s2g(gpool + (0 * CDA_POOL_FIELDS + f) * CAP, &S.pool[0][f][0], ob);
+            if (oa) bulk_s2g(gpool + (1 * CDA_POOL_FIELDS + f) * CAP, &S.pool[1][f][0], oa);
+        }
+        bulk_commit();
+        bulk_wait_read0();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// reset: continuousDoubleAuction_env.py:175-231 — one thread per market (cold path).
+// ------------------------------------------------------------------------------------------
+__global__ void cda_reset_kernel(CdaDevCfg cfg, unsigned char *state, int M, const unsigned long long *seeds,
+                                 const unsigned char *mask, float *obs) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    if (mask && !mask[m]) return;
+    unsigned char *blk = state + (size_t)m * cfg.stride;
+    unsigned *hdr = reinterpret_cast<unsigned *>(blk);
+    CdaRng rng;
+    if (seeds) rng_seed(rng, seeds[m]);
+    else {
+        rng.has32 = hdr[10]; rng.u32 = hdr[11];
+        const unsigned long long *r = reinterpret_cast<const unsigned long long *>(hdr + 12);
+        rng.shi = r[0]; rng.slo = r[1]; rng.ihi = r[2]; rng.ilo = r[3];
+    }
+    const int anchor = (int)rng_integers(rng, cfg.price_lo, (long long)cfg.price_hi + 1);   // :219-221
+    for (int i = 0; i < CDA_HDR_BYTES / 4; ++i) hdr[i] = 0;
+    hdr[4] = (unsigned)anchor;
+    hdr[10] = rng.has32; hdr[11] = rng.u32;
+    unsigned long long *r = reinterpret_cast<unsigned long long *>(hdr + 12);
+    r[0] = rng.shi; r[1] = rng.slo; r[2] = rng.ihi; r[3] = rng.ilo;
+    const int A = cfg.A;
+    long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct);
+    for (int a = 0; a < A; ++a) {                                                          // account.py:55-82
+        g_cash[a] = cfg.init_cash; g_cash[A + a] = 0; g_cash[2 * A + a] = 0;
+        g_cash[3 * A + a] = cfg.init_cash; g_cash[4 * A + a] = cfg.init_cash; g_cash[5 * A + a] = cfg.init_cash;
+    }
+    int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
+    for (int a = 0; a < 3 * A; ++a) g_pos[a] = 0;
+    // empty-book snapshot (state_helper.py:66-78, :163-175): zeros, log(anchor), 0
+    float *g_hist = reinterpret_cast<float *>(blk + cfg.off_hist);
+    double Mid = (double)anchor; if (Mid <= 0) Mid = 100.0;
+    const float lm = (float)log(Mid);
+    for (int h = 0; h < cfg.n_hist; ++h)
+        for (int cc = 0; cc < CDA_SNAPSHOT_DIM; ++cc) {
+            const float v = cc == 40 ? lm : 0.0f;
+            g_hist[h * CDA_SNAPSHOT_DIM + cc] = v;
+            if (obs) obs[(size_t)m * cfg.W + h * CDA_SNAPSHOT_DIM + cc] = v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// lazy info gather (info_helper.py:30-116): one thread per (market, agent)
+// ------------------------------------------------------------------------------------------
+__global__ void cda_info_kernel(CdaDevCfg cfg, const unsigned char *state, int M, int field, long long *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int A = cfg.A;
+    if (field == CDA_INFO_MARKET) {
+        if (i >= M) return;
+        const unsigned *hdr = reinterpret_cast<const unsigned *>(state + (size_t)i * cfg.stride);
+        long long *o = out + (size_t)i * 8;
+        o[0] = (int)hdr[4]; o[1] = (int)hdr[40]; o[2] = (int)hdr[41]; o[3] = hdr[0]; o[4] = hdr[1]; o[5] = hdr[3]; o[6] = hdr[6]; o[7] = hdr[7];
+        return;
+    }
+    if (i >= M * A) return;
+    const int m = i / A, a = i - m * A;
+    const unsigned char *blk = state + (size_t)m * cfg.stride;
+    const unsigned *hdr = reinterpret_cast<const unsigned *>(blk);
+    const long long *g = reinterpret_cast<const long long *>(blk + cfg.off_acct);
+    const int *g_pos = reinterpret_cast<const int *>(g + 6 * A);
+    const unsigned *g_ntr = reinterpret_cast<const unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
+    long long v = 0;
+    const unsigned ctr = g_ctr[a];
+    switch (field) {
+        case CDA_INFO_CASH: v = g[a]; break;
+        case CDA_INFO_CASH_ON_HOLD: v = g[A + a]; break;
+        case CDA_INFO_COST_BASIS: v = g[2 * A + a]; break;
+        case CDA_INFO_NAV: v = g[3 * A + a]; break;
+        case CDA_INFO_PREV_NAV: v = g[4 * A + a]; break;
+        case CDA_INFO_MAX_NAV: v = g[5 * A + a]; break;
+        case CDA_INFO_NET_POSITION: v = g_pos[a]; break;
+        case CDA_INFO_POSITION_VAL: {   // calculate.py:35-55 at the last mark-to-market
+            const long long pos = g_pos[a], ap = pos < 0 ? -pos : pos, lp = (int)hdr[4];
+            v = (hdr[5] & CDA_FLAG_TAPE) ? (pos >= 0 ? ap * lp : 2 * g[2 * A + a] - ap * lp) : 0;
+            break;
+        }
+        case CDA_INFO_NUM_TRADES: v = g_ntr[a]; break;
+        case CDA_INFO_NUM_TRADES_STEP: v = ctr & 0xfffu; break;
+        case CDA_INFO_NUM_PASSIVE_FILLS_STEP: v = (ctr >> 12) & 0xfffu; break;
+        case CDA_INFO_ORDER_STEP_PLACED: v = (ctr >> 24) & 1u; break;
+        case CDA_INFO_NUM_REJECTED_STEP: v = (ctr >> 25) & 1u; break;
+        case CDA_INFO_IS_PASS_ACTION: v = (ctr >> 26) & 1u; break;
+        default: break;
+    }
+    out[i] = v;
+}

@@ -1,0 +1,226 @@
+"""VecCDAEnv — tensor API over M independent continuous-double-auction markets on one B200.
+
+One `step` == one fused CUDA kernel launch stepping every market once (all A agents act):
+the whole `continuousDoubleAuctionEnv.step` of the reference
+(gym_continuousDoubleAuction/envs/continuousDoubleAuction_env.py:265-309) per market.
+PyTorch only supplies device buffers and the stream; the work is in csrc/ behind the C-ABI.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from .config import SNAPSHOT_DIM, resolve
+
+STATUS_BITS = {1: "order pool overflow", 2: "fill log overflow", 4: "bad action",
+               8: "price out of range", 16: "bad order size"}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class VecCDAEnv:
+    def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("VecCDAEnv needs a CUDA device (sm_100a); there is no CPU fallback")
+        cfg = resolve(config)
+        self.config = cfg
+        self.num_markets = self.M = int(num_markets)
+        self.num_of_agents = self.A = int(cfg["num_of_agents"])
+        self.n_hist = int(cfg["n_hist"])
+        self.max_step = int(cfg["max_step"])
+        self.init_cash = cfg["init_cash"]
+        self.obs_dim = self.W = self.n_hist * SNAPSHOT_DIM
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self._L = _native.lib()
+        c = _native.CdaConfig(
+            self.A, self.n_hist, self.max_step, int(cfg["tick_size"]), int(cfg["init_cash"]),
+            int(cfg["min_size"]), int(cfg["mkt_max_size"]), int(cfg["limit_size_multiple"]),
+            int(cfg["initial_price_min"]), int(cfg["initial_price_max"]), int(order_capacity),
+            int(fill_capacity), float(cfg["order_penalty"]), float(cfg["trade_penalty"]),
+            float(cfg["drawdown_penalty"]), float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]))
+        h = ctypes.c_void_p()
+        _native.check(self._L.cda_create(ctypes.byref(c), self.M, self.device.index, ctypes.byref(h)))
+        self._h = h
+        self.fill_capacity = int(fill_capacity)
+        self.order_capacity = self._L.cda_order_capacity(h)
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((self.M, self.W), dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros((self.M, self.A), dtype=torch.float64, device=self.device)
+            self.terminated = torch.zeros(self.M, dtype=torch.uint8, device=self.device)
+            self.truncated = torch.zeros(self.M, dtype=torch.uint8, device=self.device)
+        self._pinned = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ reset
+    def reset(self, seed=None, mask=None):
+        """seed: None (keep every market's stream, reference `reset(seed=None)`), an int (market m
+        is seeded with seed + m), or a length-M sequence/tensor of per-market integer seeds.
+        mask: optional bool/uint8 [M] selecting the markets to reset.  Returns obs [M, W]."""
+        seeds_t = None
+        if seed is not None:
+            if isinstance(seed, (int, np.integer)):
+                seeds = np.arange(self.M, dtype=np.uint64) + np.uint64(seed)
+            else:
+                seeds = np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed).astype(np.uint64)
+                if seeds.shape != (self.M,):
+                    raise ValueError("seed must be None, an int, or one seed per market")
+            seeds_t = torch.from_numpy(seeds.view(np.int64)).to(self.device)
+        mask_t = None
+        if mask is not None:
+            mask_t = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        _native.check(self._L.cda_reset(self._h, _ptr(seeds_t), _ptr(mask_t), _ptr(self.obs), self._stream()))
+        return self.obs
+
+    # ------------------------------------------------------------------ step (device tensors)
+    def step(self, category, size_mean, size_sigma, price, price_offset, out=None):
+        """All inputs are CUDA tensors shaped [M, A] (int32 / float32).  Returns
+        (obs f32[M,W], reward f64[M,A], terminated u8[M], truncated u8[M]) — tensors owned by the
+        env and overwritten by the next step unless `out` (a 4-tuple) is given."""
+        for t, dt in ((category, torch.int32), (size_mean, torch.float32), (size_sigma, torch.float32),
+                      (price, torch.int32), (price_offset, torch.int32)):
+            if t.dtype != dt or not t.is_cuda or not t.is_contiguous() or t.numel() != self.M * self.A:
+                raise ValueError("actions must be contiguous CUDA tensors [M, A] of int32/float32")
+        obs, rew, term, trunc = out if out is not None else (self.obs, self.reward, self.terminated, self.truncated)
+        _native.check(self._L.cda_step(self._h, _ptr(category), _ptr(size_mean), _ptr(size_sigma), _ptr(price),
+                                       _ptr(price_offset), _ptr(obs), _ptr(rew), _ptr(term), _ptr(trunc),
+                                       self._stream()))
+        return obs, rew, term, trunc
+
+    # ------------------------------------------------------------------ step (host buffers, e2e)
+    def _ensure_pinned(self):
+        if self._pinned is None:
+            M, A, W = self.M, self.A, self.W
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+            self._pinned = dict(
+                cat=pin((M, A), torch.int32), mean=pin((M, A), torch.float32), sigma=pin((M, A), torch.float32),
+                price=pin((M, A), torch.int32), off=pin((M, A), torch.int32),
+                obs=pin((M, W), torch.float32), reward=pin((M, A), torch.float64),
+                term=pin((M,), torch.uint8), trunc=pin((M,), torch.uint8))
+        return self._pinned
+
+    def step_host(self, category, size_mean, size_sigma, price, price_offset, sync=True):
+        """Host arrays in, host arrays out (numpy views of pinned buffers): the H2D copy of the
+        actions, the kernel and the D2H copy of obs/reward/flags are all inside this call."""
+        p = self._ensure_pinned()
+        for key, src in (("cat", category), ("mean", size_mean), ("sigma", size_sigma), ("price", price), ("off", price_offset)):
+            if isinstance(src, torch.Tensor):
+                p[key].copy_(src.reshape(self.M, self.A))
+            else:
+                np.copyto(p[key].numpy(), np.asarray(src).reshape(self.M, self.A), casting="same_kind")
+        return self.step_pinned(sync=sync)
+
+    def step_pinned(self, sync=True):
+        """Like step_host but the caller has already written the actions into `pinned_buffers()`."""
+        p = self._ensure_pinned()
+        _native.check(self._L.cda_step_host(self._h, _ptr(p["cat"]), _ptr(p["mean"]), _ptr(p["sigma"]), _ptr(p["price"]),
+                                            _ptr(p["off"]), _ptr(p["obs"]), _ptr(p["reward"]), _ptr(p["term"]),
+                                            _ptr(p["trunc"]), self._stream()))
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return p["obs"].numpy(), p["reward"].numpy(), p["term"].numpy(), p["trunc"].numpy()
+
+    def pinned_buffers(self):
+        return self._ensure_pinned()
+
+    # ------------------------------------------------------------------ fused random rollout
+    def rollout_random(self, num_steps, policy_seed=0):
+        _native.check(self._L.cda_rollout_random(self._h, int(num_steps), ctypes.c_uint64(policy_seed), _ptr(self.obs),
+                                                 _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
+                                                 self._stream()))
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    # ------------------------------------------------------------------ lazy info / fills
+    def info(self, field):
+        """One info field for all markets as an int64 CUDA tensor ([M, A], or [M, 8] for 'market')."""
+        idx = _native.INFO_FIELDS.index(field)
+        shape = (self.M, 8) if field == "market" else (self.M, self.A)
+        out = torch.empty(shape, dtype=torch.int64, device=self.device)
+        _native.check(self._L.cda_get_info(self._h, idx, _ptr(out), self._stream()))
+        return out
+
+    def status(self):
+        return self.info("market")[:, 7]
+
+    def check_status(self):
+        st = int(torch.bitwise_or(self.status(), torch.zeros((), dtype=torch.int64, device=self.device)).max().item()) if self.M else 0
+        allbits = 0
+        s = self.status()
+        for b in STATUS_BITS:
+            if bool(((s & b) != 0).any().item()):
+                allbits |= b
+        if allbits:
+            raise RuntimeError("cda_b200 market status: " + ", ".join(v for b, v in STATUS_BITS.items() if allbits & b))
+        return st
+
+    def fills(self):
+        if not self.fill_capacity:
+            raise ValueError("construct the env with fill_capacity > 0 to log fills")
+        f = torch.empty((self.M, self.fill_capacity, 8), dtype=torch.int32, device=self.device)
+        n = torch.empty(self.M, dtype=torch.int32, device=self.device)
+        _native.check(self._L.cda_get_fills(self._h, _ptr(f), _ptr(n), self._stream()))
+        return f, n
+
+    # ------------------------------------------------------------------ canonical dump (tests)
+    def dump(self, m=0, max_rows=1024):
+        """Same schema as the oracle's dump: used for bit-exact parity checks."""
+        bids = np.zeros((max_rows, 5), np.int64)
+        asks = np.zeros((max_rows, 5), np.int64)
+        bmap = np.zeros(max_rows, np.int64)
+        amap = np.zeros(max_rows, np.int64)
+        counts = np.zeros(2, np.int32)
+        rng = np.zeros(6, np.uint64)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _native.check(self._L.cda_dump_market(self._h, int(m), vp(bids), vp(asks), vp(bmap), vp(amap), max_rows,
+                                              vp(counts), vp(rng)))
+        out = {"bids": bids[:counts[0]].copy(), "asks": asks[:counts[1]].copy(),
+               "bids_map": bmap[:counts[0]].copy(), "asks_map": amap[:counts[1]].copy(), "rng": rng}
+        mk = self.info("market")[m].cpu().numpy()
+        out.update(last_price=int(mk[0]), best_bid=int(mk[1]), best_ask=int(mk[2]), time=int(mk[3]),
+                   next_order_id=int(mk[4]), t_step=int(mk[5]), done_mask=int(mk[6]), status=int(mk[7]))
+        cols = ("cash", "cash_on_hold", "position_val", "cost_basis", "nav", "prev_nav", "max_nav", "net_position",
+                "num_trades", "num_trades_step", "num_passive_fills_step", "order_step_placed",
+                "num_rejected_step", "is_pass_action")
+        out["accounts"] = np.stack([self.info(c)[m].cpu().numpy() for c in cols], axis=1)
+        if self.fill_capacity:
+            f, n = self.fills()
+            nf = int(n[m].item())
+            out["n_fills"] = nf
+            out["fills"] = f[m, :min(nf, self.fill_capacity)].cpu().numpy()
+        return out
+
+    # ------------------------------------------------------------------ checkpoint
+    def state_dict(self):
+        nbytes = self._L.cda_state_bytes(self._h)
+        buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        _native.check(self._L.cda_save_state(self._h, _ptr(buf), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        return {"state": buf.clone(), "num_markets": self.M, "config": {k: v for k, v in self.config.items() if not k.startswith("_")},
+                "order_capacity": self.order_capacity}
+
+    def load_state_dict(self, sd):
+        if sd["num_markets"] != self.M or sd["order_capacity"] != self.order_capacity or sd["state"].numel() != self._L.cda_state_bytes(self._h):
+            raise ValueError("checkpoint does not match this env's shape")
+        buf = sd["state"].contiguous().pin_memory()
+        _native.check(self._L.cda_load_state(self._h, _ptr(buf), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.cda_kernel_launches(self._h))

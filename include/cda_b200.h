@@ -1,0 +1,157 @@
+/* cda_b200.h — C-ABI of the B200-native vectorised continuous-double-auction environment.
+ *
+ * This is the drop-in boundary for the reference's per-step env hot path.  The reference
+ * (ChuaCheowHuan/gym-continuousDoubleAuction) is pure Python and has no FFI of its own; the
+ * boundary it exposes is the `continuousDoubleAuctionEnv` class surface
+ * (gym_continuousDoubleAuction/envs/continuousDoubleAuction_env.py:21-359).  Each entry point
+ * below names the reference call it replaces.  All pointers are plain device or host pointers,
+ * sizes are plain integers, `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  No torch types appear here; PyTorch only supplies the buffers and the stream.
+ *
+ * Shapes (M = num_markets, A = num_agents, W = n_hist * 42):
+ *   actions   category i32[M][A]  (0..8, reference _CATEGORY_MAP action_helper.py:12-22;
+ *                                  -1 = agent absent from the action dict: no RNG draw)
+ *             size_mean f32[M][A], size_sigma f32[M][A], price i32[M][A] (0..9),
+ *             price_offset i32[M][A] (0..2)            (action space: action_helper.py:126-138)
+ *   obs       f32[M][W]   stacked observation, oldest snapshot first (state_helper.py:80-92)
+ *   reward    f64[M][A]   (reward_helper.py:35-103; f64 because |r| reaches 1e4 and parity is 1e-6)
+ *   terminated/truncated u8[M]  == terminateds["__all__"] / truncateds["__all__"]
+ *                                  (done_helper.py:20-55)
+ *
+ * Every function returns 0 on success or a negative CDA_E* code; cda_strerror() names it.
+ * Calls on one handle are stream-ordered and not re-entrant; use one handle per GPU/process.
+ */
+#ifndef CDA_B200_H
+#define CDA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDA_K_ROWS 10   /* observation_layout.k_rows  (config/tunable_constants.json) */
+#define CDA_SNAPSHOT_DIM 42
+#define CDA_MAX_AGENTS 32
+#define CDA_MAX_HIST 16
+#define CDA_FILL_WORDS 8 /* time, price, qty, maker, maker_order_id, maker_left(-1=None), taker, taker_side(0 bid/1 ask) */
+
+/* error codes */
+#define CDA_OK 0
+#define CDA_EINVAL (-1)   /* bad argument / config (reference raises ValueError at construction) */
+#define CDA_ECUDA (-2)    /* a CUDA runtime call failed; see cda_last_cuda_error() */
+#define CDA_ENOMEM (-3)
+#define CDA_ESTATE (-4)   /* handle used before reset, or after a sticky device error */
+
+/* per-market sticky status bits (replace the reference's sys.exit() paths, orderbook.py:42,58,159) */
+#define CDA_ST_POOL_OVERFLOW 1u   /* more resting orders on one side than order_capacity: order dropped */
+#define CDA_ST_FILL_OVERFLOW 2u   /* more fills in one step than the fill log holds (log truncated only) */
+#define CDA_ST_BAD_ACTION 4u      /* category/price/price_offset outside the action space */
+#define CDA_ST_PRICE_RANGE 8u     /* a price left [1, 2^24): outside the exactly-representable range */
+#define CDA_ST_BAD_SIZE 16u       /* order size <= 0 (reference: sys.exit in process_order) */
+
+/* Mirrors the 17 env config keys (continuousDoubleAuction_env.py:35-53) that touch the hot path. */
+typedef struct CdaConfig {
+    int32_t num_agents;          /* num_of_agents, 1..32 */
+    int32_t n_hist;              /* 1..16 */
+    int32_t max_step;
+    int32_t tick_size;           /* integral ticks only (>=1) */
+    int64_t init_cash;           /* > 0 */
+    int32_t min_size, mkt_max_size, limit_size_multiple;
+    int32_t initial_price_min, initial_price_max;   /* inclusive anchor range */
+    int32_t order_capacity;      /* resting orders per side per market: 64, 128 or 256; 0 = auto */
+    int32_t fill_capacity;       /* fills logged per market per step (0 = no fill log) */
+    double order_penalty, trade_penalty, drawdown_penalty, passive_bonus, loss_multiplier;
+} CdaConfig;
+
+typedef struct CdaEnv CdaEnv; /* opaque handle */
+
+/* info fields for cda_get_info (info_helper.py:30-116) */
+enum CdaInfoField {
+    CDA_INFO_CASH = 0,        /* i64[M][A] */
+    CDA_INFO_CASH_ON_HOLD,    /* i64[M][A] */
+    CDA_INFO_COST_BASIS,      /* i64[M][A]  |net_position| * VWAP  (VWAP = this / |pos|) */
+    CDA_INFO_NAV,             /* i64[M][A] */
+    CDA_INFO_PREV_NAV,        /* i64[M][A] */
+    CDA_INFO_MAX_NAV,         /* i64[M][A] */
+    CDA_INFO_NET_POSITION,    /* i64[M][A] */
+    CDA_INFO_POSITION_VAL,    /* i64[M][A] */
+    CDA_INFO_NUM_TRADES,      /* i64[M][A] */
+    CDA_INFO_NUM_TRADES_STEP, /* i64[M][A] */
+    CDA_INFO_NUM_PASSIVE_FILLS_STEP, /* i64[M][A] */
+    CDA_INFO_ORDER_STEP_PLACED,      /* i64[M][A] */
+    CDA_INFO_NUM_REJECTED_STEP,      /* i64[M][A] */
+    CDA_INFO_IS_PASS_ACTION,         /* i64[M][A] */
+    CDA_INFO_MARKET,          /* i64[M][8]: last_price, best_bid(0=None), best_ask(0=None), time,
+                                 next_order_id, t_step, done_mask, status */
+    CDA_INFO__COUNT
+};
+
+/* continuousDoubleAuctionEnv.__init__ (continuousDoubleAuction_env.py:27-119), for M markets. */
+int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv **out);
+int cda_destroy(CdaEnv *env);
+
+/* env.reset(seed=...) (continuousDoubleAuction_env.py:175-231).
+ *   d_seeds: u64[M] device pointer, or NULL to keep each market's stream (reset(seed=None)).
+ *            Market m is seeded exactly like gymnasium: Generator(PCG64(SeedSequence(seed))).
+ *   d_mask:  u8[M] device pointer selecting markets to reset, or NULL for all.
+ *   d_obs:   f32[M][W] output (rows of unselected markets untouched), may be NULL. */
+int cda_reset(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *d_obs, void *stream);
+
+/* env.step(action_dict) (continuousDoubleAuction_env.py:265-309) for all M markets: one fused
+ * kernel launch; no host synchronisation.  All pointers are DEVICE pointers. */
+int cda_step(CdaEnv *env, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
+             const int32_t *d_price, const int32_t *d_price_offset, float *d_obs, double *d_reward,
+             uint8_t *d_terminated, uint8_t *d_truncated, void *stream);
+
+/* Same call with HOST buffers (pinned for full speed): copies the five action arrays to the
+ * device, steps, copies obs/reward/flags back, all on `stream`; the caller synchronises the
+ * stream before reading.  This is the end-to-end path a host-side policy uses. */
+int cda_step_host(CdaEnv *env, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                  const int32_t *h_price, const int32_t *h_price_offset, float *h_obs, double *h_reward,
+                  uint8_t *h_terminated, uint8_t *h_truncated, void *stream);
+
+/* Fused T-step rollout with the on-device uniform random policy (the RandomRLModule /
+ * CDA_rand.py workload: category U{0..8}, price U{0..9}, offset U{0..2}, mean U(-1,1), sigma U(0,1),
+ * gym_continuousDoubleAuction/train/model/model_handler.py:38-78).  Policy draws come from a
+ * separate counter-based generator keyed by (policy_seed, market, step, agent) so env streams
+ * stay numpy-exact.  Outputs hold the LAST step.  d_obs etc. may be NULL. */
+int cda_rollout_random(CdaEnv *env, int32_t num_steps, uint64_t policy_seed, float *d_obs, double *d_reward,
+                       uint8_t *d_terminated, uint8_t *d_truncated, void *stream);
+
+/* Lazy info (info_helper.py:30-116): gathers one field for all markets into d_out. */
+int cda_get_info(CdaEnv *env, int32_t field, int64_t *d_out, void *stream);
+
+/* Fill log of the last step (the reference's per-step `seq_trades`, action_helper.py:201-239):
+ * d_fills i32[M][fill_capacity][8], d_counts i32[M].  Requires fill_capacity > 0. */
+int cda_get_fills(CdaEnv *env, int32_t *d_fills, int32_t *d_counts, void *stream);
+
+/* Canonical dump of one market for bit-exact checks (host buffers; synchronises).
+ *   book rows (priority order: bids price desc / asks price asc, FIFO inside a level):
+ *     price, qty, trader, order_id, timestamp           -> h_bids/h_asks i64[max_rows][5]
+ *   map rows: order ids in the reference's order_map iteration order -> i64[max_rows]
+ *   h_counts[2] receive the number of orders per side. */
+int cda_dump_market(CdaEnv *env, int32_t market, int64_t *h_bids, int64_t *h_asks, int64_t *h_bids_map,
+                    int64_t *h_asks_map, int32_t max_rows, int32_t *h_counts, uint64_t *h_rng6);
+
+/* Device-state checkpoint (the reference has none). */
+size_t cda_state_bytes(const CdaEnv *env);
+int cda_save_state(CdaEnv *env, void *h_dst, void *stream);
+int cda_load_state(CdaEnv *env, const void *h_src, void *stream);
+
+/* Introspection */
+int32_t cda_num_markets(const CdaEnv *env);
+int32_t cda_obs_dim(const CdaEnv *env);
+int32_t cda_order_capacity(const CdaEnv *env);
+int64_t cda_kernel_launches(const CdaEnv *env); /* kernels launched by this handle so far */
+const char *cda_strerror(int code);
+const char *cda_last_cuda_error(void);
+const char *cda_build_info(void);
+
+/* Host-side helper: the PCG64 state numpy gives for `seed` (state_hi, state_lo, inc_hi, inc_lo). */
+void cda_seed_to_pcg64(uint64_t seed, uint64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDA_B200_H */

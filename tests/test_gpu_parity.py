@@ -1,0 +1,175 @@
+"""GPU parity tests: the CUDA env (through the C-ABI) against the CPU oracle on identical seeds
+and action sequences.  Integer state (book, order-map order, ledger, fills, RNG stream) must be
+BIT-EXACT; observations (f32) and rewards (f64) within 1e-6 (they are normally bit-equal too).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.cda_oracle import OracleEnv
+from parity_utils import assert_dump_equal
+
+import gym_continuousdoubleauction_b200 as cda
+from gym_continuousdoubleauction_b200.workloads import make_actions
+
+pytestmark = pytest.mark.gpu
+
+OBS_TOL = 1e-6   # north-star tolerance for observations (float32)
+REW_TOL = 1e-6   # north-star tolerance for rewards (float64)
+
+
+def run_pair(cfg, M, T, mix, seed, dump_every=25, dump_markets=(0, 1, 2), absent_p=0.0, order_capacity=0):
+    A = cfg["num_of_agents"]
+    env = cda.VecCDAEnv(cfg, num_markets=M, fill_capacity=64, order_capacity=order_capacity)
+    orc = OracleEnv(cfg, M)
+    seeds = np.arange(M, dtype=np.uint64) + np.uint64(seed)
+    o_g = env.reset(seed=seeds).cpu().numpy()
+    o_c = orc.reset(seeds=seeds)
+    assert np.array_equal(o_g, o_c), "reset observation differs"
+    acts = make_actions(seed + 99, T, M, A, mix)
+    if absent_p > 0:
+        rng = np.random.default_rng(seed + 5)
+        acts[0][rng.random(acts[0].shape) < absent_p] = -1
+    max_obs = max_rew = 0.0
+    for t in range(T):
+        step = [torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts]
+        og, rg, teg, trg = env.step(*step)
+        oc, rc, tec, trc = orc.step(*[a[t] for a in acts], nthreads=4)
+        og, rg = og.cpu().numpy(), rg.cpu().numpy()
+        d_obs = np.abs(og.astype(np.float64) - oc.astype(np.float64)).max()
+        d_rew = np.abs(rg - rc).max()
+        max_obs, max_rew = max(max_obs, d_obs), max(max_rew, d_rew)
+        assert d_obs <= OBS_TOL, f"step {t}: obs differs by {d_obs}"
+        assert d_rew <= REW_TOL, f"step {t}: reward differs by {d_rew}"
+        assert np.array_equal(teg.cpu().numpy(), tec) and np.array_equal(trg.cpu().numpy(), trc), f"step {t}: flags"
+        if t % dump_every == 0 or t == T - 1:
+            for m in dump_markets:
+                if m < M:
+                    assert_dump_equal(env.dump(m), orc.dump(m), ctx=f"t={t} m={m}")
+    st = env.status().cpu().numpy()
+    assert (st == 0).all(), f"sticky status bits set: {np.unique(st)}"
+    env.close()
+    return max_obs, max_rew
+
+
+def base_cfg(**kw):
+    cfg = dict(num_of_agents=4, init_cash=1_000_000, max_step=10_000, n_hist=4)
+    cfg.update(kw)
+    return cfg
+
+
+def test_config2_uniform_4x1024_bit_exact():
+    """BASELINE config 2 shape: 4 agents x 1024 markets, uniform random actions; every market's
+    final book/ledger/fills/RNG compared bit-exactly at the end, 3 markets every 25 steps."""
+    cfg = base_cfg()
+    M, T = 1024, 96
+    env = cda.VecCDAEnv(cfg, num_markets=M, fill_capacity=64)
+    orc = OracleEnv(cfg, M)
+    seeds = np.arange(M, dtype=np.uint64) + np.uint64(1000)
+    env.reset(seed=seeds); orc.reset(seeds=seeds)
+    acts = make_actions(7, T, M, 4, "uniform")
+    for t in range(T):
+        og, rg, _, _ = env.step(*[torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts])
+        oc, rc, _, _ = orc.step(*[a[t] for a in acts], nthreads=8)
+    assert np.abs(og.cpu().numpy().astype(np.float64) - oc).max() <= OBS_TOL
+    assert np.abs(rg.cpu().numpy() - rc).max() <= REW_TOL
+    for m in range(M):
+        assert_dump_equal(env.dump(m), orc.dump(m), ctx=f"m={m}")
+    env.close()
+
+
+def test_uniform_small_every_step_dump():
+    run_pair(base_cfg(), M=8, T=150, mix="uniform", seed=11, dump_every=1, dump_markets=range(8))
+
+
+def test_config3_limit_market_mix():
+    run_pair(base_cfg(), M=256, T=128, mix="limit_market", seed=21)
+
+
+def test_config4_modify_heavy_8_agents():
+    run_pair(base_cfg(num_of_agents=8), M=128, T=160, mix="modify_heavy", seed=31)
+
+
+def test_low_cash_rejections_and_bankruptcy():
+    run_pair(base_cfg(init_cash=3000), M=64, T=200, mix="uniform", seed=41, dump_every=10)
+
+
+@pytest.mark.parametrize("n_hist", [1, 2, 6, 10])
+def test_n_hist_variants(n_hist):
+    run_pair(base_cfg(n_hist=n_hist, num_of_agents=3), M=16, T=40, mix="limit_market", seed=50 + n_hist, dump_every=10)
+
+
+def test_absent_agents_partial_action_dicts():
+    run_pair(base_cfg(num_of_agents=5), M=32, T=120, mix="uniform", seed=61, absent_p=0.3, dump_every=10)
+
+
+def test_16_agents_and_capacity_256():
+    run_pair(base_cfg(num_of_agents=16), M=16, T=100, mix="uniform", seed=71, dump_every=20, order_capacity=256)
+
+
+def test_truncation_flag_lands_on_max_step():
+    cfg = base_cfg(max_step=5)
+    env = cda.VecCDAEnv(cfg, num_markets=4)
+    env.reset(seed=3)
+    acts = make_actions(1, 6, 4, 4, "uniform")
+    flags = []
+    for t in range(6):
+        _, _, _, tr = env.step(*[torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts])
+        flags.append(int(tr[0].item()))
+    assert flags == [0, 0, 0, 0, 1, 1]
+    env.close()
+
+
+def test_reset_seed_none_keeps_stream_and_masked_reset():
+    cfg = base_cfg()
+    M = 8
+    env = cda.VecCDAEnv(cfg, num_markets=M)
+    orc = OracleEnv(cfg, M)
+    seeds = np.arange(M, dtype=np.uint64) + np.uint64(500)
+    env.reset(seed=seeds); orc.reset(seeds=seeds)
+    acts = make_actions(3, 40, M, 4, "uniform")
+    for t in range(20):
+        env.step(*[torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts])
+        orc.step(*[a[t] for a in acts])
+    mask = np.array([1, 0, 1, 0, 0, 1, 0, 0], np.uint8)
+    og = env.reset(seed=None, mask=mask).cpu().numpy()
+    oc = orc.reset(seeds=None, mask=mask)
+    assert np.array_equal(og[mask == 1], oc[mask == 1])
+    for t in range(20, 40):
+        og, rg, _, _ = env.step(*[torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts])
+        oc, rc, _, _ = orc.step(*[a[t] for a in acts])
+    assert np.abs(og.cpu().numpy().astype(np.float64) - oc).max() <= OBS_TOL
+    for m in range(M):
+        assert_dump_equal(env.dump(m), orc.dump(m), ctx=f"m={m}", fills=False)
+    env.close()
+
+
+def test_step_host_matches_device_step():
+    cfg = base_cfg()
+    M = 64
+    e1 = cda.VecCDAEnv(cfg, num_markets=M)
+    e2 = cda.VecCDAEnv(cfg, num_markets=M)
+    e1.reset(seed=9); e2.reset(seed=9)
+    acts = make_actions(4, 30, M, 4, "uniform")
+    for t in range(30):
+        o1, r1, _, _ = e1.step(*[torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts])
+        o2, r2, _, _ = e2.step_host(*[a[t] for a in acts])
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+    e1.close(); e2.close()
+
+
+def test_checkpoint_roundtrip():
+    cfg = base_cfg()
+    M = 16
+    env = cda.VecCDAEnv(cfg, num_markets=M)
+    env.reset(seed=77)
+    acts = make_actions(8, 40, M, 4, "uniform")
+    dev = lambda t: [torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts]
+    for t in range(20):
+        env.step(*dev(t))
+    sd = env.state_dict()
+    ref = [env.step(*dev(t))[0].clone() for t in range(20, 40)]
+    env.load_state_dict(sd)
+    for i, t in enumerate(range(20, 40)):
+        assert torch.equal(env.step(*dev(t))[0], ref[i])
+    env.close()
