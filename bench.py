@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the CDA env-step hot path on N B200s (one process per GPU).
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path over one batch: every one of the M markets on a GPU consumes
+its A agents' actions once (== M reference `env.step` calls).  1 env-step = 1 market step.
+
+  value   device-resident: actions already in HBM, K steps each timed with its own CUDA-event
+          pair on the launching stream, L2 flushed between steps; max over ranks.
+  e2e     the same metric through the public host API (VecCDAEnv.step_host): per step the five
+          action arrays go pinned-host -> device, the kernel runs, obs/reward/flags come back to
+          pinned host memory and the stream is synchronised (what a host-side policy sees).
+  roofline   HBM-bound: achieved = B_alg(A) * M / kernel_time, B_alg(A) = 1986 + 188*A bytes per
+          market-step (SURVEY.md §8d / DESIGN.md), peak = MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (C restatement of the reference algorithm, "port") on all host
+          cores, bounded sample of the same workload (rank 0, N=1 only).
+`--impl reference` times that CPU path alone and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (agents, markets per GPU, mix)  — BASELINE.json configs
+    "cfg2_uniform_4x1024": (4, 1024, "uniform"),
+    "cfg3_limit_market_4x4096": (4, 4096, "limit_market"),   # the config the >=1M steps/s target is quoted on
+    "cfg4_modify_heavy_8x8192": (8, 8192, "modify_heavy"),
+}
+DEFAULT_WORKLOAD = "cfg3_limit_market_4x4096"
+METRIC = "env-steps/sec (agents x markets)"
+UNIT = "env-steps/s"
+
+
+def b_alg(A):
+    return 1986 + 188 * A
+
+
+def env_config(A):
+    return dict(num_of_agents=A, init_cash=1_000_000, max_step=1 << 30, n_hist=4, tick_size=1,
+                initial_price_min=10, initial_price_max=100, min_size=1, mkt_max_size=100,
+                limit_size_multiple=10, order_penalty=0.1, trade_penalty=0.05, drawdown_penalty=0.2,
+                passive_bonus=0.1, loss_multiplier=1.5)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_path(A, M, mix, seconds_target, threads):
+    """Time the CPU oracle (kind 'port') on a bounded sample of the workload."""
+    from oracle.cda_oracle import OracleEnv
+    from gym_continuousdoubleauction_b200.workloads import make_actions
+    cfg = env_config(A)
+    orc = OracleEnv(cfg, M)
+    orc.reset(seeds=np.arange(M, dtype=np.uint64) + np.uint64(1000))
+    warm = make_actions(7, 64, M, A, mix)
+    orc.rollout(*warm, nthreads=threads)            # populate the books (untimed)
+    probe = make_actions(8, 8, M, A, mix)
+    t0 = time.perf_counter(); orc.rollout(*probe, nthreads=threads); dt = time.perf_counter() - t0
+    T = int(max(16, min(4096, seconds_target / max(dt / 8, 1e-6))))
+    acts = make_actions(9, T, M, A, mix)
+    t0 = time.perf_counter(); orc.rollout(*acts, nthreads=threads); dt = time.perf_counter() - t0
+    return {"value": M * T / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{T} steps x {M} markets x {A} agents ({mix}), {dt:.2f} s wall, C oracle of the reference algorithm, {threads} threads",
+            "seconds": dt, "steps": T}
+
+
+def run_reference(args, rank, world):
+    A, M, mix = WORKLOADS[args.workload]
+    if args.markets:
+        M = args.markets
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from oracle.cda_oracle import OracleEnv
+    from gym_continuousdoubleauction_b200.workloads import make_actions
+    cfg = env_config(A)
+    Mtot = M * world
+    orc = OracleEnv(cfg, Mtot)
+    orc.reset(seeds=np.arange(Mtot, dtype=np.uint64) + np.uint64(1000))
+    orc.rollout(*make_actions(7, 64, Mtot, A, mix), nthreads=threads)
+    # each "step" = a bounded sample: `inner` consecutive env steps over all markets
+    inner = max(1, args.ref_inner)
+    per = []
+    for i in range(args.warmup + args.steps):
+        acts = make_actions(100 + i, inner, Mtot, A, mix)
+        t0 = time.perf_counter(); orc.rollout(*acts, nthreads=threads); dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            per.append(dt)
+    tot = float(np.sum(per))
+    value = Mtot * inner * len(per) / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(per), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64 ledger / f64 obs math / f32 obs", "data": "synthetic",
+        "config": {"workload": args.workload, "agents": A, "markets": Mtot, "mix": mix,
+                   "note": "reference is pure Python and cannot travel to the GPU box; this arm times the C oracle "
+                           "(port of the reference algorithm, pinned bit-exact to it) on all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(per)} x {inner} steps x {Mtot} markets x {A} agents ({mix})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--markets", type=int, default=0, help="markets per GPU (default: the workload's)")
+    ap.add_argument("--prewarm", type=int, default=256, help="untimed steps that populate the books")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-inner", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--allgather", action="store_true", help="N>1: also time an NCCL all-gather of obs/reward per step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gym_continuousdoubleauction_b200 as cda
+    from gym_continuousdoubleauction_b200.workloads import make_actions
+
+    A, M, mix = WORKLOADS[args.workload]
+    if args.markets:
+        M = args.markets
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    env = cda.VecCDAEnv(env_config(A), num_markets=M, device=local)
+    # markets are keyed by GLOBAL market id so results do not depend on the GPU count
+    gseeds = np.arange(M, dtype=np.uint64) + np.uint64(1000 + rank * M)
+    env.reset(seed=gseeds)
+
+    P = 32  # distinct action batches cycled through (device-resident for `value`, pinned for `e2e`)
+    acts_np = make_actions(7 + rank, P, M, A, mix)
+    acts_dev = [torch.from_numpy(a).to(dev) for a in acts_np]
+    acts_pin = [torch.from_numpy(a).pin_memory() for a in acts_np]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def dev_step(i):
+        k = i % P
+        return env.step(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k])
+
+    pre = make_actions(1000 + rank, 1, M, A, mix)  # shape only; prewarm reuses the cycled batches
+    del pre
+    for i in range(args.prewarm):
+        dev_step(i)
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ value (device-resident)
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = env.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        if not args.no_l2_flush:
+            flush_buf.fill_(i & 0xff)
+        ev[i][0].record()
+        dev_step(i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = env.kernel_launches - launches0
+    per_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    clocks = sampler.stop()
+    total_ms = float(per_ms.sum())
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * M * args.steps / (total_ms_max * 1e-3)
+    kern_ms = float(np.mean(per_ms))
+
+    # L2-hot variant (no flush), reported beside the headline for context
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for i in range(args.steps):
+        dev_step(i)
+    e1.record(); torch.cuda.synchronize()
+    hot_ms = e0.elapsed_time(e1) / args.steps
+
+    # ------------------------------------------------------------------ e2e (host buffers in/out)
+    e2e = None
+    if not args.no_e2e:
+        for i in range(max(3, args.warmup // 2)):
+            k = i % P
+            env.step_host(acts_pin[0][k], acts_pin[1][k], acts_pin[2][k], acts_pin[3][k], acts_pin[4][k])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for i in range(args.steps):
+            k = i % P
+            if not args.no_l2_flush:
+                flush_buf.fill_(i & 0xff); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            o, r, te, tr = env.step_host(acts_pin[0][k], acts_pin[1][k], acts_pin[2][k], acts_pin[3][k], acts_pin[4][k])
+            _ = float(r[0, 0])   # the host reads the step's result
+            tot += time.perf_counter() - t0
+        tt = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * M * args.steps / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(M * A * 20), "d2h_bytes_per_step": int(M * env.W * 4 + M * A * 8 + 2 * M),
+               "ms_per_step": 1e3 * float(tt.item()) / args.steps,
+               "api": "VecCDAEnv.step_host -> cda_step_host (pinned host buffers, stream sync per step)"}
+
+    # ------------------------------------------------------------------ optional obs all-gather
+    ag = None
+    if world > 1 and args.allgather:
+        obs_all = torch.empty((world * M, env.W), dtype=torch.float32, device=dev)
+        rew_all = torch.empty((world * M, A), dtype=torch.float64, device=dev)
+        for i in range(5):
+            o, r, _, _ = dev_step(i); dist.all_gather_into_tensor(obs_all, o); dist.all_gather_into_tensor(rew_all, r)
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record()
+        for i in range(args.steps):
+            o, r, _, _ = dev_step(i)
+            dist.all_gather_into_tensor(obs_all, o); dist.all_gather_into_tensor(rew_all, r)
+        e1.record(); torch.cuda.synchronize()
+        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        ag = {"value": world * M * args.steps / (float(tg.item()) * 1e-3), "unit": UNIT,
+              "note": "step + NCCL all_gather of obs f32[M,168] and reward f64[M,A] per step (policy batch spanning GPUs), L2-hot"}
+
+    status_bits = int(env.status().max().item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = b_alg(A) * M / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
+                "kernel": "cda_step_kernel", "kernel_ms": kern_ms, "alg_bytes_per_market_step": b_alg(A),
+                "l2_hot_kernel_ms": hot_ms, "l2_hot_achieved": b_alg(A) * M / (hot_ms * 1e-3) / 1e9}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_path(A, M, mix, args.cpu_seconds, os.cpu_count() or 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64 ledger / int32 book / f64 obs+reward math, f32 obs out", "data": "synthetic",
+        "config": {"workload": args.workload, "agents": A, "markets_per_gpu": M, "markets_total": world * M, "mix": mix,
+                   "order_capacity": env.order_capacity, "prewarm_steps": args.prewarm,
+                   "l2": "flushed between timed steps (256 MiB write)" if not args.no_l2_flush else "not flushed",
+                   "rng": "numpy-exact PCG64+ziggurat on device", "seeds": "1000 + global market id",
+                   "agent_steps_per_s": value * A, "status_bits": status_bits,
+                   "value_l2_hot": world * M / (hot_ms * 1e-3)},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    if ag:
+        line["with_obs_allgather"] = ag
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

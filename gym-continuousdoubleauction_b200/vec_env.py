@@ -119,7 +119,17 @@ class VecCDAEnv:
         """Host arrays in, host arrays out (numpy views of pinned buffers): the H2D copy of the
         actions, the kernel and the D2H copy of obs/reward/flags are all inside this call."""
         p = self._ensure_pinned()
-        for key, src in (("cat", category), ("mean", size_mean), ("sigma", size_sigma), ("price", price), ("off", price_offset)):
+        srcs = (category, size_mean, size_sigma, price, price_offset)
+        dts = (torch.int32, torch.float32, torch.float32, torch.int32, torch.int32)
+        if all(isinstance(s, torch.Tensor) and s.is_pinned() and s.is_contiguous() and s.dtype == d
+               and s.numel() == self.M * self.A for s, d in zip(srcs, dts)):
+            # zero-copy: the caller's pinned tensors are the H2D source
+            _native.check(self._L.cda_step_host(self._h, *[_ptr(s) for s in srcs], _ptr(p["obs"]), _ptr(p["reward"]),
+                                                _ptr(p["term"]), _ptr(p["trunc"]), self._stream()))
+            if sync:
+                torch.cuda.current_stream(self.device).synchronize()
+            return p["obs"].numpy(), p["reward"].numpy(), p["term"].numpy(), p["trunc"].numpy()
+        for key, src in zip(("cat", "mean", "sigma", "price", "off"), srcs):
             if isinstance(src, torch.Tensor):
                 p[key].copy_(src.reshape(self.M, self.A))
             else:
@@ -159,15 +169,13 @@ class VecCDAEnv:
         return self.info("market")[:, 7]
 
     def check_status(self):
-        st = int(torch.bitwise_or(self.status(), torch.zeros((), dtype=torch.int64, device=self.device)).max().item()) if self.M else 0
-        allbits = 0
-        s = self.status()
-        for b in STATUS_BITS:
-            if bool(((s & b) != 0).any().item()):
-                allbits |= b
-        if allbits:
-            raise RuntimeError("cda_b200 market status: " + ", ".join(v for b, v in STATUS_BITS.items() if allbits & b))
-        return st
+        """Raise if any market carries a sticky status bit (the reference would have sys.exit()ed)."""
+        bits = 0
+        for v in torch.unique(self.status()).cpu().tolist():
+            bits |= int(v)
+        if bits:
+            raise RuntimeError("cda_b200 market status: " + ", ".join(v for b, v in STATUS_BITS.items() if bits & b))
+        return 0
 
     def fills(self):
         if not self.fill_capacity:
