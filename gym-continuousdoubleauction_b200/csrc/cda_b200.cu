@@ -61,6 +61,7 @@ static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cuda
     switch (e->dev.cap) {
         case 64: return launch_step<64>(e, p, st);
         case 128: return launch_step<128>(e, p, st);
+        case 192: return launch_step<192>(e, p, st);
         default: return launch_step<256>(e, p, st);
     }
 }
@@ -103,8 +104,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     if (cfg->initial_price_min < 1 || cfg->initial_price_max < cfg->initial_price_min) return CDA_EINVAL;
     if (cfg->min_size < 0 || cfg->mkt_max_size < 1 || cfg->limit_size_multiple < 1) return CDA_EINVAL;
     int cap = cfg->order_capacity;
-    if (cap == 0) cap = cfg->num_agents <= 4 ? 128 : 256;
-    if (cap != 64 && cap != 128 && cap != 256) return CDA_EINVAL;
+    if (cap == 0) cap = cfg->num_agents <= 8 ? 192 : 256;
+    if (cap != 64 && cap != 128 && cap != 192 && cap != 256) return CDA_EINVAL;
     if (cfg->fill_capacity < 0 || cfg->fill_capacity > 1024) return CDA_EINVAL;
     CUDA_TRY(cudaSetDevice(device));
     CdaEnv *e = new (std::nothrow) CdaEnv();

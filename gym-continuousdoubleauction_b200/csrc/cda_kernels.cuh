@@ -258,185 +258,178 @@ __device__ __forceinline__ void acct_fill(CdaAcct &a, int party, int side /*0 bi
 }
 
 // ------------------------------------- market context --------------------------------------
+// Warp-uniform book state, held in registers by every lane.  No member is an array that is
+// indexed at run time (that would force the struct into local memory): the two sides are
+// addressed arithmetically through SOFF(side).
 template <int CAP>
-struct CdaCtx {
-    unsigned *pool[2];   // shared memory, [5][CAP] per side (0 bid, 1 ask)
-    int n[2];
+struct CdaMkt {
+    unsigned *pool;      // shared memory u32[2 sides][5 fields][CAP]
+    int nb, na;          // live orders per side
     unsigned time, next_id, seqctr, status;
     int tape_nonempty, tape_px;
     int lane;
-    CdaAcct ac;          // this lane's account (valid for lane < A)
     int *fills; int fill_cap, n_fills;
+    __device__ __forceinline__ unsigned *side_base(int side) const { return pool + side * (CDA_POOL_FIELDS * CAP); }
+    __device__ __forceinline__ int count(int side) const { return side ? na : nb; }
+    __device__ __forceinline__ void set_count(int side, int v) { if (side) na = v; else nb = v; }
 };
 
-template <int CAP> __device__ __forceinline__ int pool_best(const CdaCtx<CAP> &c, int side) {
-    const unsigned *pt = c.pool[side];
-    const int n = c.n[side];
+template <int CAP> __device__ __forceinline__ int pool_best(const CdaMkt<CAP> &k, int side) {
+    const unsigned *pt = k.side_base(side);
+    const int n = k.count(side);
     if (n == 0) return -1;
     unsigned loc = side == 0 ? 0u : 0xffffffffu;
-    for (int i = c.lane; i < n; i += 32) {
-        unsigned p = pt[i] & CDA_PRICE_MASK;
+    for (int i = k.lane; i < n; i += 32) {
+        const unsigned p = pt[i] & CDA_PRICE_MASK;
         loc = side == 0 ? max(loc, p) : min(loc, p);
     }
     return (int)(side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc));
 }
-// index of the entry with the smallest key[field] among entries whose pt matches (pt & mask) == want
-template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaCtx<CAP> &c, int side, unsigned mask, unsigned want, int field) {
-    const unsigned *pt = c.pool[side];
-    const unsigned *key = c.pool[side] + field * CAP;
-    const int n = c.n[side];
+// index of the entry with the smallest key[field] among entries with (pt & mask) == want, or -1
+template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> &k, int side, unsigned mask, unsigned want, int field) {
+    const unsigned *pt = k.side_base(side);
+    const unsigned *key = pt + field * CAP;
+    const int n = k.count(side);
     unsigned bk = 0xffffffffu; int bi = -1;
-    for (int i = c.lane; i < n; i += 32) {
-        if ((pt[i] & mask) == want) { unsigned k = key[i]; if (k < bk) { bk = k; bi = i; } }
+    for (int i = k.lane; i < n; i += 32) {
+        if ((pt[i] & mask) == want) { const unsigned kk = key[i]; if (kk < bk) { bk = kk; bi = i; } }
     }
-    unsigned mk = __reduce_min_sync(CDA_FULL, bk);
+    const unsigned mk = __reduce_min_sync(CDA_FULL, bk);
     if (mk == 0xffffffffu) return -1;
-    unsigned b = __ballot_sync(CDA_FULL, bk == mk);
+    const unsigned b = __ballot_sync(CDA_FULL, bk == mk);
     return __shfl_sync(CDA_FULL, bi, __ffs(b) - 1);
 }
 // ordertree.py:70-77 remove_order_by_id: dense pool => move the last entry into the hole
-template <int CAP> __device__ __forceinline__ void pool_remove(CdaCtx<CAP> &c, int side, int idx) {
-    const int last = c.n[side] - 1;
+template <int CAP> __device__ __forceinline__ void pool_remove(CdaMkt<CAP> &k, int side, int idx) {
+    const int last = k.count(side) - 1;
     __syncwarp();
-    if (idx != last && c.lane < CDA_POOL_FIELDS) {
-        unsigned *f = c.pool[side] + c.lane * CAP;
+    if (idx != last && k.lane < CDA_POOL_FIELDS) {
+        unsigned *f = k.side_base(side) + k.lane * CAP;
         f[idx] = f[last];
     }
-    c.n[side] = last;
+    k.set_count(side, last);
     __syncwarp();
 }
 // ordertree.py:44-55 insert_order: append with a fresh seq (tail of the level's FIFO and of order_map)
-template <int CAP> __device__ __forceinline__ bool pool_append(CdaCtx<CAP> &c, int side, unsigned price, unsigned qty, int trader, unsigned oid, unsigned ts) {
-    const int n = c.n[side];
-    if (n >= CAP) { c.status |= CDA_ST_POOL_OVERFLOW; return false; }
-    const unsigned seq = c.seqctr++;
+template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, int side, unsigned price, unsigned qty, int trader, unsigned oid, unsigned ts) {
+    const int n = k.count(side);
+    if (n >= CAP) { k.status |= CDA_ST_POOL_OVERFLOW; return false; }
+    const unsigned seq = k.seqctr++;
     __syncwarp();
-    if (c.lane < CDA_POOL_FIELDS) {
-        unsigned v = c.lane == 0 ? (((unsigned)trader << 24) | price) : c.lane == 1 ? qty : c.lane == 2 ? oid : c.lane == 3 ? ts : seq;
-        c.pool[side][c.lane * CAP + n] = v;
+    if (k.lane < CDA_POOL_FIELDS) {
+        const unsigned v = k.lane == 0 ? (((unsigned)trader << 24) | price) : k.lane == 1 ? qty : k.lane == 2 ? oid : k.lane == 3 ? ts : seq;
+        k.side_base(side)[k.lane * CAP + n] = v;
     }
-    c.n[side] = n + 1;
+    k.set_count(side, n + 1);
     __syncwarp();
     return true;
 }
 
-// orderbook.py:61-142 process_order_list + :144-194 loops, with settlement applied per fill
-// (trader.py:303-328 settles after the match; matching never reads accounts, so the order of
-// ledger updates is identical).  limit < 0 => market order.  Returns the unfilled quantity.
-template <int CAP> __device__ __forceinline__ unsigned match_incoming(CdaCtx<CAP> &c, int side, unsigned qty, int limit, int taker) {
-    const int opp = 1 - side;
+// trader.py:49-106 place_order as ONE straight-line flow with a single matching loop (keeps the
+// SASS small enough for the instruction cache).  All arguments are warp-uniform.
+// type: 0 market, 1 limit, 2 modify, 3 cancel.   `ac` is this lane's account.
+template <int CAP>
+__device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, int type, int side, long long size, int price) {
+    const int opp = side ^ 1;
+    const bool is_t = k.lane == t;
+    // ---- trader.py:108-151 _order_approved (on the trader's lane; market orders need the best opposite quote)
+    int best_opp = -1;
+    if (type == 0) best_opp = pool_best(k, opp);
+    int ok_l = 0;
+    if (is_t && ac.nav > 0) {
+        long long opening;
+        if ((side == 0 && ac.pos >= 0) || (side == 1 && ac.pos <= 0)) opening = size;
+        else { const long long ap = ac.pos < 0 ? -ac.pos : ac.pos; opening = size - ap; if (opening < 0) opening = 0; }
+        if (opening <= 0) ok_l = 1;
+        else {
+            const long long est = type == 0 ? (best_opp > 0 ? best_opp : (k.tape_nonempty ? k.tape_px : 1)) : price;
+            ok_l = ac.cash >= opening * est;
+        }
+    }
+    if (!__shfl_sync(CDA_FULL, ok_l, t)) { if (is_t) ac.rejected++; return; }
+    if (type <= 1 && is_t) ac.placed = 1;                               // trader.py:75-76
+    if (size <= 0 && type <= 1) { k.status |= CDA_ST_BAD_SIZE; return; }  // reference: sys.exit in process_order
+
+    // ---- trader.py:254-287 _get_order_ID: limit/cancel = first in order_map order at that price (min seq);
+    //      modify = oldest timestamp at any price
+    int idx = -1;
+    if (type != 0) {
+        const unsigned mask = type == 2 ? 0xff000000u : 0xffffffffu;
+        const unsigned want = type == 2 ? ((unsigned)t << 24) : (((unsigned)t << 24) | (unsigned)price);
+        idx = pool_argmin(k, side, mask, want, type == 2 ? 3 : 4);
+    }
+    if (type >= 2 && idx < 0) return;                                    // nothing to modify / cancel: no book op
+
+    unsigned oid;
+    if (idx >= 0) {
+        // trader.py:219-235 / :237-252: release the old order's escrow (cash_processor.py:85-97), then touch the book
+        unsigned *pl = k.side_base(side);
+        const unsigned op = pl[idx] & CDA_PRICE_MASK, oq = pl[CAP + idx];
+        oid = pl[2 * CAP + idx];
+        if (is_t) { const long long ov = (long long)op * oq; ac.hold -= ov; ac.cash += ov; }
+        k.time++;                                                        // orderbook.py:196-200, :212-215
+        if (type == 3) { pool_remove(k, side, idx); return; }
+        if ((unsigned)price == op && (unsigned long long)size <= oq) {   // orderbook.py:245-248 in place
+            __syncwarp();
+            if (k.lane == 0) { pl[CAP + idx] = (unsigned)size; pl[3 * CAP + idx] = k.time; }
+            __syncwarp();
+            if (is_t) { const long long v = (long long)price * size; ac.cash -= v; ac.hold += v; }
+            return;
+        }
+        pool_remove(k, side, idx);                                       // orderbook.py:250-266 re-process, same id
+    } else {
+        k.time++; k.next_id++;                                           // orderbook.py:33-44 process_order
+        oid = k.next_id;
+    }
+
+    // ---- orderbook.py:61-194: sweep the opposite side by price-time priority; settle each fill
+    //      (trader.py:303-328 settles after the sweep; the sweep never reads accounts, so the ledger
+    //      sees the same sequence of updates)
+    const int limit = type == 0 ? -1 : price;
+    unsigned qty = (unsigned)size;
+    unsigned *po = k.side_base(opp);
     while (qty > 0) {
-        const int P = pool_best(c, opp);
+        const int P = pool_best(k, opp);
         if (P < 0) break;
         if (limit >= 0 && (side == 0 ? limit < P : limit > P)) break;
-        const int idx = pool_argmin(c, opp, CDA_PRICE_MASK, (unsigned)P, 4);
-        unsigned *pl = c.pool[opp];
-        const unsigned hq = pl[1 * CAP + idx];
-        const int maker = (int)(pl[idx] >> 24);
-        const unsigned oid = pl[2 * CAP + idx];
+        const int h = pool_argmin(k, opp, CDA_PRICE_MASK, (unsigned)P, 4);
+        const unsigned hq = po[CAP + h];
+        const int maker = (int)(po[h] >> 24);
+        const unsigned moid = po[2 * CAP + h];
         unsigned traded; int left = -1;
-        if (qty < hq) {            // :73-85 partial fill: resting order shrinks in place
+        if (qty < hq) {                       // :73-85 partial: resting order shrinks in place, keeps its timestamp
             traded = qty; left = (int)(hq - qty);
             __syncwarp();
-            if (c.lane == 0) pl[1 * CAP + idx] = hq - qty;
+            if (k.lane == 0) po[CAP + h] = hq - qty;
             __syncwarp();
             qty = 0;
-        } else {                   // :86-100 resting order consumed
+        } else {                              // :86-100 resting order consumed
             traded = hq;
-            pool_remove(c, opp, idx);
+            pool_remove(k, opp, h);
             qty -= traded;
         }
-        // trade record (:109-141): price = resting price
-        c.tape_nonempty = 1; c.tape_px = P;
-        if (c.fills) {
-            if (c.n_fills < c.fill_cap) {
-                if (c.lane < CDA_FILL_WORDS) {
-                    int v = c.lane == 0 ? (int)c.time : c.lane == 1 ? P : c.lane == 2 ? (int)traded : c.lane == 3 ? maker
-                          : c.lane == 4 ? (int)oid : c.lane == 5 ? left : c.lane == 6 ? taker : side;
-                    c.fills[c.n_fills * CDA_FILL_WORDS + c.lane] = v;
+        k.tape_nonempty = 1; k.tape_px = P;   // :140 tape.append (trade price = resting price)
+        if (k.fills) {
+            if (k.n_fills < k.fill_cap) {
+                if (k.lane < CDA_FILL_WORDS) {
+                    const int v = k.lane == 0 ? (int)k.time : k.lane == 1 ? P : k.lane == 2 ? (int)traded : k.lane == 3 ? maker
+                                : k.lane == 4 ? (int)moid : k.lane == 5 ? left : k.lane == 6 ? t : side;
+                    k.fills[k.n_fills * CDA_FILL_WORDS + k.lane] = v;
                 }
-            } else c.status |= CDA_ST_FILL_OVERFLOW;
+            } else k.status |= CDA_ST_FILL_OVERFLOW;
         }
-        c.n_fills++;
-        // settlement: counter party (passive) and initiator (trader.py:311-322)
-        if (maker != taker) {
-            if (c.lane == maker) acct_fill(c.ac, 1, opp, traded, P);
-            else if (c.lane == taker) acct_fill(c.ac, 0, side, traded, P);
-        } else if (c.lane == taker) {   // cash_processor.py:55-62 init_is_counter_cash_transfer
+        k.n_fills++;
+        if (maker != t) {                     // trader.py:311-322: counter party, then initiator
+            if (k.lane == maker) acct_fill(ac, 1, opp, traded, P);
+            else if (is_t) acct_fill(ac, 0, side, traded, P);
+        } else if (is_t) {                    // cash_processor.py:55-62 self-trade: escrow back to cash
             const long long tv = (long long)traded * P;
-            c.ac.hold -= tv; c.ac.cash += tv;
+            ac.hold -= tv; ac.cash += tv;
         }
     }
-    return qty;
-}
-
-// cash_processor.py:15-29 order_in_book_passive_party on the initiator's lane
-template <int CAP> __device__ __forceinline__ void escrow(CdaCtx<CAP> &c, int t, long long price, long long qty) {
-    if (c.lane == t) { const long long v = price * qty; c.ac.cash -= v; c.ac.hold += v; }
-}
-// orderbook.py:210-266 modify_order, preceded by trader.py:219-235 (release the old escrow)
-template <int CAP> __device__ __forceinline__ void modify_resting(CdaCtx<CAP> &c, int side, int idx, int t, int new_price, unsigned new_qty) {
-    unsigned *pl = c.pool[side];
-    const unsigned op = pl[idx] & CDA_PRICE_MASK, oq = pl[1 * CAP + idx], oid = pl[2 * CAP + idx];
-    if (c.lane == t) { const long long ov = (long long)op * oq; c.ac.hold -= ov; c.ac.cash += ov; }
-    c.time++;
-    if ((unsigned)new_price == op && new_qty <= oq) {   // :245-248 in place: priority kept, timestamp refreshed
-        __syncwarp();
-        if (c.lane == 0) { pl[1 * CAP + idx] = new_qty; pl[3 * CAP + idx] = c.time; }
-        __syncwarp();
-        escrow(c, t, new_price, new_qty);
-        return;
-    }
-    pool_remove(c, side, idx);                          // :250-266 remove and re-process, same order_id
-    const unsigned rem = match_incoming(c, side, new_qty, new_price, t);
-    if (rem > 0 && pool_append(c, side, (unsigned)new_price, rem, t, oid, c.time)) escrow(c, t, new_price, rem);
-}
-
-// trader.py:49-106 place_order.  All arguments are warp-uniform.  type: 0 market 1 limit 2 modify 3 cancel
-template <int CAP> __device__ __forceinline__ void place_order(CdaCtx<CAP> &c, int t, int type, int side, long long size, int price) {
-    const int opp = 1 - side;
-    // ---- trader.py:108-151 _order_approved, evaluated on the trader's lane
-    int best_opp = -1;
-    if (type == 0) best_opp = pool_best(c, opp);
-    int ok_l = 0;
-    if (c.lane == t) {
-        if (c.ac.nav > 0) {
-            long long opening;
-            if ((side == 0 && c.ac.pos >= 0) || (side == 1 && c.ac.pos <= 0)) opening = size;
-            else { long long ap = c.ac.pos < 0 ? -c.ac.pos : c.ac.pos; opening = size - ap; if (opening < 0) opening = 0; }
-            if (opening <= 0) ok_l = 1;
-            else {
-                long long est = type == 0 ? (best_opp > 0 ? best_opp : (c.tape_nonempty ? c.tape_px : 1)) : price;
-                ok_l = c.ac.cash >= opening * est;
-            }
-        }
-    }
-    const int ok = __shfl_sync(CDA_FULL, ok_l, t);
-    if (!ok) { if (c.lane == t) c.ac.rejected++; return; }
-    if (type <= 1 && c.lane == t) c.ac.placed = 1;      // trader.py:75-76
-    if (size <= 0 && type <= 1) { c.status |= CDA_ST_BAD_SIZE; return; }
-    if (type == 0) {                                     // orderbook.py:33-46, :144-160
-        c.time++; c.next_id++;
-        match_incoming(c, side, (unsigned)size, -1, t);  // unfilled remainder is dropped
-    } else if (type == 1) {                              // trader.py:189-203
-        const int idx = pool_argmin(c, side, 0xffffffffu, ((unsigned)t << 24) | (unsigned)price, 4);
-        if (idx < 0) {
-            c.time++; c.next_id++;
-            const unsigned rem = match_incoming(c, side, (unsigned)size, price, t);
-            if (rem > 0 && pool_append(c, side, (unsigned)price, rem, t, c.next_id, c.time)) escrow(c, t, price, rem);
-        } else modify_resting(c, side, idx, t, price, (unsigned)size);
-    } else if (type == 2) {                              // trader.py:205-217: oldest timestamp, any price
-        const int idx = pool_argmin(c, side, 0xff000000u, (unsigned)t << 24, 3);
-        if (idx >= 0) modify_resting(c, side, idx, t, price, (unsigned)size);
-    } else {                                             // trader.py:237-252
-        const int idx = pool_argmin(c, side, 0xffffffffu, ((unsigned)t << 24) | (unsigned)price, 4);
-        if (idx >= 0) {
-            const unsigned *pl = c.pool[side];
-            const long long ov = (long long)(pl[idx] & CDA_PRICE_MASK) * pl[1 * CAP + idx];
-            c.time++;                                    // orderbook.py:196-208
-            pool_remove(c, side, idx);
-            if (c.lane == t) { c.ac.hold -= ov; c.ac.cash += ov; }
-        }
+    // ---- residue rests (orderbook.py:174-191) and is escrowed (cash_processor.py:15-29); market remainder dropped
+    if (type != 0 && qty > 0 && pool_append(k, side, (unsigned)price, qty, t, oid, k.time)) {
+        if (is_t) { const long long v = (long long)price * qty; ac.cash -= v; ac.hold += v; }
     }
 }
 
@@ -458,14 +451,22 @@ struct CdaWarpSmem {
     unsigned pool[2][CDA_POOL_FIELDS][CAP];
     float snap[44];
     int topk[2 * CDA_K_ROWS];        // frozen pre-step raw top-K prices (agg_LOB_raw price rows)
+    unsigned vol[2 * CDA_K_ROWS];    // level volumes of the snapshot being built
     unsigned long long bar;
+    unsigned long long rng_park[4];  // PCG64 state/inc parked here while the book is being worked on
+    unsigned rng_park32[2];
     unsigned char order[32];
-    unsigned pad[2];
 };
-static_assert(sizeof(CdaWarpSmem<64>) % 16 == 0 && sizeof(CdaWarpSmem<128>) % 16 == 0 && sizeof(CdaWarpSmem<256>) % 16 == 0, "smem tile must keep 16-B alignment");
+static_assert(sizeof(CdaWarpSmem<64>) % 16 == 0 && sizeof(CdaWarpSmem<128>) % 16 == 0 &&
+              sizeof(CdaWarpSmem<192>) % 16 == 0 && sizeof(CdaWarpSmem<256>) % 16 == 0, "smem tile must keep 16-B alignment");
+
+#ifndef CDA_MIN_CTAS
+#define CDA_MIN_CTAS 7   /* 7 CTAs x 4 warps = 28 warps/SM -> 4144 resident markets on 148 SMs (>= 4096 in one wave) */
+#endif
+#define CDA_HIST_PREFETCH 4   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
 
 template <int CAP, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParams p) {
+__global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * WARPS + warp;
@@ -487,26 +488,26 @@ __global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParam
     const ulonglong2 r0 = *reinterpret_cast<const ulonglong2 *>(hdr + 12);
     const ulonglong2 r1 = *reinterpret_cast<const ulonglong2 *>(hdr + 16);
 
-    CdaCtx<CAP> c;
-    c.lane = lane;
-    c.pool[0] = &S.pool[0][0][0]; c.pool[1] = &S.pool[1][0][0];
-    c.time = h0.x; c.next_id = h0.y; c.seqctr = h0.z;
+    CdaMkt<CAP> k;
+    k.lane = lane;
+    k.pool = &S.pool[0][0][0];
+    k.time = h0.x; k.next_id = h0.y; k.seqctr = h0.z;
     unsigned t_step = h0.w;
     int last_price = (int)h1.x;
-    c.tape_nonempty = (h1.y & CDA_FLAG_TAPE) ? 1 : 0;
+    k.tape_nonempty = (h1.y & CDA_FLAG_TAPE) ? 1 : 0;
     unsigned done_mask = h1.z;
-    c.status = h1.w;
-    c.n[0] = (int)h2.x; c.n[1] = (int)h2.y;
+    k.status = h1.w;
+    k.nb = (int)h2.x; k.na = (int)h2.y;
     CdaRng rng;
     rng.has32 = h2.z; rng.u32 = h2.w;
     rng.shi = r0.x; rng.slo = r0.y; rng.ihi = r1.x; rng.ilo = r1.y;
-    c.tape_px = last_price;
-    c.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
-    c.fill_cap = cfg.fill_cap;
+    k.tape_px = last_price;
+    k.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
+    k.fill_cap = cfg.fill_cap; k.n_fills = 0;
 
     // ---- order pool: TMA bulk copies of the live prefix of each field array
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
-    const unsigned bytes_b = ((unsigned)c.n[0] * 4u + 15u) & ~15u, bytes_a = ((unsigned)c.n[1] * 4u + 15u) & ~15u;
+    const unsigned bytes_b = ((unsigned)k.nb * 4u + 15u) & ~15u, bytes_a = ((unsigned)k.na * 4u + 15u) & ~15u;
     const bool have_pool = (bytes_b | bytes_a) != 0;
     if (have_pool && lane == 0) {
         mbar_expect_tx(&S.bar, CDA_POOL_FIELDS * (bytes_b + bytes_a));
@@ -522,25 +523,42 @@ __global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParam
     long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A;
     int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
     unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
-    c.ac = CdaAcct{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (lane < A) {
-        c.ac.cash = g_cash[lane]; c.ac.hold = g_hold[lane]; c.ac.cost = g_cost[lane]; c.ac.nav = g_nav[lane];
-        c.ac.prev_nav = g_prev[lane]; c.ac.max_nav = g_max[lane]; c.ac.pos = g_pos[lane]; c.ac.ntr = g_ntr[lane];
+        ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
+        ac.prev_nav = g_prev[lane]; ac.max_nav = g_max[lane]; ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
     }
     float *g_hist = reinterpret_cast<float *>(blk + cfg.off_hist);
+    const int W_old = cfg.W - CDA_SNAPSHOT_DIM;       // obs elements that come from older snapshots
 
     bool waited = !have_pool;
     const int n_iter = p.num_steps > 0 ? p.num_steps : 1;
     for (int it = 0; it < n_iter; ++it) {
+        const bool last_it = it == n_iter - 1;
+        const int slot_new = (int)(t_step % (unsigned)cfg.n_hist);
+        // ---- prefetch the older snapshots of the stacked observation (state_helper.py:88-90)
+        float hv[CDA_HIST_PREFETCH];
+        if (p.obs && last_it) {
+#pragma unroll
+            for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
+                const int e = lane + 32 * q;
+                hv[q] = 0.f;
+                if (e < W_old) {
+                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
+                    hv[q] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                }
+            }
+        }
         // ================= set_actions: action_helper.py:145-172, :241-397 =================
         int a_cat = -1, a_pcode = 0, a_poff = 1; float a_mean = 0.f, a_sigma = 0.f;
         if (lane < A) {
             if (p.num_steps > 0) {   // fused uniform random policy (model_handler.py:38-78)
-                unsigned long long h = splitmix64(p.policy_seed ^ splitmix64(((unsigned long long)m << 32) ^ ((unsigned long long)(t_step) * 64ULL + lane)));
+                const unsigned long long h = splitmix64(p.policy_seed ^ splitmix64(((unsigned long long)m << 32) ^ ((unsigned long long)(t_step) * 64ULL + lane)));
                 a_cat = (int)(((h & 0xffffu) * 9u) >> 16);
                 a_pcode = (int)((((h >> 16) & 0xffffu) * 10u) >> 16);
                 a_poff = (int)((((h >> 32) & 0xffffu) * 3u) >> 16);
-                unsigned long long h2 = splitmix64(h);
+                const unsigned long long h2 = splitmix64(h);
                 a_mean = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
                 a_sigma = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
             } else {
@@ -548,10 +566,10 @@ __global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParam
                 a_cat = p.cat[o]; a_mean = p.mean[o]; a_sigma = p.sigma[o]; a_pcode = p.pcode[o]; a_poff = p.poff[o];
             }
         }
-        c.n_fills = 0;
-        c.ac.tr_step = c.ac.pas_step = c.ac.placed = c.ac.rejected = c.ac.is_pass = 0;
-        bool bad = lane < A && (a_cat > 8 || (a_cat > 0 && ((a_cat - 1) & 3) != 0 && (a_pcode < 0 || a_pcode >= CDA_K_ROWS || a_poff < 0 || a_poff > 2)));
-        if (__any_sync(CDA_FULL, bad)) c.status |= CDA_ST_BAD_ACTION;
+        k.n_fills = 0;
+        ac.tr_step = ac.pas_step = ac.placed = ac.rejected = ac.is_pass = 0;
+        const bool bad = lane < A && (a_cat > 8 || (a_cat > 0 && ((a_cat - 1) & 3) != 0 && (a_pcode < 0 || a_pcode >= CDA_K_ROWS || a_poff < 0 || a_poff > 2)));
+        if (__any_sync(CDA_FULL, bad)) k.status |= CDA_ST_BAD_ACTION;
         if (a_cat > 8) a_cat = 0;
         if (a_pcode < 0 || a_pcode >= CDA_K_ROWS) a_pcode = 0;
         if (a_poff < 0 || a_poff > 2) a_poff = 1;
@@ -570,7 +588,7 @@ __global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParam
             const float loc = __fmul_rn(a_type == 0 ? cfg.mkt_mul : cfg.lim_mul, a_mean);  // f32 product (NEP 50)
             const double x = (double)loc + (double)a_sigma * z;                              // numpy: loc + scale*z
             a_size = __double2ll_rn(fabs(x)) + cfg.min_size;                                 // rint half-even, :339, :276
-            if (a_cat == 0) c.ac.is_pass = 1;
+            if (a_cat == 0) ac.is_pass = 1;
             if (a_side >= 0 && a_type != 0) {            // _set_price :341-397 on the frozen pre-step top-K
                 const int raw = S.topk[a_side * CDA_K_ROWS + a_pcode];
                 const int off = a_poff - 1;
@@ -581,63 +599,105 @@ __global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParam
                 a_price = pr;
             }
         }
-        if (__any_sync(CDA_FULL, a_price >= (int)CDA_PRICE_MASK)) { c.status |= CDA_ST_PRICE_RANGE; if (a_price >= (int)CDA_PRICE_MASK) a_price = CDA_PRICE_MASK - 1; }
+        if (__any_sync(CDA_FULL, a_price >= (int)CDA_PRICE_MASK)) { k.status |= CDA_ST_PRICE_RANGE; if (a_price >= (int)CDA_PRICE_MASK) a_price = CDA_PRICE_MASK - 1; }
 
         // ================= rand_exec_seq: action_helper.py:174-199 ==========================
         const unsigned active = __ballot_sync(CDA_FULL, lane < A && a_side >= 0);
         const int n_act = __popc(active);
-        if (lane == 0) { int k = 0; for (unsigned am = active; am; am &= am - 1) S.order[k++] = (unsigned char)(__ffs(am) - 1); }
+        if (lane == 0) { int q = 0; for (unsigned am = active; am; am &= am - 1) S.order[q++] = (unsigned char)(__ffs(am) - 1); }
         for (int i = n_act - 1; i >= 1; --i) {           // Generator.permutation: Fisher-Yates from the top
             const unsigned j = rng_interval(rng, (unsigned)i);
-            if (lane == 0) { unsigned char tmp = S.order[i]; S.order[i] = S.order[j]; S.order[j] = tmp; }
+            if (lane == 0) { const unsigned char tmp = S.order[i]; S.order[i] = S.order[j]; S.order[j] = tmp; }
+        }
+        if (lane == 0) {   // park the generator: it is not needed again until the next step / the final store
+            S.rng_park[0] = rng.shi; S.rng_park[1] = rng.slo; S.rng_park[2] = rng.ihi; S.rng_park[3] = rng.ilo;
+            S.rng_park32[0] = rng.has32; S.rng_park32[1] = rng.u32;
         }
         __syncwarp();
 
         if (!waited) { mbar_wait(&S.bar, 0); waited = true; }
 
         // ================= do_actions: action_helper.py:201-239 =============================
-        for (int k = 0; k < n_act; ++k) {
-            const int t = S.order[k];
+        for (int q = 0; q < n_act; ++q) {
+            const int t = S.order[q];
             const int type = __shfl_sync(CDA_FULL, a_type, t);
             const int side = __shfl_sync(CDA_FULL, a_side, t);
             const long long size = __shfl_sync(CDA_FULL, a_size, t);
             const int price = __shfl_sync(CDA_FULL, a_price, t);
-            place_order(c, t, type, side, size, price);
+            place_order(k, ac, t, type, side, size, price);
         }
 
         // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
-        if (c.tape_nonempty) {
-            last_price = c.tape_px;
+        if (k.tape_nonempty) {
+            last_price = k.tape_px;
             if (lane < A) {
-                const long long ap = c.ac.pos < 0 ? -c.ac.pos : c.ac.pos;
-                const long long pv = c.ac.pos >= 0 ? ap * last_price : 2 * c.ac.cost - ap * last_price;
-                c.ac.prev_nav = c.ac.nav;
-                c.ac.nav = c.ac.cash + c.ac.hold + pv;
-                if (c.ac.nav > c.ac.max_nav) c.ac.max_nav = c.ac.nav;
+                const long long ap = ac.pos < 0 ? -ac.pos : ac.pos;
+                const long long pv = ac.pos >= 0 ? ap * last_price : 2 * ac.cost - ap * last_price;
+                ac.prev_nav = ac.nav;
+                ac.nav = ac.cash + ac.hold + pv;
+                if (ac.nav > ac.max_nav) ac.max_nav = ac.nav;
             }
         }
 
         // ================= set_agg_LOB: state_helper.py:113-214 =============================
+        // Top-K levels per side in ONE sweep: the distinct prices within 64 ticks of the best form
+        // a 64-bit occupancy mask (redux.or); a level's rank is the popcount below its bit; level
+        // volumes accumulate with shared-memory atomics.  Levels beyond the window (rare) are
+        // finished by the generic next-best search.
         int myP = 0; unsigned myV = 0;     // lane l<10: bid level l; 10<=l<20: ask level l-10
+        __syncwarp();
+        if (lane < 2 * CDA_K_ROWS) S.vol[lane] = 0;
         __syncwarp();
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
-            const unsigned *pt = c.pool[side], *qy = c.pool[side] + CAP;
-            const int n = c.n[side];
-            unsigned prev = side == 0 ? 0x7fffffffu : 0u;
-            for (int k = 0; k < CDA_K_ROWS; ++k) {
-                unsigned loc = side == 0 ? 0u : 0xffffffffu;
-                for (int i = lane; i < n; i += 32) {
-                    unsigned pp = pt[i] & CDA_PRICE_MASK;
-                    if (side == 0 ? pp < prev : pp > prev) loc = side == 0 ? max(loc, pp) : min(loc, pp);
+            const unsigned *pt = k.side_base(side), *qy = pt + CAP;
+            const int n = k.count(side);
+            if (n == 0) continue;
+            unsigned loc = side == 0 ? 0u : 0xffffffffu;
+            for (int i = lane; i < n; i += 32) { const unsigned pp = pt[i] & CDA_PRICE_MASK; loc = side == 0 ? max(loc, pp) : min(loc, pp); }
+            const unsigned B = side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc);
+            unsigned mlo = 0, mhi = 0; bool far = false;
+            for (int i = lane; i < n; i += 32) {
+                const unsigned pp = pt[i] & CDA_PRICE_MASK;
+                const unsigned d = side == 0 ? B - pp : pp - B;
+                if (d < 32) mlo |= 1u << d; else if (d < 64) mhi |= 1u << (d - 32); else far = true;
+            }
+            mlo = __reduce_or_sync(CDA_FULL, mlo); mhi = __reduce_or_sync(CDA_FULL, mhi);
+            const bool far_any = __any_sync(CDA_FULL, far);
+            const int nlo = __popc(mlo), nlev = nlo + __popc(mhi);
+            for (int i = lane; i < n; i += 32) {
+                const unsigned pp = pt[i] & CDA_PRICE_MASK;
+                const unsigned d = side == 0 ? B - pp : pp - B;
+                if (d < 64) {
+                    const int rank = d < 32 ? __popc(mlo & ((1u << d) - 1u)) : nlo + __popc(mhi & ((1u << (d - 32)) - 1u));
+                    if (rank < CDA_K_ROWS) atomicAdd(&S.vol[side * CDA_K_ROWS + rank], qy[i]);
                 }
-                const unsigned P = side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc);
-                if (P == (side == 0 ? 0u : 0xffffffffu)) break;
-                unsigned s = 0;
-                for (int i = lane; i < n; i += 32) if ((pt[i] & CDA_PRICE_MASK) == P) s += qy[i];
-                const unsigned V = __reduce_add_sync(CDA_FULL, s);
-                if (lane == side * CDA_K_ROWS + k) { myP = (int)P; myV = V; }
-                prev = P;
+            }
+            __syncwarp();
+            const int li = lane - side * CDA_K_ROWS;
+            if (li >= 0 && li < CDA_K_ROWS && li < nlev) {
+                unsigned long long mm = ((unsigned long long)mhi << 32) | mlo;
+                for (int j = 0; j < li; ++j) mm &= mm - 1;
+                const int pos = __ffsll((long long)mm) - 1;
+                myP = side == 0 ? (int)B - pos : (int)B + pos;
+                myV = S.vol[lane];
+            }
+            if (nlev < CDA_K_ROWS && far_any) {        // levels further than 64 ticks from the best: generic search
+                unsigned prev = side == 0 ? B - 63u : B + 63u;
+                for (int lv = nlev; lv < CDA_K_ROWS; ++lv) {
+                    unsigned l2 = side == 0 ? 0u : 0xffffffffu;
+                    for (int i = lane; i < n; i += 32) {
+                        const unsigned pp = pt[i] & CDA_PRICE_MASK;
+                        if (side == 0 ? pp < prev : pp > prev) l2 = side == 0 ? max(l2, pp) : min(l2, pp);
+                    }
+                    const unsigned P = side == 0 ? __reduce_max_sync(CDA_FULL, l2) : __reduce_min_sync(CDA_FULL, l2);
+                    if (P == (side == 0 ? 0u : 0xffffffffu)) break;
+                    unsigned s = 0;
+                    for (int i = lane; i < n; i += 32) if ((pt[i] & CDA_PRICE_MASK) == P) s += qy[i];
+                    const unsigned V = __reduce_add_sync(CDA_FULL, s);
+                    if (lane == side * CDA_K_ROWS + lv) { myP = (int)P; myV = V; }
+                    prev = P;
+                }
             }
         }
         const int best_bid = __shfl_sync(CDA_FULL, myP, 0), best_ask = __shfl_sync(CDA_FULL, myP, CDA_K_ROWS);
@@ -661,21 +721,22 @@ __global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParam
             S.snap[40] = (float)log(Mid);
         } else if (lane == 21) {
             float v = 0.0f;
-            if (best_bid > 0 && best_ask > 0) { double st = ((double)best_ask - (double)best_bid) / (double)cfg.tick; v = (float)log1p(st > 0.0 ? st : 0.0); }
+            if (best_bid > 0 && best_ask > 0) { const double st = ((double)best_ask - (double)best_bid) / (double)cfg.tick; v = (float)log1p(st > 0.0 ? st : 0.0); }
             S.snap[41] = v;
         }
         __syncwarp();
 
         // ================= prep_next_state: state_helper.py:80-92 (ring + stacked obs) ======
-        const int slot_new = (int)(t_step % (unsigned)cfg.n_hist);
-        const bool last_it = it == n_iter - 1;
         if (p.obs && last_it) {
             float *o = p.obs + (size_t)m * cfg.W;
-            for (int e = lane; e < cfg.W; e += 32) {
+#pragma unroll
+            for (int q = 0; q < CDA_HIST_PREFETCH; ++q) { const int e = lane + 32 * q; if (e < W_old) o[e] = hv[q]; }
+            for (int e = lane + 32 * CDA_HIST_PREFETCH; e < W_old; e += 32) {   // n_hist > 4: not prefetched
                 const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
                 int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
-                o[e] = (j == cfg.n_hist - 1) ? S.snap[cc] : g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                o[e] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
             }
+            for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) o[W_old + cc] = S.snap[cc];
         }
         __syncwarp();
         for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = S.snap[cc];
@@ -683,48 +744,51 @@ __global__ void __launch_bounds__(WARPS * 32) cda_step_kernel(const CdaStepParam
         // ================= set_reward / set_done: reward_helper.py:35-103, done_helper.py ===
         bool broke = false;
         if (lane < A) {
-            const double nav_change = (double)(c.ac.nav - c.ac.prev_nav);
+            const double nav_change = (double)(ac.nav - ac.prev_nav);
             const double nav_term = nav_change * (nav_change < 0 ? cfg.c_loss : 1.0);
-            long long ddi = c.ac.max_nav - c.ac.nav; if (ddi < 0) ddi = 0;
+            long long ddi = ac.max_nav - ac.nav; if (ddi < 0) ddi = 0;
             double r = 0.0;
             r = r + nav_term;
-            r = r + -(cfg.c_order * (double)c.ac.placed);
-            r = r + -(cfg.c_trade * (double)c.ac.tr_step);
+            r = r + -(cfg.c_order * (double)ac.placed);
+            r = r + -(cfg.c_trade * (double)ac.tr_step);
             r = r + -(cfg.c_dd * (double)ddi);
-            r = r + cfg.c_passive * (double)c.ac.pas_step;
+            r = r + cfg.c_passive * (double)ac.pas_step;
             if (p.reward && last_it) p.reward[(size_t)m * A + lane] = r;
-            broke = c.ac.nav <= 0;
+            broke = ac.nav <= 0;
         }
         done_mask |= __ballot_sync(CDA_FULL, broke);
         const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
         if (lane == 0 && last_it) {
             if (p.term) p.term[m] = (done_mask & all) == all;
             if (p.trunc) p.trunc[m] = (t_step + 1 >= (unsigned)cfg.max_step);
-            if (p.fill_counts) p.fill_counts[m] = c.n_fills;
+            if (p.fill_counts) p.fill_counts[m] = k.n_fills;
+            hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask;
         }
         t_step++;
-        if (lane == 0) { hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask; }
         __syncwarp();
+        if (!last_it) {    // multi-step rollout: bring the generator back for the next step's draws
+            rng.shi = S.rng_park[0]; rng.slo = S.rng_park[1]; rng.ihi = S.rng_park[2]; rng.ilo = S.rng_park[3];
+            rng.has32 = S.rng_park32[0]; rng.u32 = S.rng_park32[1];
+        }
     }
-    if (!waited) mbar_wait(&S.bar, 0);   // (only when n_iter == 0; keeps the barrier phase consistent)
 
     // ---- store: header, accounts, pool prefix
     if (lane == 0) {
-        *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(c.time, c.next_id, c.seqctr, t_step);
-        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)last_price, c.tape_nonempty ? CDA_FLAG_TAPE : 0u, done_mask, c.status);
-        *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)c.n[0], (unsigned)c.n[1], rng.has32, rng.u32);
-        *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(rng.shi, rng.slo);
-        *reinterpret_cast<ulonglong2 *>(hdr + 16) = make_ulonglong2(rng.ihi, rng.ilo);
+        *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
+        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)last_price, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, done_mask, k.status);
+        *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)k.nb, (unsigned)k.na, S.rng_park32[0], S.rng_park32[1]);
+        *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(S.rng_park[0], S.rng_park[1]);
+        *reinterpret_cast<ulonglong2 *>(hdr + 16) = make_ulonglong2(S.rng_park[2], S.rng_park[3]);
     }
     if (lane < A) {
-        g_cash[lane] = c.ac.cash; g_hold[lane] = c.ac.hold; g_cost[lane] = c.ac.cost; g_nav[lane] = c.ac.nav;
-        g_prev[lane] = c.ac.prev_nav; g_max[lane] = c.ac.max_nav; g_pos[lane] = (int)c.ac.pos; g_ntr[lane] = c.ac.ntr;
-        g_ctr[lane] = (c.ac.tr_step & 0xfffu) | ((c.ac.pas_step & 0xfffu) << 12) | ((c.ac.placed & 1u) << 24) |
-                      ((c.ac.rejected & 1u) << 25) | ((c.ac.is_pass & 1u) << 26);
+        g_cash[lane] = ac.cash; g_hold[lane] = ac.hold; g_cost[lane] = ac.cost; g_nav[lane] = ac.nav;
+        g_prev[lane] = ac.prev_nav; g_max[lane] = ac.max_nav; g_pos[lane] = (int)ac.pos; g_ntr[lane] = ac.ntr;
+        g_ctr[lane] = (ac.tr_step & 0xfffu) | ((ac.pas_step & 0xfffu) << 12) | ((ac.placed & 1u) << 24) |
+                      ((ac.rejected & 1u) << 25) | ((ac.is_pass & 1u) << 26);
     }
     fence_proxy_async();   // every lane: its generic-proxy smem writes become visible to the async proxy
     __syncwarp();
-    const unsigned ob = ((unsigned)c.n[0] * 4u + 15u) & ~15u, oa = ((unsigned)c.n[1] * 4u + 15u) & ~15u;
+    const unsigned ob = ((unsigned)k.nb * 4u + 15u) & ~15u, oa = ((unsigned)k.na * 4u + 15u) & ~15u;
     if (lane == 0 && (ob | oa)) {
 #pragma unroll
         for (int f = 0; f < CDA_POOL_FIELDS; ++f) {
