@@ -61,6 +61,7 @@ static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cuda
     switch (e->dev.cap) {
         case 64: return launch_step<64>(e, p, st);
         case 128: return launch_step<128>(e, p, st);
+        case 160: return launch_step<160>(e, p, st);
         case 192: return launch_step<192>(e, p, st);
         default: return launch_step<256>(e, p, st);
     }
@@ -104,8 +105,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     if (cfg->initial_price_min < 1 || cfg->initial_price_max < cfg->initial_price_min) return CDA_EINVAL;
     if (cfg->min_size < 0 || cfg->mkt_max_size < 1 || cfg->limit_size_multiple < 1) return CDA_EINVAL;
     int cap = cfg->order_capacity;
-    if (cap == 0) cap = cfg->num_agents <= 8 ? 192 : 256;
-    if (cap != 64 && cap != 128 && cap != 192 && cap != 256) return CDA_EINVAL;
+    if (cap == 0) cap = cfg->num_agents <= 8 ? 160 : 256;
+    if (cap != 64 && cap != 128 && cap != 160 && cap != 192 && cap != 256) return CDA_EINVAL;
     if (cfg->fill_capacity < 0 || cfg->fill_capacity > 1024) return CDA_EINVAL;
     CUDA_TRY(cudaSetDevice(device));
     CdaEnv *e = new (std::nothrow) CdaEnv();
@@ -136,9 +137,9 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
         if (err == cudaSuccess) err = cudaMalloc(&e->fill_counts, (size_t)num_markets * sizeof(int));
     }
     if (err == cudaSuccess) err = cudaMalloc(&e->s_cat, MA * 4 * 5);
-    if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4);
-    if (err == cudaSuccess) err = cudaMalloc(&e->s_reward, MA * 8);
-    if (err == cudaSuccess) err = cudaMalloc(&e->s_term, (size_t)num_markets * 2);
+    // one contiguous output staging block: obs | reward | terminated | truncated  (single D2H when the
+    // caller's host buffers are laid out the same way)
+    if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4 + MA * 8 + (size_t)num_markets * 2);
     if (err != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc failed: %s", cudaGetErrorString(err));
         cda_destroy(e);
@@ -148,6 +149,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     e->s_sigma = reinterpret_cast<float *>(e->s_cat + 2 * MA);
     e->s_pcode = e->s_cat + 3 * MA;
     e->s_poff = e->s_cat + 4 * MA;
+    e->s_reward = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(e->s_obs) + (size_t)num_markets * d.W * 4);
+    e->s_term = reinterpret_cast<unsigned char *>(e->s_reward) + MA * 8;
     e->s_trunc = e->s_term + num_markets;
     CUDA_TRY(cudaMemset(e->state, 0, e->state_bytes));
     *out = e;
@@ -158,7 +161,7 @@ int cda_destroy(CdaEnv *e) {
     if (!e) return CDA_OK;
     cudaSetDevice(e->device);
     cudaFree(e->state); cudaFree(e->fills); cudaFree(e->fill_counts);
-    cudaFree(e->s_cat); cudaFree(e->s_obs); cudaFree(e->s_reward); cudaFree(e->s_term);
+    cudaFree(e->s_cat); cudaFree(e->s_obs);
     delete e;
     return CDA_OK;
 }
@@ -203,21 +206,37 @@ int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean
     if (!e->was_reset) return CDA_ESTATE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t MA = (size_t)e->M * e->dev.A;
-    CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_category, MA * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->s_mean, h_size_mean, MA * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->s_sigma, h_size_sigma, MA * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->s_pcode, h_price, MA * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->s_poff, h_price_offset, MA * 4, cudaMemcpyHostToDevice, st));
+    // actions: one H2D when the five host arrays are one contiguous [5][M][A] block, else five
+    const char *hc = reinterpret_cast<const char *>(h_category);
+    const bool in_contig = reinterpret_cast<const char *>(h_size_mean) == hc + MA * 4 && reinterpret_cast<const char *>(h_size_sigma) == hc + 2 * MA * 4 &&
+                           reinterpret_cast<const char *>(h_price) == hc + 3 * MA * 4 && reinterpret_cast<const char *>(h_price_offset) == hc + 4 * MA * 4;
+    if (in_contig) {
+        CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_category, MA * 4 * 5, cudaMemcpyHostToDevice, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_category, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_mean, h_size_mean, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_sigma, h_size_sigma, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_pcode, h_price, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_poff, h_price_offset, MA * 4, cudaMemcpyHostToDevice, st));
+    }
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
     p.cat = e->s_cat; p.mean = e->s_mean; p.sigma = e->s_sigma; p.pcode = e->s_pcode; p.poff = e->s_poff;
     p.obs = e->s_obs; p.reward = e->s_reward; p.term = e->s_term; p.trunc = e->s_trunc;
     int rc = step_common(e, p, st);
     if (rc) return rc;
-    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, e->s_obs, (size_t)e->M * e->dev.W * 4, cudaMemcpyDeviceToHost, st));
-    if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, e->s_reward, MA * 8, cudaMemcpyDeviceToHost, st));
-    if (h_terminated) CUDA_TRY(cudaMemcpyAsync(h_terminated, e->s_term, e->M, cudaMemcpyDeviceToHost, st));
-    if (h_truncated) CUDA_TRY(cudaMemcpyAsync(h_truncated, e->s_trunc, e->M, cudaMemcpyDeviceToHost, st));
+    const size_t obs_bytes = (size_t)e->M * e->dev.W * 4;
+    char *ho = reinterpret_cast<char *>(h_obs);
+    const bool out_contig = h_obs && h_reward && h_terminated && h_truncated && reinterpret_cast<char *>(h_reward) == ho + obs_bytes &&
+                            reinterpret_cast<char *>(h_terminated) == ho + obs_bytes + MA * 8 && reinterpret_cast<char *>(h_truncated) == ho + obs_bytes + MA * 8 + e->M;
+    if (out_contig) {
+        CUDA_TRY(cudaMemcpyAsync(h_obs, e->s_obs, obs_bytes + MA * 8 + 2 * (size_t)e->M, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, e->s_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+        if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, e->s_reward, MA * 8, cudaMemcpyDeviceToHost, st));
+        if (h_terminated) CUDA_TRY(cudaMemcpyAsync(h_terminated, e->s_term, e->M, cudaMemcpyDeviceToHost, st));
+        if (h_truncated) CUDA_TRY(cudaMemcpyAsync(h_truncated, e->s_trunc, e->M, cudaMemcpyDeviceToHost, st));
+    }
     return CDA_OK;
 }
 
@@ -262,24 +281,25 @@ int cda_dump_market(CdaEnv *e, int32_t market, int64_t *h_bids, int64_t *h_asks,
     const int cap = e->dev.cap;
     for (int side = 0; side < 2; ++side) {
         const int n = (int)hdr[8 + side];
-        const unsigned *f = pool + (size_t)side * CDA_POOL_FIELDS * cap;
+        const unsigned *sb = pool + (size_t)side * CDA_POOL_FIELDS * cap;
+        auto fld = [&](int i, int f) { return sb[CDA_EOFF(i) + f * 32]; };
         std::vector<int> idx(n);
         for (int i = 0; i < n; ++i) idx[i] = i;
         std::sort(idx.begin(), idx.end(), [&](int a, int b) {
-            unsigned pa = f[a] & CDA_PRICE_MASK, pb = f[b] & CDA_PRICE_MASK;
+            unsigned pa = fld(a, 0) & CDA_PRICE_MASK, pb = fld(b, 0) & CDA_PRICE_MASK;
             if (pa != pb) return side == 0 ? pa > pb : pa < pb;
-            return f[4 * cap + a] < f[4 * cap + b];
+            return fld(a, 4) < fld(b, 4);
         });
         int64_t *rows = side == 0 ? h_bids : h_asks;
         if (rows)
-            for (int k = 0; k < n && k < max_rows; ++k) {
-                int i = idx[k];
-                rows[k * 5 + 0] = f[i] & CDA_PRICE_MASK; rows[k * 5 + 1] = f[cap + i]; rows[k * 5 + 2] = f[i] >> 24;
-                rows[k * 5 + 3] = f[2 * cap + i]; rows[k * 5 + 4] = f[3 * cap + i];
+            for (int q = 0; q < n && q < max_rows; ++q) {
+                int i = idx[q];
+                rows[q * 5 + 0] = fld(i, 0) & CDA_PRICE_MASK; rows[q * 5 + 1] = fld(i, 1); rows[q * 5 + 2] = fld(i, 0) >> 24;
+                rows[q * 5 + 3] = fld(i, 2); rows[q * 5 + 4] = fld(i, 3);
             }
-        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return f[4 * cap + a] < f[4 * cap + b]; });
+        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return fld(a, 4) < fld(b, 4); });
         int64_t *mp = side == 0 ? h_bids_map : h_asks_map;
-        if (mp) for (int k = 0; k < n && k < max_rows; ++k) mp[k] = f[2 * cap + idx[k]];
+        if (mp) for (int q = 0; q < n && q < max_rows; ++q) mp[q] = fld(idx[q], 2);
         h_counts[side] = n;
     }
     if (h_rng6) {

@@ -30,6 +30,9 @@
 #define CDA_POOL_FIELDS 5 /* 0 pt (trader<<24|price), 1 qty, 2 order_id, 3 timestamp, 4 seq */
 #define CDA_PRICE_MASK 0x00ffffffu
 #define CDA_FLAG_TAPE 1u
+#define CDA_TILE_WORDS (CDA_POOL_FIELDS * 32)   /* one tile: 5 fields x 32 orders */
+// word offset of order i inside a side (field 0); field f is at + f*32
+#define CDA_EOFF(i) ((((i) >> 5) * CDA_TILE_WORDS) + ((i) & 31))
 
 // ------------------------------------------------------------------------------------------
 // Per-market block in HBM (stride bytes, 128-B aligned), see DESIGN.md "Data layout":
@@ -37,7 +40,9 @@
 //   [off_acct, ...)    accounts, SoA inside the market: cash[A] hold[A] cost[A] nav[A] prev_nav[A]
 //                      max_nav[A] (i64), pos[A] (i32), num_trades[A] (u32), stepctr[A] (u32)
 //   [off_hist, ...)    snapshot ring  f32[n_hist][42]
-//   [off_pool, ...)    order pool     u32[2 sides][5 fields][cap]
+//   [off_pool, ...)    order pool     u32[2 sides][cap/32 tiles][5 fields][32]  ("blocked SoA": the live
+//                      prefix of a side is ONE contiguous run of whole tiles => one bulk copy per side,
+//                      and a lane-strided scan reads 32 consecutive words => no bank conflicts)
 // Header words (u32 index):
 //   0 time  1 next_order_id  2 seqctr  3 t_step  4 last_price  5 flags  6 done_mask  7 status
 //   8 n_bid 9 n_ask 10 rng_has_uint32 11 rng_uinteger 12..19 rng state_hi,state_lo,inc_hi,inc_lo (u64)
@@ -263,7 +268,7 @@ __device__ __forceinline__ void acct_fill(CdaAcct &a, int party, int side /*0 bi
 // addressed arithmetically through SOFF(side).
 template <int CAP>
 struct CdaMkt {
-    unsigned *pool;      // shared memory u32[2 sides][5 fields][CAP]
+    unsigned *pool;      // shared memory u32[2 sides][CAP/32 tiles][5 fields][32]
     int nb, na;          // live orders per side
     unsigned time, next_id, seqctr, status;
     int tape_nonempty, tape_px;
@@ -275,24 +280,23 @@ struct CdaMkt {
 };
 
 template <int CAP> __device__ __forceinline__ int pool_best(const CdaMkt<CAP> &k, int side) {
-    const unsigned *pt = k.side_base(side);
+    const unsigned *pt = k.side_base(side) + k.lane;
     const int n = k.count(side);
     if (n == 0) return -1;
     unsigned loc = side == 0 ? 0u : 0xffffffffu;
-    for (int i = k.lane; i < n; i += 32) {
-        const unsigned p = pt[i] & CDA_PRICE_MASK;
+    for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
+        const unsigned p = *pt & CDA_PRICE_MASK;
         loc = side == 0 ? max(loc, p) : min(loc, p);
     }
     return (int)(side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc));
 }
 // index of the entry with the smallest key[field] among entries with (pt & mask) == want, or -1
 template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> &k, int side, unsigned mask, unsigned want, int field) {
-    const unsigned *pt = k.side_base(side);
-    const unsigned *key = pt + field * CAP;
+    const unsigned *pt = k.side_base(side) + k.lane;
     const int n = k.count(side);
     unsigned bk = 0xffffffffu; int bi = -1;
-    for (int i = k.lane; i < n; i += 32) {
-        if ((pt[i] & mask) == want) { const unsigned kk = key[i]; if (kk < bk) { bk = kk; bi = i; } }
+    for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
+        if ((*pt & mask) == want) { const unsigned kk = pt[field * 32]; if (kk < bk) { bk = kk; bi = i; } }
     }
     const unsigned mk = __reduce_min_sync(CDA_FULL, bk);
     if (mk == 0xffffffffu) return -1;
@@ -304,8 +308,8 @@ template <int CAP> __device__ __forceinline__ void pool_remove(CdaMkt<CAP> &k, i
     const int last = k.count(side) - 1;
     __syncwarp();
     if (idx != last && k.lane < CDA_POOL_FIELDS) {
-        unsigned *f = k.side_base(side) + k.lane * CAP;
-        f[idx] = f[last];
+        unsigned *f = k.side_base(side) + k.lane * 32;
+        f[CDA_EOFF(idx)] = f[CDA_EOFF(last)];
     }
     k.set_count(side, last);
     __syncwarp();
@@ -318,7 +322,7 @@ template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, i
     __syncwarp();
     if (k.lane < CDA_POOL_FIELDS) {
         const unsigned v = k.lane == 0 ? (((unsigned)trader << 24) | price) : k.lane == 1 ? qty : k.lane == 2 ? oid : k.lane == 3 ? ts : seq;
-        k.side_base(side)[k.lane * CAP + n] = v;
+        k.side_base(side)[CDA_EOFF(n) + k.lane * 32] = v;
     }
     k.set_count(side, n + 1);
     __syncwarp();
@@ -363,15 +367,15 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
     unsigned oid;
     if (idx >= 0) {
         // trader.py:219-235 / :237-252: release the old order's escrow (cash_processor.py:85-97), then touch the book
-        unsigned *pl = k.side_base(side);
-        const unsigned op = pl[idx] & CDA_PRICE_MASK, oq = pl[CAP + idx];
-        oid = pl[2 * CAP + idx];
+        unsigned *pl = k.side_base(side) + CDA_EOFF(idx);
+        const unsigned op = pl[0] & CDA_PRICE_MASK, oq = pl[32];
+        oid = pl[64];
         if (is_t) { const long long ov = (long long)op * oq; ac.hold -= ov; ac.cash += ov; }
         k.time++;                                                        // orderbook.py:196-200, :212-215
         if (type == 3) { pool_remove(k, side, idx); return; }
         if ((unsigned)price == op && (unsigned long long)size <= oq) {   // orderbook.py:245-248 in place
             __syncwarp();
-            if (k.lane == 0) { pl[CAP + idx] = (unsigned)size; pl[3 * CAP + idx] = k.time; }
+            if (k.lane == 0) { pl[32] = (unsigned)size; pl[96] = k.time; }
             __syncwarp();
             if (is_t) { const long long v = (long long)price * size; ac.cash -= v; ac.hold += v; }
             return;
@@ -387,20 +391,20 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
     //      sees the same sequence of updates)
     const int limit = type == 0 ? -1 : price;
     unsigned qty = (unsigned)size;
-    unsigned *po = k.side_base(opp);
     while (qty > 0) {
         const int P = pool_best(k, opp);
         if (P < 0) break;
         if (limit >= 0 && (side == 0 ? limit < P : limit > P)) break;
         const int h = pool_argmin(k, opp, CDA_PRICE_MASK, (unsigned)P, 4);
-        const unsigned hq = po[CAP + h];
-        const int maker = (int)(po[h] >> 24);
-        const unsigned moid = po[2 * CAP + h];
+        unsigned *po = k.side_base(opp) + CDA_EOFF(h);
+        const unsigned hq = po[32];
+        const int maker = (int)(po[0] >> 24);
+        const unsigned moid = po[64];
         unsigned traded; int left = -1;
         if (qty < hq) {                       // :73-85 partial: resting order shrinks in place, keeps its timestamp
             traded = qty; left = (int)(hq - qty);
             __syncwarp();
-            if (k.lane == 0) po[CAP + h] = hq - qty;
+            if (k.lane == 0) po[32] = hq - qty;
             __syncwarp();
             qty = 0;
         } else {                              // :86-100 resting order consumed
@@ -448,7 +452,7 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 // ------------------------------------------------------------------------------------------
 template <int CAP>
 struct CdaWarpSmem {
-    unsigned pool[2][CDA_POOL_FIELDS][CAP];
+    unsigned pool[2][CAP / 32][CDA_POOL_FIELDS][32];
     float snap[44];
     int topk[2 * CDA_K_ROWS];        // frozen pre-step raw top-K prices (agg_LOB_raw price rows)
     unsigned vol[2 * CDA_K_ROWS];    // level volumes of the snapshot being built
@@ -457,7 +461,7 @@ struct CdaWarpSmem {
     unsigned rng_park32[2];
     unsigned char order[32];
 };
-static_assert(sizeof(CdaWarpSmem<64>) % 16 == 0 && sizeof(CdaWarpSmem<128>) % 16 == 0 &&
+static_assert(sizeof(CdaWarpSmem<64>) % 16 == 0 && sizeof(CdaWarpSmem<128>) % 16 == 0 && sizeof(CdaWarpSmem<160>) % 16 == 0 &&
               sizeof(CdaWarpSmem<192>) % 16 == 0 && sizeof(CdaWarpSmem<256>) % 16 == 0, "smem tile must keep 16-B alignment");
 
 #ifndef CDA_MIN_CTAS
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 
     CdaMkt<CAP> k;
     k.lane = lane;
-    k.pool = &S.pool[0][0][0];
+    k.pool = &S.pool[0][0][0][0];
     k.time = h0.x; k.next_id = h0.y; k.seqctr = h0.z;
     unsigned t_step = h0.w;
     int last_price = (int)h1.x;
@@ -505,17 +509,14 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     k.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0;
 
-    // ---- order pool: TMA bulk copies of the live prefix of each field array
+    // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
-    const unsigned bytes_b = ((unsigned)k.nb * 4u + 15u) & ~15u, bytes_a = ((unsigned)k.na * 4u + 15u) & ~15u;
+    const unsigned bytes_b = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), bytes_a = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
     const bool have_pool = (bytes_b | bytes_a) != 0;
     if (have_pool && lane == 0) {
-        mbar_expect_tx(&S.bar, CDA_POOL_FIELDS * (bytes_b + bytes_a));
-#pragma unroll
-        for (int f = 0; f < CDA_POOL_FIELDS; ++f) {
-            if (bytes_b) bulk_g2s(&S.pool[0][f][0], gpool + (0 * CDA_POOL_FIELDS + f) * CAP, bytes_b, &S.bar);
-            if (bytes_a) bulk_g2s(&S.pool[1][f][0], gpool + (1 * CDA_POOL_FIELDS + f) * CAP, bytes_a, &S.bar);
-        }
+        mbar_expect_tx(&S.bar, bytes_b + bytes_a);
+        if (bytes_b) bulk_g2s(&S.pool[0][0][0][0], gpool, bytes_b, &S.bar);
+        if (bytes_a) bulk_g2s(&S.pool[1][0][0][0], gpool + CDA_POOL_FIELDS * CAP, bytes_a, &S.bar);
     }
 
     // ---- accounts into lanes 0..A-1
@@ -650,27 +651,28 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         __syncwarp();
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
-            const unsigned *pt = k.side_base(side), *qy = pt + CAP;
+            const unsigned *pt = k.side_base(side) + lane;   // this lane's column of every tile
             const int n = k.count(side);
             if (n == 0) continue;
+            const int nt = (n - lane + 31) >> 5;              // tiles in which this lane owns a live order
             unsigned loc = side == 0 ? 0u : 0xffffffffu;
-            for (int i = lane; i < n; i += 32) { const unsigned pp = pt[i] & CDA_PRICE_MASK; loc = side == 0 ? max(loc, pp) : min(loc, pp); }
+            for (int it = 0; it < nt; ++it) { const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK; loc = side == 0 ? max(loc, pp) : min(loc, pp); }
             const unsigned B = side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc);
             unsigned mlo = 0, mhi = 0; bool far = false;
-            for (int i = lane; i < n; i += 32) {
-                const unsigned pp = pt[i] & CDA_PRICE_MASK;
+            for (int it = 0; it < nt; ++it) {
+                const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK;
                 const unsigned d = side == 0 ? B - pp : pp - B;
                 if (d < 32) mlo |= 1u << d; else if (d < 64) mhi |= 1u << (d - 32); else far = true;
             }
             mlo = __reduce_or_sync(CDA_FULL, mlo); mhi = __reduce_or_sync(CDA_FULL, mhi);
             const bool far_any = __any_sync(CDA_FULL, far);
             const int nlo = __popc(mlo), nlev = nlo + __popc(mhi);
-            for (int i = lane; i < n; i += 32) {
-                const unsigned pp = pt[i] & CDA_PRICE_MASK;
+            for (int it = 0; it < nt; ++it) {
+                const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK;
                 const unsigned d = side == 0 ? B - pp : pp - B;
                 if (d < 64) {
                     const int rank = d < 32 ? __popc(mlo & ((1u << d) - 1u)) : nlo + __popc(mhi & ((1u << (d - 32)) - 1u));
-                    if (rank < CDA_K_ROWS) atomicAdd(&S.vol[side * CDA_K_ROWS + rank], qy[i]);
+                    if (rank < CDA_K_ROWS) atomicAdd(&S.vol[side * CDA_K_ROWS + rank], pt[it * CDA_TILE_WORDS + 32]);
                 }
             }
             __syncwarp();
@@ -686,14 +688,14 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 unsigned prev = side == 0 ? B - 63u : B + 63u;
                 for (int lv = nlev; lv < CDA_K_ROWS; ++lv) {
                     unsigned l2 = side == 0 ? 0u : 0xffffffffu;
-                    for (int i = lane; i < n; i += 32) {
-                        const unsigned pp = pt[i] & CDA_PRICE_MASK;
+                    for (int it = 0; it < nt; ++it) {
+                        const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK;
                         if (side == 0 ? pp < prev : pp > prev) l2 = side == 0 ? max(l2, pp) : min(l2, pp);
                     }
                     const unsigned P = side == 0 ? __reduce_max_sync(CDA_FULL, l2) : __reduce_min_sync(CDA_FULL, l2);
                     if (P == (side == 0 ? 0u : 0xffffffffu)) break;
                     unsigned s = 0;
-                    for (int i = lane; i < n; i += 32) if ((pt[i] & CDA_PRICE_MASK) == P) s += qy[i];
+                    for (int it = 0; it < nt; ++it) if ((pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK) == P) s += pt[it * CDA_TILE_WORDS + 32];
                     const unsigned V = __reduce_add_sync(CDA_FULL, s);
                     if (lane == side * CDA_K_ROWS + lv) { myP = (int)P; myV = V; }
                     prev = P;
@@ -706,23 +708,31 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         else if (best_bid > 0) Mid = (double)best_bid;
         else if (best_ask > 0) Mid = (double)best_ask;
         else { Mid = (double)last_price; if (Mid <= 0) Mid = 100.0; }
+        // The reference evaluates these in f64 and casts once to f32 (state_helper.py:180-212).  For the
+        // price/size rows the operands are small exact integers/half-integers, so a correctly rounded
+        // f32 divide / sqrt returns the same bits as f64-then-round (double rounding is innocuous for
+        // / and sqrt when 53 >= 2*24+2).  log_mid and log1p_spread go through ONE f64 log() call:
+        // lane 20 takes log(M), lane 21 log(1 + spread_ticks) (1 + st is exact).
         if (lane < 2 * CDA_K_ROWS) {
-            const double pz = (double)myP, vz = (double)myV;
-            double pn, sn;
-            if (lane < CDA_K_ROWS) { pn = myP > 0 ? (Mid - pz) / Mid : 0.0; sn = myV > 0 ? sqrt(vz) : 0.0; }
-            else                   { pn = myP > 0 ? -((pz - Mid) / Mid) : 0.0; sn = myV > 0 ? -sqrt(vz) : 0.0; }
+            const float Mf = (float)Mid, pz = (float)myP;       // exact: prices < 2^24, Mid is a half-integer
+            float pn = 0.f, sn = 0.f;
+            if (myP > 0) pn = lane < CDA_K_ROWS ? __fdiv_rn(Mf - pz, Mf) : -__fdiv_rn(pz - Mf, Mf);
+            if (myV > 0) { const float sq = __fsqrt_rn((float)myV); sn = lane < CDA_K_ROWS ? sq : -sq; }
             const int l = lane < CDA_K_ROWS ? lane : lane - CDA_K_ROWS;
             const int b = lane < CDA_K_ROWS ? 0 : 2 * CDA_K_ROWS;
-            S.snap[b + l] = (float)pn;
-            S.snap[b + CDA_K_ROWS + l] = (float)sn;
+            S.snap[b + l] = pn;
+            S.snap[b + CDA_K_ROWS + l] = sn;
             S.topk[lane] = myP;                          // frozen raw top-K for the next step's _set_price
             hdr[20 + lane] = (unsigned)myP;
-        } else if (lane == 20) {
-            S.snap[40] = (float)log(Mid);
-        } else if (lane == 21) {
-            float v = 0.0f;
-            if (best_bid > 0 && best_ask > 0) { const double st = ((double)best_ask - (double)best_bid) / (double)cfg.tick; v = (float)log1p(st > 0.0 ? st : 0.0); }
-            S.snap[41] = v;
+        } else if (lane < 22) {
+            double x = Mid; bool live = true;
+            if (lane == 21) {
+                live = best_bid > 0 && best_ask > 0;
+                const double st = ((double)best_ask - (double)best_bid) / (double)cfg.tick;
+                x = 1.0 + (st > 0.0 ? st : 0.0);
+            }
+            const double lg = log(x);
+            S.snap[20 + lane] = live ? (float)lg : 0.0f;
         }
         __syncwarp();
 
@@ -788,13 +798,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     }
     fence_proxy_async();   // every lane: its generic-proxy smem writes become visible to the async proxy
     __syncwarp();
-    const unsigned ob = ((unsigned)k.nb * 4u + 15u) & ~15u, oa = ((unsigned)k.na * 4u + 15u) & ~15u;
+    const unsigned ob = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), oa = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
     if (lane == 0 && (ob | oa)) {
-#pragma unroll
-        for (int f = 0; f < CDA_POOL_FIELDS; ++f) {
-            if (ob) bulk_s2g(gpool + (0 * CDA_POOL_FIELDS + f) * CAP, &S.pool[0][f][0], ob);
-            if (oa) bulk_s2g(gpool + (1 * CDA_POOL_FIELDS + f) * CAP, &S.pool[1][f][0], oa);
-        }
+        if (ob) bulk_s2g(gpool, &S.pool[0][0][0][0], ob);
+        if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, &S.pool[1][0][0][0], oa);
         bulk_commit();
         bulk_wait_read0();
     }

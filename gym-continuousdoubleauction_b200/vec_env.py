@@ -105,14 +105,19 @@ class VecCDAEnv:
 
     # ------------------------------------------------------------------ step (host buffers, e2e)
     def _ensure_pinned(self):
+        """Pinned host buffers laid out so that cda_step_host needs ONE H2D and ONE D2H copy:
+        actions = one [5, M, A] 4-byte block; outputs = obs | reward | terminated | truncated."""
         if self._pinned is None:
             M, A, W = self.M, self.A, self.W
-            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+            act = torch.empty((5, M, A), dtype=torch.int32, pin_memory=True)
+            nb_obs, nb_rew = M * W * 4, M * A * 8
+            out = torch.empty(nb_obs + nb_rew + 2 * M, dtype=torch.uint8, pin_memory=True)
             self._pinned = dict(
-                cat=pin((M, A), torch.int32), mean=pin((M, A), torch.float32), sigma=pin((M, A), torch.float32),
-                price=pin((M, A), torch.int32), off=pin((M, A), torch.int32),
-                obs=pin((M, W), torch.float32), reward=pin((M, A), torch.float64),
-                term=pin((M,), torch.uint8), trunc=pin((M,), torch.uint8))
+                act=act, out=out,
+                cat=act[0], mean=act[1].view(torch.float32), sigma=act[2].view(torch.float32), price=act[3], off=act[4],
+                obs=out[:nb_obs].view(torch.float32).view(M, W),
+                reward=out[nb_obs:nb_obs + nb_rew].view(torch.float64).view(M, A),
+                term=out[nb_obs + nb_rew:nb_obs + nb_rew + M], trunc=out[nb_obs + nb_rew + M:])
         return self._pinned
 
     def step_host(self, category, size_mean, size_sigma, price, price_offset, sync=True):

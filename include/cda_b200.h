@@ -59,7 +59,7 @@ typedef struct CdaConfig {
     int64_t init_cash;           /* > 0 */
     int32_t min_size, mkt_max_size, limit_size_multiple;
     int32_t initial_price_min, initial_price_max;   /* inclusive anchor range */
-    int32_t order_capacity;      /* resting orders per side per market: 64, 128, 192 or 256; 0 = auto (192 up to 8 agents, else 256) */
+    int32_t order_capacity;      /* resting orders per side per market: 64, 128, 160, 192 or 256; 0 = auto (160 up to 8 agents, else 256) */
     int32_t fill_capacity;       /* fills logged per market per step (0 = no fill log) */
     double order_penalty, trade_penalty, drawdown_penalty, passive_bonus, loss_multiplier;
 } CdaConfig;
