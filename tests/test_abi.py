@@ -1,0 +1,57 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/cda_b200.h declares."""
+import ctypes
+import os
+import re
+
+import gym_continuousdoubleauction_b200 as cda
+from gym_continuousdoubleauction_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "cda_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cda_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    cda.build()
+    L = ctypes.CDLL(_native.SO_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 18
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(_native.EXPORTS) == syms
+
+
+def test_host_side_seeding_matches_numpy():
+    import numpy as np
+    L = _native.lib()
+    for seed in (0, 7, 2**33 + 1, 2**64 - 1):
+        out = (ctypes.c_uint64 * 4)()
+        L.cda_seed_to_pcg64(ctypes.c_uint64(seed), out)
+        st = np.random.PCG64(np.random.SeedSequence(seed)).state["state"]
+        assert (out[0] << 64 | out[1]) == st["state"] and (out[2] << 64 | out[3]) == st["inc"]
+
+
+def test_config_struct_matches_header_layout():
+    # 12 int32-sized slots (with the int64 aligned at offset 16) + 5 doubles
+    assert ctypes.sizeof(_native.CdaConfig) == 96
+    assert _native.CdaConfig.init_cash.offset == 16
+    assert _native.CdaConfig.order_penalty.offset == 56
+
+
+def test_no_cpu_fallback_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        cda.VecCDAEnv({"num_of_agents": 4}, num_markets=2)
+
+
+def test_strerror_and_build_info():
+    L = _native.lib()
+    assert b"sm_100a" in L.cda_build_info()
+    assert L.cda_strerror(-1) and L.cda_strerror(0) == b"ok"
