@@ -44,7 +44,7 @@ INFO_MARKET_COLS = ("last_price", "best_bid", "best_ask", "time", "next_order_id
 
 EXPORTS = (
     "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_rollout_random",
-    "cda_get_info", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
+    "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
     "cda_seed_to_pcg64",
@@ -95,6 +95,7 @@ def lib():
     L.cda_step_host.argtypes = [vp] * 11
     L.cda_rollout_random.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp]
     L.cda_get_info.argtypes = [vp, i32, vp, vp]
+    L.cda_get_info_all.argtypes = [vp, vp, vp]
     L.cda_get_fills.argtypes = [vp, vp, vp, vp]
     L.cda_dump_market.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]
     L.cda_state_bytes.argtypes = [vp]

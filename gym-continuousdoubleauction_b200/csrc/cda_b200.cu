@@ -261,6 +261,16 @@ int cda_get_info(CdaEnv *e, int32_t field, int64_t *d_out, void *stream) {
     return CDA_OK;
 }
 
+int cda_get_info_all(CdaEnv *e, int64_t *d_out, void *stream) {
+    if (!e || !d_out) return CDA_EINVAL;
+    const int n = CDA_INFO_MARKET * e->M * e->dev.A + e->M;
+    const int threads = 256, grid = (n + threads - 1) / threads;
+    cda_info_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, -1, (long long *)d_out);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return CDA_OK;
+}
+
 int cda_get_fills(CdaEnv *e, int32_t *d_fills, int32_t *d_counts, void *stream) {
     if (!e || !e->fills) return CDA_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;

@@ -854,8 +854,14 @@ __global__ void cda_reset_kernel(CdaDevCfg cfg, unsigned char *state, int M, con
 // lazy info gather (info_helper.py:30-116): one thread per (market, agent)
 // ------------------------------------------------------------------------------------------
 __global__ void cda_info_kernel(CdaDevCfg cfg, const unsigned char *state, int M, int field, long long *out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int A = cfg.A;
+    if (field < 0) {   // all fields: [CDA_INFO_MARKET][M][A] then the market block [M][8]
+        const int per = M * A;
+        if (i >= CDA_INFO_MARKET * per + M) return;
+        if (i < CDA_INFO_MARKET * per) { field = i / per; i -= field * per; out += (size_t)field * per; }
+        else { i -= CDA_INFO_MARKET * per; field = CDA_INFO_MARKET; out += (size_t)CDA_INFO_MARKET * per; }
+    }
     if (field == CDA_INFO_MARKET) {
         if (i >= M) return;
         const unsigned *hdr = reinterpret_cast<const unsigned *>(state + (size_t)i * cfg.stride);

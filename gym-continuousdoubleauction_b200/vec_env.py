@@ -170,6 +170,17 @@ class VecCDAEnv:
         _native.check(self._L.cda_get_info(self._h, idx, _ptr(out), self._stream()))
         return out
 
+    def info_all(self):
+        """Every per-agent info field in one launch: dict name -> int64 CUDA tensor [M, A], plus
+        'market' [M, 8] (columns: _native.INFO_MARKET_COLS)."""
+        n = len(_native.INFO_FIELDS) - 1
+        buf = torch.empty(n * self.M * self.A + self.M * 8, dtype=torch.int64, device=self.device)
+        _native.check(self._L.cda_get_info_all(self._h, _ptr(buf), self._stream()))
+        out = {name: buf[i * self.M * self.A:(i + 1) * self.M * self.A].view(self.M, self.A)
+               for i, name in enumerate(_native.INFO_FIELDS[:-1])}
+        out["market"] = buf[n * self.M * self.A:].view(self.M, 8)
+        return out
+
     def status(self):
         return self.info("market")[:, 7]
 

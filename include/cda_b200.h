@@ -122,6 +122,10 @@ int cda_rollout_random(CdaEnv *env, int32_t num_steps, uint64_t policy_seed, flo
 /* Lazy info (info_helper.py:30-116): gathers one field for all markets into d_out. */
 int cda_get_info(CdaEnv *env, int32_t field, int64_t *d_out, void *stream);
 
+/* All per-agent fields at once: d_out i64[CDA_INFO_MARKET][M][A] followed by the market block
+ * i64[M][8] (one kernel launch; what the dict adapter uses to build the reference's info dict). */
+int cda_get_info_all(CdaEnv *env, int64_t *d_out, void *stream);
+
 /* Fill log of the last step (the reference's per-step `seq_trades`, action_helper.py:201-239):
  * d_fills i32[M][fill_capacity][8], d_counts i32[M].  Requires fill_capacity > 0. */
 int cda_get_fills(CdaEnv *env, int32_t *d_fills, int32_t *d_counts, void *stream);

@@ -1,0 +1,123 @@
+"""The reference-compatible dict adapter (continuousDoubleAuctionEnv surface) on the GPU path.
+Modelled on the reference's own tests: test_info_dict.py (keys, terms sum exactly to reward, NAV
+string), test_seeding.py (same seed + same actions => identical), test_env_lifecycle.py
+(truncation lands on max_step), test_observation_history.py (all agents share one obs)."""
+import json
+import os
+from decimal import Decimal
+
+import numpy as np
+import pytest
+
+import gym_continuousdoubleauction_b200 as cda
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+INFO_KEYS = {"reward", "NAV", "num_trades", "net_position", "VWAP", "cash", "cash_on_hold", "position_val",
+             "drawdown", "max_nav", "num_trades_step", "num_passive_fills_step", "order_step_placed",
+             "num_rejected_step", "is_pass_action", "reward_terms", "last_price", "best_bid", "best_ask", "spread",
+             "model_action"}
+
+
+def acts_at(g, t, A):
+    d = {}
+    for i in range(A):
+        if g["cat"][t, i] < 0:
+            continue
+        d[f"agent_{i}"] = {"category": int(g["cat"][t, i]), "size_mean": np.array([g["mean"][t, i]], np.float32),
+                           "size_sigma": np.array([g["sigma"][t, i]], np.float32), "price": int(g["price"][t, i]),
+                           "price_offset": int(g["off"][t, i])}
+    return d
+
+
+@pytest.mark.parametrize("name", ["uniform_a4", "modify_heavy_a8", "nhist2_a5_absent", "appendix_d"])
+def test_dict_api_reproduces_reference_golden(name):
+    g = np.load(os.path.join(GOLD, f"traj_{name}.npz"))
+    cfg = {str(k): (int(v) if float(v).is_integer() else float(v)) for k, v in zip(g["cfg_keys"], g["cfg_vals"])}
+    env = cda.continuousDoubleAuctionEnv(cfg)
+    A = env.num_of_agents
+    obs, infos = env.reset(seed=int(g["seed"]))
+    assert set(obs) == set(env.agents) and all(v == {} for v in infos.values())
+    assert np.array_equal(obs["agent_0"], g["obs0"])
+    for t in range(g["cat"].shape[0]):
+        o, r, te, tr, info = env.step(acts_at(g, t, A))
+        assert o["agent_0"] is o[f"agent_{A - 1}"]                         # one shared array
+        assert o["agent_0"].dtype == np.float32 and o["agent_0"].shape == (env.n_hist * 42,)
+        assert np.abs(o["agent_0"].astype(np.float64) - g["obs"][t]).max() <= 1e-6
+        assert np.abs(np.array([r[a] for a in env.agents]) - g["reward"][t]).max() <= 1e-6
+        assert te["__all__"] == bool(g["terminated"][t]) and tr["__all__"] == bool(g["truncated"][t])
+        assert all(te[a] is False and tr[a] is False for a in env.agents)
+        for i, a in enumerate(env.agents):
+            inf = info[a]
+            assert set(inf) - {"model_action"} == INFO_KEYS - {"model_action"}
+            acc = g["accounts"][t][i]
+            assert Decimal(inf["NAV"]) == int(acc[4]) and inf["net_position"] == int(acc[7])
+            assert inf["cash"] == float(acc[0]) and inf["cash_on_hold"] == float(acc[1]) and inf["position_val"] == float(acc[2])
+            assert inf["num_trades"] == int(acc[8]) and inf["num_trades_step"] == int(acc[9])
+            assert inf["is_pass_action"] == bool(acc[13])
+            s = 0.0
+            for v in inf["reward_terms"].values():                          # naive left-to-right sum, exactly
+                s += v
+            assert s == inf["reward"] == r[a]
+            json.dumps(inf)                                                 # JSON-safe
+        assert info["agent_0"]["last_price"] == float(g["scalars"][t][2])
+    fills = env.fills()
+    f0, f1 = int(g["fill_ptr"][-2]), int(g["fill_ptr"][-1])
+    assert np.array_equal(fills, g["fills"][f0:f1])
+    env.close()
+
+
+def test_nav_conservation_and_random_driver():
+    from gym_continuousdoubleauction_b200.cda_rand import run_random
+    out = run_random(num_agents=4, max_step=200, init_cash=1_000_000, seed=3)
+    assert out["steps"] == 200
+    assert out["total_nav"] == 4 * 1_000_000      # SelfPlayCallback's |sum NAV - init_cash*A| <= 1e-6 check, exactly
+
+
+def test_same_seed_same_actions_identical_and_seed_none_differs():
+    def run(seed_second):
+        env = cda.continuousDoubleAuctionEnv({"num_of_agents": 4, "max_step": 50})
+        rng = np.random.default_rng(0)
+        env.reset(seed=123)
+        outs = []
+        for ep in range(2):
+            if ep == 1:
+                env.reset(seed=seed_second)
+            for t in range(30):
+                a = {f"agent_{i}": {"category": int(rng.integers(0, 9)), "size_mean": rng.uniform(-1, 1, 1).astype(np.float32),
+                                    "size_sigma": rng.uniform(0, 1, 1).astype(np.float32), "price": int(rng.integers(0, 10)),
+                                    "price_offset": int(rng.integers(0, 3))} for i in range(4)}
+                o, r, *_ = env.step(a)
+                outs.append((o["agent_0"].copy(), dict(r)))
+        env.close()
+        return outs
+    a, b, c = run(123), run(123), run(None)
+    assert all(np.array_equal(x[0], y[0]) and x[1] == y[1] for x, y in zip(a, b))
+    assert not all(np.array_equal(x[0], y[0]) for x, y in zip(a[30:], c[30:]))   # seed=None keeps the stream
+
+
+@pytest.mark.parametrize("max_step", [1, 2, 5, 10, 64])
+def test_truncation_lands_exactly_on_max_step(max_step):
+    env = cda.continuousDoubleAuctionEnv({"num_of_agents": 2, "max_step": max_step})
+    env.reset(seed=1)
+    n = 0
+    while True:
+        _, _, te, tr, _ = env.step({"agent_0": {"category": 0, "size_mean": np.zeros(1, np.float32), "size_sigma": np.zeros(1, np.float32)}})
+        n += 1
+        if tr["__all__"]:
+            break
+    assert n == max_step
+    env.close()
+
+
+def test_spaces_and_attributes():
+    env = cda.continuousDoubleAuctionEnv({"num_of_agents": 3, "n_hist": 6})
+    assert env.agents == env.possible_agents == ["agent_0", "agent_1", "agent_2"]
+    assert env.get_observation_space("agent_1").shape == (6 * 42,)
+    s = env.get_action_space("agent_0").sample()
+    assert set(s) == {"category", "size_mean", "size_sigma", "price", "price_offset"}
+    assert env.num_of_agents == 3 and env.init_cash == 1000000 and env.n_hist == 6
+    with pytest.raises(ValueError):
+        cda.continuousDoubleAuctionEnv({"tick_size": 0.5})
+    env.close()
