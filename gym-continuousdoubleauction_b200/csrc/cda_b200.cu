@@ -38,6 +38,8 @@ struct CdaEnv {
     int *s_cat; float *s_mean; float *s_sigma; int *s_pcode; int *s_poff;
     float *s_obs; double *s_reward; unsigned char *s_term; unsigned char *s_trunc;
     bool was_reset;
+    int zerocopy;              // cda_step_host: let the kernel store outputs straight into mapped pinned host memory
+    const void *zc_host; void *zc_dev;   // last host obs pointer checked and its device alias (NULL = not mapped)
     long long launches;
     size_t smem_bytes;
 };
@@ -47,7 +49,7 @@ static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 template <int CAP>
 static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {
     const int grid = (e->M + CDA_WARPS_PER_CTA - 1) / CDA_WARPS_PER_CTA;
-    const size_t smem = sizeof(CdaWarpSmem<CAP>) * CDA_WARPS_PER_CTA;
+    const size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA;
     static bool attr_set[16] = {false};
     if (!attr_set[e->device & 15]) {
         cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -153,6 +155,10 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     e->s_term = reinterpret_cast<unsigned char *>(e->s_reward) + MA * 8;
     e->s_trunc = e->s_term + num_markets;
     CUDA_TRY(cudaMemset(e->state, 0, e->state_bytes));
+    {
+        const char *zc = getenv("CDA_ZEROCOPY");
+        e->zerocopy = zc ? atoi(zc) : 1;
+    }
     *out = e;
     return CDA_OK;
 }
@@ -219,16 +225,34 @@ int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean
         CUDA_TRY(cudaMemcpyAsync(e->s_pcode, h_price, MA * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(e->s_poff, h_price_offset, MA * 4, cudaMemcpyHostToDevice, st));
     }
-    CdaStepParams p;
-    memset(&p, 0, sizeof(p));
-    p.cat = e->s_cat; p.mean = e->s_mean; p.sigma = e->s_sigma; p.pcode = e->s_pcode; p.poff = e->s_poff;
-    p.obs = e->s_obs; p.reward = e->s_reward; p.term = e->s_term; p.trunc = e->s_trunc;
-    int rc = step_common(e, p, st);
-    if (rc) return rc;
     const size_t obs_bytes = (size_t)e->M * e->dev.W * 4;
     char *ho = reinterpret_cast<char *>(h_obs);
     const bool out_contig = h_obs && h_reward && h_terminated && h_truncated && reinterpret_cast<char *>(h_reward) == ho + obs_bytes &&
                             reinterpret_cast<char *>(h_terminated) == ho + obs_bytes + MA * 8 && reinterpret_cast<char *>(h_truncated) == ho + obs_bytes + MA * 8 + e->M;
+    // Zero-copy outputs: when the caller's output block is pinned + mapped (UVA: every cudaHostAlloc /
+    // torch pin_memory buffer is), the kernel stores obs/reward/flags straight into host memory, so the
+    // PCIe transfer overlaps the step instead of following it.
+    char *zc = nullptr;
+    if (e->zerocopy && out_contig) {
+        if (e->zc_host != h_obs) {
+            cudaPointerAttributes at;
+            e->zc_host = h_obs; e->zc_dev = nullptr;
+            if (cudaPointerGetAttributes(&at, h_obs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) e->zc_dev = at.devicePointer;
+            else cudaGetLastError();
+        }
+        zc = reinterpret_cast<char *>(e->zc_dev);
+    }
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cat = e->s_cat; p.mean = e->s_mean; p.sigma = e->s_sigma; p.pcode = e->s_pcode; p.poff = e->s_poff;
+    if (zc) {
+        p.obs = reinterpret_cast<float *>(zc); p.reward = reinterpret_cast<double *>(zc + obs_bytes);
+        p.term = reinterpret_cast<unsigned char *>(zc + obs_bytes + MA * 8); p.trunc = p.term + e->M;
+        return step_common(e, p, st);
+    }
+    p.obs = e->s_obs; p.reward = e->s_reward; p.term = e->s_term; p.trunc = e->s_trunc;
+    int rc = step_common(e, p, st);
+    if (rc) return rc;
     if (out_contig) {
         CUDA_TRY(cudaMemcpyAsync(h_obs, e->s_obs, obs_bytes + MA * 8 + 2 * (size_t)e->M, cudaMemcpyDeviceToHost, st));
     } else {

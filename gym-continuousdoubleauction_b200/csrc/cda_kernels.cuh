@@ -26,6 +26,14 @@
 #include "cda_zig_tables.cuh"
 
 #define CDA_FULL 0xffffffffu
+#ifndef CDA_SCAN_MODE
+#define CDA_SCAN_MODE 1
+#endif
+#if CDA_SCAN_MODE == 1
+#define CDA_SCAN_PRAGMA _Pragma("unroll 1")
+#else
+#define CDA_SCAN_PRAGMA
+#endif
 #define CDA_HDR_BYTES 192
 #define CDA_POOL_FIELDS 5 /* 0 pt (trader<<24|price), 1 qty, 2 order_id, 3 timestamp, 4 seq */
 #define CDA_PRICE_MASK 0x00ffffffu
@@ -266,38 +274,80 @@ __device__ __forceinline__ void acct_fill(CdaAcct &a, int party, int side /*0 bi
 // Warp-uniform book state, held in registers by every lane.  No member is an array that is
 // indexed at run time (that would force the struct into local memory): the two sides are
 // addressed arithmetically through SOFF(side).
+// All shared-memory traffic goes through 32-bit word indices into ONE dynamic array: an LDS/STS then
+// takes a 32-bit register + immediate, instead of re-deriving 64-bit generic addresses at every use.
+extern __shared__ __align__(128) unsigned smw[];
+#define SMW(i) smw[(i)]
+
+// Per-warp shared-memory tile, in 32-bit words.
+template <int CAP>
+struct CdaSmemLayout {
+    static constexpr int POOL = 0;                                   // u32[2 sides][CAP/32 tiles][5 fields][32]
+    static constexpr int SNAP = 2 * CDA_POOL_FIELDS * CAP;           // f32[44] newest snapshot
+    static constexpr int TOPK = SNAP + 44;                           // i32[20] frozen pre-step raw top-K prices
+    static constexpr int VOL = TOPK + 2 * CDA_K_ROWS;                // u32[20] level volumes being accumulated
+    static constexpr int ORDER = VOL + 2 * CDA_K_ROWS;               // u32[32] shuffled execution order
+    static constexpr int PARK = ORDER + 32;                          // 10 words: parked PCG64 state (+2 pad)
+    static constexpr int BAR = PARK + 12;                            // mbarrier (8-B aligned)
+    static constexpr int WORDS = ((BAR + 2 + 3) / 4) * 4;            // keep 16-B alignment of the next tile
+    static constexpr int BYTES = WORDS * 4;
+    static_assert(BAR % 2 == 0, "mbarrier must be 8-B aligned");
+};
+
 template <int CAP>
 struct CdaMkt {
-    unsigned *pool;      // shared memory u32[2 sides][CAP/32 tiles][5 fields][32]
+    int pool_w;          // word index of this warp's pool in smw
     int nb, na;          // live orders per side
     unsigned time, next_id, seqctr, status;
     int tape_nonempty, tape_px;
     int lane;
     int *fills; int fill_cap, n_fills;
-    __device__ __forceinline__ unsigned *side_base(int side) const { return pool + side * (CDA_POOL_FIELDS * CAP); }
+    __device__ __forceinline__ int side_w(int side) const { return pool_w + side * (CDA_POOL_FIELDS * CAP); }
     __device__ __forceinline__ int count(int side) const { return side ? na : nb; }
     __device__ __forceinline__ void set_count(int side, int v) { if (side) na = v; else nb = v; }
 };
 
 template <int CAP> __device__ __forceinline__ int pool_best(const CdaMkt<CAP> &k, int side) {
-    const unsigned *pt = k.side_base(side) + k.lane;
+    int pt = k.side_w(side) + k.lane;
     const int n = k.count(side);
     if (n == 0) return -1;
     unsigned loc = side == 0 ? 0u : 0xffffffffu;
-    for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
-        const unsigned p = *pt & CDA_PRICE_MASK;
+#if CDA_SCAN_MODE == 2
+    const int nt = (n - k.lane + 31) >> 5;
+#pragma unroll
+    for (int it = 0; it < CAP / 32; ++it) {
+        const unsigned p = it < nt ? (SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) : loc;
         loc = side == 0 ? max(loc, p) : min(loc, p);
     }
+#else
+    CDA_SCAN_PRAGMA
+    for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
+        const unsigned p = SMW(pt) & CDA_PRICE_MASK;
+        loc = side == 0 ? max(loc, p) : min(loc, p);
+    }
+#endif
     return (int)(side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc));
 }
 // index of the entry with the smallest key[field] among entries with (pt & mask) == want, or -1
 template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> &k, int side, unsigned mask, unsigned want, int field) {
-    const unsigned *pt = k.side_base(side) + k.lane;
+    int pt = k.side_w(side) + k.lane;
     const int n = k.count(side);
     unsigned bk = 0xffffffffu; int bi = -1;
-    for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
-        if ((*pt & mask) == want) { const unsigned kk = pt[field * 32]; if (kk < bk) { bk = kk; bi = i; } }
+#if CDA_SCAN_MODE == 2
+    const int nt = (n - k.lane + 31) >> 5;
+#pragma unroll
+    for (int it = 0; it < CAP / 32; ++it) {
+        if (it < nt && (SMW(pt + it * CDA_TILE_WORDS) & mask) == want) {
+            const unsigned kk = SMW(pt + it * CDA_TILE_WORDS + field * 32);
+            if (kk < bk) { bk = kk; bi = k.lane + 32 * it; }
+        }
     }
+#else
+    CDA_SCAN_PRAGMA
+    for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
+        if ((SMW(pt) & mask) == want) { const unsigned kk = SMW(pt + field * 32); if (kk < bk) { bk = kk; bi = i; } }
+    }
+#endif
     const unsigned mk = __reduce_min_sync(CDA_FULL, bk);
     if (mk == 0xffffffffu) return -1;
     const unsigned b = __ballot_sync(CDA_FULL, bk == mk);
@@ -308,8 +358,8 @@ template <int CAP> __device__ __forceinline__ void pool_remove(CdaMkt<CAP> &k, i
     const int last = k.count(side) - 1;
     __syncwarp();
     if (idx != last && k.lane < CDA_POOL_FIELDS) {
-        unsigned *f = k.side_base(side) + k.lane * 32;
-        f[CDA_EOFF(idx)] = f[CDA_EOFF(last)];
+        const int f = k.side_w(side) + k.lane * 32;
+        SMW(f + CDA_EOFF(idx)) = SMW(f + CDA_EOFF(last));
     }
     k.set_count(side, last);
     __syncwarp();
@@ -322,7 +372,7 @@ template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, i
     __syncwarp();
     if (k.lane < CDA_POOL_FIELDS) {
         const unsigned v = k.lane == 0 ? (((unsigned)trader << 24) | price) : k.lane == 1 ? qty : k.lane == 2 ? oid : k.lane == 3 ? ts : seq;
-        k.side_base(side)[CDA_EOFF(n) + k.lane * 32] = v;
+        SMW(k.side_w(side) + CDA_EOFF(n) + k.lane * 32) = v;
     }
     k.set_count(side, n + 1);
     __syncwarp();
@@ -367,15 +417,15 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
     unsigned oid;
     if (idx >= 0) {
         // trader.py:219-235 / :237-252: release the old order's escrow (cash_processor.py:85-97), then touch the book
-        unsigned *pl = k.side_base(side) + CDA_EOFF(idx);
-        const unsigned op = pl[0] & CDA_PRICE_MASK, oq = pl[32];
-        oid = pl[64];
+        const int pl = k.side_w(side) + CDA_EOFF(idx);
+        const unsigned op = SMW(pl) & CDA_PRICE_MASK, oq = SMW(pl + 32);
+        oid = SMW(pl + 64);
         if (is_t) { const long long ov = (long long)op * oq; ac.hold -= ov; ac.cash += ov; }
         k.time++;                                                        // orderbook.py:196-200, :212-215
         if (type == 3) { pool_remove(k, side, idx); return; }
         if ((unsigned)price == op && (unsigned long long)size <= oq) {   // orderbook.py:245-248 in place
             __syncwarp();
-            if (k.lane == 0) { pl[32] = (unsigned)size; pl[96] = k.time; }
+            if (k.lane == 0) { SMW(pl + 32) = (unsigned)size; SMW(pl + 96) = k.time; }
             __syncwarp();
             if (is_t) { const long long v = (long long)price * size; ac.cash -= v; ac.hold += v; }
             return;
@@ -396,15 +446,15 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
         if (P < 0) break;
         if (limit >= 0 && (side == 0 ? limit < P : limit > P)) break;
         const int h = pool_argmin(k, opp, CDA_PRICE_MASK, (unsigned)P, 4);
-        unsigned *po = k.side_base(opp) + CDA_EOFF(h);
-        const unsigned hq = po[32];
-        const int maker = (int)(po[0] >> 24);
-        const unsigned moid = po[64];
+        const int po = k.side_w(opp) + CDA_EOFF(h);
+        const unsigned hq = SMW(po + 32);
+        const int maker = (int)(SMW(po) >> 24);
+        const unsigned moid = SMW(po + 64);
         unsigned traded; int left = -1;
         if (qty < hq) {                       // :73-85 partial: resting order shrinks in place, keeps its timestamp
             traded = qty; left = (int)(hq - qty);
             __syncwarp();
-            if (k.lane == 0) po[32] = hq - qty;
+            if (k.lane == 0) SMW(po + 32) = hq - qty;
             __syncwarp();
             qty = 0;
         } else {                              // :86-100 resting order consumed
@@ -423,9 +473,8 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
             } else k.status |= CDA_ST_FILL_OVERFLOW;
         }
         k.n_fills++;
-        if (maker != t) {                     // trader.py:311-322: counter party, then initiator
-            if (k.lane == maker) acct_fill(ac, 1, opp, traded, P);
-            else if (is_t) acct_fill(ac, 0, side, traded, P);
+        if (maker != t) {                     // trader.py:311-322: counter party, then initiator (disjoint lanes)
+            if (k.lane == maker || is_t) acct_fill(ac, is_t ? 0 : 1, is_t ? side : opp, traded, P);
         } else if (is_t) {                    // cash_processor.py:55-62 self-trade: escrow back to cash
             const long long tv = (long long)traded * P;
             ac.hold -= tv; ac.cash += tv;
@@ -450,20 +499,6 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 // -> store, one warp per market.  WARPS warps per CTA share nothing but the CTA's shared memory
 // carve-up, so there is no __syncthreads anywhere.
 // ------------------------------------------------------------------------------------------
-template <int CAP>
-struct CdaWarpSmem {
-    unsigned pool[2][CAP / 32][CDA_POOL_FIELDS][32];
-    float snap[44];
-    int topk[2 * CDA_K_ROWS];        // frozen pre-step raw top-K prices (agg_LOB_raw price rows)
-    unsigned vol[2 * CDA_K_ROWS];    // level volumes of the snapshot being built
-    unsigned long long bar;
-    unsigned long long rng_park[4];  // PCG64 state/inc parked here while the book is being worked on
-    unsigned rng_park32[2];
-    unsigned char order[32];
-};
-static_assert(sizeof(CdaWarpSmem<64>) % 16 == 0 && sizeof(CdaWarpSmem<128>) % 16 == 0 && sizeof(CdaWarpSmem<160>) % 16 == 0 &&
-              sizeof(CdaWarpSmem<192>) % 16 == 0 && sizeof(CdaWarpSmem<256>) % 16 == 0, "smem tile must keep 16-B alignment");
-
 #ifndef CDA_MIN_CTAS
 #define CDA_MIN_CTAS 7   /* 7 CTAs x 4 warps = 28 warps/SM -> 4144 resident markets on 148 SMs (>= 4096 in one wave) */
 #endif
@@ -471,18 +506,19 @@ static_assert(sizeof(CdaWarpSmem<64>) % 16 == 0 && sizeof(CdaWarpSmem<128>) % 16
 
 template <int CAP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using L = CdaSmemLayout<CAP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * WARPS + warp;
     if (m >= p.M) return;
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
-    CdaWarpSmem<CAP> &S = reinterpret_cast<CdaWarpSmem<CAP> *>(smem_raw)[warp];
+    const int wb = warp * L::WORDS;                       // this warp's tile in smw
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(&smw[wb + L::BAR]);
     unsigned char *blk = p.state + (size_t)m * cfg.stride;
     unsigned *hdr = reinterpret_cast<unsigned *>(blk);
 
-    if (lane == 0) mbar_init(&S.bar, 1);
-    if (lane < 2 * CDA_K_ROWS) S.topk[lane] = (int)hdr[20 + lane];
+    if (lane == 0) mbar_init(bar, 1);
+    if (lane < 2 * CDA_K_ROWS) SMW(wb + L::TOPK + lane) = hdr[20 + lane];
     __syncwarp();
 
     // ---- header (warp-uniform 128-bit loads: one request each, value in every lane)
@@ -494,7 +530,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 
     CdaMkt<CAP> k;
     k.lane = lane;
-    k.pool = &S.pool[0][0][0][0];
+    k.pool_w = wb + L::POOL;
     k.time = h0.x; k.next_id = h0.y; k.seqctr = h0.z;
     unsigned t_step = h0.w;
     int last_price = (int)h1.x;
@@ -514,9 +550,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const unsigned bytes_b = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), bytes_a = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
     const bool have_pool = (bytes_b | bytes_a) != 0;
     if (have_pool && lane == 0) {
-        mbar_expect_tx(&S.bar, bytes_b + bytes_a);
-        if (bytes_b) bulk_g2s(&S.pool[0][0][0][0], gpool, bytes_b, &S.bar);
-        if (bytes_a) bulk_g2s(&S.pool[1][0][0][0], gpool + CDA_POOL_FIELDS * CAP, bytes_a, &S.bar);
+        mbar_expect_tx(bar, bytes_b + bytes_a);
+        if (bytes_b) bulk_g2s(&smw[wb + L::POOL], gpool, bytes_b, bar);
+        if (bytes_a) bulk_g2s(&smw[wb + L::POOL + CDA_POOL_FIELDS * CAP], gpool + CDA_POOL_FIELDS * CAP, bytes_a, bar);
     }
 
     // ---- accounts into lanes 0..A-1
@@ -591,7 +627,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             a_size = __double2ll_rn(fabs(x)) + cfg.min_size;                                 // rint half-even, :339, :276
             if (a_cat == 0) ac.is_pass = 1;
             if (a_side >= 0 && a_type != 0) {            // _set_price :341-397 on the frozen pre-step top-K
-                const int raw = S.topk[a_side * CDA_K_ROWS + a_pcode];
+                const int raw = (int)SMW(wb + L::TOPK + a_side * CDA_K_ROWS + a_pcode);
                 const int off = a_poff - 1;
                 int base, pr;
                 if (a_side == 0) { base = raw == 0 ? last_price - (a_pcode + 1) * cfg.tick : raw; pr = base + off * cfg.tick; }
@@ -605,22 +641,23 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // ================= rand_exec_seq: action_helper.py:174-199 ==========================
         const unsigned active = __ballot_sync(CDA_FULL, lane < A && a_side >= 0);
         const int n_act = __popc(active);
-        if (lane == 0) { int q = 0; for (unsigned am = active; am; am &= am - 1) S.order[q++] = (unsigned char)(__ffs(am) - 1); }
+        if (lane == 0) { int q = 0; for (unsigned am = active; am; am &= am - 1) SMW(wb + L::ORDER + q++) = (unsigned)(__ffs(am) - 1); }
         for (int i = n_act - 1; i >= 1; --i) {           // Generator.permutation: Fisher-Yates from the top
             const unsigned j = rng_interval(rng, (unsigned)i);
-            if (lane == 0) { const unsigned char tmp = S.order[i]; S.order[i] = S.order[j]; S.order[j] = tmp; }
+            if (lane == 0) { const unsigned tmp = SMW(wb + L::ORDER + i); SMW(wb + L::ORDER + i) = SMW(wb + L::ORDER + j); SMW(wb + L::ORDER + j) = tmp; }
         }
         if (lane == 0) {   // park the generator: it is not needed again until the next step / the final store
-            S.rng_park[0] = rng.shi; S.rng_park[1] = rng.slo; S.rng_park[2] = rng.ihi; S.rng_park[3] = rng.ilo;
-            S.rng_park32[0] = rng.has32; S.rng_park32[1] = rng.u32;
+            unsigned long long *pk = reinterpret_cast<unsigned long long *>(&smw[wb + L::PARK]);
+            pk[0] = rng.shi; pk[1] = rng.slo; pk[2] = rng.ihi; pk[3] = rng.ilo;
+            SMW(wb + L::PARK + 8) = rng.has32; SMW(wb + L::PARK + 9) = rng.u32;
         }
         __syncwarp();
 
-        if (!waited) { mbar_wait(&S.bar, 0); waited = true; }
+        if (!waited) { mbar_wait(bar, 0); waited = true; }
 
         // ================= do_actions: action_helper.py:201-239 =============================
         for (int q = 0; q < n_act; ++q) {
-            const int t = S.order[q];
+            const int t = (int)SMW(wb + L::ORDER + q);
             const int type = __shfl_sync(CDA_FULL, a_type, t);
             const int side = __shfl_sync(CDA_FULL, a_side, t);
             const long long size = __shfl_sync(CDA_FULL, a_size, t);
@@ -647,32 +684,35 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // finished by the generic next-best search.
         int myP = 0; unsigned myV = 0;     // lane l<10: bid level l; 10<=l<20: ask level l-10
         __syncwarp();
-        if (lane < 2 * CDA_K_ROWS) S.vol[lane] = 0;
+        if (lane < 2 * CDA_K_ROWS) SMW(wb + L::VOL + lane) = 0;
         __syncwarp();
-#pragma unroll
+#pragma unroll 1
         for (int side = 0; side < 2; ++side) {
-            const unsigned *pt = k.side_base(side) + lane;   // this lane's column of every tile
+            const int pt = k.side_w(side) + lane;            // this lane's column of every tile
             const int n = k.count(side);
             if (n == 0) continue;
             const int nt = (n - lane + 31) >> 5;              // tiles in which this lane owns a live order
             unsigned loc = side == 0 ? 0u : 0xffffffffu;
-            for (int it = 0; it < nt; ++it) { const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK; loc = side == 0 ? max(loc, pp) : min(loc, pp); }
+            CDA_SCAN_PRAGMA
+            for (int it = 0; it < nt; ++it) { const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK; loc = side == 0 ? max(loc, pp) : min(loc, pp); }
             const unsigned B = side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc);
             unsigned mlo = 0, mhi = 0; bool far = false;
+            CDA_SCAN_PRAGMA
             for (int it = 0; it < nt; ++it) {
-                const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK;
+                const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK;
                 const unsigned d = side == 0 ? B - pp : pp - B;
                 if (d < 32) mlo |= 1u << d; else if (d < 64) mhi |= 1u << (d - 32); else far = true;
             }
             mlo = __reduce_or_sync(CDA_FULL, mlo); mhi = __reduce_or_sync(CDA_FULL, mhi);
             const bool far_any = __any_sync(CDA_FULL, far);
             const int nlo = __popc(mlo), nlev = nlo + __popc(mhi);
+            CDA_SCAN_PRAGMA
             for (int it = 0; it < nt; ++it) {
-                const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK;
+                const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK;
                 const unsigned d = side == 0 ? B - pp : pp - B;
                 if (d < 64) {
                     const int rank = d < 32 ? __popc(mlo & ((1u << d) - 1u)) : nlo + __popc(mhi & ((1u << (d - 32)) - 1u));
-                    if (rank < CDA_K_ROWS) atomicAdd(&S.vol[side * CDA_K_ROWS + rank], pt[it * CDA_TILE_WORDS + 32]);
+                    if (rank < CDA_K_ROWS) atomicAdd(&smw[wb + L::VOL + side * CDA_K_ROWS + rank], SMW(pt + it * CDA_TILE_WORDS + 32));
                 }
             }
             __syncwarp();
@@ -682,20 +722,22 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 for (int j = 0; j < li; ++j) mm &= mm - 1;
                 const int pos = __ffsll((long long)mm) - 1;
                 myP = side == 0 ? (int)B - pos : (int)B + pos;
-                myV = S.vol[lane];
+                myV = SMW(wb + L::VOL + lane);
             }
             if (nlev < CDA_K_ROWS && far_any) {        // levels further than 64 ticks from the best: generic search
                 unsigned prev = side == 0 ? B - 63u : B + 63u;
                 for (int lv = nlev; lv < CDA_K_ROWS; ++lv) {
                     unsigned l2 = side == 0 ? 0u : 0xffffffffu;
+                    _Pragma("unroll 1")
                     for (int it = 0; it < nt; ++it) {
-                        const unsigned pp = pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK;
+                        const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK;
                         if (side == 0 ? pp < prev : pp > prev) l2 = side == 0 ? max(l2, pp) : min(l2, pp);
                     }
                     const unsigned P = side == 0 ? __reduce_max_sync(CDA_FULL, l2) : __reduce_min_sync(CDA_FULL, l2);
                     if (P == (side == 0 ? 0u : 0xffffffffu)) break;
                     unsigned s = 0;
-                    for (int it = 0; it < nt; ++it) if ((pt[it * CDA_TILE_WORDS] & CDA_PRICE_MASK) == P) s += pt[it * CDA_TILE_WORDS + 32];
+                    _Pragma("unroll 1")
+                    for (int it = 0; it < nt; ++it) if ((SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) == P) s += SMW(pt + it * CDA_TILE_WORDS + 32);
                     const unsigned V = __reduce_add_sync(CDA_FULL, s);
                     if (lane == side * CDA_K_ROWS + lv) { myP = (int)P; myV = V; }
                     prev = P;
@@ -720,9 +762,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             if (myV > 0) { const float sq = __fsqrt_rn((float)myV); sn = lane < CDA_K_ROWS ? sq : -sq; }
             const int l = lane < CDA_K_ROWS ? lane : lane - CDA_K_ROWS;
             const int b = lane < CDA_K_ROWS ? 0 : 2 * CDA_K_ROWS;
-            S.snap[b + l] = pn;
-            S.snap[b + CDA_K_ROWS + l] = sn;
-            S.topk[lane] = myP;                          // frozen raw top-K for the next step's _set_price
+            SMW(wb + L::SNAP + b + l) = __float_as_uint(pn);
+            SMW(wb + L::SNAP + b + CDA_K_ROWS + l) = __float_as_uint(sn);
+            SMW(wb + L::TOPK + lane) = (unsigned)myP;                          // frozen raw top-K for the next step's _set_price
             hdr[20 + lane] = (unsigned)myP;
         } else if (lane < 22) {
             double x = Mid; bool live = true;
@@ -732,7 +774,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 x = 1.0 + (st > 0.0 ? st : 0.0);
             }
             const double lg = log(x);
-            S.snap[20 + lane] = live ? (float)lg : 0.0f;
+            SMW(wb + L::SNAP + 20 + lane) = __float_as_uint(live ? (float)lg : 0.0f);
         }
         __syncwarp();
 
@@ -746,10 +788,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
                 o[e] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
             }
-            for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) o[W_old + cc] = S.snap[cc];
+            for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) o[W_old + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
         }
         __syncwarp();
-        for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = S.snap[cc];
+        for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
 
         // ================= set_reward / set_done: reward_helper.py:35-103, done_helper.py ===
         bool broke = false;
@@ -777,8 +819,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         t_step++;
         __syncwarp();
         if (!last_it) {    // multi-step rollout: bring the generator back for the next step's draws
-            rng.shi = S.rng_park[0]; rng.slo = S.rng_park[1]; rng.ihi = S.rng_park[2]; rng.ilo = S.rng_park[3];
-            rng.has32 = S.rng_park32[0]; rng.u32 = S.rng_park32[1];
+            const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wb + L::PARK]);
+            rng.shi = pk[0]; rng.slo = pk[1]; rng.ihi = pk[2]; rng.ilo = pk[3];
+            rng.has32 = SMW(wb + L::PARK + 8); rng.u32 = SMW(wb + L::PARK + 9);
         }
     }
 
@@ -786,9 +829,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
         *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)last_price, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, done_mask, k.status);
-        *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)k.nb, (unsigned)k.na, S.rng_park32[0], S.rng_park32[1]);
-        *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(S.rng_park[0], S.rng_park[1]);
-        *reinterpret_cast<ulonglong2 *>(hdr + 16) = make_ulonglong2(S.rng_park[2], S.rng_park[3]);
+        const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wb + L::PARK]);
+        *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)k.nb, (unsigned)k.na, SMW(wb + L::PARK + 8), SMW(wb + L::PARK + 9));
+        *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(pk[0], pk[1]);
+        *reinterpret_cast<ulonglong2 *>(hdr + 16) = make_ulonglong2(pk[2], pk[3]);
     }
     if (lane < A) {
         g_cash[lane] = ac.cash; g_hold[lane] = ac.hold; g_cost[lane] = ac.cost; g_nav[lane] = ac.nav;
@@ -800,8 +844,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     __syncwarp();
     const unsigned ob = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), oa = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
     if (lane == 0 && (ob | oa)) {
-        if (ob) bulk_s2g(gpool, &S.pool[0][0][0][0], ob);
-        if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, &S.pool[1][0][0][0], oa);
+        if (ob) bulk_s2g(gpool, &smw[wb + L::POOL], ob);
+        if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, &smw[wb + L::POOL + CDA_POOL_FIELDS * CAP], oa);
         bulk_commit();
         bulk_wait_read0();
     }
