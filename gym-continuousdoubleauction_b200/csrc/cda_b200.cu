@@ -155,6 +155,18 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     e->s_term = reinterpret_cast<unsigned char *>(e->s_reward) + MA * 8;
     e->s_trunc = e->s_term + num_markets;
     CUDA_TRY(cudaMemset(e->state, 0, e->state_bytes));
+    {   // PCG64 jump-ahead table (see rng_jump)
+        unsigned long long tab[CDA_MAX_AGENTS + 1][4];
+        const unsigned __int128 mult = (((unsigned __int128)2549297995355413924ULL) << 64) | 4865540595714422341ULL;
+        unsigned __int128 a = 1, g = 0;
+        for (int r = 0; r <= CDA_MAX_AGENTS; ++r) {
+            tab[r][0] = (unsigned long long)(a >> 64); tab[r][1] = (unsigned long long)a;
+            tab[r][2] = (unsigned long long)(g >> 64); tab[r][3] = (unsigned long long)g;
+            g = g + a;       // G_{r+1} = G_r + A^r
+            a = a * mult;
+        }
+        CUDA_TRY(cudaMemcpyToSymbol(cda_pcg_jump, tab, sizeof(tab)));
+    }
     {
         const char *zc = getenv("CDA_ZEROCOPY");
         e->zerocopy = zc ? atoi(zc) : 1;

@@ -170,6 +170,18 @@ __device__ __forceinline__ long long rng_integers(CdaRng &r, long long lo, long 
     }
     return lo + (long long)(m >> 32);
 }
+// LCG jump-ahead table: after r steps  state_r = A^r * state + G_r * inc  (mod 2^128) with
+// G_r = 1 + A + ... + A^(r-1).  Row r = {A^r hi, A^r lo, G_r hi, G_r lo}; filled by cda_create.
+// Lets lane a evaluate "its" draw of the sequential numpy stream without waiting for lanes < a.
+__constant__ unsigned long long cda_pcg_jump[CDA_MAX_AGENTS + 1][4];
+__device__ __forceinline__ void rng_jump(const CdaRng &g, int r, unsigned long long &shi, unsigned long long &slo) {
+    const unsigned long long Ah = cda_pcg_jump[r][0], Al = cda_pcg_jump[r][1], Gh = cda_pcg_jump[r][2], Gl = cda_pcg_jump[r][3];
+    const unsigned long long l1 = Al * g.slo, h1 = __umul64hi(Al, g.slo) + Ah * g.slo + Al * g.shi;
+    const unsigned long long l2 = Gl * g.ilo, h2 = __umul64hi(Gl, g.ilo) + Gh * g.ilo + Gl * g.ihi;
+    slo = l1 + l2;
+    shi = h1 + h2 + (slo < l1 ? 1ULL : 0ULL);
+}
+
 // SeedSequence(seed).generate_state(4, uint64) -> PCG64 seeding (bit_generator.pyx, pcg64.c)
 __host__ __device__ inline unsigned ss_hashmix(unsigned value, unsigned &hc) {
     value ^= hc; hc *= 0x931e8875u; value *= hc; value ^= value >> 16; return value;
@@ -210,30 +222,30 @@ __device__ __forceinline__ void rng_seed(CdaRng &r, unsigned long long seed) {
 
 // ----------------------------------- async-copy helpers ------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 // global -> shared bulk copy (TMA, non-tensor form); bytes % 16 == 0, both addresses 16-B aligned
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src_gmem, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, unsigned src_smem, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+                 ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -286,7 +298,8 @@ struct CdaSmemLayout {
     static constexpr int SNAP = 2 * CDA_POOL_FIELDS * CAP;           // f32[44] newest snapshot
     static constexpr int TOPK = SNAP + 44;                           // i32[20] frozen pre-step raw top-K prices
     static constexpr int VOL = TOPK + 2 * CDA_K_ROWS;                // u32[20] level volumes being accumulated
-    static constexpr int ORDER = VOL + 2 * CDA_K_ROWS;               // u32[32] shuffled execution order
+    static constexpr int LPX = VOL + 2 * CDA_K_ROWS;                 // u32[20] level prices of the snapshot being built
+    static constexpr int ORDER = LPX + 2 * CDA_K_ROWS;               // u32[32] shuffled execution order
     static constexpr int PARK = ORDER + 32;                          // 10 words: parked PCG64 state (+2 pad)
     static constexpr int BAR = PARK + 12;                            // mbarrier (8-B aligned)
     static constexpr int WORDS = ((BAR + 2 + 3) / 4) * 4;            // keep 16-B alignment of the next tile
@@ -513,7 +526,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
     const int wb = warp * L::WORDS;                       // this warp's tile in smw
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(&smw[wb + L::BAR]);
+    const unsigned sa = smem_u32(smw) + (unsigned)wb * 4u;   // shared-window byte address of this warp's tile
+    const unsigned bar = sa + L::BAR * 4u;
     unsigned char *blk = p.state + (size_t)m * cfg.stride;
     unsigned *hdr = reinterpret_cast<unsigned *>(blk);
 
@@ -551,8 +565,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const bool have_pool = (bytes_b | bytes_a) != 0;
     if (have_pool && lane == 0) {
         mbar_expect_tx(bar, bytes_b + bytes_a);
-        if (bytes_b) bulk_g2s(&smw[wb + L::POOL], gpool, bytes_b, bar);
-        if (bytes_a) bulk_g2s(&smw[wb + L::POOL + CDA_POOL_FIELDS * CAP], gpool + CDA_POOL_FIELDS * CAP, bytes_a, bar);
+        if (bytes_b) bulk_g2s(sa + L::POOL * 4u, gpool, bytes_b, bar);
+        if (bytes_a) bulk_g2s(sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, gpool + CDA_POOL_FIELDS * CAP, bytes_a, bar);
     }
 
     // ---- accounts into lanes 0..A-1
@@ -611,12 +625,38 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         if (a_pcode < 0 || a_pcode >= CDA_K_ROWS) a_pcode = 0;
         if (a_poff < 0 || a_poff > 2) a_poff = 1;
         const unsigned present = __ballot_sync(CDA_FULL, lane < A && a_cat >= 0);
-        // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339)
+        // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339).
+        // Fast path: lane a jumps the LCG ahead by (its rank + 1) steps and evaluates its own draw; this is
+        // the sequential stream as long as every draw returns from the first ziggurat test (98.8 % each).
+        // Otherwise (a wedge/tail draw consumes extra numbers) the draws are redone one after another.
         double z = 0.0;
-        for (unsigned pm = present; pm; pm &= pm - 1) {
-            const int a = __ffs(pm) - 1;
-            const double za = rng_normal(rng);
-            if (lane == a) z = za;
+        if (present) {
+            const bool mine = (present >> lane) & 1u;
+            const int rnk = __popc(present & ((1u << lane) - 1u));
+            unsigned long long jh, jl;
+            rng_jump(rng, mine ? rnk + 1 : 0, jh, jl);
+            const unsigned long long xr = jh ^ jl;
+            const unsigned rot = (unsigned)(jh >> 58);
+            unsigned long long r = (xr >> rot) | (xr << ((64u - rot) & 63u));
+            const int idx = (int)(r & 0xff);
+            r >>= 8;
+            const int sign = (int)(r & 1ULL);
+            const unsigned long long rabs = (r >> 1) & 0x000fffffffffffffULL;
+            double zx = (double)rabs * cda_zig_wi[idx];
+            if (sign) zx = -zx;
+            const bool fast = !mine || rabs < cda_zig_ki[idx];
+            if (__all_sync(CDA_FULL, fast)) {
+                z = mine ? zx : 0.0;
+                const int src = 31 - __clz(present);           // last present lane holds the state after all draws
+                rng.shi = __shfl_sync(CDA_FULL, jh, src);
+                rng.slo = __shfl_sync(CDA_FULL, jl, src);
+            } else {
+                for (unsigned pm = present; pm; pm &= pm - 1) {
+                    const int a = __ffs(pm) - 1;
+                    const double za = rng_normal(rng);
+                    if (lane == a) z = za;
+                }
+            }
         }
         const int a_side = a_cat <= 0 ? -1 : (a_cat <= 4 ? 0 : 1);
         const int a_type = a_cat <= 0 ? 0 : ((a_cat - 1) & 3);
@@ -712,18 +752,15 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 const unsigned d = side == 0 ? B - pp : pp - B;
                 if (d < 64) {
                     const int rank = d < 32 ? __popc(mlo & ((1u << d) - 1u)) : nlo + __popc(mhi & ((1u << (d - 32)) - 1u));
-                    if (rank < CDA_K_ROWS) atomicAdd(&smw[wb + L::VOL + side * CDA_K_ROWS + rank], SMW(pt + it * CDA_TILE_WORDS + 32));
+                    if (rank < CDA_K_ROWS) {      // every order of a level writes the same price: benign same-value race
+                        atomicAdd(&smw[wb + L::VOL + side * CDA_K_ROWS + rank], SMW(pt + it * CDA_TILE_WORDS + 32));
+                        SMW(wb + L::LPX + side * CDA_K_ROWS + rank) = pp;
+                    }
                 }
             }
             __syncwarp();
             const int li = lane - side * CDA_K_ROWS;
-            if (li >= 0 && li < CDA_K_ROWS && li < nlev) {
-                unsigned long long mm = ((unsigned long long)mhi << 32) | mlo;
-                for (int j = 0; j < li; ++j) mm &= mm - 1;
-                const int pos = __ffsll((long long)mm) - 1;
-                myP = side == 0 ? (int)B - pos : (int)B + pos;
-                myV = SMW(wb + L::VOL + lane);
-            }
+            if (li >= 0 && li < CDA_K_ROWS && li < nlev) { myP = (int)SMW(wb + L::LPX + lane); myV = SMW(wb + L::VOL + lane); }
             if (nlev < CDA_K_ROWS && far_any) {        // levels further than 64 ticks from the best: generic search
                 unsigned prev = side == 0 ? B - 63u : B + 63u;
                 for (int lv = nlev; lv < CDA_K_ROWS; ++lv) {
@@ -844,8 +881,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     __syncwarp();
     const unsigned ob = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), oa = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
     if (lane == 0 && (ob | oa)) {
-        if (ob) bulk_s2g(gpool, &smw[wb + L::POOL], ob);
-        if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, &smw[wb + L::POOL + CDA_POOL_FIELDS * CAP], oa);
+        if (ob) bulk_s2g(gpool, sa + L::POOL * 4u, ob);
+        if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, oa);
         bulk_commit();
         bulk_wait_read0();
     }
