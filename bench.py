@@ -216,9 +216,10 @@ def main():
     pin_blk[:, 1].view(torch.float32).copy_(torch.from_numpy(acts_np[1][:PH]))
     pin_blk[:, 2].view(torch.float32).copy_(torch.from_numpy(acts_np[2][:PH]))
 
+    pin_steps = [pin_blk[i] for i in range(PH)]
+
     def host_step(i):
-        b = pin_blk[i % PH]
-        return env.step_host(b[0], b[1].view(torch.float32), b[2].view(torch.float32), b[3], b[4])
+        return env.step_host_block(pin_steps[i % PH])
 
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     step_ctr = [0]
@@ -254,7 +255,6 @@ def main():
     torch.cuda.synchronize()
     launches = env.kernel_launches - launches0
     per_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    clocks = sampler.stop()
     total_ms = float(per_ms.sum())
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -293,7 +293,9 @@ def main():
         e2e = {"value": world * M * args.steps / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(M * A * 20), "d2h_bytes_per_step": int(M * env.W * 4 + M * A * 8 + 2 * M),
                "ms_per_step": 1e3 * float(tt.item()) / args.steps,
-               "api": "VecCDAEnv.step_host -> cda_step_host (pinned host buffers: 1 H2D + kernel + 1 D2H, stream sync per step)"}
+               "api": "VecCDAEnv.step_host_block -> cda_step_host (pinned [5,M,A] action block read in place by the kernel, obs|reward|flags written to the pinned output block, stream sync per step)"}
+
+    clocks = sampler.stop()   # sampled across the device-timed, L2-hot and end-to-end regions
 
     # ------------------------------------------------------------------ optional obs all-gather
     ag = None

@@ -47,7 +47,7 @@ EXPORTS = (
     "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
-    "cda_seed_to_pcg64",
+    "cda_seed_to_pcg64", "cda_debug_phase_buffer",
 )
 
 
@@ -111,6 +111,7 @@ def lib():
         getattr(L, name).restype = ctypes.c_char_p
     L.cda_strerror.argtypes = [i32]
     L.cda_seed_to_pcg64.argtypes = [u64, ctypes.POINTER(u64)]
+    L.cda_debug_phase_buffer.restype = ctypes.c_void_p
     _lib = L
     return L
 

@@ -77,6 +77,7 @@ struct CdaStepParams {
     int *fills; int *fill_counts;
     // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
     int num_steps; unsigned long long policy_seed;
+    unsigned long long *prof;   // CDA_PROFILE_PHASES builds: per-phase cycle sums [16]
 };
 
 // ------------------------------------ numpy-exact RNG --------------------------------------
@@ -311,6 +312,7 @@ template <int CAP>
 struct CdaMkt {
     int pool_w;          // word index of this warp's pool in smw
     int nb, na;          // live orders per side
+    unsigned dirty;      // bit (side*8 + tile): pool tile modified this launch -> must be written back
     unsigned time, next_id, seqctr, status;
     int tape_nonempty, tape_px;
     int lane;
@@ -318,6 +320,7 @@ struct CdaMkt {
     __device__ __forceinline__ int side_w(int side) const { return pool_w + side * (CDA_POOL_FIELDS * CAP); }
     __device__ __forceinline__ int count(int side) const { return side ? na : nb; }
     __device__ __forceinline__ void set_count(int side, int v) { if (side) na = v; else nb = v; }
+    __device__ __forceinline__ void touch(int side, int idx) { dirty |= 1u << (side * 8 + (idx >> 5)); }
 };
 
 template <int CAP> __device__ __forceinline__ int pool_best(const CdaMkt<CAP> &k, int side) {
@@ -374,6 +377,7 @@ template <int CAP> __device__ __forceinline__ void pool_remove(CdaMkt<CAP> &k, i
         const int f = k.side_w(side) + k.lane * 32;
         SMW(f + CDA_EOFF(idx)) = SMW(f + CDA_EOFF(last));
     }
+    if (idx != last) k.touch(side, idx);
     k.set_count(side, last);
     __syncwarp();
 }
@@ -387,6 +391,7 @@ template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, i
         const unsigned v = k.lane == 0 ? (((unsigned)trader << 24) | price) : k.lane == 1 ? qty : k.lane == 2 ? oid : k.lane == 3 ? ts : seq;
         SMW(k.side_w(side) + CDA_EOFF(n) + k.lane * 32) = v;
     }
+    k.touch(side, n);
     k.set_count(side, n + 1);
     __syncwarp();
     return true;
@@ -439,6 +444,7 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
         if ((unsigned)price == op && (unsigned long long)size <= oq) {   // orderbook.py:245-248 in place
             __syncwarp();
             if (k.lane == 0) { SMW(pl + 32) = (unsigned)size; SMW(pl + 96) = k.time; }
+            k.touch(side, idx);
             __syncwarp();
             if (is_t) { const long long v = (long long)price * size; ac.cash -= v; ac.hold += v; }
             return;
@@ -468,6 +474,7 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
             traded = qty; left = (int)(hq - qty);
             __syncwarp();
             if (k.lane == 0) SMW(po + 32) = hq - qty;
+            k.touch(opp, h);
             __syncwarp();
             qty = 0;
         } else {                              // :86-100 resting order consumed
@@ -515,6 +522,17 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #ifndef CDA_MIN_CTAS
 #define CDA_MIN_CTAS 7   /* 7 CTAs x 4 warps = 28 warps/SM -> 4144 resident markets on 148 SMs (>= 4096 in one wave) */
 #endif
+#ifdef CDA_PROFILE_PHASES
+#define CDA_TICK(i) do { const long long t__ = clock64(); if (lane == 0 && p.prof) p.prof[(size_t)m * 16 + (i)] += (unsigned long long)(t__ - tprev); tprev = t__; } while (0)
+#else
+#define CDA_TICK(i) do {} while (0)
+#endif
+#ifndef CDA_EARLY_HIST
+#define CDA_EARLY_HIST 0      /* 1: fetch the older snapshots at the top of the step, 0: after the matching phase */
+#endif
+#ifndef CDA_BULK_STORE
+#define CDA_BULK_STORE 1      /* 1: write the whole live pool prefix back with cp.async.bulk (measured 4 % faster), 0: dirty tiles with plain stores */
+#endif
 #define CDA_HIST_PREFETCH 4   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
 
 template <int CAP, int WARPS>
@@ -525,12 +543,32 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     if (m >= p.M) return;
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
+#ifdef CDA_PROFILE_PHASES
+    long long tprev = clock64();
+#endif
     const int wb = warp * L::WORDS;                       // this warp's tile in smw
     const unsigned sa = smem_u32(smw) + (unsigned)wb * 4u;   // shared-window byte address of this warp's tile
     const unsigned bar = sa + L::BAR * 4u;
     unsigned char *blk = p.state + (size_t)m * cfg.stride;
     unsigned *hdr = reinterpret_cast<unsigned *>(blk);
 
+    // ---- issue the loads in the order they are consumed: this step's actions and the accounts (decode and
+    //      the cash gate need them first), then the header, then the pool tiles; the older snapshots of the
+    //      stacked observation are only needed at the very end and are fetched after the matching phase.
+    int a_cat0 = -1, a_pcode0 = 0, a_poff0 = 1; float a_mean0 = 0.f, a_sigma0 = 0.f;
+    if (lane < A && p.num_steps == 0) {
+        const size_t o = (size_t)m * A + lane;
+        a_cat0 = p.cat[o]; a_mean0 = p.mean[o]; a_sigma0 = p.sigma[o]; a_pcode0 = p.pcode[o]; a_poff0 = p.poff[o];
+    }
+    long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct);
+    long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A;
+    int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
+    unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
+    CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane < A) {
+        ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
+        ac.prev_nav = g_prev[lane]; ac.max_nav = g_max[lane]; ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
+    }
     if (lane == 0) mbar_init(bar, 1);
     if (lane < 2 * CDA_K_ROWS) SMW(wb + L::TOPK + lane) = hdr[20 + lane];
     __syncwarp();
@@ -544,6 +582,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 
     CdaMkt<CAP> k;
     k.lane = lane;
+    if (h0.x == 0xffffffffu) return;  // (keeps the header loads ahead of the first tick)
+    CDA_TICK(0);   // header arrived
     k.pool_w = wb + L::POOL;
     k.time = h0.x; k.next_id = h0.y; k.seqctr = h0.z;
     unsigned t_step = h0.w;
@@ -557,7 +597,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     rng.shi = r0.x; rng.slo = r0.y; rng.ihi = r1.x; rng.ilo = r1.y;
     k.tape_px = last_price;
     k.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
-    k.fill_cap = cfg.fill_cap; k.n_fills = 0;
+    k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
 
     // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
@@ -569,16 +609,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         if (bytes_a) bulk_g2s(sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, gpool + CDA_POOL_FIELDS * CAP, bytes_a, bar);
     }
 
-    // ---- accounts into lanes 0..A-1
-    long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct);
-    long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A;
-    int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
-    unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
-    CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (lane < A) {
-        ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
-        ac.prev_nav = g_prev[lane]; ac.max_nav = g_max[lane]; ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
-    }
     float *g_hist = reinterpret_cast<float *>(blk + cfg.off_hist);
     const int W_old = cfg.W - CDA_SNAPSHOT_DIM;       // obs elements that come from older snapshots
 
@@ -587,8 +617,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     for (int it = 0; it < n_iter; ++it) {
         const bool last_it = it == n_iter - 1;
         const int slot_new = (int)(t_step % (unsigned)cfg.n_hist);
-        // ---- prefetch the older snapshots of the stacked observation (state_helper.py:88-90)
         float hv[CDA_HIST_PREFETCH];
+#if CDA_EARLY_HIST
         if (p.obs && last_it) {
 #pragma unroll
             for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
@@ -601,6 +631,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
+#endif
         // ================= set_actions: action_helper.py:145-172, :241-397 =================
         int a_cat = -1, a_pcode = 0, a_poff = 1; float a_mean = 0.f, a_sigma = 0.f;
         if (lane < A) {
@@ -613,8 +644,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 a_mean = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
                 a_sigma = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
             } else {
-                const size_t o = (size_t)m * A + lane;
-                a_cat = p.cat[o]; a_mean = p.mean[o]; a_sigma = p.sigma[o]; a_pcode = p.pcode[o]; a_poff = p.poff[o];
+                a_cat = a_cat0; a_mean = a_mean0; a_sigma = a_sigma0; a_pcode = a_pcode0; a_poff = a_poff0;
             }
         }
         k.n_fills = 0;
@@ -625,6 +655,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         if (a_pcode < 0 || a_pcode >= CDA_K_ROWS) a_pcode = 0;
         if (a_poff < 0 || a_poff > 2) a_poff = 1;
         const unsigned present = __ballot_sync(CDA_FULL, lane < A && a_cat >= 0);
+        CDA_TICK(10);  // actions arrived
         // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339).
         // Fast path: lane a jumps the LCG ahead by (its rank + 1) steps and evaluates its own draw; this is
         // the sequential stream as long as every draw returns from the first ziggurat test (98.8 % each).
@@ -658,6 +689,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
+        CDA_TICK(11);  // draws done
         const int a_side = a_cat <= 0 ? -1 : (a_cat <= 4 ? 0 : 1);
         const int a_type = a_cat <= 0 ? 0 : ((a_cat - 1) & 3);
         long long a_size = 0; int a_price = -1;
@@ -678,6 +710,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
         if (__any_sync(CDA_FULL, a_price >= (int)CDA_PRICE_MASK)) { k.status |= CDA_ST_PRICE_RANGE; if (a_price >= (int)CDA_PRICE_MASK) a_price = CDA_PRICE_MASK - 1; }
 
+        CDA_TICK(1);   // accounts + actions arrived, draws + decode done
         // ================= rand_exec_seq: action_helper.py:174-199 ==========================
         const unsigned active = __ballot_sync(CDA_FULL, lane < A && a_side >= 0);
         const int n_act = __popc(active);
@@ -693,7 +726,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
         __syncwarp();
 
+        CDA_TICK(2);   // shuffle done
         if (!waited) { mbar_wait(bar, 0); waited = true; }
+        CDA_TICK(3);   // pool tiles landed
 
         // ================= do_actions: action_helper.py:201-239 =============================
         for (int q = 0; q < n_act; ++q) {
@@ -705,6 +740,22 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             place_order(k, ac, t, type, side, size, price);
         }
 
+#if !CDA_EARLY_HIST
+        // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90): latency hides behind mtm + top-K
+        if (p.obs && last_it) {
+#pragma unroll
+            for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
+                const int e = lane + 32 * q;
+                hv[q] = 0.f;
+                if (e < W_old) {
+                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
+                    hv[q] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                }
+            }
+        }
+#endif
+        CDA_TICK(4);   // do_actions done
         // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
         if (k.tape_nonempty) {
             last_price = k.tape_px;
@@ -781,6 +832,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
+        CDA_TICK(5);   // mtm + top-K levels done
         const int best_bid = __shfl_sync(CDA_FULL, myP, 0), best_ask = __shfl_sync(CDA_FULL, myP, CDA_K_ROWS);
         double Mid;
         if (best_bid > 0 && best_ask > 0) Mid = ((double)best_bid + (double)best_ask) / 2.0;
@@ -815,6 +867,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
         __syncwarp();
 
+        CDA_TICK(6);   // obs math done
         // ================= prep_next_state: state_helper.py:80-92 (ring + stacked obs) ======
         if (p.obs && last_it) {
             float *o = p.obs + (size_t)m * cfg.W;
@@ -830,6 +883,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         __syncwarp();
         for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
 
+        CDA_TICK(7);   // obs + ring written
         // ================= set_reward / set_done: reward_helper.py:35-103, done_helper.py ===
         bool broke = false;
         if (lane < A) {
@@ -862,6 +916,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
     }
 
+    CDA_TICK(8);   // reward/done
     // ---- store: header, accounts, pool prefix
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
@@ -877,15 +932,33 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         g_ctr[lane] = (ac.tr_step & 0xfffu) | ((ac.pas_step & 0xfffu) << 12) | ((ac.placed & 1u) << 24) |
                       ((ac.rejected & 1u) << 25) | ((ac.is_pass & 1u) << 26);
     }
-    fence_proxy_async();   // every lane: its generic-proxy smem writes become visible to the async proxy
+#if CDA_BULK_STORE
+    fence_proxy_async();
     __syncwarp();
-    const unsigned ob = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), oa = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
-    if (lane == 0 && (ob | oa)) {
-        if (ob) bulk_s2g(gpool, sa + L::POOL * 4u, ob);
-        if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, oa);
-        bulk_commit();
-        bulk_wait_read0();
+    {
+        const unsigned ob = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), oa = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
+        if (lane == 0 && (ob | oa)) {
+            if (ob) bulk_s2g(gpool, sa + L::POOL * 4u, ob);
+            if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, oa);
+            bulk_commit();
+            bulk_wait_read0();
+        }
     }
+#else
+    // ---- pool write-back: only the tiles this launch modified, as plain coalesced 128-B stores (fire and
+    //      forget: nothing to wait for, unlike a bulk store whose source smem must outlive the read)
+    __syncwarp();
+#pragma unroll 1
+    for (unsigned dm = k.dirty; dm; dm &= dm - 1) {
+        const int b = __ffs(dm) - 1, side = b >> 3, tile = b & 7;
+        if (tile * 32 >= k.count(side)) continue;               // tile fell off the live prefix
+        const int sw = k.side_w(side) + tile * CDA_TILE_WORDS + lane;
+        unsigned *gw = gpool + side * (CDA_POOL_FIELDS * CAP) + tile * CDA_TILE_WORDS + lane;
+#pragma unroll
+        for (int f = 0; f < CDA_POOL_FIELDS; ++f) gw[f * 32] = SMW(sw + f * 32);
+    }
+#endif
+    CDA_TICK(9);   // state stored
 }
 
 // ------------------------------------------------------------------------------------------

@@ -118,6 +118,9 @@ class VecCDAEnv:
                 obs=out[:nb_obs].view(torch.float32).view(M, W),
                 reward=out[nb_obs:nb_obs + nb_rew].view(torch.float64).view(M, A),
                 term=out[nb_obs + nb_rew:nb_obs + nb_rew + M], trunc=out[nb_obs + nb_rew + M:])
+            pp = self._pinned
+            self._out_ptrs = tuple(_ptr(pp[k]) for k in ("obs", "reward", "term", "trunc"))
+            self._out_np = (pp["obs"].numpy(), pp["reward"].numpy(), pp["term"].numpy(), pp["trunc"].numpy())
         return self._pinned
 
     def step_host(self, category, size_mean, size_sigma, price, price_offset, sync=True):
@@ -140,6 +143,21 @@ class VecCDAEnv:
             else:
                 np.copyto(p[key].numpy(), np.asarray(src).reshape(self.M, self.A), casting="same_kind")
         return self.step_pinned(sync=sync)
+
+    def step_host_block(self, action_block, sync=True):
+        """Lowest-overhead host path: `action_block` is ONE pinned int32 tensor [5, M, A] holding
+        category, size_mean (float32 bits), size_sigma (float32 bits), price, price_offset.  The kernel
+        reads it in place (mapped pinned memory) and writes obs/reward/flags into this env's pinned
+        output block; returns numpy views of that block."""
+        p = self._ensure_pinned()
+        base = action_block.data_ptr()
+        n = self.M * self.A * 4
+        vp = ctypes.c_void_p
+        _native.check(self._L.cda_step_host(self._h, vp(base), vp(base + n), vp(base + 2 * n), vp(base + 3 * n), vp(base + 4 * n),
+                                            self._out_ptrs[0], self._out_ptrs[1], self._out_ptrs[2], self._out_ptrs[3], self._stream()))
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return self._out_np
 
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""

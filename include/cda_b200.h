@@ -152,6 +152,9 @@ const char *cda_strerror(int code);
 const char *cda_last_cuda_error(void);
 const char *cda_build_info(void);
 
+/* Debug builds only (-DCDA_PROFILE_PHASES): device buffer of 16 per-phase cycle sums, else NULL. */
+unsigned long long *cda_debug_phase_buffer(void);
+
 /* Host-side helper: the PCG64 state numpy gives for `seed` (state_hi, state_lo, inc_hi, inc_lo). */
 void cda_seed_to_pcg64(uint64_t seed, uint64_t out[4]);
 
