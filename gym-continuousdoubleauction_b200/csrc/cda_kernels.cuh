@@ -527,6 +527,14 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #else
 #define CDA_TICK(i) do {} while (0)
 #endif
+#ifndef CDA_EARLY_ACCT
+#define CDA_EARLY_ACCT 1      /* 1: load the accounts at kernel entry (measured best); 0: after the normal draws (the RNG phase is the
+                                 register-pressure peak: values loaded before it get spilled, and the spill store has
+                                 to wait for the load, exposing its latency) */
+#endif
+#ifndef CDA_LATE_HIST
+#define CDA_LATE_HIST 0       /* 1: fetch the older snapshots after the top-K sweep instead of after do_actions (no gain measured) */
+#endif
 #ifndef CDA_EARLY_HIST
 #define CDA_EARLY_HIST 0      /* 1: fetch the older snapshots at the top of the step, 0: after the matching phase */
 #endif
@@ -565,10 +573,12 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
     unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
     CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#if CDA_EARLY_ACCT
     if (lane < A) {
         ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
         ac.prev_nav = g_prev[lane]; ac.max_nav = g_max[lane]; ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
     }
+#endif
     if (lane == 0) mbar_init(bar, 1);
     if (lane < 2 * CDA_K_ROWS) SMW(wb + L::TOPK + lane) = hdr[20 + lane];
     __syncwarp();
@@ -689,6 +699,12 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
+#if !CDA_EARLY_ACCT
+        if (it == 0 && lane < A) {   // accounts: needed from do_actions on; the shuffle below covers their latency
+            ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
+            ac.prev_nav = g_prev[lane]; ac.max_nav = g_max[lane]; ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
+        }
+#endif
         CDA_TICK(11);  // draws done
         const int a_side = a_cat <= 0 ? -1 : (a_cat <= 4 ? 0 : 1);
         const int a_type = a_cat <= 0 ? 0 : ((a_cat - 1) & 3);
@@ -740,7 +756,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             place_order(k, ac, t, type, side, size, price);
         }
 
-#if !CDA_EARLY_HIST
+#if !CDA_EARLY_HIST && !CDA_LATE_HIST
         // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90): latency hides behind mtm + top-K
         if (p.obs && last_it) {
 #pragma unroll
@@ -832,6 +848,21 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
+#if !CDA_EARLY_HIST && CDA_LATE_HIST
+        // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90): latency hides behind the f32/f64 observation math
+        if (p.obs && last_it) {
+#pragma unroll
+            for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
+                const int e = lane + 32 * q;
+                hv[q] = 0.f;
+                if (e < W_old) {
+                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
+                    hv[q] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                }
+            }
+        }
+#endif
         CDA_TICK(5);   // mtm + top-K levels done
         const int best_bid = __shfl_sync(CDA_FULL, myP, 0), best_ask = __shfl_sync(CDA_FULL, myP, CDA_K_ROWS);
         double Mid;
