@@ -300,20 +300,48 @@ def main():
     # ------------------------------------------------------------------ optional obs all-gather
     ag = None
     if world > 1 and args.allgather:
-        obs_all = torch.empty((world * M, env.W), dtype=torch.float32, device=dev)
-        rew_all = torch.empty((world * M, A), dtype=torch.float64, device=dev)
+        # (a) baseline: step, then ONE NCCL all-gather of the packed obs|reward|flags block
+        blk_bytes = M * env.W * 4 + M * A * 8 + 2 * M
+        loc = torch.empty(blk_bytes, dtype=torch.uint8, device=dev)
+        outs = (loc[:M * env.W * 4].view(torch.float32).view(M, env.W), loc[M * env.W * 4:M * env.W * 4 + M * A * 8].view(torch.float64).view(M, A),
+                loc[M * env.W * 4 + M * A * 8:M * env.W * 4 + M * A * 8 + M], loc[M * env.W * 4 + M * A * 8 + M:])
+        allb = torch.empty(world * blk_bytes, dtype=torch.uint8, device=dev)
+
+        def nccl_step():
+            k = step_ctr[0] % P; step_ctr[0] += 1
+            env.step(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k], out=outs)
+            dist.all_gather_into_tensor(allb, loc)
         for i in range(5):
-            o, r, _, _ = dev_step(i); dist.all_gather_into_tensor(obs_all, o); dist.all_gather_into_tensor(rew_all, r)
+            nccl_step()
         torch.cuda.synchronize(); dist.barrier()
         e0.record()
         for i in range(args.steps):
-            o, r, _, _ = dev_step(i)
-            dist.all_gather_into_tensor(obs_all, o); dist.all_gather_into_tensor(rew_all, r)
+            nccl_step()
         e1.record(); torch.cuda.synchronize()
         tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        ag = {"value": world * M * args.steps / (float(tg.item()) * 1e-3), "unit": UNIT,
-              "note": "step + NCCL all_gather of obs f32[M,168] and reward f64[M,A] per step (policy batch spanning GPUs), L2-hot"}
+        # (b) fused: the step kernel's epilogue stores into every peer's gather buffer over NVLink; a 1-element
+        #     all-reduce orders the consumers
+        env.enable_peer_gather()
+        tiny = torch.zeros(1, device=dev)
+
+        def fused_step():
+            k = step_ctr[0] % P; step_ctr[0] += 1
+            env.step_gather(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k])
+            dist.all_reduce(tiny)
+        for i in range(5):
+            fused_step()
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record()
+        for i in range(args.steps):
+            fused_step()
+        e1.record(); torch.cuda.synchronize()
+        tf = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        ag = {"nccl_allgather": {"value": world * M * args.steps / (float(tg.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tg.item()) / args.steps,
+                                 "note": "step + one NCCL all_gather of the packed obs|reward|flags block per step, L2-hot"},
+              "fused_peer_gather": {"value": world * M * args.steps / (float(tf.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tf.item()) / args.steps,
+                                    "note": "cda_step_gather: kernel epilogue stores to all peers over NVLink (CUDA IPC) + 1-element all-reduce, L2-hot"}}
 
     status_bits = int(env.status().max().item())
     if rank != 0:

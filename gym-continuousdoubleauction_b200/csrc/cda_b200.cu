@@ -38,6 +38,8 @@ struct CdaEnv {
     int *s_cat; float *s_mean; float *s_sigma; int *s_pcode; int *s_poff;
     float *s_obs; double *s_reward; unsigned char *s_term; unsigned char *s_trunc;
     bool was_reset;
+    // fused all-gather
+    int g_world, g_rank; unsigned char *g_local; size_t g_bytes; unsigned char *g_peer[CDA_MAX_PEERS]; bool g_connected;
     int zerocopy;              // cda_step_host: let the kernel store outputs straight into mapped pinned host memory
     const void *zc_host; void *zc_dev;   // last host obs pointer checked and its device alias (NULL = not mapped)
     int zerocopy_in; const void *zi_host; void *zi_dev;   // same for the action block (kernel reads pinned host memory)
@@ -181,6 +183,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
 int cda_destroy(CdaEnv *e) {
     if (!e) return CDA_OK;
     cudaSetDevice(e->device);
+    if (e->g_connected) for (int g = 0; g < e->g_world; ++g) if (g != e->g_rank && e->g_peer[g]) cudaIpcCloseMemHandle(e->g_peer[g]);
+    cudaFree(e->g_local);
     cudaFree(e->state); cudaFree(e->fills); cudaFree(e->fill_counts);
     cudaFree(e->s_cat); cudaFree(e->s_obs);
     delete e;
@@ -306,6 +310,54 @@ int cda_rollout_random(CdaEnv *e, int32_t num_steps, uint64_t policy_seed, float
     memset(&p, 0, sizeof(p));
     p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated;
     p.num_steps = num_steps; p.policy_seed = policy_seed;
+    return step_common(e, p, (cudaStream_t)stream);
+}
+
+int cda_gather_create(CdaEnv *e, int32_t world, int32_t rank, void *ipc_handle_out64, void **d_local_buf, uint64_t *bytes) {
+    if (!e || world < 1 || world > CDA_MAX_PEERS || rank < 0 || rank >= world || !ipc_handle_out64) return CDA_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (e->g_local) return CDA_EINVAL;
+    const size_t rows = (size_t)world * e->M;
+    e->g_bytes = rows * ((size_t)e->dev.W * 4 + (size_t)e->dev.A * 8 + 2);
+    CUDA_TRY(cudaMalloc(&e->g_local, e->g_bytes));
+    CUDA_TRY(cudaMemset(e->g_local, 0, e->g_bytes));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, e->g_local));
+    memcpy(ipc_handle_out64, &h, 64);
+    e->g_world = world; e->g_rank = rank; e->g_connected = false;
+    if (d_local_buf) *d_local_buf = e->g_local;
+    if (bytes) *bytes = e->g_bytes;
+    return CDA_OK;
+}
+
+int cda_gather_connect(CdaEnv *e, const void *all_handles) {
+    if (!e || !e->g_local || !all_handles) return CDA_EINVAL;
+    CUDA_TRY(cudaSetDevice(e->device));
+    for (int g = 0; g < e->g_world; ++g) {
+        if (g == e->g_rank) { e->g_peer[g] = e->g_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const char *>(all_handles) + (size_t)g * 64, 64);
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        e->g_peer[g] = reinterpret_cast<unsigned char *>(ptr);
+    }
+    e->g_connected = true;
+    return CDA_OK;
+}
+
+int cda_step_gather(CdaEnv *e, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
+                    const int32_t *d_price, const int32_t *d_price_offset, void *stream) {
+    if (!e || !d_category || !d_size_mean || !d_size_sigma || !d_price || !d_price_offset) return CDA_EINVAL;
+    if (!e->was_reset || !e->g_connected) return CDA_ESTATE;
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cat = d_category; p.mean = d_size_mean; p.sigma = d_size_sigma; p.pcode = d_price; p.poff = d_price_offset;
+    p.gather_world = e->g_world; p.gather_row0 = e->g_rank * e->M; p.gather_rows = e->g_world * e->M;
+    for (int g = 0; g < e->g_world; ++g) p.gather_peer[g] = e->g_peer[g];
+    // non-null markers so the epilogue runs (the destinations come from gather_peer)
+    p.obs = reinterpret_cast<float *>(e->g_local); p.reward = reinterpret_cast<double *>(e->g_local);
+    p.term = e->g_local; p.trunc = e->g_local;
     return step_common(e, p, (cudaStream_t)stream);
 }
 

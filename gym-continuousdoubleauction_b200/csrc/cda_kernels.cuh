@@ -78,6 +78,9 @@ struct CdaStepParams {
     // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
     int num_steps; unsigned long long policy_seed;
     unsigned long long *prof;   // CDA_PROFILE_PHASES builds: per-phase cycle sums [16]
+    // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
+    int gather_world, gather_row0, gather_rows;
+    unsigned char *gather_peer[CDA_MAX_PEERS];
 };
 
 // ------------------------------------ numpy-exact RNG --------------------------------------
@@ -901,15 +904,22 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         CDA_TICK(6);   // obs math done
         // ================= prep_next_state: state_helper.py:80-92 (ring + stacked obs) ======
         if (p.obs && last_it) {
-            float *o = p.obs + (size_t)m * cfg.W;
+            // one destination normally; with the fused all-gather, row (row0 + m) of EVERY peer's buffer
+            // (plain stores to peer-mapped addresses: they travel over NVLink while other warps still match)
+            const int nd = p.gather_world > 0 ? p.gather_world : 1;
+#pragma unroll 1
+            for (int g = 0; g < nd; ++g) {
+                float *o = p.gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[g]) + (size_t)(p.gather_row0 + m) * cfg.W
+                                              : p.obs + (size_t)m * cfg.W;
 #pragma unroll
-            for (int q = 0; q < CDA_HIST_PREFETCH; ++q) { const int e = lane + 32 * q; if (e < W_old) o[e] = hv[q]; }
-            for (int e = lane + 32 * CDA_HIST_PREFETCH; e < W_old; e += 32) {   // n_hist > 4: not prefetched
-                const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
-                int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
-                o[e] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                for (int q = 0; q < CDA_HIST_PREFETCH; ++q) { const int e = lane + 32 * q; if (e < W_old) o[e] = hv[q]; }
+                for (int e = lane + 32 * CDA_HIST_PREFETCH; e < W_old; e += 32) {   // n_hist > 4: not prefetched
+                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
+                    o[e] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                }
+                for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) o[W_old + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
             }
-            for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) o[W_old + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
         }
         __syncwarp();
         for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
@@ -927,14 +937,25 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             r = r + -(cfg.c_trade * (double)ac.tr_step);
             r = r + -(cfg.c_dd * (double)ddi);
             r = r + cfg.c_passive * (double)ac.pas_step;
-            if (p.reward && last_it) p.reward[(size_t)m * A + lane] = r;
+            if (p.reward && last_it) {
+                if (p.gather_world > 0) {
+                    const size_t off = (size_t)p.gather_rows * cfg.W * 4 + ((size_t)(p.gather_row0 + m) * A + lane) * 8;
+                    for (int g = 0; g < p.gather_world; ++g) *reinterpret_cast<double *>(p.gather_peer[g] + off) = r;
+                } else p.reward[(size_t)m * A + lane] = r;
+            }
             broke = ac.nav <= 0;
         }
         done_mask |= __ballot_sync(CDA_FULL, broke);
         const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
         if (lane == 0 && last_it) {
-            if (p.term) p.term[m] = (done_mask & all) == all;
-            if (p.trunc) p.trunc[m] = (t_step + 1 >= (unsigned)cfg.max_step);
+            const unsigned char f_term = (done_mask & all) == all, f_trunc = (t_step + 1 >= (unsigned)cfg.max_step);
+            if (p.gather_world > 0) {
+                const size_t off = (size_t)p.gather_rows * ((size_t)cfg.W * 4 + (size_t)A * 8) + (size_t)(p.gather_row0 + m);
+                for (int g = 0; g < p.gather_world; ++g) { p.gather_peer[g][off] = f_term; p.gather_peer[g][off + p.gather_rows] = f_trunc; }
+            } else {
+                if (p.term) p.term[m] = f_term;
+                if (p.trunc) p.trunc[m] = f_trunc;
+            }
             if (p.fill_counts) p.fill_counts[m] = k.n_fills;
             hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask;
         }

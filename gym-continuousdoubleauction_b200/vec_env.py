@@ -172,6 +172,40 @@ class VecCDAEnv:
     def pinned_buffers(self):
         return self._ensure_pinned()
 
+    # ------------------------------------------------------------------ fused step + all-gather (multi-GPU)
+    def enable_peer_gather(self, group=None):
+        """Set up the NVLink peer-memory gather (one process per GPU, torch.distributed initialised).
+        Returns (obs f32[G*M,W], reward f64[G*M,A], terminated u8[G*M], truncated u8[G*M]) — CUDA tensors
+        viewing THIS rank's gather buffer, which every rank's step kernel fills directly."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handle = (ctypes.c_ubyte * 64)()
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_uint64()
+        _native.check(self._L.cda_gather_create(self._h, world, rank, handle, ctypes.byref(ptr), ctypes.byref(nbytes)))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        _native.check(self._L.cda_gather_connect(self._h, blob))
+        rows = world * self.M
+
+        class _Raw:   # expose the cudaMalloc'ed buffer to torch without copying
+            def __init__(s, p, n):
+                s.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
+        raw = torch.as_tensor(_Raw(ptr.value, nbytes.value), device=self.device)
+        o_b, r_b = rows * self.W * 4, rows * self.A * 8
+        self._gather = (raw[:o_b].view(torch.float32).view(rows, self.W), raw[o_b:o_b + r_b].view(torch.float64).view(rows, self.A),
+                        raw[o_b + r_b:o_b + r_b + rows], raw[o_b + r_b + rows:o_b + r_b + 2 * rows])
+        self._gather_raw = raw
+        dist.barrier(group=group)
+        return self._gather
+
+    def step_gather(self, category, size_mean, size_sigma, price, price_offset):
+        """cda_step whose epilogue writes this rank's rows into every rank's gather buffer (P2P stores).
+        Order the consumers with a cross-rank barrier (e.g. a 1-element all-reduce on the same stream)."""
+        _native.check(self._L.cda_step_gather(self._h, _ptr(category), _ptr(size_mean), _ptr(size_sigma), _ptr(price),
+                                              _ptr(price_offset), self._stream()))
+        return self._gather
+
     # ------------------------------------------------------------------ fused random rollout
     def rollout_random(self, num_steps, policy_seed=0):
         _native.check(self._L.cda_rollout_random(self._h, int(num_steps), ctypes.c_uint64(policy_seed), _ptr(self.obs),

@@ -119,6 +119,20 @@ int cda_step_host(CdaEnv *env, const int32_t *h_category, const float *h_size_me
 int cda_rollout_random(CdaEnv *env, int32_t num_steps, uint64_t policy_seed, float *d_obs, double *d_reward,
                        uint8_t *d_terminated, uint8_t *d_truncated, void *stream);
 
+/* ---- fused step + all-gather over NVLink peer memory (one policy batch spanning G GPUs) ----
+ * Each rank owns M markets (global rows [rank*M, (rank+1)*M)).  cda_gather_create allocates this rank's
+ * gather buffer  obs f32[G*M][W] | reward f64[G*M][A] | terminated u8[G*M] | truncated u8[G*M]  and
+ * returns its 64-byte CUDA IPC handle; after the ranks exchange handles (any transport),
+ * cda_gather_connect maps every peer's buffer.  cda_step_gather is cda_step whose epilogue stores each
+ * market's outputs straight into ALL G buffers (P2P stores over NVLink/NVSwitch), so the transfer overlaps
+ * the matching work of other warps and no separate collective moves the data.  The caller orders the
+ * consumers with any tiny cross-rank barrier (e.g. a 1-element NCCL all-reduce) after the call. */
+#define CDA_MAX_PEERS 8
+int cda_gather_create(CdaEnv *env, int32_t world, int32_t rank, void *ipc_handle_out64, void **d_local_buf, uint64_t *bytes);
+int cda_gather_connect(CdaEnv *env, const void *all_ipc_handles /* [world][64] */);
+int cda_step_gather(CdaEnv *env, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
+                    const int32_t *d_price, const int32_t *d_price_offset, void *stream);
+
 /* Lazy info (info_helper.py:30-116): gathers one field for all markets into d_out. */
 int cda_get_info(CdaEnv *env, int32_t field, int64_t *d_out, void *stream);
 

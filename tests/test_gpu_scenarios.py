@@ -1,0 +1,80 @@
+"""Known-answer scenarios + sticky status bits on the CUDA env."""
+import numpy as np
+import pytest
+import torch
+
+import scenarios
+from test_scenarios_oracle import run
+import gym_continuousdoubleauction_b200 as cda
+
+pytestmark = pytest.mark.gpu
+
+
+class GpuBackend:
+    def __init__(self, cfg):
+        self.e = cda.VecCDAEnv(cfg, num_markets=1, fill_capacity=32)
+
+    def reset_one(self, seed):
+        return self.e.reset(seed=[seed]).cpu().numpy()[0]
+
+    def step_one(self, cat, mean, sigma, price, off):
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)[None]).cuda()
+        return self.e.step(t(cat, np.int32), t(mean, np.float32), t(sigma, np.float32), t(price, np.int32), t(off, np.int32))
+
+    def dump_one(self):
+        return self.e.dump(0)
+
+
+@pytest.mark.parametrize("scn", scenarios.ALL, ids=[f.__name__ for f in scenarios.ALL])
+def test_scenario_on_gpu(scn):
+    run(scn, GpuBackend)
+
+
+def test_pool_overflow_sets_sticky_status_and_raises():
+    """64-order capacity, 8 agents stacking limit bids at distinct ghost levels: the reference would
+    keep growing; we flag the market (sticky) instead of corrupting it."""
+    env = cda.VecCDAEnv(dict(num_of_agents=8, max_step=100000, initial_price_min=5000, initial_price_max=5000),
+                        num_markets=2, order_capacity=64)
+    env.reset(seed=1)
+    M, A = 2, 8
+    for t in range(40):
+        cat = torch.full((M, A), 2, dtype=torch.int32, device="cuda")          # bid limit
+        cat[1] = 0                                                              # market 1 only passes
+        mean = torch.zeros((M, A), dtype=torch.float32, device="cuda")
+        sig = torch.zeros_like(mean)
+        price = torch.full((M, A), 9, dtype=torch.int32, device="cuda")        # deepest level -> new price each step
+        off = torch.zeros((M, A), dtype=torch.int32, device="cuda")            # passive: one tick further
+        env.step(cat, mean, sig, price, off)
+    st = env.status().cpu().numpy()
+    assert st[0] & 1 and st[1] == 0
+    with pytest.raises(RuntimeError, match="order pool overflow"):
+        env.check_status()
+    env.close()
+
+
+def test_bad_action_sets_status_not_crash():
+    env = cda.VecCDAEnv(dict(num_of_agents=4), num_markets=1)
+    env.reset(seed=1)
+    z = lambda v, dt: torch.full((1, 4), v, dtype=dt, device="cuda")
+    env.step(z(11, torch.int32), z(0.0, torch.float32), z(0.0, torch.float32), z(3, torch.int32), z(1, torch.int32))
+    assert int(env.status()[0].item()) & 4
+    env.close()
+
+
+def test_rollout_random_conserves_nav_and_matches_stepwise_rng_state():
+    """The fused T-step rollout is the same state machine: NAV is conserved exactly and the env RNG stream
+    advances exactly as a step-by-step run with the same (device-generated) policy would."""
+    cfg = dict(num_of_agents=4, max_step=100000)
+    a = cda.VecCDAEnv(cfg, num_markets=64); b = cda.VecCDAEnv(cfg, num_markets=64)
+    a.reset(seed=5); b.reset(seed=5)
+    a.rollout_random(48, policy_seed=9)
+    for _ in range(48):
+        b.rollout_random(1, policy_seed=9)
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.reward, b.reward)
+    for m in (0, 31, 63):
+        da, db = a.dump(m), b.dump(m)
+        assert np.array_equal(da["bids"], db["bids"]) and np.array_equal(da["asks"], db["asks"])
+        assert np.array_equal(da["rng"], db["rng"]) and np.array_equal(da["accounts"], db["accounts"])
+    nav = a.info("nav").sum(1)
+    assert bool((nav == 4 * 1_000_000).all())
+    a.close(); b.close()
