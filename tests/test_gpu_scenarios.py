@@ -37,13 +37,14 @@ def test_pool_overflow_sets_sticky_status_and_raises():
                         num_markets=2, order_capacity=64)
     env.reset(seed=1)
     M, A = 2, 8
-    for t in range(40):
-        cat = torch.full((M, A), 2, dtype=torch.int32, device="cuda")          # bid limit
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for t in range(120):
+        cat = torch.full((M, A), 2, dtype=torch.int32, device="cuda")          # bid limits only: nothing ever trades
         cat[1] = 0                                                              # market 1 only passes
         mean = torch.zeros((M, A), dtype=torch.float32, device="cuda")
         sig = torch.zeros_like(mean)
-        price = torch.full((M, A), 9, dtype=torch.int32, device="cuda")        # deepest level -> new price each step
-        off = torch.zeros((M, A), dtype=torch.int32, device="cuda")            # passive: one tick further
+        price = torch.randint(0, 10, (M, A), device="cuda", generator=g, dtype=torch.int32)
+        off = torch.randint(0, 3, (M, A), device="cuda", generator=g, dtype=torch.int32)
         env.step(cat, mean, sig, price, off)
     st = env.status().cpu().numpy()
     assert st[0] & 1 and st[1] == 0
