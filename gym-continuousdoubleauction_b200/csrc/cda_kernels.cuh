@@ -316,6 +316,7 @@ struct CdaMkt {
     int pool_w;          // word index of this warp's pool in smw
     int nb, na;          // live orders per side
     unsigned dirty;      // bit (side*8 + tile): pool tile modified this launch -> must be written back
+    int bestb, besta;    // cached best bid / best ask: price, -1 = side empty, -2 = unknown (recomputed by a scan on demand)
     unsigned time, next_id, seqctr, status;
     int tape_nonempty, tape_px;
     int lane;
@@ -324,9 +325,11 @@ struct CdaMkt {
     __device__ __forceinline__ int count(int side) const { return side ? na : nb; }
     __device__ __forceinline__ void set_count(int side, int v) { if (side) na = v; else nb = v; }
     __device__ __forceinline__ void touch(int side, int idx) { dirty |= 1u << (side * 8 + (idx >> 5)); }
+    __device__ __forceinline__ int cached_best(int side) const { return side ? besta : bestb; }
+    __device__ __forceinline__ void set_best(int side, int v) { if (side) besta = v; else bestb = v; }
 };
 
-template <int CAP> __device__ __forceinline__ int pool_best(const CdaMkt<CAP> &k, int side) {
+template <int CAP> __device__ __forceinline__ int pool_best_scan(const CdaMkt<CAP> &k, int side) {
     int pt = k.side_w(side) + k.lane;
     const int n = k.count(side);
     if (n == 0) return -1;
@@ -346,6 +349,12 @@ template <int CAP> __device__ __forceinline__ int pool_best(const CdaMkt<CAP> &k
     }
 #endif
     return (int)(side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc));
+}
+// best price of a side through the cache (a scan only after an order AT the best price was removed)
+template <int CAP> __device__ __forceinline__ int pool_best(CdaMkt<CAP> &k, int side) {
+    int b = k.cached_best(side);
+    if (b == -2) { b = pool_best_scan(k, side); k.set_best(side, b); }
+    return b;
 }
 // index of the entry with the smallest key[field] among entries with (pt & mask) == want, or -1
 template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> &k, int side, unsigned mask, unsigned want, int field) {
@@ -375,6 +384,11 @@ template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> 
 // ordertree.py:70-77 remove_order_by_id: dense pool => move the last entry into the hole
 template <int CAP> __device__ __forceinline__ void pool_remove(CdaMkt<CAP> &k, int side, int idx) {
     const int last = k.count(side) - 1;
+    {   // best-price cache: an order leaving the best level may empty it -> unknown; an emptied side -> -1
+        const int cb = k.cached_best(side);
+        if (last == 0) k.set_best(side, -1);
+        else if (cb >= 0 && (int)(SMW(k.side_w(side) + CDA_EOFF(idx)) & CDA_PRICE_MASK) == cb) k.set_best(side, -2);
+    }
     __syncwarp();
     if (idx != last && k.lane < CDA_POOL_FIELDS) {
         const int f = k.side_w(side) + k.lane * 32;
@@ -389,6 +403,10 @@ template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, i
     const int n = k.count(side);
     if (n >= CAP) { k.status |= CDA_ST_POOL_OVERFLOW; return false; }
     const unsigned seq = k.seqctr++;
+    {   // best-price cache: a better (or first) price becomes the best; unknown stays unknown
+        const int cb = k.cached_best(side);
+        if (cb == -1 || (cb >= 0 && (side == 0 ? (int)price > cb : (int)price < cb))) k.set_best(side, (int)price);
+    }
     __syncwarp();
     if (k.lane < CDA_POOL_FIELDS) {
         const unsigned v = k.lane == 0 ? (((unsigned)trader << 24) | price) : k.lane == 1 ? qty : k.lane == 2 ? oid : k.lane == 3 ? ts : seq;
@@ -592,6 +610,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const uint4 h2 = *reinterpret_cast<const uint4 *>(hdr + 8);
     const ulonglong2 r0 = *reinterpret_cast<const ulonglong2 *>(hdr + 12);
     const ulonglong2 r1 = *reinterpret_cast<const ulonglong2 *>(hdr + 16);
+    const uint2 hb = *reinterpret_cast<const uint2 *>(hdr + 40);     // best bid / best ask after the previous step (0 = none)
 
     CdaMkt<CAP> k;
     k.lane = lane;
@@ -611,6 +630,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     k.tape_px = last_price;
     k.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
+    k.bestb = k.nb ? (hb.x ? (int)hb.x : -2) : -1; k.besta = k.na ? (hb.y ? (int)hb.y : -2) : -1;
 
     // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
@@ -802,10 +822,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const int n = k.count(side);
             if (n == 0) continue;
             const int nt = (n - lane + 31) >> 5;              // tiles in which this lane owns a live order
-            unsigned loc = side == 0 ? 0u : 0xffffffffu;
-            CDA_SCAN_PRAGMA
-            for (int it = 0; it < nt; ++it) { const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK; loc = side == 0 ? max(loc, pp) : min(loc, pp); }
-            const unsigned B = side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc);
+            const unsigned B = (unsigned)pool_best(k, side);      // usually cached by the matching phase
             unsigned mlo = 0, mhi = 0; bool far = false;
             CDA_SCAN_PRAGMA
             for (int it = 0; it < nt; ++it) {
