@@ -298,10 +298,13 @@ def main():
                "ms_per_step": 1e3 * float(tt.item()) / args.steps,
                "api": "VecCDAEnv.step_host_block -> cda_step_host (pinned [5,M,A] action block read in place by the kernel, obs|reward|flags written to the pinned output block, stream sync per step)"}
 
+    status_bits = int(env.status().max().item())   # sticky per-market status over everything measured above
     # keep the same load running for ~0.6 s so the 100 ms nvidia-smi sampler sees several samples under load
+    # (episodes of 400 steps: the books are reset in between, as an RL loop would at max_step)
     t_end = time.perf_counter() + 0.6
     while time.perf_counter() < t_end:
-        for _ in range(50):
+        env.reset(seed=gseeds)
+        for _ in range(400):
             dev_step()
         torch.cuda.synchronize()
     clocks = sampler.stop()   # sampled across the device-timed, L2-hot, end-to-end regions + 0.6 s of sustained stepping
@@ -353,7 +356,6 @@ def main():
               "fused_peer_gather": {"value": world * M * args.steps / (float(tf.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tf.item()) / args.steps,
                                     "note": "cda_step_gather: kernel epilogue stores to all peers over NVLink (CUDA IPC) + 1-element all-reduce, L2-hot"}}
 
-    status_bits = int(env.status().max().item())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

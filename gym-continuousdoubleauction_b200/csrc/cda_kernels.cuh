@@ -352,9 +352,13 @@ template <int CAP> __device__ __forceinline__ int pool_best_scan(const CdaMkt<CA
 }
 // best price of a side through the cache (a scan only after an order AT the best price was removed)
 template <int CAP> __device__ __forceinline__ int pool_best(CdaMkt<CAP> &k, int side) {
+#if CDA_BEST_CACHE
     int b = k.cached_best(side);
     if (b == -2) { b = pool_best_scan(k, side); k.set_best(side, b); }
     return b;
+#else
+    return pool_best_scan(k, side);
+#endif
 }
 // index of the entry with the smallest key[field] among entries with (pt & mask) == want, or -1
 template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> &k, int side, unsigned mask, unsigned want, int field) {
@@ -547,6 +551,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #define CDA_TICK(i) do { const long long t__ = clock64(); if (lane == 0 && p.prof) p.prof[(size_t)m * 16 + (i)] += (unsigned long long)(t__ - tprev); tprev = t__; } while (0)
 #else
 #define CDA_TICK(i) do {} while (0)
+#endif
+#ifndef CDA_BEST_CACHE
+#define CDA_BEST_CACHE 1
 #endif
 #ifndef CDA_EARLY_ACCT
 #define CDA_EARLY_ACCT 1      /* 1: load the accounts at kernel entry (measured best); 0: after the normal draws (the RNG phase is the
