@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--prewarm", type=int, default=256, help="untimed steps that populate the books")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ref-inner", type=int, default=8)
+    ap.add_argument("--ref-inner", type=int, default=64, help="env steps per reference-arm bench step (amortises the thread start-up of the CPU path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="N>1: also time an NCCL all-gather of obs/reward per step")

@@ -17,13 +17,16 @@ MIXES = {
 
 def make_actions(seed, steps, num_markets, num_agents, mix="uniform"):
     """Returns 5 arrays shaped [steps, M, A]: category i32, size_mean f32, size_sigma f32,
-    price i32, price_offset i32."""
+    price i32, price_offset i32.  (Vectorised float32 draws: generating the actions must not dominate
+    the CPU baseline it feeds.)"""
     rng = np.random.default_rng(seed)
     shape = (steps, num_markets, num_agents)
     p = MIXES[mix]
-    cat = rng.choice(9, size=shape, p=p / p.sum()).astype(np.int32)
-    mean = rng.uniform(-1.0, 1.0, shape).astype(np.float32)
-    sigma = rng.uniform(0.0, 1.0, shape).astype(np.float32)
-    price = rng.integers(0, 10, shape).astype(np.int32)
-    off = rng.integers(0, 3, shape).astype(np.int32)
+    cum = np.cumsum(p / p.sum()).astype(np.float32)
+    cum[-1] = 1.0
+    cat = np.minimum(np.searchsorted(cum, rng.random(shape, dtype=np.float32), side="right"), 8).astype(np.int32)
+    mean = rng.random(shape, dtype=np.float32) * np.float32(2.0) - np.float32(1.0)
+    sigma = rng.random(shape, dtype=np.float32)
+    price = rng.integers(0, 10, shape, dtype=np.int32)
+    off = rng.integers(0, 3, shape, dtype=np.int32)
     return cat, mean, sigma, price, off
