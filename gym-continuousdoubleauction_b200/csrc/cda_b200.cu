@@ -55,11 +55,14 @@ static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStre
     const size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA;
     static bool attr_set[16] = {false};
     if (!attr_set[e->device & 15]) {
-        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set[e->device & 15] = true;
     }
-    cda_step_kernel<CAP, CDA_WARPS_PER_CTA><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    if (p.num_steps > 0) cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    else cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {

@@ -257,8 +257,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // --------------------------------------- accounts ------------------------------------------
 struct CdaAcct {
-    long long cash, hold, cost, nav, prev_nav, max_nav, pos;
-    unsigned ntr, tr_step, pas_step, placed, rejected, is_pass;
+    long long cash, hold, cost, nav, pos;
+    unsigned ntr;
+    unsigned ctr;   // per-step counters, packed as stored: trades[0:12) passive[12:24) placed[24] rejected[25] is_pass[26]
 };
 // account.py:215-231 process_acc with the ledger restated on integers (cost = |pos|*VWAP):
 //   open/increase: cost += q*p (account.py:124-133, :173-176); decrease: cost -= q*p (:151-157);
@@ -266,8 +267,8 @@ struct CdaAcct {
 //   (:135-149 with calculate.py:24-33); flip: cover |pos| then open (q-|pos|) at p (:163-171).
 // party: 0 init_party, 1 counter_party; cash moves per cash_processor.py:31-53.
 __device__ __forceinline__ void acct_fill(CdaAcct &a, int party, int side /*0 bid,1 ask*/, long long q, long long p) {
-    a.ntr++; a.tr_step++;
-    if (party) a.pas_step++;
+    a.ntr++;
+    a.ctr += party ? 0x1001u : 0x1u;
     const long long tv = q * p;
     long long inc = 0, dec = 0;      // value moved by size_increase / size_decrease transfers
     const long long ap = a.pos < 0 ? -a.pos : a.pos;
@@ -304,7 +305,8 @@ struct CdaSmemLayout {
     static constexpr int VOL = TOPK + 2 * CDA_K_ROWS;                // u32[20] level volumes being accumulated
     static constexpr int LPX = VOL + 2 * CDA_K_ROWS;                 // u32[20] level prices of the snapshot being built
     static constexpr int ORDER = LPX + 2 * CDA_K_ROWS;               // u32[32] shuffled execution order
-    static constexpr int PARK = ORDER + 32;                          // 10 words: parked PCG64 state (+2 pad)
+    static constexpr int ACT = ORDER + 32;                           // u32[32][3] decoded actions: type|side<<8, size, price
+    static constexpr int PARK = ACT + 96;                            // 10 words: parked PCG64 state (+2 pad)
     static constexpr int BAR = PARK + 12;                            // mbarrier (8-B aligned)
     static constexpr int WORDS = ((BAR + 2 + 3) / 4) * 4;            // keep 16-B alignment of the next tile
     static constexpr int BYTES = WORDS * 4;
@@ -443,8 +445,8 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
             ok_l = ac.cash >= opening * est;
         }
     }
-    if (!__shfl_sync(CDA_FULL, ok_l, t)) { if (is_t) ac.rejected++; return; }
-    if (type <= 1 && is_t) ac.placed = 1;                               // trader.py:75-76
+    if (!__shfl_sync(CDA_FULL, ok_l, t)) { if (is_t) ac.ctr |= 1u << 25; return; }
+    if (type <= 1 && is_t) ac.ctr |= 1u << 24;                          // trader.py:75-76
     if (size <= 0 && type <= 1) { k.status |= CDA_ST_BAD_SIZE; return; }  // reference: sys.exit in process_order
 
     // ---- trader.py:254-287 _get_order_ID: limit/cancel = first in order_map order at that price (min seq);
@@ -571,7 +573,7 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #endif
 #define CDA_HIST_PREFETCH 4   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
 
-template <int CAP, int WARPS>
+template <int CAP, int WARPS, bool ROLLOUT>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
     using L = CdaSmemLayout<CAP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -588,23 +590,17 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     unsigned char *blk = p.state + (size_t)m * cfg.stride;
     unsigned *hdr = reinterpret_cast<unsigned *>(blk);
 
-    // ---- issue the loads in the order they are consumed: this step's actions and the accounts (decode and
-    //      the cash gate need them first), then the header, then the pool tiles; the older snapshots of the
-    //      stacked observation are only needed at the very end and are fetched after the matching phase.
-    int a_cat0 = -1, a_pcode0 = 0, a_poff0 = 1; float a_mean0 = 0.f, a_sigma0 = 0.f;
-    if (lane < A && p.num_steps == 0) {
-        const size_t o = (size_t)m * A + lane;
-        a_cat0 = p.cat[o]; a_mean0 = p.mean[o]; a_sigma0 = p.sigma[o]; a_pcode0 = p.pcode[o]; a_poff0 = p.poff[o];
-    }
+    // ---- loads are issued where their values are first needed (anything loaded far ahead of its use is
+    //      spilled by the register allocator, and the spill store then waits for the load)
     long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct);
     long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A;
     int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
     unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
-    CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0};
 #if CDA_EARLY_ACCT
     if (lane < A) {
         ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
-        ac.prev_nav = g_prev[lane]; ac.max_nav = g_max[lane]; ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
+        ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
     }
 #endif
     if (lane == 0) mbar_init(bar, 1);
@@ -615,8 +611,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const uint4 h0 = *reinterpret_cast<const uint4 *>(hdr + 0);
     const uint4 h1 = *reinterpret_cast<const uint4 *>(hdr + 4);
     const uint4 h2 = *reinterpret_cast<const uint4 *>(hdr + 8);
-    const ulonglong2 r0 = *reinterpret_cast<const ulonglong2 *>(hdr + 12);
-    const ulonglong2 r1 = *reinterpret_cast<const ulonglong2 *>(hdr + 16);
     const uint2 hb = *reinterpret_cast<const uint2 *>(hdr + 40);     // best bid / best ask after the previous step (0 = none)
 
     CdaMkt<CAP> k;
@@ -633,7 +627,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     k.nb = (int)h2.x; k.na = (int)h2.y;
     CdaRng rng;
     rng.has32 = h2.z; rng.u32 = h2.w;
-    rng.shi = r0.x; rng.slo = r0.y; rng.ihi = r1.x; rng.ilo = r1.y;
     k.tape_px = last_price;
     k.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
@@ -653,9 +646,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const int W_old = cfg.W - CDA_SNAPSHOT_DIM;       // obs elements that come from older snapshots
 
     bool waited = !have_pool;
-    const int n_iter = p.num_steps > 0 ? p.num_steps : 1;
+    long long nav_max_carry = 0, nav_prev_carry = 0;   // multi-step rollout: carry max_nav / prev_nav between steps
+    const int n_iter = ROLLOUT ? p.num_steps : 1;
     for (int it = 0; it < n_iter; ++it) {
-        const bool last_it = it == n_iter - 1;
+        const bool last_it = !ROLLOUT || it == n_iter - 1;
         const int slot_new = (int)(t_step % (unsigned)cfg.n_hist);
         float hv[CDA_HIST_PREFETCH];
 #if CDA_EARLY_HIST
@@ -675,7 +669,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // ================= set_actions: action_helper.py:145-172, :241-397 =================
         int a_cat = -1, a_pcode = 0, a_poff = 1; float a_mean = 0.f, a_sigma = 0.f;
         if (lane < A) {
-            if (p.num_steps > 0) {   // fused uniform random policy (model_handler.py:38-78)
+            if (ROLLOUT) {   // fused uniform random policy (model_handler.py:38-78)
                 const unsigned long long h = splitmix64(p.policy_seed ^ splitmix64(((unsigned long long)m << 32) ^ ((unsigned long long)(t_step) * 64ULL + lane)));
                 a_cat = (int)(((h & 0xffffu) * 9u) >> 16);
                 a_pcode = (int)((((h >> 16) & 0xffffu) * 10u) >> 16);
@@ -684,11 +678,17 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 a_mean = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
                 a_sigma = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
             } else {
-                a_cat = a_cat0; a_mean = a_mean0; a_sigma = a_sigma0; a_pcode = a_pcode0; a_poff = a_poff0;
+                const size_t o = (size_t)m * A + lane;
+                a_cat = p.cat[o]; a_mean = p.mean[o]; a_sigma = p.sigma[o]; a_pcode = p.pcode[o]; a_poff = p.poff[o];
             }
         }
+        if (!ROLLOUT || it == 0) {   // the generator is needed from here on (not earlier)
+            const ulonglong2 r0 = *reinterpret_cast<const ulonglong2 *>(hdr + 12);
+            const ulonglong2 r1 = *reinterpret_cast<const ulonglong2 *>(hdr + 16);
+            rng.shi = r0.x; rng.slo = r0.y; rng.ihi = r1.x; rng.ilo = r1.y;
+        }
         k.n_fills = 0;
-        ac.tr_step = ac.pas_step = ac.placed = ac.rejected = ac.is_pass = 0;
+        ac.ctr = 0;
         const bool bad = lane < A && (a_cat > 8 || (a_cat > 0 && ((a_cat - 1) & 3) != 0 && (a_pcode < 0 || a_pcode >= CDA_K_ROWS || a_poff < 0 || a_poff > 2)));
         if (__any_sync(CDA_FULL, bad)) k.status |= CDA_ST_BAD_ACTION;
         if (a_cat > 8) a_cat = 0;
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 #if !CDA_EARLY_ACCT
         if (it == 0 && lane < A) {   // accounts: needed from do_actions on; the shuffle below covers their latency
             ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
-            ac.prev_nav = g_prev[lane]; ac.max_nav = g_max[lane]; ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
+            ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
         }
 #endif
         CDA_TICK(11);  // draws done
@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const float loc = __fmul_rn(a_type == 0 ? cfg.mkt_mul : cfg.lim_mul, a_mean);  // f32 product (NEP 50)
             const double x = (double)loc + (double)a_sigma * z;                              // numpy: loc + scale*z
             a_size = __double2ll_rn(fabs(x)) + cfg.min_size;                                 // rint half-even, :339, :276
-            if (a_cat == 0) ac.is_pass = 1;
+            if (a_cat == 0) ac.ctr |= 1u << 26;
             if (a_side >= 0 && a_type != 0) {            // _set_price :341-397 on the frozen pre-step top-K
                 const int raw = (int)SMW(wb + L::TOPK + a_side * CDA_K_ROWS + a_pcode);
                 const int off = a_poff - 1;
@@ -757,6 +757,13 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         if (__any_sync(CDA_FULL, a_price >= (int)CDA_PRICE_MASK)) { k.status |= CDA_ST_PRICE_RANGE; if (a_price >= (int)CDA_PRICE_MASK) a_price = CDA_PRICE_MASK - 1; }
 
         CDA_TICK(1);   // accounts + actions arrived, draws + decode done
+        // park the decoded actions in shared memory: the matching phase reads them with uniform loads, and the
+        // dozen registers they occupied are free while the book is being worked on
+        if (lane < A && a_side >= 0) {
+            SMW(wb + L::ACT + 3 * lane) = (unsigned)a_type | ((unsigned)a_side << 8);
+            SMW(wb + L::ACT + 3 * lane + 1) = (unsigned)a_size;
+            SMW(wb + L::ACT + 3 * lane + 2) = (unsigned)a_price;
+        }
         // ================= rand_exec_seq: action_helper.py:174-199 ==========================
         const unsigned active = __ballot_sync(CDA_FULL, lane < A && a_side >= 0);
         const int n_act = __popc(active);
@@ -779,11 +786,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // ================= do_actions: action_helper.py:201-239 =============================
         for (int q = 0; q < n_act; ++q) {
             const int t = (int)SMW(wb + L::ORDER + q);
-            const int type = __shfl_sync(CDA_FULL, a_type, t);
-            const int side = __shfl_sync(CDA_FULL, a_side, t);
-            const long long size = __shfl_sync(CDA_FULL, a_size, t);
-            const int price = __shfl_sync(CDA_FULL, a_price, t);
-            place_order(k, ac, t, type, side, size, price);
+            const unsigned ts_ = SMW(wb + L::ACT + 3 * t);
+            const long long size = (long long)SMW(wb + L::ACT + 3 * t + 1);
+            const int price = (int)SMW(wb + L::ACT + 3 * t + 2);
+            place_order(k, ac, t, (int)(ts_ & 0xffu), (int)(ts_ >> 8), size, price);
         }
 
 #if !CDA_EARLY_HIST && !CDA_LATE_HIST
@@ -803,16 +809,18 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 #endif
         CDA_TICK(4);   // do_actions done
         // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
+        long long nav_prev = ac.nav, nav_max = 0;   // calculate.py:49-51: prev_nav = nav (only when a tape exists)
+        if (lane < A) nav_max = (!ROLLOUT || it == 0) ? g_max[lane] : nav_max_carry;
         if (k.tape_nonempty) {
             last_price = k.tape_px;
             if (lane < A) {
                 const long long ap = ac.pos < 0 ? -ac.pos : ac.pos;
                 const long long pv = ac.pos >= 0 ? ap * last_price : 2 * ac.cost - ap * last_price;
-                ac.prev_nav = ac.nav;
                 ac.nav = ac.cash + ac.hold + pv;
-                if (ac.nav > ac.max_nav) ac.max_nav = ac.nav;
+                if (ac.nav > nav_max) nav_max = ac.nav;
             }
-        }
+        } else if (lane < A) nav_prev = (!ROLLOUT || it == 0) ? g_prev[lane] : nav_prev_carry;   // never marked yet: keep the stored value
+        nav_max_carry = nav_max; nav_prev_carry = nav_prev;
 
         // ================= set_agg_LOB: state_helper.py:113-214 =============================
         // Top-K levels per side in ONE sweep: the distinct prices within 64 ticks of the best form
@@ -952,15 +960,15 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // ================= set_reward / set_done: reward_helper.py:35-103, done_helper.py ===
         bool broke = false;
         if (lane < A) {
-            const double nav_change = (double)(ac.nav - ac.prev_nav);
+            const double nav_change = (double)(ac.nav - nav_prev);
             const double nav_term = nav_change * (nav_change < 0 ? cfg.c_loss : 1.0);
-            long long ddi = ac.max_nav - ac.nav; if (ddi < 0) ddi = 0;
+            long long ddi = nav_max - ac.nav; if (ddi < 0) ddi = 0;
             double r = 0.0;
             r = r + nav_term;
-            r = r + -(cfg.c_order * (double)ac.placed);
-            r = r + -(cfg.c_trade * (double)ac.tr_step);
+            r = r + -(cfg.c_order * (double)((ac.ctr >> 24) & 1u));
+            r = r + -(cfg.c_trade * (double)(ac.ctr & 0xfffu));
             r = r + -(cfg.c_dd * (double)ddi);
-            r = r + cfg.c_passive * (double)ac.pas_step;
+            r = r + cfg.c_passive * (double)((ac.ctr >> 12) & 0xfffu);
             if (p.reward && last_it) {
                 if (p.gather_world > 0) {
                     const size_t off = (size_t)p.gather_rows * cfg.W * 4 + ((size_t)(p.gather_row0 + m) * A + lane) * 8;
@@ -985,7 +993,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
         t_step++;
         __syncwarp();
-        if (!last_it) {    // multi-step rollout: bring the generator back for the next step's draws
+        if (ROLLOUT && !last_it) {    // multi-step rollout: bring the generator back for the next step's draws
             const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wb + L::PARK]);
             rng.shi = pk[0]; rng.slo = pk[1]; rng.ihi = pk[2]; rng.ilo = pk[3];
             rng.has32 = SMW(wb + L::PARK + 8); rng.u32 = SMW(wb + L::PARK + 9);
@@ -1004,9 +1012,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     }
     if (lane < A) {
         g_cash[lane] = ac.cash; g_hold[lane] = ac.hold; g_cost[lane] = ac.cost; g_nav[lane] = ac.nav;
-        g_prev[lane] = ac.prev_nav; g_max[lane] = ac.max_nav; g_pos[lane] = (int)ac.pos; g_ntr[lane] = ac.ntr;
-        g_ctr[lane] = (ac.tr_step & 0xfffu) | ((ac.pas_step & 0xfffu) << 12) | ((ac.placed & 1u) << 24) |
-                      ((ac.rejected & 1u) << 25) | ((ac.is_pass & 1u) << 26);
+        g_prev[lane] = nav_prev_carry; g_max[lane] = nav_max_carry; g_pos[lane] = (int)ac.pos; g_ntr[lane] = ac.ntr;
+        g_ctr[lane] = ac.ctr;
     }
 #if CDA_BULK_STORE
     fence_proxy_async();
