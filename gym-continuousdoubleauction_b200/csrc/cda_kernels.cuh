@@ -116,19 +116,24 @@ __device__ __forceinline__ unsigned rng_u32(CdaRng &r) {
 __device__ __forceinline__ double rng_double(CdaRng &r) {
     return (double)(rng_u64(r) >> 11) * (1.0 / 9007199254740992.0);
 }
-__device__ __noinline__ double rng_normal_slow(CdaRng &g, int idx, unsigned long long rabs, double x) {
-    // wedge / tail of the ziggurat (~1.2 % of draws); may recurse into fresh draws
+// wedge / tail of the ziggurat (~1.2 % of draws); may consume further numbers.  Takes and returns the
+// generator BY VALUE: a by-reference parameter of a non-inlined function would force the caller's
+// generator state into local memory for the whole kernel.
+struct CdaNormalRet { double x; unsigned long long shi, slo; };
+__device__ __noinline__ CdaNormalRet rng_normal_slow(unsigned long long shi, unsigned long long slo, unsigned long long ihi,
+                                                     unsigned long long ilo, int idx, unsigned long long rabs, double x) {
+    CdaRng g; g.shi = shi; g.slo = slo; g.ihi = ihi; g.ilo = ilo; g.has32 = 0; g.u32 = 0;
     for (;;) {
         if (idx == 0) {
             for (;;) {
                 double xx = -CDA_ZIG_NOR_INV_R * log1p(-rng_double(g));
                 double yy = -log1p(-rng_double(g));
                 if (yy + yy > xx * xx)
-                    return ((rabs >> 8) & 1ULL) ? -(CDA_ZIG_NOR_R + xx) : CDA_ZIG_NOR_R + xx;
+                    return CdaNormalRet{((rabs >> 8) & 1ULL) ? -(CDA_ZIG_NOR_R + xx) : CDA_ZIG_NOR_R + xx, g.shi, g.slo};
             }
         } else {
             double u = rng_double(g);
-            if (((cda_zig_fi[idx - 1] - cda_zig_fi[idx]) * u + cda_zig_fi[idx]) < exp(-0.5 * x * x)) return x;
+            if (((cda_zig_fi[idx - 1] - cda_zig_fi[idx]) * u + cda_zig_fi[idx]) < exp(-0.5 * x * x)) return CdaNormalRet{x, g.shi, g.slo};
         }
         unsigned long long r = rng_u64(g);
         idx = (int)(r & 0xff);
@@ -137,7 +142,7 @@ __device__ __noinline__ double rng_normal_slow(CdaRng &g, int idx, unsigned long
         rabs = (r >> 1) & 0x000fffffffffffffULL;
         x = (double)rabs * cda_zig_wi[idx];
         if (sign) x = -x;
-        if (rabs < cda_zig_ki[idx]) return x;
+        if (rabs < cda_zig_ki[idx]) return CdaNormalRet{x, g.shi, g.slo};
     }
 }
 __device__ __forceinline__ double rng_normal(CdaRng &g) {
@@ -149,7 +154,9 @@ __device__ __forceinline__ double rng_normal(CdaRng &g) {
     double x = (double)rabs * cda_zig_wi[idx];
     if (sign) x = -x;
     if (rabs < cda_zig_ki[idx]) return x;
-    return rng_normal_slow(g, idx, rabs, x);
+    const CdaNormalRet rr = rng_normal_slow(g.shi, g.slo, g.ihi, g.ilo, idx, rabs, x);
+    g.shi = rr.shi; g.slo = rr.slo;
+    return rr.x;
 }
 __device__ __forceinline__ unsigned rng_interval(CdaRng &r, unsigned max) {
     if (max == 0) return 0;
