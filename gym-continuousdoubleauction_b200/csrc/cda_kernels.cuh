@@ -329,7 +329,7 @@ struct CdaMkt {
     unsigned time, next_id, seqctr, status;
     int tape_nonempty, tape_px;
     int lane;
-    int *fills; int fill_cap, n_fills;
+    int *fills_base; int fill_cap, n_fills, mkt;   // fill log: row = fills_base + mkt * fill_cap * 8 (computed when a fill happens)
     __device__ __forceinline__ int side_w(int side) const { return pool_w + side * (CDA_POOL_FIELDS * CAP); }
     __device__ __forceinline__ int count(int side) const { return side ? na : nb; }
     __device__ __forceinline__ void set_count(int side, int v) { if (side) na = v; else nb = v; }
@@ -517,12 +517,13 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
             qty -= traded;
         }
         k.tape_nonempty = 1; k.tape_px = P;   // :140 tape.append (trade price = resting price)
-        if (k.fills) {
+        if (k.fills_base) {
             if (k.n_fills < k.fill_cap) {
                 if (k.lane < CDA_FILL_WORDS) {
+                    int *frow = k.fills_base + (size_t)k.mkt * k.fill_cap * CDA_FILL_WORDS;
                     const int v = k.lane == 0 ? (int)k.time : k.lane == 1 ? P : k.lane == 2 ? (int)traded : k.lane == 3 ? maker
                                 : k.lane == 4 ? (int)moid : k.lane == 5 ? left : k.lane == 6 ? t : side;
-                    k.fills[k.n_fills * CDA_FILL_WORDS + k.lane] = v;
+                    frow[k.n_fills * CDA_FILL_WORDS + k.lane] = v;
                 }
             } else k.status |= CDA_ST_FILL_OVERFLOW;
         }
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     CdaRng rng;
     rng.has32 = h2.z; rng.u32 = h2.w;
     k.tape_px = last_price;
-    k.fills = p.fills ? p.fills + (size_t)m * cfg.fill_cap * CDA_FILL_WORDS : nullptr;
+    k.fills_base = p.fills; k.mkt = m;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
     k.bestb = k.nb ? (hb.x ? (int)hb.x : -2) : -1; k.besta = k.na ? (hb.y ? (int)hb.y : -2) : -1;
 
@@ -657,9 +658,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const int n_iter = ROLLOUT ? p.num_steps : 1;
     for (int it = 0; it < n_iter; ++it) {
         const bool last_it = !ROLLOUT || it == n_iter - 1;
-        const int slot_new = (int)(t_step % (unsigned)cfg.n_hist);
         float hv[CDA_HIST_PREFETCH];
+        int slot_new = 0;
 #if CDA_EARLY_HIST
+        slot_new = (int)(t_step % (unsigned)cfg.n_hist);
         if (p.obs && last_it) {
 #pragma unroll
             for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
@@ -800,6 +802,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
 
 #if !CDA_EARLY_HIST && !CDA_LATE_HIST
+        slot_new = (int)(t_step % (unsigned)cfg.n_hist);
         // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90): latency hides behind mtm + top-K
         if (p.obs && last_it) {
 #pragma unroll
@@ -891,6 +894,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             }
         }
 #if !CDA_EARLY_HIST && CDA_LATE_HIST
+        slot_new = (int)(t_step % (unsigned)cfg.n_hist);
         // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90): latency hides behind the f32/f64 observation math
         if (p.obs && last_it) {
 #pragma unroll
