@@ -566,12 +566,12 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #define CDA_BEST_CACHE 1
 #endif
 #ifndef CDA_EARLY_ACCT
-#define CDA_EARLY_ACCT 1      /* 1: load the accounts at kernel entry (measured best); 0: after the normal draws (the RNG phase is the
+#define CDA_EARLY_ACCT 0      /* 1: load the accounts at kernel entry; 0 (measured best once spills were gone): after the normal draws (the RNG phase is the
                                  register-pressure peak: values loaded before it get spilled, and the spill store has
                                  to wait for the load, exposing its latency) */
 #endif
 #ifndef CDA_LATE_HIST
-#define CDA_LATE_HIST 0       /* 1: fetch the older snapshots after the top-K sweep instead of after do_actions (no gain measured) */
+#define CDA_LATE_HIST 1       /* 1: fetch the older snapshots after the top-K sweep instead of after do_actions */
 #endif
 #ifndef CDA_EARLY_HIST
 #define CDA_EARLY_HIST 0      /* 1: fetch the older snapshots at the top of the step, 0: after the matching phase */
