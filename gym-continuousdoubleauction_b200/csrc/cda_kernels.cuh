@@ -612,8 +612,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     }
 #endif
     if (lane == 0) mbar_init(bar, 1);
-    if (lane < 2 * CDA_K_ROWS) SMW(wb + L::TOPK + lane) = hdr[20 + lane];
-    __syncwarp();
+    const unsigned tk0 = lane < 2 * CDA_K_ROWS ? hdr[20 + lane] : 0u;   // consumed below, after the header loads are in flight
 
     // ---- header (warp-uniform 128-bit loads: one request each, value in every lane)
     const uint4 h0 = *reinterpret_cast<const uint4 *>(hdr + 0);
@@ -621,6 +620,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const uint4 h2 = *reinterpret_cast<const uint4 *>(hdr + 8);
     const uint2 hb = *reinterpret_cast<const uint2 *>(hdr + 40);     // best bid / best ask after the previous step (0 = none)
 
+    if (lane < 2 * CDA_K_ROWS) SMW(wb + L::TOPK + lane) = tk0;
+    __syncwarp();
     CdaMkt<CAP> k;
     k.lane = lane;
     if (h0.x == 0xffffffffu) return;  // (keeps the header loads ahead of the first tick)
@@ -818,19 +819,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
 #endif
         CDA_TICK(4);   // do_actions done
-        // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
-        long long nav_prev = ac.nav, nav_max = 0;   // calculate.py:49-51: prev_nav = nav (only when a tape exists)
-        if (lane < A) nav_max = (!ROLLOUT || it == 0) ? g_max[lane] : nav_max_carry;
-        if (k.tape_nonempty) {
-            last_price = k.tape_px;
-            if (lane < A) {
-                const long long ap = ac.pos < 0 ? -ac.pos : ac.pos;
-                const long long pv = ac.pos >= 0 ? ap * last_price : 2 * ac.cost - ap * last_price;
-                ac.nav = ac.cash + ac.hold + pv;
-                if (ac.nav > nav_max) nav_max = ac.nav;
-            }
-        } else if (lane < A) nav_prev = (!ROLLOUT || it == 0) ? g_prev[lane] : nav_prev_carry;   // never marked yet: keep the stored value
-        nav_max_carry = nav_max; nav_prev_carry = nav_prev;
+        // mark-to-market needs max_nav / prev_nav from the state block: issue those loads now, do the top-K sweep
+        // (which does not depend on the accounts), then mark to market
+        long long ld_max = 0, ld_prev = 0;
+        if (lane < A && (!ROLLOUT || it == 0)) { ld_max = g_max[lane]; ld_prev = g_prev[lane]; }
+        if (k.tape_nonempty) last_price = k.tape_px;   // exchg_helper.py:62-63 (the snapshot's midpoint fallback reads it)
 
         // ================= set_agg_LOB: state_helper.py:113-214 =============================
         // Top-K levels per side in ONE sweep: the distinct prices within 64 ticks of the best form
@@ -909,7 +902,18 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             }
         }
 #endif
-        CDA_TICK(5);   // mtm + top-K levels done
+        // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
+        long long nav_prev = ac.nav, nav_max = (!ROLLOUT || it == 0) ? ld_max : nav_max_carry;   // calculate.py:49-51
+        if (k.tape_nonempty) {
+            if (lane < A) {
+                const long long ap = ac.pos < 0 ? -ac.pos : ac.pos;
+                const long long pv = ac.pos >= 0 ? ap * last_price : 2 * ac.cost - ap * last_price;
+                ac.nav = ac.cash + ac.hold + pv;
+                if (ac.nav > nav_max) nav_max = ac.nav;
+            }
+        } else nav_prev = (!ROLLOUT || it == 0) ? ld_prev : nav_prev_carry;   // never marked yet: keep the stored value
+        nav_max_carry = nav_max; nav_prev_carry = nav_prev;
+        CDA_TICK(5);   // top-K levels + mtm done
         const int best_bid = __shfl_sync(CDA_FULL, myP, 0), best_ask = __shfl_sync(CDA_FULL, myP, CDA_K_ROWS);
         double Mid;
         if (best_bid > 0 && best_ask > 0) Mid = ((double)best_bid + (double)best_ask) / 2.0;
