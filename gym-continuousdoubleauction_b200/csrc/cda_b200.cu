@@ -305,6 +305,57 @@ int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean
     return CDA_OK;
 }
 
+static void *mapped_alias(const void *h) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    cudaGetLastError();
+    return nullptr;
+}
+
+int cda_step_host_ring(CdaEnv *e, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                       const int32_t *h_price, const int32_t *h_price_offset, float *h_ring, double *h_reward,
+                       uint8_t *h_terminated, uint8_t *h_truncated, int64_t ring_pos, void *stream) {
+    if (!e || !h_category || !h_size_mean || !h_size_sigma || !h_price || !h_price_offset || !h_ring || !h_reward || !h_terminated || !h_truncated) return CDA_EINVAL;
+    if (!e->was_reset) return CDA_ESTATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t MA = (size_t)e->M * e->dev.A;
+    // all host buffers must be pinned + mapped: the kernel reads the actions and writes the outputs in place
+    static thread_local const void *c_key[6] = {nullptr}; static thread_local void *c_val[6] = {nullptr};
+    const void *hp[6] = {h_category, h_ring, h_reward, h_terminated, h_truncated, nullptr};
+    void *dp[5];
+    for (int i = 0; i < 5; ++i) {
+        if (c_key[i] != hp[i]) { c_key[i] = hp[i]; c_val[i] = mapped_alias(hp[i]); }
+        dp[i] = c_val[i];
+        if (!dp[i]) return CDA_EINVAL;
+    }
+    const char *hc = reinterpret_cast<const char *>(h_category);
+    if (!(reinterpret_cast<const char *>(h_size_mean) == hc + MA * 4 && reinterpret_cast<const char *>(h_size_sigma) == hc + 2 * MA * 4 &&
+          reinterpret_cast<const char *>(h_price) == hc + 3 * MA * 4 && reinterpret_cast<const char *>(h_price_offset) == hc + 4 * MA * 4)) return CDA_EINVAL;
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    char *zi = reinterpret_cast<char *>(dp[0]);
+    p.cat = reinterpret_cast<const int *>(zi); p.mean = reinterpret_cast<const float *>(zi + MA * 4);
+    p.sigma = reinterpret_cast<const float *>(zi + 2 * MA * 4); p.pcode = reinterpret_cast<const int *>(zi + 3 * MA * 4);
+    p.poff = reinterpret_cast<const int *>(zi + 4 * MA * 4);
+    p.ring_out = reinterpret_cast<float *>(dp[1]);
+    p.ring_slot = (int)(((ring_pos % e->dev.n_hist) + e->dev.n_hist) % e->dev.n_hist);
+    p.reward = reinterpret_cast<double *>(dp[2]); p.term = reinterpret_cast<unsigned char *>(dp[3]); p.trunc = reinterpret_cast<unsigned char *>(dp[4]);
+    return step_common(e, p, st);
+}
+
+int cda_reset_host_ring(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_ring, void *stream) {
+    if (!e || !h_ring) return CDA_EINVAL;
+    void *dr = mapped_alias(h_ring);
+    if (!dr) return CDA_EINVAL;
+    int rc = cda_reset(e, d_seeds, d_mask, nullptr, stream);
+    if (rc) return rc;
+    const int n = e->M * 2 * e->dev.n_hist * CDA_SNAPSHOT_DIM, threads = 256;
+    cda_ring_fill_kernel<<<(n + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, d_mask, reinterpret_cast<float *>(dr));
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return CDA_OK;
+}
+
 int cda_rollout_random(CdaEnv *e, int32_t num_steps, uint64_t policy_seed, float *d_obs, double *d_reward,
                        uint8_t *d_terminated, uint8_t *d_truncated, void *stream) {
     if (!e || num_steps < 1) return CDA_EINVAL;

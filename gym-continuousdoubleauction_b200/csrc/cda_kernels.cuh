@@ -78,6 +78,7 @@ struct CdaStepParams {
     // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
     int num_steps; unsigned long long policy_seed;
     unsigned long long *prof;   // CDA_PROFILE_PHASES builds: per-phase cycle sums [16]
+    float *ring_out; int ring_slot;   // mirrored host ring: newest snapshot only, at slots ring_slot and ring_slot + n_hist
     // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
     int gather_world, gather_row0, gather_rows;
     unsigned char *gather_peer[CDA_MAX_PEERS];
@@ -968,6 +969,13 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) o[W_old + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
             }
         }
+        if (p.ring_out && last_it) {   // mirrored host ring: 2 x 42 floats instead of the 168-float stack
+            float *rg = p.ring_out + (size_t)m * (2 * cfg.n_hist * CDA_SNAPSHOT_DIM) + p.ring_slot * CDA_SNAPSHOT_DIM;
+            for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) {
+                const float v = __uint_as_float(SMW(wb + L::SNAP + cc));
+                rg[cc] = v; rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
+            }
+        }
         __syncwarp();
         for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
 
@@ -1100,6 +1108,18 @@ __global__ void cda_reset_kernel(CdaDevCfg cfg, unsigned char *state, int M, con
             g_hist[h * CDA_SNAPSHOT_DIM + cc] = v;
             if (obs) obs[(size_t)m * cfg.W + h * CDA_SNAPSHOT_DIM + cc] = v;
         }
+}
+
+// fill every slot of the mirrored host ring of the selected markets with their current newest snapshot
+// (after a reset all device ring slots hold the initial snapshot)
+__global__ void cda_ring_fill_kernel(CdaDevCfg cfg, const unsigned char *state, int M, const unsigned char *mask, float *ring) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = 2 * cfg.n_hist * CDA_SNAPSHOT_DIM;
+    if (i >= M * per) return;
+    const int m = i / per, e = i - m * per;
+    if (mask && !mask[m]) return;
+    const float *g_hist = reinterpret_cast<const float *>(state + (size_t)m * cfg.stride + cfg.off_hist);
+    ring[i] = g_hist[e % CDA_SNAPSHOT_DIM];   // slot 0 (all slots are equal right after a reset)
 }
 
 // ------------------------------------------------------------------------------------------

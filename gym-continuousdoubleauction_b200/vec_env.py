@@ -159,6 +159,53 @@ class VecCDAEnv:
             torch.cuda.current_stream(self.device).synchronize()
         return self._out_np
 
+    # ---- mirrored host ring: the kernel ships only the newest snapshot; the stacked obs is a strided view
+    def _ensure_ring(self):
+        if getattr(self, "_ring", None) is None:
+            M, A, H = self.M, self.A, self.n_hist
+            self._ring = torch.empty((M, 2 * H * SNAPSHOT_DIM), dtype=torch.float32, pin_memory=True)
+            tail = torch.empty(M * A * 8 + 2 * M, dtype=torch.uint8, pin_memory=True)
+            self._ring_rew = tail[:M * A * 8].view(torch.float64).view(M, A)
+            self._ring_term, self._ring_trunc = tail[M * A * 8:M * A * 8 + M], tail[M * A * 8 + M:]
+            self._ring_np = self._ring.numpy()
+            self._ring_out_np = (self._ring_rew.numpy(), self._ring_term.numpy(), self._ring_trunc.numpy())
+            self._ring_ptrs = tuple(_ptr(t) for t in (self._ring, self._ring_rew, self._ring_term, self._ring_trunc))
+            self._ring_pos = -1
+        return self._ring
+
+    def _ring_view(self):
+        s0 = ((self._ring_pos % self.n_hist) + 1) * SNAPSHOT_DIM
+        return self._ring_np[:, s0:s0 + self.W]          # [M, n_hist*42], oldest snapshot first, zero-copy
+
+    def reset_host_ring(self, seed=None, mask=None):
+        """reset() for the ring host path: returns the stacked observation as a view of the pinned ring."""
+        self._ensure_ring()
+        seeds_t = None
+        if seed is not None:
+            seeds = (np.arange(self.M, dtype=np.uint64) + np.uint64(seed)) if isinstance(seed, (int, np.integer)) \
+                else np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed).astype(np.uint64)
+            seeds_t = torch.from_numpy(seeds.view(np.int64)).to(self.device)
+        mask_t = None if mask is None else torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        _native.check(self._L.cda_reset_host_ring(self._h, _ptr(seeds_t), _ptr(mask_t), self._ring_ptrs[0], self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._ring_view()
+
+    def step_host_ring(self, action_block, sync=True):
+        """Like step_host_block, but only the newest 42-float snapshot of every market crosses PCIe (twice,
+        mirrored); the returned obs is a strided numpy view [M, n_hist*42] of the pinned ring (row stride
+        2*n_hist*42 floats), bit-identical to step_host_block's obs.  Valid until the next call."""
+        self._ensure_ring()
+        self._ring_pos += 1
+        base = action_block.data_ptr()
+        n = self.M * self.A * 4
+        vp = ctypes.c_void_p
+        _native.check(self._L.cda_step_host_ring(self._h, vp(base), vp(base + n), vp(base + 2 * n), vp(base + 3 * n), vp(base + 4 * n),
+                                                 self._ring_ptrs[0], self._ring_ptrs[1], self._ring_ptrs[2], self._ring_ptrs[3],
+                                                 ctypes.c_int64(self._ring_pos), self._stream()))
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return (self._ring_view(),) + self._ring_out_np
+
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""
         p = self._ensure_pinned()

@@ -111,6 +111,19 @@ int cda_step_host(CdaEnv *env, const int32_t *h_category, const float *h_size_me
                   const int32_t *h_price, const int32_t *h_price_offset, float *h_obs, double *h_reward,
                   uint8_t *h_terminated, uint8_t *h_truncated, void *stream);
 
+/* Host path with a MIRRORED OBSERVATION RING (halves-and-more the PCIe traffic of cda_step_host):
+ * the stacked observation is n_hist snapshots of 42 floats of which only the newest is new each step, so
+ * the host keeps, per market, a ring of 2*n_hist snapshot slots  h_ring f32[M][2*n_hist][42]  (pinned +
+ * mapped).  Each step the kernel stores ONLY the newest snapshot, at slots `pos` and `pos + n_hist`
+ * (pos = ring_pos mod n_hist); the stacked observation of every market is then the contiguous window of
+ * n_hist slots starting at slot pos + 1 — a zero-copy strided view, oldest snapshot first, identical to
+ * cda_step_host's obs.  cda_reset_host_ring resets markets and fills all their slots with the initial
+ * snapshot.  The caller advances ring_pos by one per step (any start value). */
+int cda_step_host_ring(CdaEnv *env, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                       const int32_t *h_price, const int32_t *h_price_offset, float *h_ring, double *h_reward,
+                       uint8_t *h_terminated, uint8_t *h_truncated, int64_t ring_pos, void *stream);
+int cda_reset_host_ring(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_ring, void *stream);
+
 /* Fused T-step rollout with the on-device uniform random policy (the RandomRLModule /
  * CDA_rand.py workload: category U{0..8}, price U{0..9}, offset U{0..2}, mean U(-1,1), sigma U(0,1),
  * gym_continuousDoubleAuction/train/model/model_handler.py:38-78).  Policy draws come from a

@@ -173,3 +173,47 @@ def test_checkpoint_roundtrip():
     for i, t in enumerate(range(20, 40)):
         assert torch.equal(env.step(*dev(t))[0], ref[i])
     env.close()
+
+
+def test_host_ring_view_equals_stacked_obs_including_masked_reset():
+    """cda_step_host_ring ships only the newest snapshot (mirrored); the strided ring view must equal the
+    stacked observation of the ordinary host path bit for bit, also across per-market resets."""
+    cfg = base_cfg(n_hist=4)
+    M = 96
+    e1 = cda.VecCDAEnv(cfg, num_markets=M); e2 = cda.VecCDAEnv(cfg, num_markets=M)
+    o1 = e1.reset(seed=11).cpu().numpy(); o2 = e2.reset_host_ring(seed=11)
+    assert np.array_equal(o1, o2)
+    acts = make_actions(6, 40, M, 4, "uniform")
+    blk = torch.empty((40, 5, M, 4), dtype=torch.int32, pin_memory=True)
+    for f in (0, 3, 4):
+        blk[:, f].copy_(torch.from_numpy(acts[f]))
+    for f in (1, 2):
+        blk[:, f].view(torch.float32).copy_(torch.from_numpy(acts[f]))
+    for t in range(40):
+        if t == 17:
+            mask = (np.arange(M) % 3 == 0).astype(np.uint8)
+            a = e1.reset(seed=None, mask=mask).cpu().numpy(); b = e2.reset_host_ring(seed=None, mask=mask)
+            assert np.array_equal(a[mask == 1], b[mask == 1])
+        o1, r1, te1, tr1 = e1.step_host_block(blk[t])
+        o2, r2, te2, tr2 = e2.step_host_ring(blk[t])
+        assert o2.shape == (M, 168) and np.array_equal(o1, o2), f"t={t}"
+        assert np.array_equal(r1, r2) and np.array_equal(te1, te2) and np.array_equal(tr1, tr2)
+    e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("n_hist", [1, 3])
+def test_host_ring_other_history_depths(n_hist):
+    cfg = base_cfg(n_hist=n_hist)
+    M = 32
+    e1 = cda.VecCDAEnv(cfg, num_markets=M); e2 = cda.VecCDAEnv(cfg, num_markets=M)
+    e1.reset(seed=5); e2.reset_host_ring(seed=5)
+    acts = make_actions(2, 12, M, 4, "limit_market")
+    blk = torch.empty((12, 5, M, 4), dtype=torch.int32, pin_memory=True)
+    for f in (0, 3, 4):
+        blk[:, f].copy_(torch.from_numpy(acts[f]))
+    for f in (1, 2):
+        blk[:, f].view(torch.float32).copy_(torch.from_numpy(acts[f]))
+    for t in range(12):
+        o1 = e1.step_host_block(blk[t])[0]; o2 = e2.step_host_ring(blk[t])[0]
+        assert np.array_equal(o1, o2)
+    e1.close(); e2.close()
