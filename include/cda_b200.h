@@ -118,7 +118,10 @@ int cda_step_host(CdaEnv *env, const int32_t *h_category, const float *h_size_me
  * (pos = ring_pos mod n_hist); the stacked observation of every market is then the contiguous window of
  * n_hist slots starting at slot pos + 1 — a zero-copy strided view, oldest snapshot first, identical to
  * cda_step_host's obs.  cda_reset_host_ring resets markets and fills all their slots with the initial
- * snapshot.  The caller advances ring_pos by one per step (any start value). */
+ * snapshot.  The caller advances ring_pos by one per step (any start value).
+ * MEASURED (B200, PCIe Gen5): no faster than cda_step_host — posted PCIe writes from the SMs are bound by the
+ * number of write transactions, and 2 x 168 B per market needs as many as one 672-B row.  Kept as an option for
+ * hosts where the byte count matters (e.g. a remote/virtualised PCIe path). */
 int cda_step_host_ring(CdaEnv *env, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
                        const int32_t *h_price, const int32_t *h_price_offset, float *h_ring, double *h_reward,
                        uint8_t *h_terminated, uint8_t *h_truncated, int64_t ring_pos, void *stream);
