@@ -601,13 +601,17 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 
     // ---- loads are issued where their values are first needed (anything loaded far ahead of its use is
     //      spilled by the register allocator, and the spill store then waits for the load)
-    long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct);
-    long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A;
-    int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
-    unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A;
+    // account arrays of this market (pointers are re-derived where needed instead of living in registers)
+#define CDA_ACCT_PTRS \
+    long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct); \
+    long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A; \
+    int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A); \
+    unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A; \
+    (void)g_hold; (void)g_cost; (void)g_nav; (void)g_prev; (void)g_max; (void)g_pos; (void)g_ntr; (void)g_ctr;
     CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0};
 #if CDA_EARLY_ACCT
     if (lane < A) {
+        CDA_ACCT_PTRS
         ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
         ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
     }
@@ -742,6 +746,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
 #if !CDA_EARLY_ACCT
         if (it == 0 && lane < A) {   // accounts: needed from do_actions on; the shuffle below covers their latency
+            CDA_ACCT_PTRS
             ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
             ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
         }
@@ -823,7 +828,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // mark-to-market needs max_nav / prev_nav from the state block: issue those loads now, do the top-K sweep
         // (which does not depend on the accounts), then mark to market
         long long ld_max = 0, ld_prev = 0;
-        if (lane < A && (!ROLLOUT || it == 0)) { ld_max = g_max[lane]; ld_prev = g_prev[lane]; }
+        if (lane < A && (!ROLLOUT || it == 0)) { CDA_ACCT_PTRS ld_max = g_max[lane]; ld_prev = g_prev[lane]; }
         if (k.tape_nonempty) last_price = k.tape_px;   // exchg_helper.py:62-63 (the snapshot's midpoint fallback reads it)
 
         // ================= set_agg_LOB: state_helper.py:113-214 =============================
@@ -1034,6 +1039,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         *reinterpret_cast<ulonglong2 *>(hdr + 16) = make_ulonglong2(pk[2], pk[3]);
     }
     if (lane < A) {
+        CDA_ACCT_PTRS
         g_cash[lane] = ac.cash; g_hold[lane] = ac.hold; g_cost[lane] = ac.cost; g_nav[lane] = ac.nav;
         g_prev[lane] = nav_prev_carry; g_max[lane] = nav_max_carry; g_pos[lane] = (int)ac.pos; g_ntr[lane] = ac.ntr;
         g_ctr[lane] = ac.ctr;
