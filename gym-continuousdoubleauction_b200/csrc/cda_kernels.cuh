@@ -134,16 +134,16 @@ __device__ __noinline__ CdaNormalRet rng_normal_slow(unsigned long long shi, uns
             }
         } else {
             double u = rng_double(g);
-            if (((cda_zig_fi[idx - 1] - cda_zig_fi[idx]) * u + cda_zig_fi[idx]) < exp(-0.5 * x * x)) return CdaNormalRet{x, g.shi, g.slo};
+            if (((__ldg(&cda_zig_fi[idx - 1]) - __ldg(&cda_zig_fi[idx])) * u + __ldg(&cda_zig_fi[idx])) < exp(-0.5 * x * x)) return CdaNormalRet{x, g.shi, g.slo};
         }
         unsigned long long r = rng_u64(g);
         idx = (int)(r & 0xff);
         r >>= 8;
         int sign = (int)(r & 1ULL);
         rabs = (r >> 1) & 0x000fffffffffffffULL;
-        x = (double)rabs * cda_zig_wi[idx];
+        x = (double)rabs * __ldg(&cda_zig_wi[idx]);
         if (sign) x = -x;
-        if (rabs < cda_zig_ki[idx]) return CdaNormalRet{x, g.shi, g.slo};
+        if (rabs < __ldg(&cda_zig_ki[idx])) return CdaNormalRet{x, g.shi, g.slo};
     }
 }
 __device__ __forceinline__ double rng_normal(CdaRng &g) {
@@ -152,9 +152,9 @@ __device__ __forceinline__ double rng_normal(CdaRng &g) {
     r >>= 8;
     int sign = (int)(r & 1ULL);
     unsigned long long rabs = (r >> 1) & 0x000fffffffffffffULL;
-    double x = (double)rabs * cda_zig_wi[idx];
+    double x = (double)rabs * __ldg(&cda_zig_wi[idx]);
     if (sign) x = -x;
-    if (rabs < cda_zig_ki[idx]) return x;
+    if (rabs < __ldg(&cda_zig_ki[idx])) return x;
     const CdaNormalRet rr = rng_normal_slow(g.shi, g.slo, g.ihi, g.ilo, idx, rabs, x);
     g.shi = rr.shi; g.slo = rr.slo;
     return rr.x;
@@ -185,9 +185,10 @@ __device__ __forceinline__ long long rng_integers(CdaRng &r, long long lo, long 
 // LCG jump-ahead table: after r steps  state_r = A^r * state + G_r * inc  (mod 2^128) with
 // G_r = 1 + A + ... + A^(r-1).  Row r = {A^r hi, A^r lo, G_r hi, G_r lo}; filled by cda_create.
 // Lets lane a evaluate "its" draw of the sequential numpy stream without waiting for lanes < a.
-__constant__ unsigned long long cda_pcg_jump[CDA_MAX_AGENTS + 1][4];
+__device__ unsigned long long cda_pcg_jump[CDA_MAX_AGENTS + 1][4];   // global (lane-indexed reads; see cda_zig_tables.cuh)
 __device__ __forceinline__ void rng_jump(const CdaRng &g, int r, unsigned long long &shi, unsigned long long &slo) {
-    const unsigned long long Ah = cda_pcg_jump[r][0], Al = cda_pcg_jump[r][1], Gh = cda_pcg_jump[r][2], Gl = cda_pcg_jump[r][3];
+    const ulonglong2 aa = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][0])), gg = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][2]));
+    const unsigned long long Ah = aa.x, Al = aa.y, Gh = gg.x, Gl = gg.y;
     const unsigned long long l1 = Al * g.slo, h1 = __umul64hi(Al, g.slo) + Ah * g.slo + Al * g.shi;
     const unsigned long long l2 = Gl * g.ilo, h2 = __umul64hi(Gl, g.ilo) + Gh * g.ilo + Gl * g.ihi;
     slo = l1 + l2;
@@ -728,9 +729,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             r >>= 8;
             const int sign = (int)(r & 1ULL);
             const unsigned long long rabs = (r >> 1) & 0x000fffffffffffffULL;
-            double zx = (double)rabs * cda_zig_wi[idx];
+            double zx = (double)rabs * __ldg(&cda_zig_wi[idx]);
             if (sign) zx = -zx;
-            const bool fast = !mine || rabs < cda_zig_ki[idx];
+            const bool fast = !mine || rabs < __ldg(&cda_zig_ki[idx]);
             if (__all_sync(CDA_FULL, fast)) {
                 z = mine ? zx : 0.0;
                 const int src = 31 - __clz(present);           // last present lane holds the state after all draws
