@@ -572,16 +572,10 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
                                  register-pressure peak: values loaded before it get spilled, and the spill store has
                                  to wait for the load, exposing its latency) */
 #endif
-#ifndef CDA_LATE_HIST
-#define CDA_LATE_HIST 1       /* 1: fetch the older snapshots after the top-K sweep instead of after do_actions */
-#endif
-#ifndef CDA_EARLY_HIST
-#define CDA_EARLY_HIST 0      /* 1: fetch the older snapshots at the top of the step, 0: after the matching phase */
-#endif
 #ifndef CDA_BULK_STORE
 #define CDA_BULK_STORE 1      /* 1: write the whole live pool prefix back with cp.async.bulk (measured 4 % faster), 0: dirty tiles with plain stores */
 #endif
-#define CDA_HIST_PREFETCH 4   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
+#define CDA_HIST_PREFETCH 5   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
 
 template <int CAP, int WARPS, bool ROLLOUT>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
@@ -667,21 +661,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         const bool last_it = !ROLLOUT || it == n_iter - 1;
         float hv[CDA_HIST_PREFETCH];
         int slot_new = 0;
-#if CDA_EARLY_HIST
-        slot_new = (int)(t_step % (unsigned)cfg.n_hist);
-        if (p.obs && last_it) {
-#pragma unroll
-            for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
-                const int e = lane + 32 * q;
-                hv[q] = 0.f;
-                if (e < W_old) {
-                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
-                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
-                    hv[q] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
-                }
-            }
-        }
-#endif
         // ================= set_actions: action_helper.py:145-172, :241-397 =================
         int a_cat = -1, a_pcode = 0, a_poff = 1; float a_mean = 0.f, a_sigma = 0.f;
         if (lane < A) {
@@ -809,22 +788,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             place_order(k, ac, t, (int)(ts_ & 0xffu), (int)(ts_ >> 8), size, price);
         }
 
-#if !CDA_EARLY_HIST && !CDA_LATE_HIST
-        slot_new = (int)(t_step % (unsigned)cfg.n_hist);
-        // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90): latency hides behind mtm + top-K
-        if (p.obs && last_it) {
-#pragma unroll
-            for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
-                const int e = lane + 32 * q;
-                hv[q] = 0.f;
-                if (e < W_old) {
-                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
-                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
-                    hv[q] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
-                }
-            }
-        }
-#endif
         CDA_TICK(4);   // do_actions done
         // mark-to-market needs max_nav / prev_nav from the state block: issue those loads now, do the top-K sweep
         // (which does not depend on the accounts), then mark to market
@@ -893,22 +856,29 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
-#if !CDA_EARLY_HIST && CDA_LATE_HIST
+        // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90); latency hides behind
+        //      mark-to-market and the observation math.  Lane mapping: the output row of market m starts 32-B
+        //      aligned (672-B rows), so element e is handled by lane (e + mis) & 31 of chunk (e + mis) >> 5, where
+        //      mis = floats between the previous 128-B boundary and the row start: every warp store then covers
+        //      ONE aligned 128-B line (matters for DRAM sectors and doubles the PCIe/NVLink write efficiency when
+        //      the row lives in pinned host or peer memory).
         slot_new = (int)(t_step % (unsigned)cfg.n_hist);
-        // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90): latency hides behind the f32/f64 observation math
+        float *orow = nullptr; int mis = 0;
         if (p.obs && last_it) {
+            orow = p.gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
+                                      : p.obs + (size_t)m * cfg.W;
+            mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
 #pragma unroll
             for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
-                const int e = lane + 32 * q;
+                const int e = lane + 32 * q - mis;
                 hv[q] = 0.f;
-                if (e < W_old) {
+                if (e >= 0 && e < W_old) {
                     const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
                     int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
                     hv[q] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
                 }
             }
         }
-#endif
         // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
         long long nav_prev = ac.nav, nav_max = (!ROLLOUT || it == 0) ? ld_max : nav_max_carry;   // calculate.py:49-51
         if (k.tape_nonempty) {
@@ -963,16 +933,21 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const int nd = p.gather_world > 0 ? p.gather_world : 1;
 #pragma unroll 1
             for (int g = 0; g < nd; ++g) {
-                float *o = p.gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[g]) + (size_t)(p.gather_row0 + m) * cfg.W
-                                              : p.obs + (size_t)m * cfg.W;
+                float *o = g == 0 ? orow : reinterpret_cast<float *>(p.gather_peer[g]) + (size_t)(p.gather_row0 + m) * cfg.W;
 #pragma unroll
-                for (int q = 0; q < CDA_HIST_PREFETCH; ++q) { const int e = lane + 32 * q; if (e < W_old) o[e] = hv[q]; }
-                for (int e = lane + 32 * CDA_HIST_PREFETCH; e < W_old; e += 32) {   // n_hist > 4: not prefetched
-                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
-                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
-                    o[e] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
+                    const int e = lane + 32 * q - mis;
+                    if (e >= 0 && e < cfg.W) o[e] = e < W_old ? hv[q] : __uint_as_float(SMW(wb + L::SNAP + e - W_old));
                 }
-                for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) o[W_old + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
+                for (int e = lane + 32 * CDA_HIST_PREFETCH - mis; e < cfg.W; e += 32) {   // beyond the prefetched chunks
+                    float v;
+                    if (e < W_old) {
+                        const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+                        int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
+                        v = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
+                    } else v = __uint_as_float(SMW(wb + L::SNAP + e - W_old));
+                    o[e] = v;
+                }
             }
         }
         if (p.ring_out && last_it) {   // mirrored host ring: 2 x 42 floats instead of the 168-float stack

@@ -27,13 +27,22 @@ for zc, zi in (("1", "0"), ("0", "0"), ("0", "1"), ("1", "1")):
     for f in (1, 2): pin[:, f].view(torch.float32).copy_(torch.from_numpy(acts[f]))
     for i in range(256): env.step(*[d[i] for d in dev])
     it = [0]
+    blocks = [pin[i] for i in range(300)]
     def host_step():
-        b = pin[it[0] % 300]; it[0] += 1
-        env.step_host(b[0], b[1].view(torch.float32), b[2].view(torch.float32), b[3], b[4])
+        b = blocks[it[0] % 300]; it[0] += 1
+        env.step_host_block(b)
     def dev_step_sync():
         i = it[0] % 300; it[0] += 1
         env.step(*[d[i] for d in dev]); torch.cuda.current_stream().synchronize()
-    print(f"zerocopy out={zc} in={zi}: step_host (sync each) {t(host_step):7.1f} us | device step + sync {t(dev_step_sync):7.1f} us")
+    def host_step_nosync():
+        b = blocks[it[0] % 300]; it[0] += 1
+        env.step_host_block(b, sync=False)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); ev0.record()
+    for _ in range(100): host_step_nosync()
+    ev1.record(); torch.cuda.synchronize()
+    print(f"   back-to-back device time per step_host_block (no host sync): {ev0.elapsed_time(ev1)*10:.1f} us")
+    print(f"zerocopy out={zc} in={zi}: step_host_block (sync each) {t(host_step):7.1f} us | device step + sync {t(dev_step_sync):7.1f} us")
     env.close()
 
 # raw copies
