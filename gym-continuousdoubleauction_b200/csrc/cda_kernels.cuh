@@ -78,6 +78,7 @@ struct CdaStepParams {
     // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
     int num_steps; unsigned long long policy_seed;
     unsigned long long *prof;   // CDA_PROFILE_PHASES builds: per-phase cycle sums [16]
+    float *obs_hi; int obs_split;     // rows m >= obs_split go to obs_hi (device staging, DMA'd after the kernel) instead of obs
     float *ring_out; int ring_slot;   // mirrored host ring: newest snapshot only, at slots ring_slot and ring_slot + n_hist
     // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
     int gather_world, gather_row0, gather_rows;
@@ -866,7 +867,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         float *orow = nullptr; int mis = 0;
         if (p.obs && last_it) {
             orow = p.gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
-                                      : p.obs + (size_t)m * cfg.W;
+                                      : (m < p.obs_split ? p.obs : p.obs_hi) + (size_t)m * cfg.W;
             mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
 #pragma unroll
             for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
