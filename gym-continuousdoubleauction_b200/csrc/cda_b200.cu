@@ -37,11 +37,13 @@ struct CdaEnv {
     // device staging for cda_step_host
     int *s_cat; float *s_mean; float *s_sigma; int *s_pcode; int *s_poff;
     float *s_obs; double *s_reward; unsigned char *s_term; unsigned char *s_trunc;
+    unsigned char *s_rec;      // packed result records [M][A*8+8] (window host path)
     bool was_reset;
     // fused all-gather
     int g_world, g_rank; unsigned char *g_local; size_t g_bytes; unsigned char *g_peer[CDA_MAX_PEERS]; bool g_connected;
     int zerocopy;              // cda_step_host: let the kernel store outputs straight into mapped pinned host memory
     const void *zc_host; void *zc_dev;   // last host obs pointer checked and its device alias (NULL = not mapped)
+    const void *zr_host; void *zr_dev;   // same for the window path's record array
     int zerocopy_in; const void *zi_host; void *zi_dev;
     double zc_fraction;        // share of the obs rows the kernel writes straight to host memory (the rest is DMA'd)   // same for the action block (kernel reads pinned host memory)
     long long launches;
@@ -149,6 +151,7 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     // one contiguous output staging block: obs | reward | terminated | truncated  (single D2H when the
     // caller's host buffers are laid out the same way)
     if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4 + MA * 8 + (size_t)num_markets * 2);
+    if (err == cudaSuccess) err = cudaMalloc(&e->s_rec, (size_t)num_markets * ((size_t)d.A * 8 + 8));
     if (err != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc failed: %s", cudaGetErrorString(err));
         cda_destroy(e);
@@ -192,7 +195,7 @@ int cda_destroy(CdaEnv *e) {
     if (e->g_connected) for (int g = 0; g < e->g_world; ++g) if (g != e->g_rank && e->g_peer[g]) cudaIpcCloseMemHandle(e->g_peer[g]);
     cudaFree(e->g_local);
     cudaFree(e->state); cudaFree(e->fills); cudaFree(e->fill_counts);
-    cudaFree(e->s_cat); cudaFree(e->s_obs);
+    cudaFree(e->s_cat); cudaFree(e->s_obs); cudaFree(e->s_rec);
     delete e;
     return CDA_OK;
 }
@@ -214,6 +217,10 @@ static unsigned long long *g_prof = nullptr;
 static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st) {
     p.cfg = e->dev; p.state = e->state; p.M = e->M;
     if (!p.obs_hi) p.obs_split = e->M;   // no split: every row goes to p.obs
+    if (!p.obs_stride) p.obs_stride = e->dev.W;
+    if (!p.reward_stride) p.reward_stride = e->dev.A;
+    if (!p.flag_stride) p.flag_stride = 1;
+    if (!p.ring_stride) { p.ring_stride = 2 * e->dev.n_hist * CDA_SNAPSHOT_DIM; p.ring_mirror = 1; }
     p.prof = g_prof;
     p.fills = e->fills; p.fill_counts = e->fill_counts;
     CUDA_TRY(launch_step_any(e, p, st));
@@ -369,6 +376,92 @@ int cda_reset_host_ring(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mas
     cda_ring_fill_kernel<<<(n + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, d_mask, reinterpret_cast<float *>(dr));
     CUDA_TRY(cudaGetLastError());
     e->launches++;
+    return CDA_OK;
+}
+
+// ---- sliding observation window (see include/cda_b200.h) ------------------------------------------------
+int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                         const int32_t *h_price, const int32_t *h_price_offset, float *h_window, int32_t slots, int32_t pos,
+                         void *h_records, int32_t sync, void *stream) {
+    if (!e || !h_category || !h_size_mean || !h_size_sigma || !h_price || !h_price_offset || !h_window || !h_records) return CDA_EINVAL;
+    const int H = e->dev.n_hist;
+    if (slots < H || pos < H - 1 || pos >= slots) return CDA_EINVAL;
+    if (!e->was_reset) return CDA_ESTATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t MA = (size_t)e->M * e->dev.A;
+    const char *hc = reinterpret_cast<const char *>(h_category);
+    const bool in_contig = reinterpret_cast<const char *>(h_size_mean) == hc + MA * 4 && reinterpret_cast<const char *>(h_size_sigma) == hc + 2 * MA * 4 &&
+                           reinterpret_cast<const char *>(h_price) == hc + 3 * MA * 4 && reinterpret_cast<const char *>(h_price_offset) == hc + 4 * MA * 4;
+    char *zi = nullptr;
+    if (e->zerocopy_in && in_contig) {
+        if (e->zi_host != h_category) { e->zi_host = h_category; e->zi_dev = mapped_alias(h_category); }
+        zi = reinterpret_cast<char *>(e->zi_dev);
+    }
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cat = e->s_cat; p.mean = e->s_mean; p.sigma = e->s_sigma; p.pcode = e->s_pcode; p.poff = e->s_poff;
+    if (zi) {
+        p.cat = reinterpret_cast<const int *>(zi); p.mean = reinterpret_cast<const float *>(zi + MA * 4);
+        p.sigma = reinterpret_cast<const float *>(zi + 2 * MA * 4); p.pcode = reinterpret_cast<const int *>(zi + 3 * MA * 4);
+        p.poff = reinterpret_cast<const int *>(zi + 4 * MA * 4);
+    } else if (in_contig) {
+        CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_category, MA * 4 * 5, cudaMemcpyHostToDevice, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_category, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_mean, h_size_mean, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_sigma, h_size_sigma, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_pcode, h_price, MA * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->s_poff, h_price_offset, MA * 4, cudaMemcpyHostToDevice, st));
+    }
+    // Everything the host does not hold yet is stored by the kernel STRAIGHT into pinned host memory (posted PCIe
+    // writes that overlap the step; no copy-engine hand-off): the newest snapshot into slot `pos` of the market's window
+    // row (the whole stack when the window restarts at slot 0) and the packed result record.  When the buffers are not
+    // mapped (or CDA_ZEROCOPY=0) the same bytes are staged in HBM and follow with one strided + one contiguous copy.
+    const size_t rec_bytes = (size_t)e->dev.A * 8 + 8;
+    float *zw = nullptr; unsigned char *zr = nullptr;
+    if (e->zerocopy) {
+        if (e->zc_host != h_window) { e->zc_host = h_window; e->zc_dev = mapped_alias(h_window); }
+        if (e->zr_host != h_records) { e->zr_host = h_records; e->zr_dev = mapped_alias(h_records); }
+        zw = reinterpret_cast<float *>(e->zc_dev); zr = reinterpret_cast<unsigned char *>(e->zr_dev);
+        if (!zw || !zr) { zw = nullptr; zr = nullptr; }
+    }
+    const int wstride = slots * CDA_SNAPSHOT_DIM;
+    unsigned char *rec = zr ? zr : e->s_rec;
+    p.reward = reinterpret_cast<double *>(rec); p.reward_stride = e->dev.A + 1;
+    p.term = rec + (size_t)e->dev.A * 8; p.trunc = p.term + 1; p.flag_stride = (int)rec_bytes;
+    if (zw) {
+        if (pos == H - 1) { p.obs = zw; p.obs_stride = wstride; }
+        else { p.ring_out = zw; p.ring_stride = wstride; p.ring_slot = pos; p.ring_mirror = 0; }
+    } else p.obs = e->s_obs;
+    int rc = step_common(e, p, st);
+    if (rc) return rc;
+    if (!zw) {
+        const size_t dpitch = (size_t)wstride * 4, spitch = (size_t)e->dev.W * 4;
+        if (pos == H - 1) CUDA_TRY(cudaMemcpy2DAsync(h_window, dpitch, e->s_obs, spitch, spitch, e->M, cudaMemcpyDeviceToHost, st));
+        else CUDA_TRY(cudaMemcpy2DAsync(h_window + (size_t)pos * CDA_SNAPSHOT_DIM, dpitch, e->s_obs + (size_t)(H - 1) * CDA_SNAPSHOT_DIM, spitch,
+                                        CDA_SNAPSHOT_DIM * 4, e->M, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_records, e->s_rec, (size_t)e->M * rec_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (sync) CUDA_TRY(cudaStreamSynchronize(st));
+    return CDA_OK;
+}
+
+int cda_reset_host_window(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream) {
+    if (!e || !h_window || slots < e->dev.n_hist) return CDA_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cda_reset(e, d_seeds, d_mask, nullptr, stream);
+    if (rc) return rc;
+    // every market's stack (reset or not) goes to slots 0..n_hist-1 of its row, rebuilt from the snapshot ring in the state
+    const int n = e->M * e->dev.W, threads = 256, wstride = slots * CDA_SNAPSHOT_DIM;
+    float *zw = e->zerocopy ? reinterpret_cast<float *>(mapped_alias(h_window)) : nullptr;
+    if (zw) cda_emit_obs_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(e->dev, e->state, e->M, zw, wstride);
+    else {
+        cda_emit_obs_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(e->dev, e->state, e->M, e->s_obs, e->dev.W);
+        CUDA_TRY(cudaMemcpy2DAsync(h_window, (size_t)wstride * 4, e->s_obs, (size_t)e->dev.W * 4, (size_t)e->dev.W * 4, e->M, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    CUDA_TRY(cudaStreamSynchronize(st));
     return CDA_OK;
 }
 

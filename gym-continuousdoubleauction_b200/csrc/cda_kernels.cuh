@@ -79,7 +79,10 @@ struct CdaStepParams {
     int num_steps; unsigned long long policy_seed;
     unsigned long long *prof;   // CDA_PROFILE_PHASES builds: per-phase cycle sums [16]
     float *obs_hi; int obs_split;     // rows m >= obs_split go to obs_hi (device staging, DMA'd after the kernel) instead of obs
-    float *ring_out; int ring_slot;   // mirrored host ring: newest snapshot only, at slots ring_slot and ring_slot + n_hist
+    int obs_stride;                   // floats between consecutive markets' obs rows (W when densely packed)
+    int reward_stride, flag_stride;   // doubles between markets' reward rows (A when dense); bytes between markets' flags (1 when dense)
+    float *ring_out; int ring_slot;   // host ring / window: newest snapshot only, at slot ring_slot of row m (+ a mirror copy n_hist slots later)
+    int ring_stride, ring_mirror;     // floats per market row of ring_out; 1 = also write the mirror copy
     // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
     int gather_world, gather_row0, gather_rows;
     unsigned char *gather_peer[CDA_MAX_PEERS];
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         float *orow = nullptr; int mis = 0;
         if (p.obs && last_it) {
             orow = p.gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
-                                      : (m < p.obs_split ? p.obs : p.obs_hi) + (size_t)m * cfg.W;
+                                      : (m < p.obs_split ? p.obs : p.obs_hi) + (size_t)m * p.obs_stride;
             mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
 #pragma unroll
             for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
@@ -951,11 +954,13 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
-        if (p.ring_out && last_it) {   // mirrored host ring: 2 x 42 floats instead of the 168-float stack
-            float *rg = p.ring_out + (size_t)m * (2 * cfg.n_hist * CDA_SNAPSHOT_DIM) + p.ring_slot * CDA_SNAPSHOT_DIM;
-            for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) {
+        if (p.ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
+            float *rg = p.ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
+            for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < CDA_SNAPSHOT_DIM; cc += 32) {
+                if (cc < 0) continue;
                 const float v = __uint_as_float(SMW(wb + L::SNAP + cc));
-                rg[cc] = v; rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
+                rg[cc] = v;
+                if (p.ring_mirror) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
             }
         }
         __syncwarp();
@@ -978,7 +983,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 if (p.gather_world > 0) {
                     const size_t off = (size_t)p.gather_rows * cfg.W * 4 + ((size_t)(p.gather_row0 + m) * A + lane) * 8;
                     for (int g = 0; g < p.gather_world; ++g) *reinterpret_cast<double *>(p.gather_peer[g] + off) = r;
-                } else p.reward[(size_t)m * A + lane] = r;
+                } else p.reward[(size_t)m * p.reward_stride + lane] = r;
             }
             broke = ac.nav <= 0;
         }
@@ -990,8 +995,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 const size_t off = (size_t)p.gather_rows * ((size_t)cfg.W * 4 + (size_t)A * 8) + (size_t)(p.gather_row0 + m);
                 for (int g = 0; g < p.gather_world; ++g) { p.gather_peer[g][off] = f_term; p.gather_peer[g][off + p.gather_rows] = f_trunc; }
             } else {
-                if (p.term) p.term[m] = f_term;
-                if (p.trunc) p.trunc[m] = f_trunc;
+                if (p.term) p.term[(size_t)m * p.flag_stride] = f_term;
+                if (p.trunc) p.trunc[(size_t)m * p.flag_stride] = f_trunc;
             }
             if (p.fill_counts) p.fill_counts[m] = k.n_fills;
             hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask;
@@ -1091,6 +1096,18 @@ __global__ void cda_reset_kernel(CdaDevCfg cfg, unsigned char *state, int M, con
             g_hist[h * CDA_SNAPSHOT_DIM + cc] = v;
             if (obs) obs[(size_t)m * cfg.W + h * CDA_SNAPSHOT_DIM + cc] = v;
         }
+}
+
+// stacked observation of every market rebuilt from its snapshot ring (state_helper.py:88-90): row m of `dst`
+// (row stride in floats) receives n_hist x 42 floats, oldest snapshot first.  Cold path (reset of the host window).
+__global__ void cda_emit_obs_kernel(CdaDevCfg cfg, const unsigned char *state, int M, float *dst, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * cfg.W) return;
+    const int m = i / cfg.W, e = i - m * cfg.W, j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+    const unsigned char *blk = state + (size_t)m * cfg.stride;
+    const unsigned t_step = reinterpret_cast<const unsigned *>(blk)[3];
+    const float *g_hist = reinterpret_cast<const float *>(blk + cfg.off_hist);
+    dst[(size_t)m * stride + e] = g_hist[((t_step + (unsigned)j) % (unsigned)cfg.n_hist) * CDA_SNAPSHOT_DIM + cc];
 }
 
 // fill every slot of the mirrored host ring of the selected markets with their current newest snapshot

@@ -206,6 +206,61 @@ class VecCDAEnv:
             torch.cuda.current_stream(self.device).synchronize()
         return (self._ring_view(),) + self._ring_out_np
 
+    # ---- sliding host window: only the newest snapshot of every market crosses PCIe (one strided DMA)
+    WINDOW_SLOTS = 16
+
+    def _ensure_window(self):
+        if getattr(self, "_win", None) is None:
+            M, A = self.M, self.A
+            self._win = torch.empty((M, self.WINDOW_SLOTS * SNAPSHOT_DIM), dtype=torch.float32, pin_memory=True)
+            rs = 8 * (A + 1)                                   # packed record: reward f64[A] | terminated u8 | truncated u8 | pad
+            self._win_rec = torch.zeros(M * rs, dtype=torch.uint8, pin_memory=True)
+            rec = self._win_rec.numpy()
+            self._win_np = self._win.numpy()
+            self._win_out_np = (np.ndarray((M, A), np.float64, rec, 0, (rs, 8)), np.ndarray((M,), np.uint8, rec, 8 * A, (rs,)),
+                                np.ndarray((M,), np.uint8, rec, 8 * A + 1, (rs,)))
+            self._win_ptrs = (_ptr(self._win), _ptr(self._win_rec))
+            self._win_pos = None
+        return self._win
+
+    def _window_view(self):
+        s0 = (self._win_pos - self.n_hist + 1) * SNAPSHOT_DIM
+        return self._win_np[:, s0:s0 + self.W]          # [M, n_hist*42] oldest snapshot first; rows are contiguous
+
+    def reset_host_window(self, seed=None, mask=None):
+        """reset() for the window host path: returns the stacked observation as a view of the pinned window."""
+        self._ensure_window()
+        seeds_t = None
+        if seed is not None:
+            seeds = (np.arange(self.M, dtype=np.uint64) + np.uint64(seed)) if isinstance(seed, (int, np.integer)) \
+                else np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed).astype(np.uint64)
+            seeds_t = torch.from_numpy(seeds.view(np.int64)).to(self.device)
+        mask_t = None if mask is None else torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        _native.check(self._L.cda_reset_host_window(self._h, _ptr(seeds_t), _ptr(mask_t), self._win_ptrs[0], self.WINDOW_SLOTS, self._stream()))
+        self._win_pos = self.n_hist - 1
+        return self._window_view()
+
+    def step_host_window(self, action_block, sync=True):
+        """Lowest-traffic host path.  `action_block` as in step_host_block (ONE pinned int32 tensor [5, M, A], read in
+        place by the kernel).  Per step only the newest 42-float snapshot of every market crosses PCIe, into the
+        next slot of that market's row of a pinned [M, 16, 42] window; the returned obs is the numpy view
+        [M, n_hist*42] of the n_hist most recent slots (row stride 16*42 floats, each row contiguous), bit-identical
+        to step_host_block's obs.  Views are valid until the next call.  Launch, copy and stream synchronisation
+        happen inside ONE C call."""
+        if getattr(self, "_win_pos", None) is None:
+            raise RuntimeError("call reset_host_window() before step_host_window()")
+        pos = self._win_pos + 1
+        if pos >= self.WINDOW_SLOTS:
+            pos = self.n_hist - 1        # window restarts: the whole stack is re-sent into slots 0..n_hist-1
+        base = action_block.data_ptr()
+        n = self.M * self.A * 4
+        vp = ctypes.c_void_p
+        _native.check(self._L.cda_step_host_window(self._h, vp(base), vp(base + n), vp(base + 2 * n), vp(base + 3 * n), vp(base + 4 * n),
+                                                   self._win_ptrs[0], self.WINDOW_SLOTS, pos, self._win_ptrs[1],
+                                                   1 if sync else 0, self._stream()))
+        self._win_pos = pos
+        return (self._window_view(),) + self._win_out_np
+
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""
         p = self._ensure_pinned()

@@ -127,6 +127,27 @@ int cda_step_host_ring(CdaEnv *env, const int32_t *h_category, const float *h_si
                        uint8_t *h_terminated, uint8_t *h_truncated, int64_t ring_pos, void *stream);
 int cda_reset_host_ring(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_ring, void *stream);
 
+/* Host path with a SLIDING OBSERVATION WINDOW — the lowest-traffic end-to-end path.
+ * Of the n_hist snapshots in a stacked observation only the newest is new each step (state_helper.py:80-92:
+ * the deque drops the oldest and appends one), so the host keeps, per market, a row of `slots` snapshot slots
+ *     h_window f32[M][slots][42]   (pinned; slots >= n_hist, e.g. 64)
+ * and each step only the newest snapshot crosses PCIe, into slot `pos` of every row (ONE strided copy-engine
+ * transfer of M x 168 B instead of M x 672 B).  The stacked observation of market m is then the contiguous run of
+ * n_hist slots ending at `pos` — h_window[m][pos-n_hist+1 .. pos] — a zero-copy view with the same 168 floats, oldest
+ * first, as cda_step_host's obs row.  The caller advances pos by one per step; when it would reach `slots` it passes
+ * pos = n_hist-1 instead, which re-sends the whole stack into slots 0..n_hist-1 (amortised over slots-n_hist+1 steps).
+ * cda_reset_host_window resets the selected markets and sends every market's stack to slots 0..n_hist-1 (the next
+ * step uses pos = n_hist).  Actions as in cda_step_host (read in place when the five arrays are one pinned block).
+ * The other per-step results arrive as ONE packed record per market,
+ *     h_records: M records of 8*(A+1) bytes = { double reward[A]; uint8_t terminated, truncated; uint8_t pad[6]; }
+ * (pinned; written by one store instruction per market, or one contiguous copy when the buffer is not mapped).
+ * sync != 0: the call returns after the stream has been synchronised (outputs readable).  Use this path consistently
+ * between resets: it keeps the device copy of the full stack in the handle's own staging buffer. */
+int cda_step_host_window(CdaEnv *env, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                         const int32_t *h_price, const int32_t *h_price_offset, float *h_window, int32_t slots, int32_t pos,
+                         void *h_records, int32_t sync, void *stream);
+int cda_reset_host_window(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream);
+
 /* Fused T-step rollout with the on-device uniform random policy (the RandomRLModule /
  * CDA_rand.py workload: category U{0..8}, price U{0..9}, offset U{0..2}, mean U(-1,1), sigma U(0,1),
  * gym_continuousDoubleAuction/train/model/model_handler.py:38-78).  Policy draws come from a

@@ -217,3 +217,46 @@ def test_host_ring_other_history_depths(n_hist):
         o1 = e1.step_host_block(blk[t])[0]; o2 = e2.step_host_ring(blk[t])[0]
         assert np.array_equal(o1, o2)
     e1.close(); e2.close()
+
+
+def _pinned_block(acts, T, M, A):
+    blk = torch.empty((T, 5, M, A), dtype=torch.int32, pin_memory=True)
+    for f in (0, 3, 4):
+        blk[:, f].copy_(torch.from_numpy(acts[f]))
+    for f in (1, 2):
+        blk[:, f].view(torch.float32).copy_(torch.from_numpy(acts[f]))
+    return blk
+
+
+@pytest.mark.parametrize("n_hist,T", [(4, 60), (1, 40), (6, 45)])
+def test_host_window_view_equals_stacked_obs_across_wraps_and_masked_reset(n_hist, T):
+    """cda_step_host_window ships only the newest snapshot into the next slot of a 16-slot pinned window per market;
+    the view of the n_hist latest slots must equal the ordinary host path's stacked observation bit for bit —
+    across window restarts (T > 16 steps) and per-market resets."""
+    cfg = base_cfg(n_hist=n_hist)
+    M, A = 96, 4
+    e1 = cda.VecCDAEnv(cfg, num_markets=M); e2 = cda.VecCDAEnv(cfg, num_markets=M)
+    o1 = e1.reset(seed=11).cpu().numpy(); o2 = e2.reset_host_window(seed=11)
+    assert o2.shape == (M, n_hist * 42) and np.array_equal(o1, o2)
+    blk = _pinned_block(make_actions(6, T, M, A, "uniform"), T, M, A)
+    for t in range(T):
+        if t in (7, 12, 13, 30):
+            mask = (np.arange(M) % 3 == t % 3).astype(np.uint8)
+            a = e1.reset(seed=None, mask=mask).cpu().numpy(); b = e2.reset_host_window(seed=None, mask=mask)
+            assert np.array_equal(a[mask == 1], b[mask == 1])
+            if t > 0:
+                assert np.array_equal(prev[mask == 0], b[mask == 0])     # untouched markets keep their stack
+        o1, r1, te1, tr1 = e1.step_host_block(blk[t])
+        o2, r2, te2, tr2 = e2.step_host_window(blk[t])
+        assert np.array_equal(o1, o2), f"t={t}"
+        assert np.array_equal(r1, r2) and np.array_equal(te1, te2) and np.array_equal(tr1, tr2)
+        prev = o1.copy()
+    e1.close(); e2.close()
+
+
+def test_host_window_needs_reset_first():
+    env = cda.VecCDAEnv(base_cfg(), num_markets=8)
+    blk = torch.zeros((5, 8, 4), dtype=torch.int32, pin_memory=True)
+    with pytest.raises(RuntimeError):
+        env.step_host_window(blk)
+    env.close()
