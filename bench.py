@@ -7,9 +7,11 @@ its A agents' actions once (== M reference `env.step` calls).  1 env-step = 1 ma
 
   value   device-resident: actions already in HBM, K steps each timed with its own CUDA-event
           pair on the launching stream, L2 flushed between steps; max over ranks.
-  e2e     the same metric through the public host API (VecCDAEnv.step_host): per step the five
-          action arrays go pinned-host -> device, the kernel runs, obs/reward/flags come back to
-          pinned host memory and the stream is synchronised (what a host-side policy sees).
+  e2e     the same metric through the public host API (VecCDAEnv.step_host_window): per step the
+          pinned action block is read by the kernel, obs/reward/flags land in pinned host memory and
+          the stream is synchronised (what a host-side policy sees).  Of the 168-float stacked
+          observation only the newest 42-float snapshot is new each step, so only that crosses PCIe;
+          the full-stack host path (step_host_block) is timed beside it.
   roofline   HBM-bound: achieved = B_alg(A) * M / kernel_time, B_alg(A) = 1986 + 188*A bytes per
           market-step (SURVEY.md §8d / DESIGN.md), peak = MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm, "port") on all host
@@ -222,7 +224,11 @@ def main():
     pin_steps = [pin_blk[i] for i in range(PH)]
 
     def host_step(i):
-        return env.step_host_block(pin_steps[i % PH])     # actions read in place, obs|reward|flags written to pinned memory
+        # actions read in place from the pinned block; newest snapshot + result record written straight to pinned memory
+        return env.step_host_window(pin_steps[i % PH])
+
+    def host_step_full(i):
+        return env.step_host_block(pin_steps[i % PH])     # same, but the whole 168-float stack of every market crosses PCIe
 
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     step_ctr = [0]
@@ -277,26 +283,40 @@ def main():
     # ------------------------------------------------------------------ e2e (host buffers in/out)
     e2e = None
     if not args.no_e2e:
-        for i in range(max(3, args.warmup // 2)):
-            host_step(i)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        tot = 0.0
-        for i in range(args.steps):
-            if not args.no_l2_flush:
-                flush_buf.fill_(i & 0xff); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            o, r, te, tr = host_step(i + args.warmup)
-            _ = float(r[0, 0])   # the host reads the step's result
-            tot += time.perf_counter() - t0
-        tt = torch.tensor([tot], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * M * args.steps / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(M * A * 20), "d2h_bytes_per_step": int(M * env.W * 4 + M * A * 8 + 2 * M),
-               "ms_per_step": 1e3 * float(tt.item()) / args.steps,
-               "api": "VecCDAEnv.step_host_block -> cda_step_host (pinned [5,M,A] action block read in place by the kernel, obs|reward|flags written to the pinned output block, stream sync per step)"}
+        def timed_host(fn):
+            for i in range(max(3, args.warmup // 2)):
+                fn(i)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for i in range(args.steps):
+                if not args.no_l2_flush:
+                    flush_buf.fill_(i & 0xff); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                o, r, te, tr = fn(i + args.warmup)
+                _ = float(r[0, 0]) + float(o[M - 1, env.W - 1])   # the host reads the step's result
+                tot += time.perf_counter() - t0
+            tt = torch.tensor([tot], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        t_full = timed_host(host_step_full)
+        env.attach_host_window()   # hand every market's current stack to the host window (no market is reset)
+        t_win = timed_host(host_step)
+        S, H = env.WINDOW_SLOTS, env.n_hist
+        rec = M * (8 * (A + 1) + 63) // 64 * 64
+        d2h_win = rec + M * 4 * 42 * ((S - H) + H) / (S - H + 1)     # per window cycle: S-H newest-only steps + one whole-stack step
+        e2e = {"value": world * M * args.steps / t_win, "unit": UNIT,
+               "h2d_bytes_per_step": int(M * A * 20), "d2h_bytes_per_step": int(d2h_win),
+               "ms_per_step": 1e3 * t_win / args.steps,
+               "api": "VecCDAEnv.step_host_window -> cda_step_host_window: pinned [5,M,A] action block staged by the kernel (cp.async.bulk from mapped host memory); "
+                      "the kernel stores the newest 42-float snapshot of every market into that market's row of a pinned [M,16,42] sliding window and a 64-B result "
+                      "record (reward f64[A], terminated, truncated) straight into pinned host memory; obs returned = [M,168] view of the window, bit-identical to the "
+                      "full stack (tests/test_gpu_parity.py); launch + stream sync inside one C call per step",
+               "full_stack_variant": {"value": world * M * args.steps / t_full, "ms_per_step": 1e3 * t_full / args.steps,
+                                      "d2h_bytes_per_step": int(M * env.W * 4 + M * A * 8 + 2 * M),
+                                      "api": "VecCDAEnv.step_host_block -> cda_step_host (the whole 168-float stack of every market crosses PCIe each step)"}}
 
     status_bits = int(env.status().max().item())   # sticky per-market status over everything measured above
     # keep the same load running for ~0.6 s so the 100 ms nvidia-smi sampler sees several samples under load

@@ -45,7 +45,7 @@ INFO_MARKET_COLS = ("last_price", "best_bid", "best_ask", "time", "next_order_id
 EXPORTS = (
     "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_step_host_ring", "cda_reset_host_ring", "cda_step_host_window", "cda_reset_host_window", "cda_rollout_random",
     "cda_gather_create", "cda_gather_connect", "cda_step_gather", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
-    "cda_load_state", "cda_num_markets", "cda_obs_dim", "cda_order_capacity",
+    "cda_load_state", "cda_num_markets", "cda_record_bytes", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
     "cda_seed_to_pcg64", "cda_debug_phase_buffer",
 )
@@ -109,7 +109,7 @@ def lib():
     L.cda_state_bytes.restype = ctypes.c_size_t
     L.cda_save_state.argtypes = [vp, vp, vp]
     L.cda_load_state.argtypes = [vp, vp, vp]
-    for name in ("cda_num_markets", "cda_obs_dim", "cda_order_capacity"):
+    for name in ("cda_num_markets", "cda_obs_dim", "cda_order_capacity", "cda_record_bytes"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = i32
     L.cda_kernel_launches.argtypes = [vp]

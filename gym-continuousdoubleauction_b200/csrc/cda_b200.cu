@@ -4,6 +4,7 @@
 //  test with separately rounded multiplies and adds; contracting them into FMAs would change
 //  results in the last bit.)
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +46,7 @@ struct CdaEnv {
     const void *zc_host; void *zc_dev;   // last host obs pointer checked and its device alias (NULL = not mapped)
     const void *zr_host; void *zr_dev;   // same for the window path's record array
     int zerocopy_in; const void *zi_host; void *zi_dev;
+    int act_tma;               // CDA_ACT_TMA (default 1): stage the action rows with cp.async.bulk
     double zc_fraction;        // share of the obs rows the kernel writes straight to host memory (the rest is DMA'd)   // same for the action block (kernel reads pinned host memory)
     long long launches;
     size_t smem_bytes;
@@ -55,14 +57,15 @@ static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 template <int CAP>
 static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {
     const int grid = (e->M + CDA_WARPS_PER_CTA - 1) / CDA_WARPS_PER_CTA;
-    const size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA;
-    static bool attr_set[16] = {false};
-    if (!attr_set[e->device & 15]) {
+    // per-warp tiles, then the CTA's action tile u32[5][WARPS][A] and its mbarrier
+    const size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16;
+    static size_t attr_set[16] = {0};
+    if (attr_set[e->device & 15] < smem) {
         cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set[e->device & 15] = true;
+        attr_set[e->device & 15] = smem;
     }
     if (p.num_steps > 0) cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
     else cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
@@ -151,7 +154,7 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     // one contiguous output staging block: obs | reward | terminated | truncated  (single D2H when the
     // caller's host buffers are laid out the same way)
     if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4 + MA * 8 + (size_t)num_markets * 2);
-    if (err == cudaSuccess) err = cudaMalloc(&e->s_rec, (size_t)num_markets * ((size_t)d.A * 8 + 8));
+    if (err == cudaSuccess) err = cudaMalloc(&e->s_rec, (size_t)num_markets * (((size_t)d.A * 8 + 8 + 63) / 64 * 64));
     if (err != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc failed: %s", cudaGetErrorString(err));
         cda_destroy(e);
@@ -182,6 +185,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
         e->zerocopy = zc ? atoi(zc) : 1;
         const char *zi = getenv("CDA_ZEROCOPY_IN");
         e->zerocopy_in = zi ? atoi(zi) : 1;
+        const char *at = getenv("CDA_ACT_TMA");
+        e->act_tma = at ? atoi(at) : 1;
         const char *zf = getenv("CDA_ZC_FRACTION");
         e->zc_fraction = zf ? atof(zf) : 0.25;   // SM stores to host reach ~25 GB/s but overlap the kernel; the copy engine does ~53 GB/s after it   // measured: kernel reading the pinned action block beats a separate H2D copy by ~10 us
     }
@@ -223,6 +228,9 @@ static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st) {
     if (!p.ring_stride) { p.ring_stride = 2 * e->dev.n_hist * CDA_SNAPSHOT_DIM; p.ring_mirror = 1; }
     p.prof = g_prof;
     p.fills = e->fills; p.fill_counts = e->fill_counts;
+    // TMA staging of the action rows: rows of A 4-byte words must be multiples of 16 B and the arrays 16-B aligned
+    p.act_tma = e->act_tma && p.num_steps == 0 && (e->dev.A % 4) == 0 &&
+                (((uintptr_t)p.cat | (uintptr_t)p.mean | (uintptr_t)p.sigma | (uintptr_t)p.pcode | (uintptr_t)p.poff) & 15) == 0;
     CUDA_TRY(launch_step_any(e, p, st));
     e->launches++;
     return CDA_OK;
@@ -397,10 +405,17 @@ int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_si
         if (e->zi_host != h_category) { e->zi_host = h_category; e->zi_dev = mapped_alias(h_category); }
         zi = reinterpret_cast<char *>(e->zi_dev);
     }
+    // timing experiments only (tools/e2e_timeline.py): 1 = reuse the actions already staged on the device (no input
+    // transfer after the first call), 2 = keep the outputs on the device (no output transfer), 3 = both
+    static const int dbg = getenv("CDA_DEBUG_WINDOW") ? atoi(getenv("CDA_DEBUG_WINDOW")) : 0;
+    static int dbg_calls = 0;
+    const bool dbg_skip_in = (dbg & 1) && dbg_calls++ > 0, dbg_dev_out = (dbg & 2) != 0;
+    if (dbg & 1) zi = nullptr;
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
     p.cat = e->s_cat; p.mean = e->s_mean; p.sigma = e->s_sigma; p.pcode = e->s_pcode; p.poff = e->s_poff;
-    if (zi) {
+    if (dbg_skip_in) {
+    } else if (zi) {
         p.cat = reinterpret_cast<const int *>(zi); p.mean = reinterpret_cast<const float *>(zi + MA * 4);
         p.sigma = reinterpret_cast<const float *>(zi + 2 * MA * 4); p.pcode = reinterpret_cast<const int *>(zi + 3 * MA * 4);
         p.poff = reinterpret_cast<const int *>(zi + 4 * MA * 4);
@@ -417,25 +432,25 @@ int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_si
     // writes that overlap the step; no copy-engine hand-off): the newest snapshot into slot `pos` of the market's window
     // row (the whole stack when the window restarts at slot 0) and the packed result record.  When the buffers are not
     // mapped (or CDA_ZEROCOPY=0) the same bytes are staged in HBM and follow with one strided + one contiguous copy.
-    const size_t rec_bytes = (size_t)e->dev.A * 8 + 8;
+    const size_t rec_bytes = cda_record_bytes(e);
     float *zw = nullptr; unsigned char *zr = nullptr;
     if (e->zerocopy) {
         if (e->zc_host != h_window) { e->zc_host = h_window; e->zc_dev = mapped_alias(h_window); }
         if (e->zr_host != h_records) { e->zr_host = h_records; e->zr_dev = mapped_alias(h_records); }
         zw = reinterpret_cast<float *>(e->zc_dev); zr = reinterpret_cast<unsigned char *>(e->zr_dev);
-        if (!zw || !zr) { zw = nullptr; zr = nullptr; }
+        if (!zw || !zr || dbg_dev_out) { zw = nullptr; zr = nullptr; }
     }
     const int wstride = slots * CDA_SNAPSHOT_DIM;
     unsigned char *rec = zr ? zr : e->s_rec;
-    p.reward = reinterpret_cast<double *>(rec); p.reward_stride = e->dev.A + 1;
-    p.term = rec + (size_t)e->dev.A * 8; p.trunc = p.term + 1; p.flag_stride = (int)rec_bytes;
+    p.reward = reinterpret_cast<double *>(rec); p.reward_stride = (int)(rec_bytes / 8);
+    p.term = rec + (size_t)e->dev.A * 8; p.trunc = p.term + 1; p.flag_stride = (int)rec_bytes; p.flag_pack = 1;
     if (zw) {
         if (pos == H - 1) { p.obs = zw; p.obs_stride = wstride; }
         else { p.ring_out = zw; p.ring_stride = wstride; p.ring_slot = pos; p.ring_mirror = 0; }
     } else p.obs = e->s_obs;
     int rc = step_common(e, p, st);
     if (rc) return rc;
-    if (!zw) {
+    if (!zw && !dbg_dev_out) {
         const size_t dpitch = (size_t)wstride * 4, spitch = (size_t)e->dev.W * 4;
         if (pos == H - 1) CUDA_TRY(cudaMemcpy2DAsync(h_window, dpitch, e->s_obs, spitch, spitch, e->M, cudaMemcpyDeviceToHost, st));
         else CUDA_TRY(cudaMemcpy2DAsync(h_window + (size_t)pos * CDA_SNAPSHOT_DIM, dpitch, e->s_obs + (size_t)(H - 1) * CDA_SNAPSHOT_DIM, spitch,
@@ -611,6 +626,7 @@ int cda_load_state(CdaEnv *e, const void *h_src, void *stream) {
     e->was_reset = true;
     return CDA_OK;
 }
+int32_t cda_record_bytes(const CdaEnv *e) { return e ? (int32_t)(((size_t)e->dev.A * 8 + 8 + 63) / 64 * 64) : 0; }
 int32_t cda_num_markets(const CdaEnv *e) { return e ? e->M : 0; }
 int32_t cda_obs_dim(const CdaEnv *e) { return e ? e->dev.W : 0; }
 int32_t cda_order_capacity(const CdaEnv *e) { return e ? e->dev.cap : 0; }

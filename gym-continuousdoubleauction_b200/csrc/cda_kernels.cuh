@@ -73,6 +73,7 @@ struct CdaStepParams {
     unsigned char *state;
     int M;
     const int *cat; const float *mean; const float *sigma; const int *pcode; const int *poff;
+    int act_tma;   // 1: every CTA stages its markets' five action rows global/pinned-host -> shared with cp.async.bulk (needs A % 4 == 0, 16-B aligned arrays)
     float *obs; double *reward; unsigned char *term; unsigned char *trunc;
     int *fills; int *fill_counts;
     // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
@@ -80,6 +81,7 @@ struct CdaStepParams {
     unsigned long long *prof;   // CDA_PROFILE_PHASES builds: per-phase cycle sums [16]
     float *obs_hi; int obs_split;     // rows m >= obs_split go to obs_hi (device staging, DMA'd after the kernel) instead of obs
     int obs_stride;                   // floats between consecutive markets' obs rows (W when densely packed)
+    int flag_pack;                    // 1: truncated lives in the byte after terminated (packed result records): both leave in one 16-bit store
     int reward_stride, flag_stride;   // doubles between markets' reward rows (A when dense); bytes between markets' flags (1 when dense)
     float *ring_out; int ring_slot;   // host ring / window: newest snapshot only, at slot ring_slot of row m (+ a mirror copy n_hist slots later)
     int ring_stride, ring_mirror;     // floats per market row of ring_out; 1 = also write the mirror copy
@@ -586,9 +588,31 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     using L = CdaSmemLayout<CAP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * WARPS + warp;
-    if (m >= p.M) return;
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
+    // ---- action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A]
+    //      array) behind one CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns
+    //      20 sector-sized PCIe reads per CTA into 5 requests issued at the very start of the kernel.
+    const int actb = WARPS * L::WORDS;                 // word index of the CTA's action tile: u32[5][WARPS][A], then the mbarrier
+    const int cbar_w = actb + 5 * WARPS * A;           // (even: A % 4 == 0 on this path)
+    if (!ROLLOUT && p.act_tma) {
+        if (threadIdx.x == 0) {
+            const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w * 4u;
+            const int m0 = blockIdx.x * WARPS, nm = min(WARPS, p.M - m0);
+            const unsigned fb = (unsigned)(nm * A) * 4u;
+            mbar_init(cbar, 1);
+            mbar_expect_tx(cbar, 5u * fb);
+            const unsigned dst = smem_u32(smw) + (unsigned)actb * 4u, fs = (unsigned)(WARPS * A) * 4u;
+            const size_t so = (size_t)m0 * A;
+            bulk_g2s(dst, p.cat + so, fb, cbar);
+            bulk_g2s(dst + fs, p.mean + so, fb, cbar);
+            bulk_g2s(dst + 2u * fs, p.sigma + so, fb, cbar);
+            bulk_g2s(dst + 3u * fs, p.pcode + so, fb, cbar);
+            bulk_g2s(dst + 4u * fs, p.poff + so, fb, cbar);
+        }
+        __syncthreads();                               // mbarrier initialised before any warp waits on it
+    }
+    if (m >= p.M) return;
 #ifdef CDA_PROFILE_PHASES
     long long tprev = clock64();
 #endif
@@ -676,9 +700,17 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 const unsigned long long h2 = splitmix64(h);
                 a_mean = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
                 a_sigma = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
-            } else {
+            } else if (!p.act_tma) {
                 const size_t o = (size_t)m * A + lane;
                 a_cat = p.cat[o]; a_mean = p.mean[o]; a_sigma = p.sigma[o]; a_pcode = p.pcode[o]; a_poff = p.poff[o];
+            }
+        }
+        if (!ROLLOUT && p.act_tma) {
+            mbar_wait(smem_u32(smw) + (unsigned)cbar_w * 4u, 0);
+            if (lane < A) {
+                const int o = actb + warp * A + lane, fs = WARPS * A;
+                a_cat = (int)SMW(o); a_mean = __uint_as_float(SMW(o + fs)); a_sigma = __uint_as_float(SMW(o + 2 * fs));
+                a_pcode = (int)SMW(o + 3 * fs); a_poff = (int)SMW(o + 4 * fs);
             }
         }
         if (!ROLLOUT || it == 0) {   // the generator is needed from here on (not earlier)
@@ -995,8 +1027,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 const size_t off = (size_t)p.gather_rows * ((size_t)cfg.W * 4 + (size_t)A * 8) + (size_t)(p.gather_row0 + m);
                 for (int g = 0; g < p.gather_world; ++g) { p.gather_peer[g][off] = f_term; p.gather_peer[g][off + p.gather_rows] = f_trunc; }
             } else {
-                if (p.term) p.term[(size_t)m * p.flag_stride] = f_term;
-                if (p.trunc) p.trunc[(size_t)m * p.flag_stride] = f_trunc;
+                if (p.flag_pack) *reinterpret_cast<unsigned short *>(p.term + (size_t)m * p.flag_stride) = (unsigned short)(f_term | (f_trunc << 8));   // adjacent bytes: one store
+                else {
+                    if (p.term) p.term[(size_t)m * p.flag_stride] = f_term;
+                    if (p.trunc) p.trunc[(size_t)m * p.flag_stride] = f_trunc;
+                }
             }
             if (p.fill_counts) p.fill_counts[m] = k.n_fills;
             hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask;

@@ -213,7 +213,7 @@ class VecCDAEnv:
         if getattr(self, "_win", None) is None:
             M, A = self.M, self.A
             self._win = torch.empty((M, self.WINDOW_SLOTS * SNAPSHOT_DIM), dtype=torch.float32, pin_memory=True)
-            rs = 8 * (A + 1)                                   # packed record: reward f64[A] | terminated u8 | truncated u8 | pad
+            rs = self._L.cda_record_bytes(self._h)             # packed record: reward f64[A] | terminated u8 | truncated u8 | pad (multiple of 64 B)
             self._win_rec = torch.zeros(M * rs, dtype=torch.uint8, pin_memory=True)
             rec = self._win_rec.numpy()
             self._win_np = self._win.numpy()
@@ -221,6 +221,7 @@ class VecCDAEnv:
                                 np.ndarray((M,), np.uint8, rec, 8 * A + 1, (rs,)))
             self._win_ptrs = (_ptr(self._win), _ptr(self._win_rec))
             self._win_pos = None
+            self._win_n = M * A * 4
         return self._win
 
     def _window_view(self):
@@ -240,6 +241,11 @@ class VecCDAEnv:
         self._win_pos = self.n_hist - 1
         return self._window_view()
 
+    def attach_host_window(self):
+        """Start (or re-synchronise) the host window from the device state WITHOUT resetting any market — e.g. after
+        stepping through another path.  Returns the stacked observation view."""
+        return self.reset_host_window(seed=None, mask=np.zeros(self.M, dtype=np.uint8))
+
     def step_host_window(self, action_block, sync=True):
         """Lowest-traffic host path.  `action_block` as in step_host_block (ONE pinned int32 tensor [5, M, A], read in
         place by the kernel).  Per step only the newest 42-float snapshot of every market crosses PCIe, into the
@@ -247,19 +253,22 @@ class VecCDAEnv:
         [M, n_hist*42] of the n_hist most recent slots (row stride 16*42 floats, each row contiguous), bit-identical
         to step_host_block's obs.  Views are valid until the next call.  Launch, copy and stream synchronisation
         happen inside ONE C call."""
-        if getattr(self, "_win_pos", None) is None:
+        pos = getattr(self, "_win_pos", None)
+        if pos is None:
             raise RuntimeError("call reset_host_window() before step_host_window()")
-        pos = self._win_pos + 1
+        pos += 1
         if pos >= self.WINDOW_SLOTS:
             pos = self.n_hist - 1        # window restarts: the whole stack is re-sent into slots 0..n_hist-1
         base = action_block.data_ptr()
-        n = self.M * self.A * 4
-        vp = ctypes.c_void_p
-        _native.check(self._L.cda_step_host_window(self._h, vp(base), vp(base + n), vp(base + 2 * n), vp(base + 3 * n), vp(base + 4 * n),
-                                                   self._win_ptrs[0], self.WINDOW_SLOTS, pos, self._win_ptrs[1],
-                                                   1 if sync else 0, self._stream()))
+        n = self._win_n
+        rc = self._L.cda_step_host_window(self._h, base, base + n, base + 2 * n, base + 3 * n, base + 4 * n,
+                                          self._win_ptrs[0], self.WINDOW_SLOTS, pos, self._win_ptrs[1], 1 if sync else 0,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _native.check(rc)
         self._win_pos = pos
-        return (self._window_view(),) + self._win_out_np
+        s0 = (pos - self.n_hist + 1) * SNAPSHOT_DIM
+        return (self._win_np[:, s0:s0 + self.W],) + self._win_out_np
 
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""

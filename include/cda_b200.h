@@ -139,8 +139,9 @@ int cda_reset_host_ring(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_m
  * cda_reset_host_window resets the selected markets and sends every market's stack to slots 0..n_hist-1 (the next
  * step uses pos = n_hist).  Actions as in cda_step_host (read in place when the five arrays are one pinned block).
  * The other per-step results arrive as ONE packed record per market,
- *     h_records: M records of 8*(A+1) bytes = { double reward[A]; uint8_t terminated, truncated; uint8_t pad[6]; }
- * (pinned; written by one store instruction per market, or one contiguous copy when the buffer is not mapped).
+ *     h_records: M records of cda_record_bytes() bytes = { double reward[A]; uint8_t terminated, truncated; pad }
+ * (8*(A+1) rounded up to a multiple of 64, so a record never straddles a 64-byte line: with a pinned + mapped, 64-B
+ * aligned array the kernel writes it with two stores per market; otherwise it is staged and copied contiguously).
  * sync != 0: the call returns after the stream has been synchronised (outputs readable).  Use this path consistently
  * between resets: it keeps the device copy of the full stack in the handle's own staging buffer. */
 int cda_step_host_window(CdaEnv *env, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
@@ -196,6 +197,7 @@ int cda_load_state(CdaEnv *env, const void *h_src, void *stream);
 
 /* Introspection */
 int32_t cda_num_markets(const CdaEnv *env);
+int32_t cda_record_bytes(const CdaEnv *env);   /* size of one packed result record of cda_step_host_window */
 int32_t cda_obs_dim(const CdaEnv *env);
 int32_t cda_order_capacity(const CdaEnv *env);
 int64_t cda_kernel_launches(const CdaEnv *env); /* kernels launched by this handle so far */

@@ -40,9 +40,9 @@ e1.record(); torch.cuda.synchronize()
 print("%%-46s device %%6.1f us/step   host-synced %%6.1f us/step   (plain device step %%5.1f us)" %% (os.environ.get("TAG"), dev_us, host_us, e0.elapsed_time(e1) * 5))
 ''' % ROOT
 
-for tag, env in (("zc-in + SM stores to the host window (16 slots)", dict(CDA_ZEROCOPY="1", CDA_ZEROCOPY_IN="1", WSLOTS="16")),
-                 ("zc-in + SM stores to the host window (64 slots)", dict(CDA_ZEROCOPY="1", CDA_ZEROCOPY_IN="1", WSLOTS="64")),
-                 ("H2D copy + SM stores to the host window (16)", dict(CDA_ZEROCOPY="1", CDA_ZEROCOPY_IN="0", WSLOTS="16")),
-                 ("zc-in + staged, strided DMA + records DMA (16)", dict(CDA_ZEROCOPY="0", CDA_ZEROCOPY_IN="1", WSLOTS="16"))):
-    e = dict(os.environ); e.update(env); e["TAG"] = tag
+for tag, env in (("full path: zc-in (TMA) + SM stores to host window", dict()),
+                 ("no input transfer (actions resident), SM stores", dict(CDA_DEBUG_WINDOW="1")),
+                 ("zc-in, outputs stay on the device", dict(CDA_DEBUG_WINDOW="2")),
+                 ("no input, no output transfer (launch+kernel+sync)", dict(CDA_DEBUG_WINDOW="3"))):
+    e = dict(os.environ); e.update(env); e["TAG"] = tag; e.setdefault("WSLOTS", "16")
     subprocess.run([sys.executable, "-c", CHILD], env=e)
