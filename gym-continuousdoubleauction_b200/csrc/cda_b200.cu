@@ -58,7 +58,9 @@ template <int CAP>
 static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {
     const int grid = (e->M + CDA_WARPS_PER_CTA - 1) / CDA_WARPS_PER_CTA;
     // per-warp tiles, then the CTA's action tile u32[5][WARPS][A] and its mbarrier
-    const size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16;
+    //     then one 16-B aligned account tile (60*A bytes) per warp
+    const size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
+                        (size_t)CDA_WARPS_PER_CTA * (((15 * e->dev.A + 3) & ~3) * 4);
     static size_t attr_set[16] = {0};
     if (attr_set[e->device & 15] < smem) {
         cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -229,6 +231,8 @@ static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st) {
     p.prof = g_prof;
     p.fills = e->fills; p.fill_counts = e->fill_counts;
     // TMA staging of the action rows: rows of A 4-byte words must be multiples of 16 B and the arrays 16-B aligned
+    static const int dbg_acct_tma = getenv("CDA_ACCT_TMA") ? atoi(getenv("CDA_ACCT_TMA")) : 1;
+    p.acct_tma = dbg_acct_tma && (e->dev.A % 4) == 0;
     p.act_tma = e->act_tma && p.num_steps == 0 && (e->dev.A % 4) == 0 &&
                 (((uintptr_t)p.cat | (uintptr_t)p.mean | (uintptr_t)p.sigma | (uintptr_t)p.pcode | (uintptr_t)p.poff) & 15) == 0;
     CUDA_TRY(launch_step_any(e, p, st));

@@ -73,6 +73,7 @@ struct CdaStepParams {
     unsigned char *state;
     int M;
     const int *cat; const float *mean; const float *sigma; const int *pcode; const int *poff;
+    int acct_tma;  // 1: the market's account block (60*A bytes) is staged global -> shared with cp.async.bulk (needs A % 4 == 0); 0: plain loads fill the same tile
     int act_tma;   // 1: every CTA stages its markets' five action rows global/pinned-host -> shared with cp.async.bulk (needs A % 4 == 0, 16-B aligned arrays)
     float *obs; double *reward; unsigned char *term; unsigned char *trunc;
     int *fills; int *fill_counts;
@@ -248,6 +249,10 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -573,6 +578,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #ifndef CDA_BEST_CACHE
 #define CDA_BEST_CACHE 1
 #endif
+#ifndef CDA_PREFETCH_TABLES
+#define CDA_PREFETCH_TABLES 0
+#endif
 #ifndef CDA_EARLY_ACCT
 #define CDA_EARLY_ACCT 0      /* 1: load the accounts at kernel entry; 0 (measured best once spills were gone): after the normal draws (the RNG phase is the
                                  register-pressure peak: values loaded before it get spilled, and the spill store has
@@ -594,7 +602,20 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     //      array) behind one CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns
     //      20 sector-sized PCIe reads per CTA into 5 requests issued at the very start of the kernel.
     const int actb = WARPS * L::WORDS;                 // word index of the CTA's action tile: u32[5][WARPS][A], then the mbarrier
-    const int cbar_w = actb + 5 * WARPS * A;           // (even: A % 4 == 0 on this path)
+    const int cbar_w = actb + 5 * WARPS * A;           // (16-B aligned: 20*A words)
+    // the RNG tables are indexed by data that arrives ~2 us into the kernel: start pulling them into L1 now
+    // (L1 is cold at every launch; without this the ziggurat / jump-ahead reads wait a full L2 or HBM round trip)
+#if CDA_PREFETCH_TABLES == 1
+    prefetch_l1(lane < 16 ? reinterpret_cast<const char *>(cda_zig_wi) + lane * 128 : reinterpret_cast<const char *>(cda_zig_ki) + (lane - 16) * 128);
+    if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
+#elif CDA_PREFETCH_TABLES == 2   /* one warp per CTA */
+    if (warp == 0) {
+        prefetch_l1(lane < 16 ? reinterpret_cast<const char *>(cda_zig_wi) + lane * 128 : reinterpret_cast<const char *>(cda_zig_ki) + (lane - 16) * 128);
+        if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
+    }
+#elif CDA_PREFETCH_TABLES == 3   /* only the jump-ahead rows (always the same few lines) */
+    if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
+#endif
     if (!ROLLOUT && p.act_tma) {
         if (threadIdx.x == 0) {
             const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w * 4u;
@@ -615,6 +636,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     if (m >= p.M) return;
 #ifdef CDA_PROFILE_PHASES
     long long tprev = clock64();
+    { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); if (lane == 0 && p.prof) p.prof[(size_t)m * 16 + 12] = gt; }   // warp start (ns)
 #endif
     const int wb = warp * L::WORDS;                       // this warp's tile in smw
     const unsigned sa = smem_u32(smw) + (unsigned)wb * 4u;   // shared-window byte address of this warp's tile
@@ -632,14 +654,22 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A; \
     (void)g_hold; (void)g_cost; (void)g_nav; (void)g_prev; (void)g_max; (void)g_pos; (void)g_ntr; (void)g_ctr;
     CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0};
-#if CDA_EARLY_ACCT
-    if (lane < A) {
-        CDA_ACCT_PTRS
-        ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
-        ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
+    // ---- account tile: the market's whole account block (cash hold cost nav prev_nav max_nav i64[A], pos ntr ctr
+    //      u32[A]: 60*A contiguous bytes) goes global -> shared with ONE bulk copy issued before anything else; the
+    //      lanes pick their fields out of shared memory when do_actions / mark-to-market need them, so no register
+    //      holds an account value across the decode / RNG phases and no global-load latency is exposed later.
+    //      The warp's mbarrier counts two arrivals: this copy and the order-pool copy issued once the header is here.
+    const int acct_w = cbar_w + 4 + warp * ((15 * A + 3) & ~3);      // word index of this warp's account tile (16-B aligned)
+    if (lane == 0) {
+        mbar_init(bar, 2);
+        if (p.acct_tma) { mbar_expect_tx(bar, 60u * (unsigned)A); bulk_g2s(smem_u32(smw) + (unsigned)acct_w * 4u, blk + cfg.off_acct, 60u * (unsigned)A, bar); }
     }
-#endif
-    if (lane == 0) mbar_init(bar, 1);
+    if (!p.acct_tma) {   // A % 4 != 0: same tile, filled by plain loads
+        const unsigned *ga = reinterpret_cast<const unsigned *>(blk + cfg.off_acct);
+        for (int i = lane; i < 15 * A; i += 32) SMW(acct_w + i) = ga[i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+    }
     const unsigned tk0 = lane < 2 * CDA_K_ROWS ? hdr[20 + lane] : 0u;   // consumed below, after the header loads are in flight
 
     // ---- header (warp-uniform 128-bit loads: one request each, value in every lane)
@@ -672,9 +702,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
     const unsigned bytes_b = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), bytes_a = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
-    const bool have_pool = (bytes_b | bytes_a) != 0;
-    if (have_pool && lane == 0) {
-        mbar_expect_tx(bar, bytes_b + bytes_a);
+    if (lane == 0) {
+        if (bytes_b | bytes_a) mbar_expect_tx(bar, bytes_b + bytes_a); else mbar_arrive(bar);
         if (bytes_b) bulk_g2s(sa + L::POOL * 4u, gpool, bytes_b, bar);
         if (bytes_a) bulk_g2s(sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, gpool + CDA_POOL_FIELDS * CAP, bytes_a, bar);
     }
@@ -682,7 +711,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     float *g_hist = reinterpret_cast<float *>(blk + cfg.off_hist);
     const int W_old = cfg.W - CDA_SNAPSHOT_DIM;       // obs elements that come from older snapshots
 
-    bool waited = !have_pool;
+    bool waited = false;
     long long nav_max_carry = 0, nav_prev_carry = 0;   // multi-step rollout: carry max_nav / prev_nav between steps
     const int n_iter = ROLLOUT ? p.num_steps : 1;
     for (int it = 0; it < n_iter; ++it) {
@@ -728,13 +757,13 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         const unsigned present = __ballot_sync(CDA_FULL, lane < A && a_cat >= 0);
         CDA_TICK(10);  // actions arrived
         // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339).
-        // Fast path: lane a jumps the LCG ahead by (its rank + 1) steps and evaluates its own draw; this is
-        // the sequential stream as long as every draw returns from the first ziggurat test (98.8 % each).
-        // Otherwise (a wedge/tail draw consumes extra numbers) the draws are redone one after another.
+        // Lane a jumps the LCG ahead by (its rank + 1) steps and evaluates its own draw; this is the sequential
+        // stream as long as every draw returns from the first ziggurat test (98.8 % each).
         double z = 0.0;
-        if (present) {
-            const bool mine = (present >> lane) & 1u;
-            const int rnk = __popc(present & ((1u << lane) - 1u));
+#pragma unroll 1
+        for (unsigned todo = present; todo;) {   // agents whose draw is still to be made, in agent order
+            const bool mine = (todo >> lane) & 1u;
+            const int rnk = __popc(todo & ((1u << lane) - 1u));
             unsigned long long jh, jl;
             rng_jump(rng, mine ? rnk + 1 : 0, jh, jl);
             const unsigned long long xr = jh ^ jl;
@@ -746,27 +775,25 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const unsigned long long rabs = (r >> 1) & 0x000fffffffffffffULL;
             double zx = (double)rabs * __ldg(&cda_zig_wi[idx]);
             if (sign) zx = -zx;
-            const bool fast = !mine || rabs < __ldg(&cda_zig_ki[idx]);
-            if (__all_sync(CDA_FULL, fast)) {
-                z = mine ? zx : 0.0;
-                const int src = 31 - __clz(present);           // last present lane holds the state after all draws
+            const unsigned fail = __ballot_sync(CDA_FULL, mine && !(rabs < __ldg(&cda_zig_ki[idx])));
+            // the draws AHEAD of the first wedge/tail draw are exactly the sequential stream: keep them, move the
+            // generator past them, make that one draw the slow way (it consumes extra numbers), and go round again
+            // for the agents behind it (one round in 95 % of the steps)
+            const unsigned acc = fail ? (todo & ((1u << (__ffs(fail) - 1)) - 1u)) : todo;
+            if ((acc >> lane) & 1u) z = zx;
+            if (acc) {
+                const int src = 31 - __clz(acc);               // last accepted lane holds the state after its draw
                 rng.shi = __shfl_sync(CDA_FULL, jh, src);
                 rng.slo = __shfl_sync(CDA_FULL, jl, src);
-            } else {
-                for (unsigned pm = present; pm; pm &= pm - 1) {
-                    const int a = __ffs(pm) - 1;
-                    const double za = rng_normal(rng);
-                    if (lane == a) z = za;
-                }
+            }
+            todo &= ~acc;
+            if (fail) {
+                const int a = __ffs(fail) - 1;
+                const double za = rng_normal(rng);
+                if (lane == a) z = za;
+                todo &= ~(1u << a);
             }
         }
-#if !CDA_EARLY_ACCT
-        if (it == 0 && lane < A) {   // accounts: needed from do_actions on; the shuffle below covers their latency
-            CDA_ACCT_PTRS
-            ac.cash = g_cash[lane]; ac.hold = g_hold[lane]; ac.cost = g_cost[lane]; ac.nav = g_nav[lane];
-            ac.pos = g_pos[lane]; ac.ntr = g_ntr[lane];
-        }
-#endif
         CDA_TICK(11);  // draws done
         const int a_side = a_cat <= 0 ? -1 : (a_cat <= 4 ? 0 : 1);
         const int a_type = a_cat <= 0 ? 0 : ((a_cat - 1) & 3);
@@ -799,10 +826,14 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // ================= rand_exec_seq: action_helper.py:174-199 ==========================
         const unsigned active = __ballot_sync(CDA_FULL, lane < A && a_side >= 0);
         const int n_act = __popc(active);
-        if (lane == 0) { int q = 0; for (unsigned am = active; am; am &= am - 1) SMW(wb + L::ORDER + q++) = (unsigned)(__ffs(am) - 1); }
+        // the execution order lives in a register: lane q holds the q-th action's agent (scatter by rank, read back by lane)
+        if ((active >> lane) & 1u) SMW(wb + L::ORDER + __popc(active & ((1u << lane) - 1u))) = (unsigned)lane;
+        __syncwarp();
+        int ord = (int)SMW(wb + L::ORDER + lane);
         for (int i = n_act - 1; i >= 1; --i) {           // Generator.permutation: Fisher-Yates from the top
-            const unsigned j = rng_interval(rng, (unsigned)i);
-            if (lane == 0) { const unsigned tmp = SMW(wb + L::ORDER + i); SMW(wb + L::ORDER + i) = SMW(wb + L::ORDER + j); SMW(wb + L::ORDER + j) = tmp; }
+            const int j = (int)rng_interval(rng, (unsigned)i);
+            const int vi = __shfl_sync(CDA_FULL, ord, i), vj = __shfl_sync(CDA_FULL, ord, j);
+            ord = lane == i ? vj : (lane == j ? vi : ord);
         }
         if (lane == 0) {   // park the generator: it is not needed again until the next step / the final store
             unsigned long long *pk = reinterpret_cast<unsigned long long *>(&smw[wb + L::PARK]);
@@ -812,12 +843,19 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         __syncwarp();
 
         CDA_TICK(2);   // shuffle done
-        if (!waited) { mbar_wait(bar, 0); waited = true; }
-        CDA_TICK(3);   // pool tiles landed
+        if (!waited) {
+            mbar_wait(bar, 0); waited = true;
+            if (lane < A) {   // this lane's account, out of the account tile
+                const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
+                ac.cash = sq[lane]; ac.hold = sq[A + lane]; ac.cost = sq[2 * A + lane]; ac.nav = sq[3 * A + lane];
+                ac.pos = (int)SMW(acct_w + 12 * A + lane); ac.ntr = SMW(acct_w + 13 * A + lane);
+            }
+        }
+        CDA_TICK(3);   // pool + account tiles landed
 
         // ================= do_actions: action_helper.py:201-239 =============================
         for (int q = 0; q < n_act; ++q) {
-            const int t = (int)SMW(wb + L::ORDER + q);
+            const int t = __shfl_sync(CDA_FULL, ord, q);
             const unsigned ts_ = SMW(wb + L::ACT + 3 * t);
             const long long size = (long long)SMW(wb + L::ACT + 3 * t + 1);
             const int price = (int)SMW(wb + L::ACT + 3 * t + 2);
@@ -827,8 +865,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         CDA_TICK(4);   // do_actions done
         // mark-to-market needs max_nav / prev_nav from the state block: issue those loads now, do the top-K sweep
         // (which does not depend on the accounts), then mark to market
-        long long ld_max = 0, ld_prev = 0;
-        if (lane < A && (!ROLLOUT || it == 0)) { CDA_ACCT_PTRS ld_max = g_max[lane]; ld_prev = g_prev[lane]; }
         if (k.tape_nonempty) last_price = k.tape_px;   // exchg_helper.py:62-63 (the snapshot's midpoint fallback reads it)
 
         // ================= set_agg_LOB: state_helper.py:113-214 =============================
@@ -916,6 +952,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             }
         }
         // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
+        long long ld_max = 0, ld_prev = 0;
+        if (lane < A && (!ROLLOUT || it == 0)) {
+            const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
+            ld_prev = sq[4 * A + lane]; ld_max = sq[5 * A + lane];
+        }
         long long nav_prev = ac.nav, nav_max = (!ROLLOUT || it == 0) ? ld_max : nav_max_carry;   // calculate.py:49-51
         if (k.tape_nonempty) {
             if (lane < A) {
@@ -1088,6 +1129,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     }
 #endif
     CDA_TICK(9);   // state stored
+#ifdef CDA_PROFILE_PHASES
+    { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); if (lane == 0 && p.prof) p.prof[(size_t)m * 16 + 13] = gt; }   // warp end (ns)
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

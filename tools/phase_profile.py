@@ -27,7 +27,8 @@ acts = [torch.from_numpy(a).cuda() for a in make_actions(7, T, M, A, mix)]
 L = _native.lib()
 buf = L.cda_debug_phase_buffer()
 prof = torch.zeros(16, dtype=torch.int64, device="cuda")
-for t in range(T - 20):
+NS = int(os.environ.get('PP_STEPS', 20))
+for t in range(T - NS):
     env.step(*[a[t] for a in acts])
 torch.cuda.synchronize()
 ctypes.cdll.LoadLibrary("libcudart.so.12") if False else None
@@ -36,20 +37,33 @@ cudart = C.CDLL("libcudart.so.12")
 cudart.cudaMemset(C.c_void_p(buf), 0, C.c_size_t(M * 128))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for t in range(T - 20, T):
+for t in range(T - NS, T):
     env.step(*[a[t] for a in acts])
 e1.record(); torch.cuda.synchronize()
 raw = (C.c_uint64 * (16 * M))()
 cudart.cudaMemcpy(raw, C.c_void_p(buf), C.c_size_t(M * 128), 2)
 arr = np.frombuffer(raw, dtype=np.uint64).reshape(M, 16).astype(np.float64)
 host = arr.sum(0)
-per_mkt = arr[:, :12].sum(1) / 20
+per_mkt = arr[:, :12].sum(1) / NS
 print('per-market total cycles/step: mean %.0f  p50 %.0f  p90 %.0f  p99 %.0f  max %.0f' % (per_mkt.mean(), np.percentile(per_mkt, 50), np.percentile(per_mkt, 90), np.percentile(per_mkt, 99), per_mkt.max()))
+st, en = arr[:, 12], arr[:, 13]     # globaltimer (ns) of the LAST instrumented step: warp start / end
+t0 = st.min()
+print("last step, ns relative to the first warp's start: warp starts p50 %.0f p90 %.0f max %.0f | warp ends min %.0f p50 %.0f p99 %.0f max %.0f | lifetime mean %.0f max %.0f" % (
+    np.percentile(st - t0, 50), np.percentile(st - t0, 90), (st - t0).max(), (en - t0).min(), np.percentile(en - t0, 50), np.percentile(en - t0, 99), (en - t0).max(),
+    (en - st).mean(), (en - st).max()))
 names = ["header load", "decode (after draws)", "shuffle", "wait pool tiles", "do_actions", "mtm+topK", "obs math", "obs+ring write", "reward/done", "state store"]
 tot = sum(host[:12])
 names += ["wait actions (+accts issue)", "normal draws"]
-print(f"M={M} mix={mix}: {e0.elapsed_time(e1)/20*1e3:.1f} us per step (instrumented), mean cycles per warp-step = {tot/(20*M):.0f}")
+print(f"M={M} mix={mix}: {e0.elapsed_time(e1)/NS*1e3:.1f} us per step (instrumented), mean cycles per warp-step = {tot/(NS*M):.0f}")
 for i, n in enumerate(names):
-    print(f"  {n:30s} {host[i]/(20*M):9.0f} cyc  {100*host[i]/tot:5.1f}%")
+    print(f"  {n:30s} {host[i]/(NS*M):9.0f} cyc  {100*host[i]/tot:5.1f}%")
+order = np.argsort(per_mkt)
+slow = order[-max(1, M // 100):]
+print("slowest 1%% of markets: mean %.0f cycles/step; phase breakdown (cycles per step) vs all markets:" % per_mkt[slow].mean())
+for i, n in enumerate(names):
+    print(f"  {n:30s} slow {arr[slow, i].mean()/NS:9.0f}   all {arr[:, i].mean()/NS:9.0f}")
+info = env.info_all()
+mk = info["market"].cpu().numpy()
+print("slow markets: mean trades this step %.2f (all %.2f)" % (info["num_trades_step"].cpu().numpy()[slow].sum(1).mean() / 2, info["num_trades_step"].cpu().numpy().sum(1).mean() / 2))
 subprocess.check_call(["nvcc"] + _native.NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", _native.CSRC,
                        "-o", _native.SO_PATH, os.path.join(_native.CSRC, "cda_b200.cu")])
