@@ -311,7 +311,7 @@ def main():
                "h2d_bytes_per_step": int(M * A * 20), "d2h_bytes_per_step": int(d2h_win),
                "ms_per_step": 1e3 * t_win / args.steps,
                "api": "VecCDAEnv.step_host_window -> cda_step_host_window: pinned [5,M,A] action block staged by the kernel (cp.async.bulk from mapped host memory); "
-                      "the kernel stores the newest 42-float snapshot of every market into that market's row of a pinned [M,16,42] sliding window and a 64-B result "
+                      "the kernel stores the newest 42-float snapshot of every market into that market's row of a pinned [M,32,42] sliding window and a 64-B result "
                       "record (reward f64[A], terminated, truncated) straight into pinned host memory; obs returned = [M,168] view of the window, bit-identical to the "
                       "full stack (tests/test_gpu_parity.py); launch + stream sync inside one C call per step",
                "full_stack_variant": {"value": world * M * args.steps / t_full, "ms_per_step": 1e3 * t_full / args.steps,

@@ -43,7 +43,7 @@ INFO_MARKET_COLS = ("last_price", "best_bid", "best_ask", "time", "next_order_id
                     "done_mask", "status")
 
 EXPORTS = (
-    "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_step_host_ring", "cda_reset_host_ring", "cda_step_host_window", "cda_reset_host_window", "cda_rollout_random",
+    "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_step_host_ring", "cda_reset_host_ring", "cda_step_host_window", "cda_reset_host_window", "cda_window_bind", "cda_step_window", "cda_rollout_random",
     "cda_gather_create", "cda_gather_connect", "cda_step_gather", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_record_bytes", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
@@ -97,6 +97,8 @@ def lib():
     L.cda_reset_host_ring.argtypes = [vp, vp, vp, vp, vp]
     L.cda_step_host_window.argtypes = [vp] * 7 + [i32, i32, vp, i32, vp]
     L.cda_reset_host_window.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.cda_window_bind.argtypes = [vp, vp, i32, vp, vp]
+    L.cda_step_window.argtypes = [vp, vp, i32, i32]
     L.cda_rollout_random.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp]
     L.cda_gather_create.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.cda_gather_connect.argtypes = [vp, vp]

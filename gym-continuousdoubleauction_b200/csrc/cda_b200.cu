@@ -45,6 +45,7 @@ struct CdaEnv {
     int zerocopy;              // cda_step_host: let the kernel store outputs straight into mapped pinned host memory
     const void *zc_host; void *zc_dev;   // last host obs pointer checked and its device alias (NULL = not mapped)
     const void *zr_host; void *zr_dev;   // same for the window path's record array
+    float *w_window; int w_slots; void *w_records; void *w_stream;   // cda_window_bind
     int zerocopy_in; const void *zi_host; void *zi_dev;
     int act_tma;               // CDA_ACT_TMA (default 1): stage the action rows with cp.async.bulk
     double zc_fraction;        // share of the obs rows the kernel writes straight to host memory (the rest is DMA'd)   // same for the action block (kernel reads pinned host memory)
@@ -463,6 +464,20 @@ int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_si
     }
     if (sync) CUDA_TRY(cudaStreamSynchronize(st));
     return CDA_OK;
+}
+
+// ---- bound form: the buffers are registered once, the per-step call carries three arguments -------------------
+int cda_window_bind(CdaEnv *e, float *h_window, int32_t slots, void *h_records, void *stream) {
+    if (!e || !h_window || !h_records || slots < e->dev.n_hist) return CDA_EINVAL;
+    e->w_window = h_window; e->w_slots = slots; e->w_records = h_records; e->w_stream = stream;
+    return CDA_OK;
+}
+int cda_step_window(CdaEnv *e, const int32_t *h_action_block, int32_t pos, int32_t sync) {
+    if (!e || !e->w_window || !h_action_block) return CDA_EINVAL;
+    const size_t MA = (size_t)e->M * e->dev.A;
+    const int32_t *b = h_action_block;
+    return cda_step_host_window(e, b, reinterpret_cast<const float *>(b + MA), reinterpret_cast<const float *>(b + 2 * MA), b + 3 * MA, b + 4 * MA,
+                                e->w_window, e->w_slots, pos, e->w_records, sync, e->w_stream);
 }
 
 int cda_reset_host_window(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream) {

@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     if (m >= p.M) return;
 #ifdef CDA_PROFILE_PHASES
     long long tprev = clock64();
-    { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); if (lane == 0 && p.prof) p.prof[(size_t)m * 16 + 12] = gt; }   // warp start (ns)
+    { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); if (lane == 0 && p.prof) { p.prof[(size_t)m * 16 + 12] = gt; unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.prof[(size_t)m * 16 + 14] = sm; } }   // warp start (ns), SM id
 #endif
     const int wb = warp * L::WORDS;                       // this warp's tile in smw
     const unsigned sa = smem_u32(smw) + (unsigned)wb * 4u;   // shared-window byte address of this warp's tile

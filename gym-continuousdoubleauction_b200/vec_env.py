@@ -207,7 +207,7 @@ class VecCDAEnv:
         return (self._ring_view(),) + self._ring_out_np
 
     # ---- sliding host window: only the newest snapshot of every market crosses PCIe (one strided DMA)
-    WINDOW_SLOTS = 16
+    WINDOW_SLOTS = 32
 
     def _ensure_window(self):
         if getattr(self, "_win", None) is None:
@@ -221,7 +221,12 @@ class VecCDAEnv:
                                 np.ndarray((M,), np.uint8, rec, 8 * A + 1, (rs,)))
             self._win_ptrs = (_ptr(self._win), _ptr(self._win_rec))
             self._win_pos = None
-            self._win_n = M * A * 4
+            H, W = self.n_hist, self.W
+            # one precomputed result tuple per slot position: (obs view [M, W], reward [M, A], terminated [M], truncated [M])
+            self._win_views = [None] * self.WINDOW_SLOTS
+            for pos in range(H - 1, self.WINDOW_SLOTS):
+                s0 = (pos - H + 1) * SNAPSHOT_DIM
+                self._win_views[pos] = (self._win_np[:, s0:s0 + W],) + self._win_out_np
         return self._win
 
     def _window_view(self):
@@ -237,7 +242,11 @@ class VecCDAEnv:
                 else np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed).astype(np.uint64)
             seeds_t = torch.from_numpy(seeds.view(np.int64)).to(self.device)
         mask_t = None if mask is None else torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
-        _native.check(self._L.cda_reset_host_window(self._h, _ptr(seeds_t), _ptr(mask_t), self._win_ptrs[0], self.WINDOW_SLOTS, self._stream()))
+        stream = self._stream()
+        _native.check(self._L.cda_reset_host_window(self._h, _ptr(seeds_t), _ptr(mask_t), self._win_ptrs[0], self.WINDOW_SLOTS, stream))
+        # tight-loop form: buffers + the CURRENT stream are bound once; step_host_window then makes a 4-argument call
+        _native.check(self._L.cda_window_bind(self._h, self._win_ptrs[0], self.WINDOW_SLOTS, self._win_ptrs[1], stream))
+        self._win_step = self._L.cda_step_window
         self._win_pos = self.n_hist - 1
         return self._window_view()
 
@@ -249,26 +258,21 @@ class VecCDAEnv:
     def step_host_window(self, action_block, sync=True):
         """Lowest-traffic host path.  `action_block` as in step_host_block (ONE pinned int32 tensor [5, M, A], read in
         place by the kernel).  Per step only the newest 42-float snapshot of every market crosses PCIe, into the
-        next slot of that market's row of a pinned [M, 16, 42] window; the returned obs is the numpy view
-        [M, n_hist*42] of the n_hist most recent slots (row stride 16*42 floats, each row contiguous), bit-identical
-        to step_host_block's obs.  Views are valid until the next call.  Launch, copy and stream synchronisation
-        happen inside ONE C call."""
+        next slot of that market's row of a pinned [M, 32, 42] window; the returned obs is the numpy view
+        [M, n_hist*42] of the n_hist most recent slots (row stride 32*42 floats, each row contiguous), bit-identical
+        to step_host_block's obs.  Views are valid until the next call.  Launch and stream synchronisation happen
+        inside ONE C call, on the stream that was current when reset_host_window()/attach_host_window() was called."""
         pos = getattr(self, "_win_pos", None)
         if pos is None:
             raise RuntimeError("call reset_host_window() before step_host_window()")
         pos += 1
         if pos >= self.WINDOW_SLOTS:
             pos = self.n_hist - 1        # window restarts: the whole stack is re-sent into slots 0..n_hist-1
-        base = action_block.data_ptr()
-        n = self._win_n
-        rc = self._L.cda_step_host_window(self._h, base, base + n, base + 2 * n, base + 3 * n, base + 4 * n,
-                                          self._win_ptrs[0], self.WINDOW_SLOTS, pos, self._win_ptrs[1], 1 if sync else 0,
-                                          torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self._win_step(self._h, action_block.data_ptr(), pos, 1 if sync else 0)
         if rc:
             _native.check(rc)
         self._win_pos = pos
-        s0 = (pos - self.n_hist + 1) * SNAPSHOT_DIM
-        return (self._win_np[:, s0:s0 + self.W],) + self._win_out_np
+        return self._win_views[pos]
 
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""

@@ -148,6 +148,11 @@ int cda_step_host_window(CdaEnv *env, const int32_t *h_category, const float *h_
                          const int32_t *h_price, const int32_t *h_price_offset, float *h_window, int32_t slots, int32_t pos,
                          void *h_records, int32_t sync, void *stream);
 int cda_reset_host_window(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream);
+/* Bound form of the same call for tight host loops: register the window, the record array and the stream once;
+ * each step then passes only the pinned action block  i32[5][M][A]  (category, size_mean bits, size_sigma bits,
+ * price, price_offset), the slot position and the sync flag. */
+int cda_window_bind(CdaEnv *env, float *h_window, int32_t slots, void *h_records, void *stream);
+int cda_step_window(CdaEnv *env, const int32_t *h_action_block, int32_t pos, int32_t sync);
 
 /* Fused T-step rollout with the on-device uniform random policy (the RandomRLModule /
  * CDA_rand.py workload: category U{0..8}, price U{0..9}, offset U{0..2}, mean U(-1,1), sigma U(0,1),

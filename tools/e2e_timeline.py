@@ -40,9 +40,7 @@ e1.record(); torch.cuda.synchronize()
 print("%%-46s device %%6.1f us/step   host-synced %%6.1f us/step   (plain device step %%5.1f us)" %% (os.environ.get("TAG"), dev_us, host_us, e0.elapsed_time(e1) * 5))
 ''' % ROOT
 
-for tag, env in (("full path: zc-in (TMA) + SM stores to host window", dict()),
-                 ("no input transfer (actions resident), SM stores", dict(CDA_DEBUG_WINDOW="1")),
-                 ("zc-in, outputs stay on the device", dict(CDA_DEBUG_WINDOW="2")),
+for tag, env in (("full path, 16 slots", dict(WSLOTS="16")), ("full path, 32 slots", dict(WSLOTS="32")), ("full path, 64 slots", dict(WSLOTS="64")),
                  ("no input, no output transfer (launch+kernel+sync)", dict(CDA_DEBUG_WINDOW="3"))):
     e = dict(os.environ); e.update(env); e["TAG"] = tag; e.setdefault("WSLOTS", "16")
     subprocess.run([sys.executable, "-c", CHILD], env=e)

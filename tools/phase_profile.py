@@ -62,6 +62,19 @@ slow = order[-max(1, M // 100):]
 print("slowest 1%% of markets: mean %.0f cycles/step; phase breakdown (cycles per step) vs all markets:" % per_mkt[slow].mean())
 for i, n in enumerate(names):
     print(f"  {n:30s} slow {arr[slow, i].mean()/NS:9.0f}   all {arr[:, i].mean()/NS:9.0f}")
+smid = arr[:, 14].astype(int)
+cnt = np.bincount(smid, minlength=148)
+tot_sm = np.bincount(smid, weights=per_mkt, minlength=148) / np.maximum(cnt, 1)
+mx_sm = np.array([per_mkt[smid == s_].max() if cnt[s_] else 0 for s_ in range(len(cnt))])
+print("warps per SM: min %d max %d; SMs by warp count: %s" % (cnt[cnt > 0].min(), cnt.max(), dict(zip(*np.unique(cnt, return_counts=True)))))
+for c in np.unique(cnt):
+    if c: print("   SMs with %d warps: mean warp cycles %.0f, mean of per-SM max %.0f" % (c, tot_sm[cnt == c].mean(), mx_sm[cnt == c].mean()))
+dec = np.array_split(np.arange(M), 8)
+print("mean cycles by market-index octile:", " ".join("%.0f" % per_mkt[d].mean() for d in dec))
+print("ten slowest markets (cycles per phase):")
+print("   market  total " + " ".join(f"{n[:9]:>9s}" for n in names))
+for mm in order[-10:]:
+    print(f"   {mm:6d} sm{smid[mm]:3d} n{cnt[smid[mm]]:2d} {per_mkt[mm]:6.0f} " + " ".join(f"{arr[mm, i]/NS:9.0f}" for i in range(len(names))))
 info = env.info_all()
 mk = info["market"].cpu().numpy()
 print("slow markets: mean trades this step %.2f (all %.2f)" % (info["num_trades_step"].cpu().numpy()[slow].sum(1).mean() / 2, info["num_trades_step"].cpu().numpy().sum(1).mean() / 2))
