@@ -222,10 +222,13 @@ def main():
     pin_blk[:, 2].view(torch.float32).copy_(torch.from_numpy(acts_np[2][:PH]))
 
     pin_steps = [pin_blk[i] for i in range(PH)]
+    pin_mm = torch.empty((PH, M, 5, A), dtype=torch.int32, pin_memory=True)      # market-major: one 20*A-byte action record per market
+    pin_mm.copy_(pin_blk.permute(0, 2, 1, 3))
+    pin_mm_steps = [pin_mm[i] for i in range(PH)]
 
     def host_step(i):
         # actions read in place from the pinned block; newest snapshot + result record written straight to pinned memory
-        return env.step_host_window(pin_steps[i % PH])
+        return env.step_host_window(pin_mm_steps[i % PH], market_major=True)
 
     def host_step_full(i):
         return env.step_host_block(pin_steps[i % PH])     # same, but the whole 168-float stack of every market crosses PCIe
@@ -304,16 +307,17 @@ def main():
         t_full = timed_host(host_step_full)
         env.attach_host_window()   # hand every market's current stack to the host window (no market is reset)
         t_win = timed_host(host_step)
-        S, H = env.WINDOW_SLOTS, env.n_hist
-        rec = M * (8 * (A + 1) + 63) // 64 * 64
+        S, H = env.WINDOW_SLOTS - 1, env.n_hist                     # the last slot only ever carries a record
+        rec = M * 8 * (A + 1)
         d2h_win = rec + M * 4 * 42 * ((S - H) + H) / (S - H + 1)     # per window cycle: S-H newest-only steps + one whole-stack step
         e2e = {"value": world * M * args.steps / t_win, "unit": UNIT,
                "h2d_bytes_per_step": int(M * A * 20), "d2h_bytes_per_step": int(d2h_win),
                "ms_per_step": 1e3 * t_win / args.steps,
-               "api": "VecCDAEnv.step_host_window -> cda_step_host_window: pinned [5,M,A] action block staged by the kernel (cp.async.bulk from mapped host memory); "
-                      "the kernel stores the newest 42-float snapshot of every market into that market's row of a pinned [M,32,42] sliding window and a 64-B result "
-                      "record (reward f64[A], terminated, truncated) straight into pinned host memory; obs returned = [M,168] view of the window, bit-identical to the "
-                      "full stack (tests/test_gpu_parity.py); launch + stream sync inside one C call per step",
+               "api": "VecCDAEnv.step_host_window(market_major=True) -> cda_step_window: pinned market-major action block i32[M,5,A] staged by the kernel "
+                      "(one cp.async.bulk from mapped host memory per CTA); the kernel stores the newest 42-float snapshot of every market into that market's row "
+                      "of a pinned [M,32,42] sliding window with the result record (reward f64[A], terminated, truncated) right behind it, in the same store "
+                      "instructions, straight into pinned host memory; obs returned = [M,168] view of the window, bit-identical to the full stack "
+                      "(tests/test_gpu_parity.py); launch + stream sync inside one C call per step",
                "full_stack_variant": {"value": world * M * args.steps / t_full, "ms_per_step": 1e3 * t_full / args.steps,
                                       "d2h_bytes_per_step": int(M * env.W * 4 + M * A * 8 + 2 * M),
                                       "api": "VecCDAEnv.step_host_block -> cda_step_host (the whole 168-float stack of every market crosses PCIe each step)"}}

@@ -51,17 +51,26 @@ struct CdaEnv {
     double zc_fraction;        // share of the obs rows the kernel writes straight to host memory (the rest is DMA'd)   // same for the action block (kernel reads pinned host memory)
     long long launches;
     size_t smem_bytes;
+    int host_ctas, dev_ctas;   // resident CTAs per SM for the host paths / the device path (0 = as many as fit)
 };
 
 static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
+// ctas_per_sm > 0 caps the CTAs resident on one SM by padding the dynamic shared memory request (228 KB per SM, 1 KB
+// reserved per CTA).  Used by the host paths: with fewer resident warps the grid runs as a stream of short CTAs instead
+// of ONE wave in which every market finishes at the same moment, so the outputs of early markets cross PCIe while later
+// markets are still being matched (and the action reads of later CTAs overlap the matching of earlier ones).
 template <int CAP>
-static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {
+static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st, int ctas_per_sm) {
     const int grid = (e->M + CDA_WARPS_PER_CTA - 1) / CDA_WARPS_PER_CTA;
     // per-warp tiles, then the CTA's action tile u32[5][WARPS][A] and its mbarrier
     //     then one 16-B aligned account tile (60*A bytes) per warp
-    const size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
-                        (size_t)CDA_WARPS_PER_CTA * (((15 * e->dev.A + 3) & ~3) * 4);
+    size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
+                  (size_t)CDA_WARPS_PER_CTA * (((15 * e->dev.A + 3) & ~3) * 4);
+    if (ctas_per_sm > 0) {
+        const size_t per_sm = 233472, pad = per_sm / (size_t)(ctas_per_sm + 1) - 1024 + 256;   // ctas_per_sm + 1 CTAs no longer fit
+        if (pad > smem && pad <= 232448 - 1024) smem = pad;
+    }
     static size_t attr_set[16] = {0};
     if (attr_set[e->device & 15] < smem) {
         cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -74,13 +83,13 @@ static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStre
     else cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
-static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st) {
+static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st, int ctas_per_sm) {
     switch (e->dev.cap) {
-        case 64: return launch_step<64>(e, p, st);
-        case 128: return launch_step<128>(e, p, st);
-        case 160: return launch_step<160>(e, p, st);
-        case 192: return launch_step<192>(e, p, st);
-        default: return launch_step<256>(e, p, st);
+        case 64: return launch_step<64>(e, p, st, ctas_per_sm);
+        case 128: return launch_step<128>(e, p, st, ctas_per_sm);
+        case 160: return launch_step<160>(e, p, st, ctas_per_sm);
+        case 192: return launch_step<192>(e, p, st, ctas_per_sm);
+        default: return launch_step<256>(e, p, st, ctas_per_sm);
     }
 }
 
@@ -190,6 +199,9 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
         e->zerocopy_in = zi ? atoi(zi) : 1;
         const char *at = getenv("CDA_ACT_TMA");
         e->act_tma = at ? atoi(at) : 1;
+        const char *hcs = getenv("CDA_HOST_CTAS"), *dcs = getenv("CDA_DEV_CTAS");
+        e->host_ctas = hcs ? atoi(hcs) : 0;
+        e->dev_ctas = dcs ? atoi(dcs) : 0;
         const char *zf = getenv("CDA_ZC_FRACTION");
         e->zc_fraction = zf ? atof(zf) : 0.25;   // SM stores to host reach ~25 GB/s but overlap the kernel; the copy engine does ~53 GB/s after it   // measured: kernel reading the pinned action block beats a separate H2D copy by ~10 us
     }
@@ -222,12 +234,13 @@ int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *
 }
 
 static unsigned long long *g_prof = nullptr;
-static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st) {
+static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st, bool host_path = false) {
     p.cfg = e->dev; p.state = e->state; p.M = e->M;
     if (!p.obs_hi) p.obs_split = e->M;   // no split: every row goes to p.obs
     if (!p.obs_stride) p.obs_stride = e->dev.W;
     if (!p.reward_stride) p.reward_stride = e->dev.A;
     if (!p.flag_stride) p.flag_stride = 1;
+    if (!p.act_mstride) p.act_mstride = e->dev.A;
     if (!p.ring_stride) { p.ring_stride = 2 * e->dev.n_hist * CDA_SNAPSHOT_DIM; p.ring_mirror = 1; }
     p.prof = g_prof;
     p.fills = e->fills; p.fill_counts = e->fill_counts;
@@ -236,7 +249,7 @@ static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st) {
     p.acct_tma = dbg_acct_tma && (e->dev.A % 4) == 0;
     p.act_tma = e->act_tma && p.num_steps == 0 && (e->dev.A % 4) == 0 &&
                 (((uintptr_t)p.cat | (uintptr_t)p.mean | (uintptr_t)p.sigma | (uintptr_t)p.pcode | (uintptr_t)p.poff) & 15) == 0;
-    CUDA_TRY(launch_step_any(e, p, st));
+    CUDA_TRY(launch_step_any(e, p, st, host_path ? e->host_ctas : e->dev_ctas));
     e->launches++;
     return CDA_OK;
 }
@@ -319,7 +332,7 @@ int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean
         p.obs = reinterpret_cast<float *>(zc); p.reward = reinterpret_cast<double *>(zc + obs_bytes);
         p.term = reinterpret_cast<unsigned char *>(zc + obs_bytes + MA * 8); p.trunc = p.term + e->M;
         if (split < e->M) { p.obs_hi = e->s_obs; p.obs_split = split; }
-        int rc2 = step_common(e, p, st);
+        int rc2 = step_common(e, p, st, true);
         if (rc2) return rc2;
         if (split < e->M) {
             const size_t off = (size_t)split * e->dev.W * 4;
@@ -328,7 +341,7 @@ int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean
         return CDA_OK;
     }
     p.obs = e->s_obs; p.reward = e->s_reward; p.term = e->s_term; p.trunc = e->s_trunc;
-    int rc = step_common(e, p, st);
+    int rc = step_common(e, p, st, true);
     if (rc) return rc;
     if (out_contig) {
         CUDA_TRY(cudaMemcpyAsync(h_obs, e->s_obs, obs_bytes + MA * 8 + 2 * (size_t)e->M, cudaMemcpyDeviceToHost, st));
@@ -376,7 +389,7 @@ int cda_step_host_ring(CdaEnv *e, const int32_t *h_category, const float *h_size
     p.ring_out = reinterpret_cast<float *>(dp[1]);
     p.ring_slot = (int)(((ring_pos % e->dev.n_hist) + e->dev.n_hist) % e->dev.n_hist);
     p.reward = reinterpret_cast<double *>(dp[2]); p.term = reinterpret_cast<unsigned char *>(dp[3]); p.trunc = reinterpret_cast<unsigned char *>(dp[4]);
-    return step_common(e, p, st);
+    return step_common(e, p, st, true);
 }
 
 int cda_reset_host_ring(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_ring, void *stream) {
@@ -393,18 +406,22 @@ int cda_reset_host_ring(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mas
 }
 
 // ---- sliding observation window (see include/cda_b200.h) ------------------------------------------------
-int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
-                         const int32_t *h_price, const int32_t *h_price_offset, float *h_window, int32_t slots, int32_t pos,
-                         void *h_records, int32_t sync, void *stream) {
+// market_major: the five pointers address ONE block i32[M][5][A] (h_category = its start).  inline_rec: the record of this step is
+// stored behind the newest snapshot, i.e. at the head of slot pos + 1 of every row (needs pos + 1 < slots and 2A + 2 <= 42 words).
+static int step_window_impl(CdaEnv *e, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                            const int32_t *h_price, const int32_t *h_price_offset, bool market_major, float *h_window, int32_t slots, int32_t pos,
+                            void *h_records, bool inline_rec, int32_t sync, void *stream) {
     if (!e || !h_category || !h_size_mean || !h_size_sigma || !h_price || !h_price_offset || !h_window || !h_records) return CDA_EINVAL;
-    const int H = e->dev.n_hist;
+    const int H = e->dev.n_hist, A = e->dev.A;
     if (slots < H || pos < H - 1 || pos >= slots) return CDA_EINVAL;
+    if (inline_rec && (pos + 1 >= slots || 2 * A + 2 > CDA_SNAPSHOT_DIM)) return CDA_EINVAL;
     if (!e->was_reset) return CDA_ESTATE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t MA = (size_t)e->M * e->dev.A;
     const char *hc = reinterpret_cast<const char *>(h_category);
-    const bool in_contig = reinterpret_cast<const char *>(h_size_mean) == hc + MA * 4 && reinterpret_cast<const char *>(h_size_sigma) == hc + 2 * MA * 4 &&
-                           reinterpret_cast<const char *>(h_price) == hc + 3 * MA * 4 && reinterpret_cast<const char *>(h_price_offset) == hc + 4 * MA * 4;
+    const bool in_contig = market_major ||
+                           (reinterpret_cast<const char *>(h_size_mean) == hc + MA * 4 && reinterpret_cast<const char *>(h_size_sigma) == hc + 2 * MA * 4 &&
+                            reinterpret_cast<const char *>(h_price) == hc + 3 * MA * 4 && reinterpret_cast<const char *>(h_price_offset) == hc + 4 * MA * 4);
     char *zi = nullptr;
     if (e->zerocopy_in && in_contig) {
         if (e->zi_host != h_category) { e->zi_host = h_category; e->zi_dev = mapped_alias(h_category); }
@@ -419,11 +436,18 @@ int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_si
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
     p.cat = e->s_cat; p.mean = e->s_mean; p.sigma = e->s_sigma; p.pcode = e->s_pcode; p.poff = e->s_poff;
+    const size_t fstep = market_major ? (size_t)A * 4 : MA * 4;   // bytes from one field's array to the next inside the block
+    if (market_major) {   // (also the layout of the staged copy)
+        const char *b = reinterpret_cast<const char *>(e->s_cat);
+        p.mean = reinterpret_cast<const float *>(b + fstep); p.sigma = reinterpret_cast<const float *>(b + 2 * fstep);
+        p.pcode = reinterpret_cast<const int *>(b + 3 * fstep); p.poff = reinterpret_cast<const int *>(b + 4 * fstep);
+        p.act_mstride = 5 * A; p.act_packed = 1;
+    }
     if (dbg_skip_in) {
     } else if (zi) {
-        p.cat = reinterpret_cast<const int *>(zi); p.mean = reinterpret_cast<const float *>(zi + MA * 4);
-        p.sigma = reinterpret_cast<const float *>(zi + 2 * MA * 4); p.pcode = reinterpret_cast<const int *>(zi + 3 * MA * 4);
-        p.poff = reinterpret_cast<const int *>(zi + 4 * MA * 4);
+        p.cat = reinterpret_cast<const int *>(zi); p.mean = reinterpret_cast<const float *>(zi + fstep);
+        p.sigma = reinterpret_cast<const float *>(zi + 2 * fstep); p.pcode = reinterpret_cast<const int *>(zi + 3 * fstep);
+        p.poff = reinterpret_cast<const int *>(zi + 4 * fstep);
     } else if (in_contig) {
         CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_category, MA * 4 * 5, cudaMemcpyHostToDevice, st));
     } else {
@@ -447,23 +471,42 @@ int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_si
     }
     const int wstride = slots * CDA_SNAPSHOT_DIM;
     unsigned char *rec = zr ? zr : e->s_rec;
-    p.reward = reinterpret_cast<double *>(rec); p.reward_stride = (int)(rec_bytes / 8);
-    p.term = rec + (size_t)e->dev.A * 8; p.trunc = p.term + 1; p.flag_stride = (int)rec_bytes; p.flag_pack = 1;
+    // inline_rec: the record's place is behind the newest snapshot (head of slot pos + 1).  On the zero-copy newest-snapshot
+    // steps it rides in the snapshot's own store instructions; on a window restart the kernel stores it there separately; on
+    // the staged fallback it is staged in HBM and copied there.
+    const bool rides = inline_rec && zw && pos != H - 1;
+    if (rides) p.rec_inline = 1;
+    else if (inline_rec && zw) {
+        unsigned char *ir = reinterpret_cast<unsigned char *>(zw + (size_t)(pos + 1) * CDA_SNAPSHOT_DIM);
+        p.reward = reinterpret_cast<double *>(ir); p.reward_stride = wstride / 2;
+        p.term = ir + (size_t)A * 8; p.trunc = p.term + 1; p.flag_stride = wstride * 4; p.flag_pack = 1;
+    } else {
+        if (inline_rec) rec = e->s_rec;
+        p.reward = reinterpret_cast<double *>(rec); p.reward_stride = (int)(rec_bytes / 8);
+        p.term = rec + (size_t)e->dev.A * 8; p.trunc = p.term + 1; p.flag_stride = (int)rec_bytes; p.flag_pack = 1;
+    }
     if (zw) {
         if (pos == H - 1) { p.obs = zw; p.obs_stride = wstride; }
         else { p.ring_out = zw; p.ring_stride = wstride; p.ring_slot = pos; p.ring_mirror = 0; }
     } else p.obs = e->s_obs;
-    int rc = step_common(e, p, st);
+    int rc = step_common(e, p, st, true);
     if (rc) return rc;
     if (!zw && !dbg_dev_out) {
         const size_t dpitch = (size_t)wstride * 4, spitch = (size_t)e->dev.W * 4;
         if (pos == H - 1) CUDA_TRY(cudaMemcpy2DAsync(h_window, dpitch, e->s_obs, spitch, spitch, e->M, cudaMemcpyDeviceToHost, st));
         else CUDA_TRY(cudaMemcpy2DAsync(h_window + (size_t)pos * CDA_SNAPSHOT_DIM, dpitch, e->s_obs + (size_t)(H - 1) * CDA_SNAPSHOT_DIM, spitch,
                                         CDA_SNAPSHOT_DIM * 4, e->M, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h_records, e->s_rec, (size_t)e->M * rec_bytes, cudaMemcpyDeviceToHost, st));
+        if (inline_rec) CUDA_TRY(cudaMemcpy2DAsync(h_window + (size_t)(pos + 1) * CDA_SNAPSHOT_DIM, dpitch, e->s_rec, rec_bytes, (size_t)A * 8 + 8, e->M, cudaMemcpyDeviceToHost, st));
+        else CUDA_TRY(cudaMemcpyAsync(h_records, e->s_rec, (size_t)e->M * rec_bytes, cudaMemcpyDeviceToHost, st));
     }
     if (sync) CUDA_TRY(cudaStreamSynchronize(st));
     return CDA_OK;
+}
+
+int cda_step_host_window(CdaEnv *e, const int32_t *h_category, const float *h_size_mean, const float *h_size_sigma,
+                         const int32_t *h_price, const int32_t *h_price_offset, float *h_window, int32_t slots, int32_t pos,
+                         void *h_records, int32_t sync, void *stream) {
+    return step_window_impl(e, h_category, h_size_mean, h_size_sigma, h_price, h_price_offset, false, h_window, slots, pos, h_records, false, sync, stream);
 }
 
 // ---- bound form: the buffers are registered once, the per-step call carries three arguments -------------------
@@ -472,12 +515,13 @@ int cda_window_bind(CdaEnv *e, float *h_window, int32_t slots, void *h_records, 
     e->w_window = h_window; e->w_slots = slots; e->w_records = h_records; e->w_stream = stream;
     return CDA_OK;
 }
-int cda_step_window(CdaEnv *e, const int32_t *h_action_block, int32_t pos, int32_t sync) {
+int cda_step_window(CdaEnv *e, const int32_t *h_action_block, int32_t pos, int32_t flags) {
     if (!e || !e->w_window || !h_action_block) return CDA_EINVAL;
-    const size_t MA = (size_t)e->M * e->dev.A;
+    const bool mm = (flags & CDA_WIN_MARKET_MAJOR) != 0;
+    const size_t fs = mm ? (size_t)e->dev.A : (size_t)e->M * e->dev.A;   // words between the five field arrays
     const int32_t *b = h_action_block;
-    return cda_step_host_window(e, b, reinterpret_cast<const float *>(b + MA), reinterpret_cast<const float *>(b + 2 * MA), b + 3 * MA, b + 4 * MA,
-                                e->w_window, e->w_slots, pos, e->w_records, sync, e->w_stream);
+    return step_window_impl(e, b, reinterpret_cast<const float *>(b + fs), reinterpret_cast<const float *>(b + 2 * fs), b + 3 * fs, b + 4 * fs, mm,
+                            e->w_window, e->w_slots, pos, e->w_records, (flags & CDA_WIN_INLINE_RECORD) != 0, flags & CDA_WIN_SYNC, e->w_stream);
 }
 
 int cda_reset_host_window(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream) {

@@ -75,6 +75,10 @@ struct CdaStepParams {
     const int *cat; const float *mean; const float *sigma; const int *pcode; const int *poff;
     int acct_tma;  // 1: the market's account block (60*A bytes) is staged global -> shared with cp.async.bulk (needs A % 4 == 0); 0: plain loads fill the same tile
     int act_tma;   // 1: every CTA stages its markets' five action rows global/pinned-host -> shared with cp.async.bulk (needs A % 4 == 0, 16-B aligned arrays)
+    int act_mstride;   // words between consecutive markets' rows of an action array: A (five [M][A] arrays) or 5*A (ONE market-major block i32[M][5][A])
+    int act_packed;    // 1: market-major block: the five rows of a CTA's markets are ONE contiguous run -> one bulk copy per CTA instead of five
+    int rec_inline;    // 1 (with ring_out): the result record {f64 reward[A]; u8 terminated, truncated; pad} is stored right behind the newest snapshot
+                       //    (the head of slot ring_slot + 1), in the same store instructions: no separate PCIe write transactions for it
     float *obs; double *reward; unsigned char *term; unsigned char *trunc;
     int *fills; int *fill_counts;
     // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
@@ -624,12 +628,15 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             mbar_init(cbar, 1);
             mbar_expect_tx(cbar, 5u * fb);
             const unsigned dst = smem_u32(smw) + (unsigned)actb * 4u, fs = (unsigned)(WARPS * A) * 4u;
-            const size_t so = (size_t)m0 * A;
-            bulk_g2s(dst, p.cat + so, fb, cbar);
-            bulk_g2s(dst + fs, p.mean + so, fb, cbar);
-            bulk_g2s(dst + 2u * fs, p.sigma + so, fb, cbar);
-            bulk_g2s(dst + 3u * fs, p.pcode + so, fb, cbar);
-            bulk_g2s(dst + 4u * fs, p.poff + so, fb, cbar);
+            const size_t so = (size_t)m0 * p.act_mstride;
+            if (p.act_packed) bulk_g2s(dst, p.cat + so, 5u * fb, cbar);   // tile = u32[markets][5][A]
+            else {                                                        // tile = u32[5][WARPS][A]
+                bulk_g2s(dst, p.cat + so, fb, cbar);
+                bulk_g2s(dst + fs, p.mean + so, fb, cbar);
+                bulk_g2s(dst + 2u * fs, p.sigma + so, fb, cbar);
+                bulk_g2s(dst + 3u * fs, p.pcode + so, fb, cbar);
+                bulk_g2s(dst + 4u * fs, p.poff + so, fb, cbar);
+            }
         }
         __syncthreads();                               // mbarrier initialised before any warp waits on it
     }
@@ -730,14 +737,14 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 a_mean = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
                 a_sigma = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
             } else if (!p.act_tma) {
-                const size_t o = (size_t)m * A + lane;
+                const size_t o = (size_t)m * p.act_mstride + lane;
                 a_cat = p.cat[o]; a_mean = p.mean[o]; a_sigma = p.sigma[o]; a_pcode = p.pcode[o]; a_poff = p.poff[o];
             }
         }
         if (!ROLLOUT && p.act_tma) {
             mbar_wait(smem_u32(smw) + (unsigned)cbar_w * 4u, 0);
             if (lane < A) {
-                const int o = actb + warp * A + lane, fs = WARPS * A;
+                const int o = actb + (p.act_packed ? warp * 5 * A : warp * A) + lane, fs = p.act_packed ? A : WARPS * A;
                 a_cat = (int)SMW(o); a_mean = __uint_as_float(SMW(o + fs)); a_sigma = __uint_as_float(SMW(o + 2 * fs));
                 a_pcode = (int)SMW(o + 3 * fs); a_poff = (int)SMW(o + 4 * fs);
             }
@@ -1027,15 +1034,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
-        if (p.ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
-            float *rg = p.ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
-            for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < CDA_SNAPSHOT_DIM; cc += 32) {
-                if (cc < 0) continue;
-                const float v = __uint_as_float(SMW(wb + L::SNAP + cc));
-                rg[cc] = v;
-                if (p.ring_mirror) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
-            }
-        }
         __syncwarp();
         for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
 
@@ -1059,9 +1057,26 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 } else p.reward[(size_t)m * p.reward_stride + lane] = r;
             }
             broke = ac.nav <= 0;
+            if (p.rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wb + L::ACT + 2 * lane) = (unsigned)rb; SMW(wb + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
         }
         done_mask |= __ballot_sync(CDA_FULL, broke);
         const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
+        if (p.ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
+            int nw = CDA_SNAPSHOT_DIM;
+            if (p.rec_inline) {        // ... followed by the result record, which then shares the snapshot's last write transaction (the
+                                       // decoded-action words are dead by now: their tile carries the record)
+                if (lane == 0) { SMW(wb + L::ACT + 2 * A) = ((done_mask & all) == all ? 1u : 0u) | (t_step + 1 >= (unsigned)cfg.max_step ? 0x100u : 0u); SMW(wb + L::ACT + 2 * A + 1) = 0u; }
+                nw += 2 * A + 2;
+                __syncwarp();
+            }
+            float *rg = p.ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
+            for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < nw; cc += 32) {
+                if (cc < 0) continue;
+                const float v = __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wb + L::SNAP + cc) : SMW(wb + L::ACT + cc - CDA_SNAPSHOT_DIM));
+                rg[cc] = v;
+                if (p.ring_mirror && cc < CDA_SNAPSHOT_DIM) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
+            }
+        }
         if (lane == 0 && last_it) {
             const unsigned char f_term = (done_mask & all) == all, f_trunc = (t_step + 1 >= (unsigned)cfg.max_step);
             if (p.gather_world > 0) {

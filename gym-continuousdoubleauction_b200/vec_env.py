@@ -222,11 +222,22 @@ class VecCDAEnv:
             self._win_ptrs = (_ptr(self._win), _ptr(self._win_rec))
             self._win_pos = None
             H, W = self.n_hist, self.W
+            # The result record rides behind the newest snapshot (CDA_WIN_INLINE_RECORD: head of slot pos+1, same PCIe write
+            # transactions as the snapshot's tail) whenever it fits into a slot; the last slot is then only ever a record carrier.
+            self._win_inline = 2 * A + 2 <= SNAPSHOT_DIM and self.WINDOW_SLOTS > H
+            self._win_last = self.WINDOW_SLOTS - (2 if self._win_inline else 1)     # last slot position a snapshot may take
             # one precomputed result tuple per slot position: (obs view [M, W], reward [M, A], terminated [M], truncated [M])
             self._win_views = [None] * self.WINDOW_SLOTS
-            for pos in range(H - 1, self.WINDOW_SLOTS):
+            row = self.WINDOW_SLOTS * SNAPSHOT_DIM * 4                               # bytes per market row
+            for pos in range(H - 1, self._win_last + 1):
                 s0 = (pos - H + 1) * SNAPSHOT_DIM
-                self._win_views[pos] = (self._win_np[:, s0:s0 + W],) + self._win_out_np
+                if self._win_inline:
+                    o = (pos + 1) * SNAPSHOT_DIM * 4
+                    outs = (np.ndarray((M, A), np.float64, self._win_np, o, (row, 8)), np.ndarray((M,), np.uint8, self._win_np, o + 8 * A, (row,)),
+                            np.ndarray((M,), np.uint8, self._win_np, o + 8 * A + 1, (row,)))
+                else:
+                    outs = self._win_out_np
+                self._win_views[pos] = (self._win_np[:, s0:s0 + W],) + outs
         return self._win
 
     def _window_view(self):
@@ -255,9 +266,12 @@ class VecCDAEnv:
         stepping through another path.  Returns the stacked observation view."""
         return self.reset_host_window(seed=None, mask=np.zeros(self.M, dtype=np.uint8))
 
-    def step_host_window(self, action_block, sync=True):
+    def step_host_window(self, action_block, sync=True, market_major=False):
         """Lowest-traffic host path.  `action_block` as in step_host_block (ONE pinned int32 tensor [5, M, A], read in
-        place by the kernel).  Per step only the newest 42-float snapshot of every market crosses PCIe, into the
+        place by the kernel) or, with market_major=True, [M, 5, A] (one 20*A-byte action record per market: a CTA's
+        markets are then fetched over PCIe by one bulk copy instead of five).  The reward / terminated / truncated
+        views are valid until the next call, like the observation (they live behind the newest snapshot in the window).
+        Per step only the newest 42-float snapshot of every market crosses PCIe, into the
         next slot of that market's row of a pinned [M, 32, 42] window; the returned obs is the numpy view
         [M, n_hist*42] of the n_hist most recent slots (row stride 32*42 floats, each row contiguous), bit-identical
         to step_host_block's obs.  Views are valid until the next call.  Launch and stream synchronisation happen
@@ -266,9 +280,9 @@ class VecCDAEnv:
         if pos is None:
             raise RuntimeError("call reset_host_window() before step_host_window()")
         pos += 1
-        if pos >= self.WINDOW_SLOTS:
+        if pos > self._win_last:
             pos = self.n_hist - 1        # window restarts: the whole stack is re-sent into slots 0..n_hist-1
-        rc = self._win_step(self._h, action_block.data_ptr(), pos, 1 if sync else 0)
+        rc = self._win_step(self._h, action_block.data_ptr(), pos, (1 if sync else 0) | (2 if market_major else 0) | (4 if self._win_inline else 0))
         if rc:
             _native.check(rc)
         self._win_pos = pos

@@ -149,10 +149,25 @@ int cda_step_host_window(CdaEnv *env, const int32_t *h_category, const float *h_
                          void *h_records, int32_t sync, void *stream);
 int cda_reset_host_window(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream);
 /* Bound form of the same call for tight host loops: register the window, the record array and the stream once;
- * each step then passes only the pinned action block  i32[5][M][A]  (category, size_mean bits, size_sigma bits,
- * price, price_offset), the slot position and the sync flag. */
+ * each step then passes only the pinned action block (category, size_mean bits, size_sigma bits, price,
+ * price_offset as 4-byte words), the slot position and `flags`:
+ *   CDA_WIN_SYNC           return after the stream has been synchronised
+ *   CDA_WIN_MARKET_MAJOR   the block is i32[M][5][A] (one 20*A-byte action record per market) instead of i32[5][M][A]:
+ *                          the markets of a CTA are then ONE contiguous run, fetched over PCIe by one bulk copy per CTA
+ *                          instead of five (reads from host memory are bound by the number of requests)
+ *   CDA_WIN_INLINE_RECORD  this step's result record { double reward[A]; uint8_t terminated, truncated; pad to 8 } is
+ *                          placed right BEHIND the newest snapshot — at the head of slot pos+1 of every row, i.e. at
+ *                          h_window[m][pos+1][0..] — instead of in h_records: the kernel then emits it in the same store
+ *                          instructions as the snapshot's tail, which saves two PCIe write transactions per market and
+ *                          step (posted writes from the SMs are bound by the number of transactions: measured
+ *                          tools/pcie_store_bench.cu).  Slot pos+1 is overwritten by the next step's snapshot, so the
+ *                          record is valid until the next call, like the observation view.  Needs pos+1 < slots (the
+ *                          caller wraps one slot earlier) and 2*A+2 <= 42. */
+#define CDA_WIN_SYNC 1
+#define CDA_WIN_MARKET_MAJOR 2
+#define CDA_WIN_INLINE_RECORD 4
 int cda_window_bind(CdaEnv *env, float *h_window, int32_t slots, void *h_records, void *stream);
-int cda_step_window(CdaEnv *env, const int32_t *h_action_block, int32_t pos, int32_t sync);
+int cda_step_window(CdaEnv *env, const int32_t *h_action_block, int32_t pos, int32_t flags);
 
 /* Fused T-step rollout with the on-device uniform random policy (the RandomRLModule /
  * CDA_rand.py workload: category U{0..8}, price U{0..9}, offset U{0..2}, mean U(-1,1), sigma U(0,1),

@@ -228,17 +228,28 @@ def _pinned_block(acts, T, M, A):
     return blk
 
 
-@pytest.mark.parametrize("n_hist,T", [(4, 100), (1, 70), (6, 75)])
-def test_host_window_view_equals_stacked_obs_across_wraps_and_masked_reset(n_hist, T):
-    """cda_step_host_window ships only the newest snapshot into the next slot of a 32-slot pinned window per market;
-    the view of the n_hist latest slots must equal the ordinary host path's stacked observation bit for bit —
-    across window restarts (T > 32 steps) and per-market resets."""
-    cfg = base_cfg(n_hist=n_hist)
-    M, A = 96, 4
+@pytest.mark.parametrize("n_hist,T,A,market_major,zerocopy", [
+    (4, 100, 4, False, True), (4, 100, 4, True, True), (1, 70, 4, True, True), (6, 75, 4, False, True),
+    (4, 70, 8, True, True),      # 8 agents: the record (2A+2 = 18 words) still rides behind the snapshot
+    (4, 40, 24, True, True),     # 24 agents: the record does not fit into a slot -> separate record array; A % 4 == 0 -> TMA-staged actions
+    (4, 40, 6, True, True),      # A % 4 != 0: plain action loads from the market-major block
+    (4, 70, 4, True, False),     # staged fallback (CDA_ZEROCOPY=0): copies instead of kernel stores into host memory
+])
+def test_host_window_view_equals_stacked_obs_across_wraps_and_masked_reset(n_hist, T, A, market_major, zerocopy, monkeypatch):
+    """cda_step_window ships only the newest snapshot into the next slot of a 32-slot pinned window per market (and the
+    result record right behind it); the view of the n_hist latest slots must equal the ordinary host path's stacked
+    observation bit for bit, and the record views the ordinary reward / flags — across window restarts (T > 32 steps),
+    per-market resets and truncation (max_step = 50), for both action-block layouts."""
+    if not zerocopy:
+        monkeypatch.setenv("CDA_ZEROCOPY", "0")
+    cfg = base_cfg(n_hist=n_hist, num_of_agents=A, max_step=50)
+    M = 96
     e1 = cda.VecCDAEnv(cfg, num_markets=M); e2 = cda.VecCDAEnv(cfg, num_markets=M)
     o1 = e1.reset(seed=11).cpu().numpy(); o2 = e2.reset_host_window(seed=11)
     assert o2.shape == (M, n_hist * 42) and np.array_equal(o1, o2)
     blk = _pinned_block(make_actions(6, T, M, A, "uniform"), T, M, A)
+    blk_mm = blk.permute(0, 2, 1, 3).contiguous().pin_memory()     # [T, M, 5, A]
+    seen_trunc = False
     for t in range(T):
         if t in (7, 28, 29, 60):
             mask = (np.arange(M) % 3 == t % 3).astype(np.uint8)
@@ -247,10 +258,14 @@ def test_host_window_view_equals_stacked_obs_across_wraps_and_masked_reset(n_his
             if t > 0:
                 assert np.array_equal(prev[mask == 0], b[mask == 0])     # untouched markets keep their stack
         o1, r1, te1, tr1 = e1.step_host_block(blk[t])
-        o2, r2, te2, tr2 = e2.step_host_window(blk[t])
+        o2, r2, te2, tr2 = e2.step_host_window(blk_mm[t] if market_major else blk[t], market_major=market_major)
         assert np.array_equal(o1, o2), f"t={t}"
-        assert np.array_equal(r1, r2) and np.array_equal(te1, te2) and np.array_equal(tr1, tr2)
+        assert r2.shape == (M, A) and np.array_equal(r1, r2), f"t={t}"
+        assert np.array_equal(te1, te2) and np.array_equal(tr1, tr2), f"t={t}"
+        seen_trunc |= bool(tr2.any())
         prev = o1.copy()
+    assert seen_trunc or T < 50
+    assert (e2.status().cpu().numpy() == 0).all()
     e1.close(); e2.close()
 
 

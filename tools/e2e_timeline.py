@@ -24,15 +24,21 @@ for f in (0, 3, 4): pin[:, f].copy_(torch.from_numpy(acts[f]))
 for f in (1, 2): pin[:, f].view(torch.float32).copy_(torch.from_numpy(acts[f]))
 for i in range(256): env.step(*[d[i] for d in dev])
 env.reset_host_window(seed=None)
+mm = os.environ.get("MM", "1") == "1"          # market-major action block (one bulk copy per CTA)
+if os.environ.get("INLINE", "1") != "1":       # timing only: record in the separate record array (two more stores per market)
+    env._win_inline = False; env._win_last = slots - 1
+    for q in range(slots): env._win_views[q] = env._win_views[q] or env._win_views[env.n_hist - 1]
+if mm:
+    pin = pin.permute(0, 2, 1, 3).contiguous().pin_memory()
 blocks = [pin[i] for i in range(300)]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for i in range(30): env.step_host_window(blocks[i], sync=False)
+for i in range(30): env.step_host_window(blocks[i], sync=False, market_major=mm)
 torch.cuda.synchronize(); e0.record()
-for i in range(200): env.step_host_window(blocks[(30 + i) %% 300], sync=False)
+for i in range(200): env.step_host_window(blocks[(30 + i) %% 300], sync=False, market_major=mm)
 e1.record(); torch.cuda.synchronize()
 dev_us = e0.elapsed_time(e1) * 5
 t0 = time.perf_counter()
-for i in range(200): env.step_host_window(blocks[(230 + i) %% 300], sync=True)
+for i in range(200): env.step_host_window(blocks[(230 + i) %% 300], sync=True, market_major=mm)
 host_us = (time.perf_counter() - t0) / 200 * 1e6
 e0.record()
 for i in range(200): env.step(*[d[i] for d in dev])
@@ -40,7 +46,12 @@ e1.record(); torch.cuda.synchronize()
 print("%%-46s device %%6.1f us/step   host-synced %%6.1f us/step   (plain device step %%5.1f us)" %% (os.environ.get("TAG"), dev_us, host_us, e0.elapsed_time(e1) * 5))
 ''' % ROOT
 
-for tag, env in (("full path, 16 slots", dict(WSLOTS="16")), ("full path, 32 slots", dict(WSLOTS="32")), ("full path, 64 slots", dict(WSLOTS="64")),
-                 ("no input, no output transfer (launch+kernel+sync)", dict(CDA_DEBUG_WINDOW="3"))):
+for tag, env in () if __name__ != "__main__" else (
+        ("32 slots, field-major actions, separate record", dict(WSLOTS="32", MM="0", INLINE="0")),
+        ("32 slots, market-major actions, separate record", dict(WSLOTS="32", MM="1", INLINE="0")),
+        ("32 slots, field-major actions, inline record", dict(WSLOTS="32", MM="0", INLINE="1")),
+        ("32 slots, market-major actions, inline record", dict(WSLOTS="32")), ("same, 64 slots", dict(WSLOTS="64")),
+        ("no input transfer", dict(WSLOTS="32", CDA_DEBUG_WINDOW="1")), ("no output transfer", dict(WSLOTS="32", CDA_DEBUG_WINDOW="2")),
+        ("no input, no output transfer (launch+kernel+sync)", dict(CDA_DEBUG_WINDOW="3"))):
     e = dict(os.environ); e.update(env); e["TAG"] = tag; e.setdefault("WSLOTS", "16")
     subprocess.run([sys.executable, "-c", CHILD], env=e)
