@@ -197,8 +197,18 @@ __device__ __forceinline__ long long rng_integers(CdaRng &r, long long lo, long 
 // G_r = 1 + A + ... + A^(r-1).  Row r = {A^r hi, A^r lo, G_r hi, G_r lo}; filled by cda_create.
 // Lets lane a evaluate "its" draw of the sequential numpy stream without waiting for lanes < a.
 __device__ unsigned long long cda_pcg_jump[CDA_MAX_AGENTS + 1][4];   // global (lane-indexed reads; see cda_zig_tables.cuh)
-__device__ __forceinline__ void rng_jump(const CdaRng &g, int r, unsigned long long &shi, unsigned long long &slo) {
+#ifndef CDA_JUMP_SMEM
+#define CDA_JUMP_SMEM 1       /* 1: every CTA copies the A+2 jump-ahead rows it can need into shared memory at kernel entry (the load latency
+                                 then overlaps the header / action fetch instead of sitting in front of the normal draws) */
+#endif
+extern __shared__ __align__(128) unsigned smw[];
+// jump_w: word index of the CTA's copy of the table in smw (CDA_JUMP_SMEM), ignored otherwise
+__device__ __forceinline__ void rng_jump(const CdaRng &g, int r, int jump_w, unsigned long long &shi, unsigned long long &slo) {
+#if CDA_JUMP_SMEM
+    const ulonglong2 aa = *reinterpret_cast<const ulonglong2 *>(&smw[jump_w + 8 * r]), gg = *reinterpret_cast<const ulonglong2 *>(&smw[jump_w + 8 * r + 4]);
+#else
     const ulonglong2 aa = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][0])), gg = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][2]));
+#endif
     const unsigned long long Ah = aa.x, Al = aa.y, Gh = gg.x, Gl = gg.y;
     const unsigned long long l1 = Al * g.slo, h1 = __umul64hi(Al, g.slo) + Ah * g.slo + Al * g.shi;
     const unsigned long long l2 = Gl * g.ilo, h2 = __umul64hi(Gl, g.ilo) + Gh * g.ilo + Gl * g.ihi;
@@ -317,7 +327,6 @@ __device__ __forceinline__ void acct_fill(CdaAcct &a, int party, int side /*0 bi
 // addressed arithmetically through SOFF(side).
 // All shared-memory traffic goes through 32-bit word indices into ONE dynamic array: an LDS/STS then
 // takes a 32-bit register + immediate, instead of re-deriving 64-bit generic addresses at every use.
-extern __shared__ __align__(128) unsigned smw[];
 #define SMW(i) smw[(i)]
 
 // Per-warp shared-memory tile, in 32-bit words.
@@ -593,6 +602,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #ifndef CDA_BULK_STORE
 #define CDA_BULK_STORE 1      /* 1: write the whole live pool prefix back with cp.async.bulk (measured 4 % faster), 0: dirty tiles with plain stores */
 #endif
+#ifndef CDA_FUSED_TOPK
+#define CDA_FUSED_TOPK 1      /* 1: the top-K sweep handles the bid and the ask side in one loop body (independent chains overlap) */
+#endif
 #define CDA_HIST_PREFETCH 5   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
 
 template <int CAP, int WARPS, bool ROLLOUT>
@@ -620,6 +632,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 #elif CDA_PREFETCH_TABLES == 3   /* only the jump-ahead rows (always the same few lines) */
     if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
 #endif
+    const int jump_w = cbar_w + 4 + WARPS * ((15 * A + 3) & ~3);      // CTA's copy of the jump-ahead rows 0..A+1 (behind the account tiles; 16-B aligned)
+#if CDA_JUMP_SMEM
+    if (threadIdx.x < 2 * (A + 2) && threadIdx.x < 2 * (CDA_MAX_AGENTS + 1))
+        reinterpret_cast<ulonglong2 *>(&smw[jump_w])[threadIdx.x] = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + threadIdx.x);
+#endif
     if (!ROLLOUT && p.act_tma) {
         if (threadIdx.x == 0) {
             const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w * 4u;
@@ -638,8 +655,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 bulk_g2s(dst + 4u * fs, p.poff + so, fb, cbar);
             }
         }
-        __syncthreads();                               // mbarrier initialised before any warp waits on it
     }
+    __syncthreads();                                   // mbarrier initialised (and the jump rows stored) before any warp goes on
     if (m >= p.M) return;
 #ifdef CDA_PROFILE_PHASES
     long long tprev = clock64();
@@ -772,7 +789,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const bool mine = (todo >> lane) & 1u;
             const int rnk = __popc(todo & ((1u << lane) - 1u));
             unsigned long long jh, jl;
-            rng_jump(rng, mine ? rnk + 1 : 0, jh, jl);
+            rng_jump(rng, mine ? rnk + 1 : 0, jump_w, jh, jl);
             const unsigned long long xr = jh ^ jl;
             const unsigned rot = (unsigned)(jh >> 58);
             unsigned long long r = (xr >> rot) | (xr << ((64u - rot) & 63u));
@@ -883,6 +900,83 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         __syncwarp();
         if (lane < 2 * CDA_K_ROWS) SMW(wb + L::VOL + lane) = 0;
         __syncwarp();
+#if CDA_FUSED_TOPK
+        // Both sides go through ONE loop body per pass: the bid chain and the ask chain are independent, so their
+        // shared-memory loads, the four redux.or and the rank arithmetic overlap instead of running back to back
+        // (the kernel is bound by dependent-issue latency at 7 warps per scheduler, not by issue slots).
+        unsigned far_sides = 0;            // bit s: side s has levels beyond the 64-tick window AND fewer than K inside it
+        unsigned bestB = 0, bestA = 0; int nlevB = 0, nlevA = 0;
+        {
+            const int ptB = k.side_w(0) + lane, ptA = k.side_w(1) + lane;
+            const int ntB = (k.nb - lane + 31) >> 5, ntA = (k.na - lane + 31) >> 5;   // tiles in which this lane owns a live order (0: none)
+            const int ntm = (max(k.nb, k.na) + 31) >> 5;
+            bestB = k.nb ? (unsigned)pool_best(k, 0) : 0u;      // usually cached by the matching phase
+            bestA = k.na ? (unsigned)pool_best(k, 1) : 0u;
+            unsigned bl = 0, bh = 0, al = 0, ah = 0; bool fB = false, fA = false;
+            CDA_SCAN_PRAGMA
+            for (int it = 0; it < ntm; ++it) {
+                const unsigned db = it < ntB ? bestB - (SMW(ptB + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) : 0xffffffffu;
+                const unsigned da = it < ntA ? (SMW(ptA + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) - bestA : 0xffffffffu;
+                bl |= db < 32u ? 1u << db : 0u; bh |= (db - 32u) < 32u ? 1u << (db - 32u) : 0u; fB |= (db - 64u) < 0xffffffbfu;   // 64 <= db < 2^32-1
+                al |= da < 32u ? 1u << da : 0u; ah |= (da - 32u) < 32u ? 1u << (da - 32u) : 0u; fA |= (da - 64u) < 0xffffffbfu;
+            }
+            bl = __reduce_or_sync(CDA_FULL, bl); bh = __reduce_or_sync(CDA_FULL, bh);
+            al = __reduce_or_sync(CDA_FULL, al); ah = __reduce_or_sync(CDA_FULL, ah);
+            const unsigned farb = __ballot_sync(CDA_FULL, fB), fara = __ballot_sync(CDA_FULL, fA);
+            const int nbl = __popc(bl), nal = __popc(al);
+            nlevB = nbl + __popc(bh); nlevA = nal + __popc(ah);
+            CDA_SCAN_PRAGMA
+            for (int it = 0; it < ntm; ++it) {
+                if (it < ntB) {
+                    const unsigned pp = SMW(ptB + it * CDA_TILE_WORDS) & CDA_PRICE_MASK, d = bestB - pp;
+                    if (d < 64u) {
+                        const int rank = d < 32u ? __popc(bl & ((1u << d) - 1u)) : nbl + __popc(bh & ((1u << (d - 32u)) - 1u));
+                        if (rank < CDA_K_ROWS) {      // every order of a level writes the same price: benign same-value race
+                            atomicAdd(&smw[wb + L::VOL + rank], SMW(ptB + it * CDA_TILE_WORDS + 32));
+                            SMW(wb + L::LPX + rank) = pp;
+                        }
+                    }
+                }
+                if (it < ntA) {
+                    const unsigned pp = SMW(ptA + it * CDA_TILE_WORDS) & CDA_PRICE_MASK, d = pp - bestA;
+                    if (d < 64u) {
+                        const int rank = d < 32u ? __popc(al & ((1u << d) - 1u)) : nal + __popc(ah & ((1u << (d - 32u)) - 1u));
+                        if (rank < CDA_K_ROWS) {
+                            atomicAdd(&smw[wb + L::VOL + CDA_K_ROWS + rank], SMW(ptA + it * CDA_TILE_WORDS + 32));
+                            SMW(wb + L::LPX + CDA_K_ROWS + rank) = pp;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < CDA_K_ROWS ? lane < nlevB : (lane < 2 * CDA_K_ROWS && lane - CDA_K_ROWS < nlevA)) { myP = (int)SMW(wb + L::LPX + lane); myV = SMW(wb + L::VOL + lane); }
+            far_sides = (farb && nlevB < CDA_K_ROWS ? 1u : 0u) | (fara && nlevA < CDA_K_ROWS ? 2u : 0u);
+        }
+#pragma unroll 1
+        for (int side = 0; side < 2 && far_sides; ++side) {        // levels further than 64 ticks from the best (rare): generic next-best search
+            if (!((far_sides >> side) & 1u)) continue;
+            const int pt = k.side_w(side) + lane;
+            const int nt = (k.count(side) - lane + 31) >> 5;
+            const unsigned B = side == 0 ? bestB : bestA;
+            unsigned prev = side == 0 ? B - 63u : B + 63u;
+            for (int lv = side == 0 ? nlevB : nlevA; lv < CDA_K_ROWS; ++lv) {
+                unsigned l2 = side == 0 ? 0u : 0xffffffffu;
+                _Pragma("unroll 1")
+                for (int it = 0; it < nt; ++it) {
+                    const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK;
+                    if (side == 0 ? pp < prev : pp > prev) l2 = side == 0 ? max(l2, pp) : min(l2, pp);
+                }
+                const unsigned P = side == 0 ? __reduce_max_sync(CDA_FULL, l2) : __reduce_min_sync(CDA_FULL, l2);
+                if (P == (side == 0 ? 0u : 0xffffffffu)) break;
+                unsigned sv = 0;
+                _Pragma("unroll 1")
+                for (int it = 0; it < nt; ++it) if ((SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) == P) sv += SMW(pt + it * CDA_TILE_WORDS + 32);
+                const unsigned V = __reduce_add_sync(CDA_FULL, sv);
+                if (lane == side * CDA_K_ROWS + lv) { myP = (int)P; myV = V; }
+                prev = P;
+            }
+        }
+#else
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
             const int pt = k.side_w(side) + lane;            // this lane's column of every tile
@@ -935,6 +1029,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
+#endif
         // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90); latency hides behind
         //      mark-to-market and the observation math.  Lane mapping: the output row of market m starts 32-B
         //      aligned (672-B rows), so element e is handled by lane (e + mis) & 31 of chunk (e + mis) >> 5, where
