@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libcda_b200.so")
+SO_PATH = os.environ.get("CDA_B200_LIB") or os.path.join(CSRC, "libcda_b200.so")   # CDA_B200_LIB: a variant build (tools/variant_bench.py)
 SOURCES = ("cda_b200.cu", "cda_kernels.cuh", "cda_zig_tables.cuh")
 HEADER = os.path.join(_ROOT, "include", "cda_b200.h")
 

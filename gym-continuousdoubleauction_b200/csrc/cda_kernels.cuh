@@ -352,7 +352,9 @@ struct CdaMkt {
     int nb, na;          // live orders per side
     unsigned dirty;      // bit (side*8 + tile): pool tile modified this launch -> must be written back
     int bestb, besta;    // cached best bid / best ask: price, -1 = side empty, -2 = unknown (recomputed by a scan on demand)
-    unsigned time, next_id, seqctr, status;
+    unsigned time, next_id, seqctr;
+    int status_w;        // word index of the sticky status word in smw (rarely touched: kept out of the registers)
+    __device__ __forceinline__ void raise(unsigned bits) const { smw[status_w] |= bits; }   // warp-uniform call: every lane writes the same value
     int tape_nonempty, tape_px;
     int lane;
     int *fills_base; int fill_cap, n_fills, mkt;   // fill log: row = fills_base + mkt * fill_cap * 8 (computed when a fill happens)
@@ -440,7 +442,7 @@ template <int CAP> __device__ __forceinline__ void pool_remove(CdaMkt<CAP> &k, i
 // ordertree.py:44-55 insert_order: append with a fresh seq (tail of the level's FIFO and of order_map)
 template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, int side, unsigned price, unsigned qty, int trader, unsigned oid, unsigned ts) {
     const int n = k.count(side);
-    if (n >= CAP) { k.status |= CDA_ST_POOL_OVERFLOW; return false; }
+    if (n >= CAP) { k.raise(CDA_ST_POOL_OVERFLOW); return false; }
     const unsigned seq = k.seqctr++;
     {   // best-price cache: a better (or first) price becomes the best; unknown stays unknown
         const int cb = k.cached_best(side);
@@ -480,7 +482,7 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
     }
     if (!__shfl_sync(CDA_FULL, ok_l, t)) { if (is_t) ac.ctr |= 1u << 25; return; }
     if (type <= 1 && is_t) ac.ctr |= 1u << 24;                          // trader.py:75-76
-    if (size <= 0 && type <= 1) { k.status |= CDA_ST_BAD_SIZE; return; }  // reference: sys.exit in process_order
+    if (size <= 0 && type <= 1) { k.raise(CDA_ST_BAD_SIZE); return; }  // reference: sys.exit in process_order
 
     // ---- trader.py:254-287 _get_order_ID: limit/cancel = first in order_map order at that price (min seq);
     //      modify = oldest timestamp at any price
@@ -551,7 +553,7 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
                                 : k.lane == 4 ? (int)moid : k.lane == 5 ? left : k.lane == 6 ? t : side;
                     frow[k.n_fills * CDA_FILL_WORDS + k.lane] = v;
                 }
-            } else k.status |= CDA_ST_FILL_OVERFLOW;
+            } else k.raise(CDA_ST_FILL_OVERFLOW);
         }
         k.n_fills++;
         if (maker != t) {                     // trader.py:311-322: counter party, then initiator (disjoint lanes)
@@ -629,13 +631,22 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         prefetch_l1(lane < 16 ? reinterpret_cast<const char *>(cda_zig_wi) + lane * 128 : reinterpret_cast<const char *>(cda_zig_ki) + (lane - 16) * 128);
         if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
     }
+#elif CDA_PREFETCH_TABLES == 4   /* ONE CTA pulls the ziggurat tables into L2 (they are evicted whenever something streams through L2 between
+                                    steps; the draws ~2 us later then miss L1 into L2 instead of into HBM) */
+    if (blockIdx.x == 0) {
+        const char *t = warp == 0 ? reinterpret_cast<const char *>(cda_zig_wi) : warp == 1 ? reinterpret_cast<const char *>(cda_zig_ki) : reinterpret_cast<const char *>(cda_zig_fi);
+        if (warp < 3 && lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + lane * 128));
+    }
 #elif CDA_PREFETCH_TABLES == 3   /* only the jump-ahead rows (always the same few lines) */
     if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
 #endif
-    const int jump_w = cbar_w + 4 + WARPS * ((15 * A + 3) & ~3);      // CTA's copy of the jump-ahead rows 0..A+1 (behind the account tiles; 16-B aligned)
+    // this warp's copy of the jump-ahead rows 0..A (behind the account tiles; 16-B aligned): loaded NOW, stored to shared memory
+    // just before the normal draws (by then the load has landed: nothing waits for it)
+    const int jump_w = cbar_w + 4 + WARPS * ((15 * A + 3) & ~3) + warp * 8 * (A + 1);
 #if CDA_JUMP_SMEM
-    if (threadIdx.x < 2 * (A + 2) && threadIdx.x < 2 * (CDA_MAX_AGENTS + 1))
-        reinterpret_cast<ulonglong2 *>(&smw[jump_w])[threadIdx.x] = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + threadIdx.x);
+    ulonglong2 jrow = make_ulonglong2(0ULL, 0ULL);   // lane j < 2(A+1): 16-byte piece j of the table (row j/2: A^r for even j, G_r for odd j)
+    const bool jump_early = 2 * (A + 1) <= 32;
+    if (jump_early && lane < 2 * (A + 1)) jrow = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + lane);
 #endif
     if (!ROLLOUT && p.act_tma) {
         if (threadIdx.x == 0) {
@@ -711,14 +722,17 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     k.pool_w = wb + L::POOL;
     k.time = h0.x; k.next_id = h0.y; k.seqctr = h0.z;
     unsigned t_step = h0.w;
-    int last_price = (int)h1.x;
+    // last_price (exchg_helper.py:62-63: the latest tape price, or the reset anchor while the tape is empty) and the tape price the
+    // matching loop maintains are the same number at every point where either is read: ONE register, k.tape_px
     k.tape_nonempty = (h1.y & CDA_FLAG_TAPE) ? 1 : 0;
-    unsigned done_mask = h1.z;
-    k.status = h1.w;
+    // done_mask and the sticky status are not needed until the very end: parked in shared memory (held in registers they get
+    // spilled, and the reload at the end of the kernel misses the small L1: measured 2.8 % of the kernel in one LDL)
+    k.status_w = wb + L::PARK + 11;
+    if (lane == 0) { SMW(wb + L::PARK + 10) = h1.z; SMW(wb + L::PARK + 11) = h1.w; }
     k.nb = (int)h2.x; k.na = (int)h2.y;
     CdaRng rng;
     rng.has32 = h2.z; rng.u32 = h2.w;
-    k.tape_px = last_price;
+    k.tape_px = (int)h1.x;
     k.fills_base = p.fills; k.mkt = m;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
     k.bestb = k.nb ? (hb.x ? (int)hb.x : -2) : -1; k.besta = k.na ? (hb.y ? (int)hb.y : -2) : -1;
@@ -774,12 +788,19 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         k.n_fills = 0;
         ac.ctr = 0;
         const bool bad = lane < A && (a_cat > 8 || (a_cat > 0 && ((a_cat - 1) & 3) != 0 && (a_pcode < 0 || a_pcode >= CDA_K_ROWS || a_poff < 0 || a_poff > 2)));
-        if (__any_sync(CDA_FULL, bad)) k.status |= CDA_ST_BAD_ACTION;
+        if (__any_sync(CDA_FULL, bad)) k.raise(CDA_ST_BAD_ACTION);
         if (a_cat > 8) a_cat = 0;
         if (a_pcode < 0 || a_pcode >= CDA_K_ROWS) a_pcode = 0;
         if (a_poff < 0 || a_poff > 2) a_poff = 1;
         const unsigned present = __ballot_sync(CDA_FULL, lane < A && a_cat >= 0);
         CDA_TICK(10);  // actions arrived
+#if CDA_JUMP_SMEM
+        if (!ROLLOUT || it == 0) {
+            if (jump_early) { if (lane < 2 * (A + 1)) *reinterpret_cast<ulonglong2 *>(&smw[jump_w + 4 * lane]) = jrow; }
+            else for (int j = lane; j < 2 * (A + 1); j += 32) *reinterpret_cast<ulonglong2 *>(&smw[jump_w + 4 * j]) = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + j);
+            __syncwarp();
+        }
+#endif
         // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339).
         // Lane a jumps the LCG ahead by (its rank + 1) steps and evaluates its own draw; this is the sequential
         // stream as long as every draw returns from the first ziggurat test (98.8 % each).
@@ -831,13 +852,13 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 const int raw = (int)SMW(wb + L::TOPK + a_side * CDA_K_ROWS + a_pcode);
                 const int off = a_poff - 1;
                 int base, pr;
-                if (a_side == 0) { base = raw == 0 ? last_price - (a_pcode + 1) * cfg.tick : raw; pr = base + off * cfg.tick; }
-                else             { base = raw == 0 ? last_price + (a_pcode + 1) * cfg.tick : raw; pr = base - off * cfg.tick; }
+                if (a_side == 0) { base = raw == 0 ? k.tape_px - (a_pcode + 1) * cfg.tick : raw; pr = base + off * cfg.tick; }
+                else             { base = raw == 0 ? k.tape_px + (a_pcode + 1) * cfg.tick : raw; pr = base - off * cfg.tick; }
                 if (pr < cfg.tick) pr = cfg.tick;
                 a_price = pr;
             }
         }
-        if (__any_sync(CDA_FULL, a_price >= (int)CDA_PRICE_MASK)) { k.status |= CDA_ST_PRICE_RANGE; if (a_price >= (int)CDA_PRICE_MASK) a_price = CDA_PRICE_MASK - 1; }
+        if (__any_sync(CDA_FULL, a_price >= (int)CDA_PRICE_MASK)) { k.raise(CDA_ST_PRICE_RANGE); if (a_price >= (int)CDA_PRICE_MASK) a_price = CDA_PRICE_MASK - 1; }
 
         CDA_TICK(1);   // accounts + actions arrived, draws + decode done
         // park the decoded actions in shared memory: the matching phase reads them with uniform loads, and the
@@ -889,7 +910,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         CDA_TICK(4);   // do_actions done
         // mark-to-market needs max_nav / prev_nav from the state block: issue those loads now, do the top-K sweep
         // (which does not depend on the accounts), then mark to market
-        if (k.tape_nonempty) last_price = k.tape_px;   // exchg_helper.py:62-63 (the snapshot's midpoint fallback reads it)
+        const int last_price = k.tape_px;              // exchg_helper.py:62-63 (the snapshot's midpoint fallback reads it)
 
         // ================= set_agg_LOB: state_helper.py:113-214 =============================
         // Top-K levels per side in ONE sweep: the distinct prices within 64 ticks of the best form
@@ -1154,7 +1175,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             broke = ac.nav <= 0;
             if (p.rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wb + L::ACT + 2 * lane) = (unsigned)rb; SMW(wb + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
         }
-        done_mask |= __ballot_sync(CDA_FULL, broke);
+        const unsigned done_mask = SMW(wb + L::PARK + 10) | __ballot_sync(CDA_FULL, broke);
+        __syncwarp();
+        if (lane == 0) SMW(wb + L::PARK + 10) = done_mask;
         const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
         if (p.ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
             int nw = CDA_SNAPSHOT_DIM;
@@ -1200,7 +1223,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     // ---- store: header, accounts, pool prefix
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
-        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)last_price, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, done_mask, k.status);
+        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)k.tape_px, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, SMW(wb + L::PARK + 10), SMW(wb + L::PARK + 11));
         const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wb + L::PARK]);
         *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)k.nb, (unsigned)k.na, SMW(wb + L::PARK + 8), SMW(wb + L::PARK + 9));
         *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(pk[0], pk[1]);
