@@ -7,7 +7,7 @@ include/cda_b200.h.  Importing the package does not need a GPU; constructing an 
 from . import _native, config, workloads  # noqa: F401
 from .config import SNAPSHOT_DIM, K_ROWS  # noqa: F401
 
-__all__ = ["VecCDAEnv", "continuousDoubleAuctionEnv", "build"]
+__all__ = ["VecCDAEnv", "VectorCDAEnv", "continuousDoubleAuctionEnv", "build"]
 
 
 def build(force=False, verbose=False):
@@ -18,6 +18,9 @@ def __getattr__(name):  # lazy: torch is only imported when an env class is requ
     if name == "VecCDAEnv":
         from .vec_env import VecCDAEnv
         return VecCDAEnv
+    if name == "VectorCDAEnv":
+        from .vector_env import VectorCDAEnv
+        return VectorCDAEnv
     if name == "continuousDoubleAuctionEnv":
         from .env import continuousDoubleAuctionEnv
         return continuousDoubleAuctionEnv

@@ -97,6 +97,67 @@ def _plain(v):
     return v
 
 
+def build_infos(info, m, agents, rewards, actions, coeffs):
+    """The reference's per-agent info dicts (exchg/info_helper.py:30-116, reward terms of reward_helper.py:75-81) of market
+    `m`, from one `info_all` gather (`info`: numpy arrays).  `coeffs` carries the five reward coefficients.
+    Returns (infos, pass_agents, done_agents)."""
+    mk = info["market"][m]
+    last_price = float(mk[0])
+    best_bid = float(mk[1]) if mk[1] > 0 else None
+    best_ask = float(mk[2]) if mk[2] > 0 else None
+    spread = (best_ask - best_bid) if (best_bid is not None and best_ask is not None) else None
+    infos, pass_agents, done = {}, set(), set()
+    for i, a in enumerate(agents):
+        nav, prev_nav, max_nav = int(info["nav"][m, i]), int(info["prev_nav"][m, i]), int(info["max_nav"][m, i])
+        if nav <= 0:
+            done.add(a)
+        if info["is_pass_action"][m, i]:
+            pass_agents.add(a)
+        pos = int(info["net_position"][m, i])
+        cost = int(info["cost_basis"][m, i])
+        placed, trades_step = int(info["order_step_placed"][m, i]), int(info["num_trades_step"][m, i])
+        passive = int(info["num_passive_fills_step"][m, i])
+        nav_change = float(nav - prev_nav)
+        dd = float(max(0, max_nav - nav))
+        terms = {                                             # reward_helper.py:75-81, same IEEE ops as the kernel
+            "nav_term": nav_change * (coeffs.loss_multiplier if nav_change < 0 else 1.0),
+            "order_penalty": -(coeffs.order_penalty * placed),
+            "trade_penalty": -(coeffs.trade_penalty * trades_step),
+            "drawdown_penalty": -(coeffs.drawdown_penalty * dd),
+            "passive_bonus": coeffs.passive_bonus * passive,
+        }
+        d = {
+            "reward": rewards[a], "NAV": str(nav), "num_trades": int(info["num_trades"][m, i]),
+            "net_position": pos, "VWAP": (cost / abs(pos)) if pos else 0.0,
+            "cash": float(info["cash"][m, i]), "cash_on_hold": float(info["cash_on_hold"][m, i]),
+            "position_val": float(info["position_val"][m, i]), "drawdown": dd, "max_nav": float(max_nav),
+            "num_trades_step": trades_step, "num_passive_fills_step": passive, "order_step_placed": placed,
+            "num_rejected_step": int(info["num_rejected_step"][m, i]),
+            "is_pass_action": a in pass_agents, "reward_terms": terms,
+            "last_price": last_price, "best_bid": best_bid, "best_ask": best_ask, "spread": spread,
+        }
+        if actions is not None and a in actions:
+            d["model_action"] = _plain(actions[a])
+        infos[a] = _plain(d)
+    return infos, pass_agents, done
+
+
+def pack_actions(actions, A, cat, mean, sigma, price, off, m=0):
+    """One reference action dict ({agent_i: {category, size_mean, size_sigma, price, price_offset}}) -> row m of the five
+    [M, A] arrays (absent agent: category -1).  Returns the agent indices in dict order."""
+    cat[m, :] = -1
+    idxs = []
+    for key, val in actions.items():
+        i = int(key.split("_")[1])
+        idxs.append(i)
+        cat[m, i] = int(val["category"])
+        mean[m, i] = np.float32(np.asarray(val["size_mean"], dtype=np.float32).reshape(-1)[0])
+        sigma[m, i] = np.float32(np.asarray(val["size_sigma"], dtype=np.float32).reshape(-1)[0])
+        price[m, i] = int(val.get("price", 0))
+        off[m, i] = int(val.get("price_offset", _config.PRICE_OFFSET_N // 2))
+    return idxs
+
+
 class continuousDoubleAuctionEnv(_Base):
     metadata = {"render.modes": ["human"]}
 
@@ -177,15 +238,7 @@ class continuousDoubleAuctionEnv(_Base):
         cat = np.full((1, A), -1, np.int32)
         mean = np.zeros((1, A), np.float32); sigma = np.zeros((1, A), np.float32)
         price = np.zeros((1, A), np.int32); off = np.ones((1, A), np.int32)
-        idxs = []
-        for key, val in actions.items():
-            i = int(key.split("_")[1])
-            idxs.append(i)
-            cat[0, i] = int(val["category"])
-            mean[0, i] = np.float32(np.asarray(val["size_mean"], dtype=np.float32).reshape(-1)[0])
-            sigma[0, i] = np.float32(np.asarray(val["size_sigma"], dtype=np.float32).reshape(-1)[0])
-            price[0, i] = int(val.get("price", 0))
-            off[0, i] = int(val.get("price_offset", _config.PRICE_OFFSET_N // 2))
+        idxs = pack_actions(actions, A, cat, mean, sigma, price, off)
         if idxs != sorted(idxs) and not self._warned_order:
             warnings.warn("action dict is not in agent order: the reference draws order sizes in dict order, "
                           "cda_b200 draws them in agent order (results stay valid, seed-level parity is lost)")
@@ -201,42 +254,10 @@ class continuousDoubleAuctionEnv(_Base):
         self._vec_status = int(mk[7])
         if self._vec_status:
             self._vec.check_status()
-        next_states, rewards, infos = {}, {}, {}
-        self.pass_agents = set()
-        for i, a in enumerate(self.agents):
-            next_states[a] = o                                   # one shared array, like the reference
-            rewards[a] = float(rew[0, i])
-            nav, prev_nav, max_nav = int(info["nav"][0, i]), int(info["prev_nav"][0, i]), int(info["max_nav"][0, i])
-            if nav <= 0:
-                self.done_set.add(a)
-            if info["is_pass_action"][0, i]:
-                self.pass_agents.add(a)
-            pos = int(info["net_position"][0, i])
-            cost = int(info["cost_basis"][0, i])
-            placed, trades_step = int(info["order_step_placed"][0, i]), int(info["num_trades_step"][0, i])
-            passive = int(info["num_passive_fills_step"][0, i])
-            nav_change = float(nav - prev_nav)
-            dd = float(max(0, max_nav - nav))
-            terms = {                                             # reward_helper.py:75-81, same IEEE ops as the kernel
-                "nav_term": nav_change * (self.loss_multiplier if nav_change < 0 else 1.0),
-                "order_penalty": -(self.order_penalty * placed),
-                "trade_penalty": -(self.trade_penalty * trades_step),
-                "drawdown_penalty": -(self.drawdown_penalty * dd),
-                "passive_bonus": self.passive_bonus * passive,
-            }
-            d = {
-                "reward": rewards[a], "NAV": str(nav), "num_trades": int(info["num_trades"][0, i]),
-                "net_position": pos, "VWAP": (cost / abs(pos)) if pos else 0.0,
-                "cash": float(info["cash"][0, i]), "cash_on_hold": float(info["cash_on_hold"][0, i]),
-                "position_val": float(info["position_val"][0, i]), "drawdown": dd, "max_nav": float(max_nav),
-                "num_trades_step": trades_step, "num_passive_fills_step": passive, "order_step_placed": placed,
-                "num_rejected_step": int(info["num_rejected_step"][0, i]),
-                "is_pass_action": a in self.pass_agents, "reward_terms": terms,
-                "last_price": self.last_price, "best_bid": self.best_bid, "best_ask": self.best_ask, "spread": self.spread,
-            }
-            if a in actions:
-                d["model_action"] = _plain(actions[a])
-            infos[a] = _plain(d)
+        next_states = {a: o for a in self.agents}                 # one shared array, like the reference
+        rewards = {a: float(rew[0, i]) for i, a in enumerate(self.agents)}
+        infos, self.pass_agents, newly_done = build_infos(info, 0, self.agents, rewards, actions, self)
+        self.done_set |= newly_done
         terminateds = {a: False for a in self.agents}
         truncateds = {a: False for a in self.agents}
         terminateds["__all__"] = bool(term[0])

@@ -121,3 +121,49 @@ def test_spaces_and_attributes():
     with pytest.raises(ValueError):
         cda.continuousDoubleAuctionEnv({"tick_size": 0.5})
     env.close()
+
+
+def test_vector_dict_env_matches_one_object_per_market():
+    """VectorCDAEnv (num_envs markets, one launch per step, lazy infos) == num_envs continuousDoubleAuctionEnv objects:
+    observations, rewards, flags and every info key, through partial action dicts, a per-sub-env reset and truncation."""
+    cfg = dict(num_of_agents=4, init_cash=20_000, max_step=25, n_hist=4)
+    M, T = 3, 45
+    vec = cda.VectorCDAEnv(cfg, num_envs=M)
+    singles = [cda.continuousDoubleAuctionEnv(cfg) for _ in range(M)]
+    ov, iv = vec.reset(seed=100)
+    for m in range(M):
+        o1, i1 = singles[m].reset(seed=100 + m)
+        assert np.array_equal(ov[m]["agent_0"], o1["agent_0"]) and iv[m] == i1
+        assert ov[m]["agent_0"] is ov[m]["agent_3"]                      # one array shared by the agents of a market
+    rng = np.random.default_rng(3)
+    space = singles[0].action_spaces["agent_0"]; space.seed(5)
+    stale = None
+    for t in range(T):
+        acts = []
+        for m in range(M):
+            d = {}
+            for i in range(4):
+                if rng.random() < 0.15:
+                    continue                                             # partial dict: this agent is absent
+                d[f"agent_{i}"] = space.sample()
+            acts.append(d)
+        if t == 20:                                                      # episode boundary of sub-env 1 only
+            o_a, _ = vec.reset_at(1)
+            o_b, _ = singles[1].reset(seed=None)
+            assert np.array_equal(o_a["agent_0"], o_b["agent_0"])
+        o, r, te, tr, inf = vec.step(acts)
+        for m in range(M):
+            o1, r1, te1, tr1, inf1 = singles[m].step(acts[m])
+            assert np.array_equal(o[m]["agent_0"], o1["agent_0"]), (t, m)
+            assert r[m] == r1 and te[m] == te1 and tr[m] == tr1, (t, m)
+            if t % 6 == 0 or tr1["__all__"]:
+                assert set(inf[m]) == set(inf1)
+                for a in inf1:
+                    assert dict(inf[m])[a] == inf1[a], (t, m, a)
+        if t == 3:
+            stale = inf[0]
+    with pytest.raises(RuntimeError):
+        stale["agent_0"]                                                 # lazy info of an old step: refused, not silently wrong
+    vec.close()
+    for s in singles:
+        s.close()
