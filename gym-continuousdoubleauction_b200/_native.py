@@ -88,39 +88,47 @@ def lib():
             "(there is no CPU fallback for the env step)")
     L = ctypes.CDLL(SO_PATH)
     vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
-    L.cda_create.argtypes = [ctypes.POINTER(CdaConfig), i32, i32, ctypes.POINTER(vp)]
-    L.cda_destroy.argtypes = [vp]
-    L.cda_reset.argtypes = [vp, vp, vp, vp, vp]
-    L.cda_step.argtypes = [vp] * 11
-    L.cda_step_host.argtypes = [vp] * 11
-    L.cda_step_host_ring.argtypes = [vp] * 10 + [i64, vp]
-    L.cda_reset_host_ring.argtypes = [vp, vp, vp, vp, vp]
-    L.cda_step_host_window.argtypes = [vp] * 7 + [i32, i32, vp, i32, vp]
-    L.cda_reset_host_window.argtypes = [vp, vp, vp, vp, i32, vp]
-    L.cda_window_bind.argtypes = [vp, vp, i32, vp, vp]
-    L.cda_step_window.argtypes = [vp, vp, i32, i32]
-    L.cda_rollout_random.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp]
-    L.cda_gather_create.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
-    L.cda_gather_connect.argtypes = [vp, vp]
-    L.cda_step_gather.argtypes = [vp, vp, vp, vp, vp, vp, vp]
-    L.cda_get_info.argtypes = [vp, i32, vp, vp]
-    L.cda_get_info_all.argtypes = [vp, vp, vp]
-    L.cda_get_fills.argtypes = [vp, vp, vp, vp]
-    L.cda_dump_market.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]
-    L.cda_state_bytes.argtypes = [vp]
-    L.cda_state_bytes.restype = ctypes.c_size_t
-    L.cda_save_state.argtypes = [vp, vp, vp]
-    L.cda_load_state.argtypes = [vp, vp, vp]
+    variant = bool(os.environ.get("CDA_B200_LIB"))   # a variant / older build may lack newer entry points (tools/variant_bench.py)
+
+    def sig(name, argtypes=None, restype=None):
+        if variant and not hasattr(L, name):
+            return
+        f = getattr(L, name)
+        if argtypes is not None:
+            f.argtypes = argtypes
+        if restype is not None:
+            f.restype = restype
+
+    sig("cda_create", [ctypes.POINTER(CdaConfig), i32, i32, ctypes.POINTER(vp)])
+    sig("cda_destroy", [vp])
+    sig("cda_reset", [vp, vp, vp, vp, vp])
+    sig("cda_step", [vp] * 11)
+    sig("cda_step_host", [vp] * 11)
+    sig("cda_step_host_ring", [vp] * 10 + [i64, vp])
+    sig("cda_reset_host_ring", [vp, vp, vp, vp, vp])
+    sig("cda_step_host_window", [vp] * 7 + [i32, i32, vp, i32, vp])
+    sig("cda_reset_host_window", [vp, vp, vp, vp, i32, vp])
+    sig("cda_window_bind", [vp, vp, i32, vp, vp])
+    sig("cda_step_window", [vp, vp, i32, i32])
+    sig("cda_rollout_random", [vp, i32, u64, vp, vp, vp, vp, vp])
+    sig("cda_gather_create", [vp, i32, i32, vp, ctypes.POINTER(vp), ctypes.POINTER(u64)])
+    sig("cda_gather_connect", [vp, vp])
+    sig("cda_step_gather", [vp, vp, vp, vp, vp, vp, vp])
+    sig("cda_get_info", [vp, i32, vp, vp])
+    sig("cda_get_info_all", [vp, vp, vp])
+    sig("cda_get_fills", [vp, vp, vp, vp])
+    sig("cda_dump_market", [vp, i32, vp, vp, vp, vp, i32, vp, vp])
+    sig("cda_state_bytes", [vp], ctypes.c_size_t)
+    sig("cda_save_state", [vp, vp, vp])
+    sig("cda_load_state", [vp, vp, vp])
     for name in ("cda_num_markets", "cda_obs_dim", "cda_order_capacity", "cda_record_bytes"):
-        getattr(L, name).argtypes = [vp]
-        getattr(L, name).restype = i32
-    L.cda_kernel_launches.argtypes = [vp]
-    L.cda_kernel_launches.restype = i64
-    for name in ("cda_strerror", "cda_last_cuda_error", "cda_build_info"):
-        getattr(L, name).restype = ctypes.c_char_p
-    L.cda_strerror.argtypes = [i32]
-    L.cda_seed_to_pcg64.argtypes = [u64, ctypes.POINTER(u64)]
-    L.cda_debug_phase_buffer.restype = ctypes.c_void_p
+        sig(name, [vp], i32)
+    sig("cda_kernel_launches", [vp], i64)
+    for name in ("cda_last_cuda_error", "cda_build_info"):
+        sig(name, None, ctypes.c_char_p)
+    sig("cda_strerror", [i32], ctypes.c_char_p)
+    sig("cda_seed_to_pcg64", [u64, ctypes.POINTER(u64)])
+    sig("cda_debug_phase_buffer", None, ctypes.c_void_p)
     _lib = L
     return L
 

@@ -66,7 +66,7 @@ static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStre
     // per-warp tiles, then the CTA's action tile u32[5][WARPS][A] and its mbarrier
     //     then one 16-B aligned account tile (60*A bytes) per warp
     size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
-                  (size_t)CDA_WARPS_PER_CTA * (((15 * e->dev.A + 3) & ~3) * 4) + (size_t)CDA_WARPS_PER_CTA * 32 * (e->dev.A + 1);   // + every warp's jump-ahead rows
+                  (size_t)CDA_WARPS_PER_CTA * (((15 * e->dev.A + 3) & ~3) * 4);
     if (ctas_per_sm > 0) {
         const size_t per_sm = 233472, pad = per_sm / (size_t)(ctas_per_sm + 1) - 1024 + 256;   // ctas_per_sm + 1 CTAs no longer fit
         if (pad > smem && pad <= 232448 - 1024) smem = pad;

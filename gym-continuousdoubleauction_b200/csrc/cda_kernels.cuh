@@ -198,17 +198,15 @@ __device__ __forceinline__ long long rng_integers(CdaRng &r, long long lo, long 
 // Lets lane a evaluate "its" draw of the sequential numpy stream without waiting for lanes < a.
 __device__ unsigned long long cda_pcg_jump[CDA_MAX_AGENTS + 1][4];   // global (lane-indexed reads; see cda_zig_tables.cuh)
 #ifndef CDA_JUMP_SMEM
-#define CDA_JUMP_SMEM 1       /* 1: every CTA copies the A+2 jump-ahead rows it can need into shared memory at kernel entry (the load latency
-                                 then overlaps the header / action fetch instead of sitting in front of the normal draws) */
+#define CDA_JUMP_SMEM 1       /* 1: every warp loads the A+1 jump-ahead rows it can need at kernel entry and keeps them in shared memory (the load
+                                 latency then overlaps the header / action fetch instead of sitting in front of the normal draws) */
 #endif
 extern __shared__ __align__(128) unsigned smw[];
-// jump_w: word index of the CTA's copy of the table in smw (CDA_JUMP_SMEM), ignored otherwise
+// jump_w: word index of the warp's copy of the table in smw, or -1: read the table in global memory
 __device__ __forceinline__ void rng_jump(const CdaRng &g, int r, int jump_w, unsigned long long &shi, unsigned long long &slo) {
-#if CDA_JUMP_SMEM
-    const ulonglong2 aa = *reinterpret_cast<const ulonglong2 *>(&smw[jump_w + 8 * r]), gg = *reinterpret_cast<const ulonglong2 *>(&smw[jump_w + 8 * r + 4]);
-#else
-    const ulonglong2 aa = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][0])), gg = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][2]));
-#endif
+    ulonglong2 aa, gg;
+    if (jump_w >= 0) { aa = *reinterpret_cast<const ulonglong2 *>(&smw[jump_w + 8 * r]); gg = *reinterpret_cast<const ulonglong2 *>(&smw[jump_w + 8 * r + 4]); }
+    else { aa = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][0])); gg = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[r][2])); }
     const unsigned long long Ah = aa.x, Al = aa.y, Gh = gg.x, Gl = gg.y;
     const unsigned long long l1 = Al * g.slo, h1 = __umul64hi(Al, g.slo) + Ah * g.slo + Al * g.shi;
     const unsigned long long l2 = Gl * g.ilo, h2 = __umul64hi(Gl, g.ilo) + Gh * g.ilo + Gl * g.ihi;
@@ -640,13 +638,16 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 #elif CDA_PREFETCH_TABLES == 3   /* only the jump-ahead rows (always the same few lines) */
     if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
 #endif
-    // this warp's copy of the jump-ahead rows 0..A (behind the account tiles; 16-B aligned): loaded NOW, stored to shared memory
-    // just before the normal draws (by then the load has landed: nothing waits for it)
-    const int jump_w = cbar_w + 4 + WARPS * ((15 * A + 3) & ~3) + warp * 8 * (A + 1);
+    // this warp's copy of the jump-ahead rows 0..A: loaded NOW, stored to shared memory just before the normal draws (by then the
+    // load has landed: nothing waits for it).  It lives in the tail of the decoded-action tile (u32[32][3], of which 3A words are
+    // used): no extra shared memory, so 7 CTAs per SM still fit; with more than 8 agents it does not fit and the draws read
+    // the table in global memory.
 #if CDA_JUMP_SMEM
+    const bool jump_sm = ((3 * A + 3) & ~3) + 8 * (A + 1) <= 96;
     ulonglong2 jrow = make_ulonglong2(0ULL, 0ULL);   // lane j < 2(A+1): 16-byte piece j of the table (row j/2: A^r for even j, G_r for odd j)
-    const bool jump_early = 2 * (A + 1) <= 32;
-    if (jump_early && lane < 2 * (A + 1)) jrow = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + lane);
+    if (jump_sm && lane < 2 * (A + 1)) jrow = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + lane);
+#else
+    const bool jump_sm = false;
 #endif
     if (!ROLLOUT && p.act_tma) {
         if (threadIdx.x == 0) {
@@ -796,8 +797,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         CDA_TICK(10);  // actions arrived
 #if CDA_JUMP_SMEM
         if (!ROLLOUT || it == 0) {
-            if (jump_early) { if (lane < 2 * (A + 1)) *reinterpret_cast<ulonglong2 *>(&smw[jump_w + 4 * lane]) = jrow; }
-            else for (int j = lane; j < 2 * (A + 1); j += 32) *reinterpret_cast<ulonglong2 *>(&smw[jump_w + 4 * j]) = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + j);
+            if (jump_sm && lane < 2 * (A + 1)) *reinterpret_cast<ulonglong2 *>(&smw[wb + L::ACT + ((3 * A + 3) & ~3) + 4 * lane]) = jrow;
             __syncwarp();
         }
 #endif
@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const bool mine = (todo >> lane) & 1u;
             const int rnk = __popc(todo & ((1u << lane) - 1u));
             unsigned long long jh, jl;
-            rng_jump(rng, mine ? rnk + 1 : 0, jump_w, jh, jl);
+            rng_jump(rng, mine ? rnk + 1 : 0, jump_sm ? wb + L::ACT + ((3 * A + 3) & ~3) : -1, jh, jl);
             const unsigned long long xr = jh ^ jl;
             const unsigned rot = (unsigned)(jh >> 58);
             unsigned long long r = (xr >> rot) | (xr << ((64u - rot) & 63u));
@@ -1063,15 +1063,14 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             orow = p.gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
                                       : (m < p.obs_split ? p.obs : p.obs_hi) + (size_t)m * p.obs_stride;
             mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
+            // the ring holds exactly n_hist snapshots, so the stacked old part (oldest first) is ONE circular run of the ring
+            // starting at the slot after the newest: element e lives at ring position (first + e) mod W — no division by 42
+            const int first = (slot_new + 1) * CDA_SNAPSHOT_DIM;
 #pragma unroll
             for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
                 const int e = lane + 32 * q - mis;
                 hv[q] = 0.f;
-                if (e >= 0 && e < W_old) {
-                    const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
-                    int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
-                    hv[q] = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
-                }
+                if (e >= 0 && e < W_old) { int ri = first + e; if (ri >= cfg.W) ri -= cfg.W; hv[q] = g_hist[ri]; }
             }
         }
         // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
@@ -1141,11 +1140,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
                 for (int e = lane + 32 * CDA_HIST_PREFETCH - mis; e < cfg.W; e += 32) {   // beyond the prefetched chunks
                     float v;
-                    if (e < W_old) {
-                        const int j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
-                        int slot = slot_new + 1 + j; if (slot >= cfg.n_hist) slot -= cfg.n_hist;
-                        v = g_hist[slot * CDA_SNAPSHOT_DIM + cc];
-                    } else v = __uint_as_float(SMW(wb + L::SNAP + e - W_old));
+                    if (e < W_old) { int ri = (slot_new + 1) * CDA_SNAPSHOT_DIM + e; if (ri >= cfg.W) ri -= cfg.W; v = g_hist[ri]; }
+                    else v = __uint_as_float(SMW(wb + L::SNAP + e - W_old));
                     o[e] = v;
                 }
             }

@@ -82,7 +82,8 @@ class VectorCDAEnv:
         obs = self._vec.reset_host_window(seed=seed)
         self._ever_reset = True
         self._step_id += 1
-        return [{a: obs[m] for a in self.agents} for m in range(self.num_envs)], [{a: {} for a in self.agents} for _ in range(self.num_envs)]
+        rows = [obs[m] for m in range(self.num_envs)]                     # ONE array per market, shared by its agents
+        return [{a: o for a in self.agents} for o in rows], [{a: {} for a in self.agents} for _ in range(self.num_envs)]
 
     def reset_at(self, index, seed=None):
         mask = np.zeros(self.num_envs, np.uint8); mask[index] = 1
@@ -91,7 +92,8 @@ class VectorCDAEnv:
             seeds = np.zeros(self.num_envs, np.uint64); seeds[index] = np.uint64(seed)
         obs = self._vec.reset_host_window(seed=seeds, mask=mask)
         self._step_id += 1
-        return {a: obs[index] for a in self.agents}, {a: {} for a in self.agents}
+        o = obs[index]
+        return {a: o for a in self.agents}, {a: {} for a in self.agents}
 
     # ------------------------------------------------------------------ step
     def step(self, actions):
