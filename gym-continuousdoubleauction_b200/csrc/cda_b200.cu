@@ -73,14 +73,24 @@ static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStre
     }
     static size_t attr_set[16] = {0};
     if (attr_set[e->device & 15] < smem) {
-        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        auto set = [&](const void *f) {
+            cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        };
+        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, false>);
+        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, true>);
+        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true, false>);
         attr_set[e->device & 15] = smem;
     }
-    if (p.num_steps > 0) cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
-    else cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    // routed outputs (host window / ring, packed or strided records, split rows, fused all-gather) take the full kernel; the plain
+    // device step and the fused rollout take the body without that code
+    const bool routed = p.gather_world > 0 || p.ring_out || p.rec_inline || p.flag_pack || p.obs_hi || p.obs_split != e->M ||
+                        p.obs_stride != e->dev.W || p.reward_stride != e->dev.A || p.flag_stride != 1;
+    if (p.num_steps > 0) {
+        if (routed) return cudaErrorInvalidValue;   // the rollout writes dense device arrays only
+        cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    } else if (routed) cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, true><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    else cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st, int ctas_per_sm) {

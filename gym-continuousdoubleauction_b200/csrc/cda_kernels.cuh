@@ -607,13 +607,21 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #endif
 #define CDA_HIST_PREFETCH 5   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
 
-template <int CAP, int WARPS, bool ROLLOUT>
+template <int CAP, int WARPS, bool ROLLOUT, bool ROUTED>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
     using L = CdaSmemLayout<CAP>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * WARPS + warp;
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
+    // Output routing.  ROUTED = false is the plain device step (dense obs / reward / flag arrays): everything only the host window /
+    // ring, packed-record, split-row and fused all-gather paths execute is compiled out (720 of 4600 SASS instructions; the
+    // kernel is several times larger than the 32 KB L1.5 instruction cache, and the smaller body measures 2-3 % faster once
+    // the grid runs in more than one wave, when resident warps are spread over all phases of the step).
+    const int o_gather_world = ROUTED ? p.gather_world : 0, o_rec_inline = ROUTED ? p.rec_inline : 0, o_flag_pack = ROUTED ? p.flag_pack : 0;
+    const int o_obs_split = ROUTED ? p.obs_split : p.M, o_ring_mirror = ROUTED ? p.ring_mirror : 0;
+    float *const o_ring_out = ROUTED ? p.ring_out : nullptr;
+    const int o_obs_stride = ROUTED ? p.obs_stride : cfg.W, o_reward_stride = ROUTED ? p.reward_stride : A, o_flag_stride = ROUTED ? p.flag_stride : 1;
     // ---- action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A]
     //      array) behind one CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns
     //      20 sector-sized PCIe reads per CTA into 5 requests issued at the very start of the kernel.
@@ -1060,8 +1068,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         slot_new = (int)(t_step % (unsigned)cfg.n_hist);
         float *orow = nullptr; int mis = 0;
         if (p.obs && last_it) {
-            orow = p.gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
-                                      : (m < p.obs_split ? p.obs : p.obs_hi) + (size_t)m * p.obs_stride;
+            orow = o_gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
+                                      : (m < o_obs_split ? p.obs : p.obs_hi) + (size_t)m * o_obs_stride;
             mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
             // the ring holds exactly n_hist snapshots, so the stacked old part (oldest first) is ONE circular run of the ring
             // starting at the slot after the newest: element e lives at ring position (first + e) mod W — no division by 42
@@ -1129,7 +1137,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         if (p.obs && last_it) {
             // one destination normally; with the fused all-gather, row (row0 + m) of EVERY peer's buffer
             // (plain stores to peer-mapped addresses: they travel over NVLink while other warps still match)
-            const int nd = p.gather_world > 0 ? p.gather_world : 1;
+            const int nd = o_gather_world > 0 ? o_gather_world : 1;
 #pragma unroll 1
             for (int g = 0; g < nd; ++g) {
                 float *o = g == 0 ? orow : reinterpret_cast<float *>(p.gather_peer[g]) + (size_t)(p.gather_row0 + m) * cfg.W;
@@ -1163,44 +1171,44 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             r = r + -(cfg.c_dd * (double)ddi);
             r = r + cfg.c_passive * (double)((ac.ctr >> 12) & 0xfffu);
             if (p.reward && last_it) {
-                if (p.gather_world > 0) {
+                if (o_gather_world > 0) {
                     const size_t off = (size_t)p.gather_rows * cfg.W * 4 + ((size_t)(p.gather_row0 + m) * A + lane) * 8;
-                    for (int g = 0; g < p.gather_world; ++g) *reinterpret_cast<double *>(p.gather_peer[g] + off) = r;
-                } else p.reward[(size_t)m * p.reward_stride + lane] = r;
+                    for (int g = 0; g < o_gather_world; ++g) *reinterpret_cast<double *>(p.gather_peer[g] + off) = r;
+                } else p.reward[(size_t)m * o_reward_stride + lane] = r;
             }
             broke = ac.nav <= 0;
-            if (p.rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wb + L::ACT + 2 * lane) = (unsigned)rb; SMW(wb + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
+            if (o_rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wb + L::ACT + 2 * lane) = (unsigned)rb; SMW(wb + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
         }
         const unsigned done_mask = SMW(wb + L::PARK + 10) | __ballot_sync(CDA_FULL, broke);
         __syncwarp();
         if (lane == 0) SMW(wb + L::PARK + 10) = done_mask;
         const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
-        if (p.ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
+        if (o_ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
             int nw = CDA_SNAPSHOT_DIM;
-            if (p.rec_inline) {        // ... followed by the result record, which then shares the snapshot's last write transaction (the
+            if (o_rec_inline) {        // ... followed by the result record, which then shares the snapshot's last write transaction (the
                                        // decoded-action words are dead by now: their tile carries the record)
                 if (lane == 0) { SMW(wb + L::ACT + 2 * A) = ((done_mask & all) == all ? 1u : 0u) | (t_step + 1 >= (unsigned)cfg.max_step ? 0x100u : 0u); SMW(wb + L::ACT + 2 * A + 1) = 0u; }
                 nw += 2 * A + 2;
                 __syncwarp();
             }
-            float *rg = p.ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
+            float *rg = o_ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
             for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < nw; cc += 32) {
                 if (cc < 0) continue;
                 const float v = __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wb + L::SNAP + cc) : SMW(wb + L::ACT + cc - CDA_SNAPSHOT_DIM));
                 rg[cc] = v;
-                if (p.ring_mirror && cc < CDA_SNAPSHOT_DIM) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
+                if (o_ring_mirror && cc < CDA_SNAPSHOT_DIM) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
             }
         }
         if (lane == 0 && last_it) {
             const unsigned char f_term = (done_mask & all) == all, f_trunc = (t_step + 1 >= (unsigned)cfg.max_step);
-            if (p.gather_world > 0) {
+            if (o_gather_world > 0) {
                 const size_t off = (size_t)p.gather_rows * ((size_t)cfg.W * 4 + (size_t)A * 8) + (size_t)(p.gather_row0 + m);
-                for (int g = 0; g < p.gather_world; ++g) { p.gather_peer[g][off] = f_term; p.gather_peer[g][off + p.gather_rows] = f_trunc; }
+                for (int g = 0; g < o_gather_world; ++g) { p.gather_peer[g][off] = f_term; p.gather_peer[g][off + p.gather_rows] = f_trunc; }
             } else {
-                if (p.flag_pack) *reinterpret_cast<unsigned short *>(p.term + (size_t)m * p.flag_stride) = (unsigned short)(f_term | (f_trunc << 8));   // adjacent bytes: one store
+                if (o_flag_pack) *reinterpret_cast<unsigned short *>(p.term + (size_t)m * o_flag_stride) = (unsigned short)(f_term | (f_trunc << 8));   // adjacent bytes: one store
                 else {
-                    if (p.term) p.term[(size_t)m * p.flag_stride] = f_term;
-                    if (p.trunc) p.trunc[(size_t)m * p.flag_stride] = f_trunc;
+                    if (p.term) p.term[(size_t)m * o_flag_stride] = f_term;
+                    if (p.trunc) p.trunc[(size_t)m * o_flag_stride] = f_trunc;
                 }
             }
             if (p.fill_counts) p.fill_counts[m] = k.n_fills;
