@@ -252,6 +252,7 @@ __device__ __forceinline__ void rng_seed(CdaRng &r, unsigned long long seed) {
     r.has32 = 0; r.u32 = 0;
 }
 
+__device__ __forceinline__ unsigned fresh_tid_x() { unsigned t; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t)); return t; }   // not CSE'd with earlier reads
 // ----------------------------------- async-copy helpers ------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -605,7 +606,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #ifndef CDA_FUSED_TOPK
 #define CDA_FUSED_TOPK 1      /* 1: the top-K sweep handles the bid and the ask side in one loop body (independent chains overlap) */
 #endif
-#define CDA_HIST_PREFETCH 5   /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4) */
+/* registers per lane for the old-snapshot prefetch (covers n_hist <= 4): five 128-B chunks when the output row is cut at the 128-B
+   boundaries of its destination (routed outputs: PCIe / NVLink write transactions), four when chunk 0 starts at the row start */
+#define CDA_HIST_PREFETCH (ROUTED ? 5 : 4)
 
 template <int CAP, int WARPS, bool ROLLOUT, bool ROUTED>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
@@ -812,7 +815,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339).
         // Lane a jumps the LCG ahead by (its rank + 1) steps and evaluates its own draw; this is the sequential
         // stream as long as every draw returns from the first ziggurat test (98.8 % each).
-        double z = 0.0;
+        // A lane's finished draw is parked in the (not yet used) decoded-action tile instead of a register pair: the slow path is a
+        // real call, and a double held across it is spilled to local memory and reloaded through the small L1.
+        const int zw = wb + L::ACT + 2 * lane;
 #pragma unroll 1
         for (unsigned todo = present; todo;) {   // agents whose draw is still to be made, in agent order
             const bool mine = (todo >> lane) & 1u;
@@ -833,7 +838,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             // generator past them, make that one draw the slow way (it consumes extra numbers), and go round again
             // for the agents behind it (one round in 95 % of the steps)
             const unsigned acc = fail ? (todo & ((1u << (__ffs(fail) - 1)) - 1u)) : todo;
-            if ((acc >> lane) & 1u) z = zx;
+            if ((acc >> lane) & 1u) { const unsigned long long zb = (unsigned long long)__double_as_longlong(zx); SMW(zw) = (unsigned)zb; SMW(zw + 1) = (unsigned)(zb >> 32); }
             if (acc) {
                 const int src = 31 - __clz(acc);               // last accepted lane holds the state after its draw
                 rng.shi = __shfl_sync(CDA_FULL, jh, src);
@@ -843,10 +848,13 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             if (fail) {
                 const int a = __ffs(fail) - 1;
                 const double za = rng_normal(rng);
-                if (lane == a) z = za;
+                if (lane == a) { const unsigned long long zb = (unsigned long long)__double_as_longlong(za); SMW(zw) = (unsigned)zb; SMW(zw + 1) = (unsigned)(zb >> 32); }
                 todo &= ~(1u << a);
             }
         }
+        double z = 0.0;
+        if ((present >> lane) & 1u) z = __longlong_as_double((long long)(((unsigned long long)SMW(zw + 1) << 32) | SMW(zw)));
+        __syncwarp();   // every lane has its draw back before the tile receives the decoded actions
         CDA_TICK(11);  // draws done
         const int a_side = a_cat <= 0 ? -1 : (a_cat <= 4 ? 0 : 1);
         const int a_type = a_cat <= 0 ? 0 : ((a_cat - 1) & 3);
@@ -896,13 +904,15 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         __syncwarp();
 
         CDA_TICK(2);   // shuffle done
-        if (!waited) {
-            mbar_wait(bar, 0); waited = true;
-            if (lane < A) {   // this lane's account, out of the account tile
-                const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
-                ac.cash = sq[lane]; ac.hold = sq[A + lane]; ac.cost = sq[2 * A + lane]; ac.nav = sq[3 * A + lane];
-                ac.pos = (int)SMW(acct_w + 12 * A + lane); ac.ntr = SMW(acct_w + 13 * A + lane);
-            }
+        if (!waited) { mbar_wait(bar, 0); waited = true; }
+        {   // this lane's account, out of the account tile.  In a multi-step rollout the tile is also where the
+                                             // accounts live BETWEEN steps (written back at the end of every step): nothing account-related is
+                                             // carried in registers across the decode / RNG phases of the next step.  Unconditional loads (lanes
+                                             // >= A read agent 0's words and never use them) so that the old values are dead at the loop head.
+            const int al = lane < A ? lane : 0;
+            const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
+            ac.cash = sq[al]; ac.hold = sq[A + al]; ac.cost = sq[2 * A + al]; ac.nav = sq[3 * A + al];
+            ac.pos = (int)SMW(acct_w + 12 * A + al); ac.ntr = SMW(acct_w + 13 * A + al);
         }
         CDA_TICK(3);   // pool + account tiles landed
 
@@ -1066,11 +1076,14 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         //      ONE aligned 128-B line (matters for DRAM sectors and doubles the PCIe/NVLink write efficiency when
         //      the row lives in pinned host or peer memory).
         slot_new = (int)(t_step % (unsigned)cfg.n_hist);
+        // the warp's tile index again, re-derived from %tid: the copy made at kernel entry would otherwise be spilled for the whole
+        // matching phase and reloaded here through a cold L1
+        const int wbL = (int)(fresh_tid_x() >> 5) * L::WORDS;
         float *orow = nullptr; int mis = 0;
         if (p.obs && last_it) {
             orow = o_gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
                                       : (m < o_obs_split ? p.obs : p.obs_hi) + (size_t)m * o_obs_stride;
-            mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
+            if (ROUTED) mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
             // the ring holds exactly n_hist snapshots, so the stacked old part (oldest first) is ONE circular run of the ring
             // starting at the slot after the newest: element e lives at ring position (first + e) mod W — no division by 42
             const int first = (slot_new + 1) * CDA_SNAPSHOT_DIM;
@@ -1083,11 +1096,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
         // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
         long long ld_max = 0, ld_prev = 0;
-        if (lane < A && (!ROLLOUT || it == 0)) {
+        if (lane < A) {
             const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
             ld_prev = sq[4 * A + lane]; ld_max = sq[5 * A + lane];
         }
-        long long nav_prev = ac.nav, nav_max = (!ROLLOUT || it == 0) ? ld_max : nav_max_carry;   // calculate.py:49-51
+        long long nav_prev = ac.nav, nav_max = ld_max;   // calculate.py:49-51
         if (k.tape_nonempty) {
             if (lane < A) {
                 const long long ap = ac.pos < 0 ? -ac.pos : ac.pos;
@@ -1095,7 +1108,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 ac.nav = ac.cash + ac.hold + pv;
                 if (ac.nav > nav_max) nav_max = ac.nav;
             }
-        } else nav_prev = (!ROLLOUT || it == 0) ? ld_prev : nav_prev_carry;   // never marked yet: keep the stored value
+        } else nav_prev = ld_prev;   // never marked yet: keep the stored value
         nav_max_carry = nav_max; nav_prev_carry = nav_prev;
         CDA_TICK(5);   // top-K levels + mtm done
         const int best_bid = __shfl_sync(CDA_FULL, myP, 0), best_ask = __shfl_sync(CDA_FULL, myP, CDA_K_ROWS);
@@ -1116,9 +1129,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             if (myV > 0) { const float sq = __fsqrt_rn((float)myV); sn = lane < CDA_K_ROWS ? sq : -sq; }
             const int l = lane < CDA_K_ROWS ? lane : lane - CDA_K_ROWS;
             const int b = lane < CDA_K_ROWS ? 0 : 2 * CDA_K_ROWS;
-            SMW(wb + L::SNAP + b + l) = __float_as_uint(pn);
-            SMW(wb + L::SNAP + b + CDA_K_ROWS + l) = __float_as_uint(sn);
-            SMW(wb + L::TOPK + lane) = (unsigned)myP;                          // frozen raw top-K for the next step's _set_price
+            SMW(wbL + L::SNAP + b + l) = __float_as_uint(pn);
+            SMW(wbL + L::SNAP + b + CDA_K_ROWS + l) = __float_as_uint(sn);
+            SMW(wbL + L::TOPK + lane) = (unsigned)myP;                          // frozen raw top-K for the next step's _set_price
             hdr[20 + lane] = (unsigned)myP;
         } else if (lane < 22) {
             double x = Mid; bool live = true;
@@ -1128,7 +1141,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 x = 1.0 + (st > 0.0 ? st : 0.0);
             }
             const double lg = log(x);
-            SMW(wb + L::SNAP + 20 + lane) = __float_as_uint(live ? (float)lg : 0.0f);
+            SMW(wbL + L::SNAP + 20 + lane) = __float_as_uint(live ? (float)lg : 0.0f);
         }
         __syncwarp();
 
@@ -1144,18 +1157,18 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 #pragma unroll
                 for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
                     const int e = lane + 32 * q - mis;
-                    if (e >= 0 && e < cfg.W) o[e] = e < W_old ? hv[q] : __uint_as_float(SMW(wb + L::SNAP + e - W_old));
+                    if (e >= 0 && e < cfg.W) o[e] = e < W_old ? hv[q] : __uint_as_float(SMW(wbL + L::SNAP + e - W_old));
                 }
                 for (int e = lane + 32 * CDA_HIST_PREFETCH - mis; e < cfg.W; e += 32) {   // beyond the prefetched chunks
                     float v;
                     if (e < W_old) { int ri = (slot_new + 1) * CDA_SNAPSHOT_DIM + e; if (ri >= cfg.W) ri -= cfg.W; v = g_hist[ri]; }
-                    else v = __uint_as_float(SMW(wb + L::SNAP + e - W_old));
+                    else v = __uint_as_float(SMW(wbL + L::SNAP + e - W_old));
                     o[e] = v;
                 }
             }
         }
         __syncwarp();
-        for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = __uint_as_float(SMW(wb + L::SNAP + cc));
+        for (int cc = lane; cc < CDA_SNAPSHOT_DIM; cc += 32) g_hist[slot_new * CDA_SNAPSHOT_DIM + cc] = __uint_as_float(SMW(wbL + L::SNAP + cc));
 
         CDA_TICK(7);   // obs + ring written
         // ================= set_reward / set_done: reward_helper.py:35-103, done_helper.py ===
@@ -1177,24 +1190,24 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 } else p.reward[(size_t)m * o_reward_stride + lane] = r;
             }
             broke = ac.nav <= 0;
-            if (o_rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wb + L::ACT + 2 * lane) = (unsigned)rb; SMW(wb + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
+            if (o_rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wbL + L::ACT + 2 * lane) = (unsigned)rb; SMW(wbL + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
         }
-        const unsigned done_mask = SMW(wb + L::PARK + 10) | __ballot_sync(CDA_FULL, broke);
+        const unsigned done_mask = SMW(wbL + L::PARK + 10) | __ballot_sync(CDA_FULL, broke);
         __syncwarp();
-        if (lane == 0) SMW(wb + L::PARK + 10) = done_mask;
+        if (lane == 0) SMW(wbL + L::PARK + 10) = done_mask;
         const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
         if (o_ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
             int nw = CDA_SNAPSHOT_DIM;
             if (o_rec_inline) {        // ... followed by the result record, which then shares the snapshot's last write transaction (the
                                        // decoded-action words are dead by now: their tile carries the record)
-                if (lane == 0) { SMW(wb + L::ACT + 2 * A) = ((done_mask & all) == all ? 1u : 0u) | (t_step + 1 >= (unsigned)cfg.max_step ? 0x100u : 0u); SMW(wb + L::ACT + 2 * A + 1) = 0u; }
+                if (lane == 0) { SMW(wbL + L::ACT + 2 * A) = ((done_mask & all) == all ? 1u : 0u) | (t_step + 1 >= (unsigned)cfg.max_step ? 0x100u : 0u); SMW(wbL + L::ACT + 2 * A + 1) = 0u; }
                 nw += 2 * A + 2;
                 __syncwarp();
             }
             float *rg = o_ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
             for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < nw; cc += 32) {
                 if (cc < 0) continue;
-                const float v = __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wb + L::SNAP + cc) : SMW(wb + L::ACT + cc - CDA_SNAPSHOT_DIM));
+                const float v = __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wbL + L::SNAP + cc) : SMW(wbL + L::ACT + cc - CDA_SNAPSHOT_DIM));
                 rg[cc] = v;
                 if (o_ring_mirror && cc < CDA_SNAPSHOT_DIM) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
             }
@@ -1216,20 +1229,27 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
         t_step++;
         __syncwarp();
-        if (ROLLOUT && !last_it) {    // multi-step rollout: bring the generator back for the next step's draws
-            const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wb + L::PARK]);
+        if (ROLLOUT && !last_it) {    // multi-step rollout: the accounts go back to their tile, the generator comes back for the next step's draws
+            if (lane < A) {
+                long long *sq = reinterpret_cast<long long *>(&smw[acct_w]);
+                sq[lane] = ac.cash; sq[A + lane] = ac.hold; sq[2 * A + lane] = ac.cost; sq[3 * A + lane] = ac.nav;
+                sq[4 * A + lane] = nav_prev_carry; sq[5 * A + lane] = nav_max_carry;
+                SMW(acct_w + 12 * A + lane) = (unsigned)(int)ac.pos; SMW(acct_w + 13 * A + lane) = ac.ntr;
+            }
+            const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wbL + L::PARK]);
             rng.shi = pk[0]; rng.slo = pk[1]; rng.ihi = pk[2]; rng.ilo = pk[3];
-            rng.has32 = SMW(wb + L::PARK + 8); rng.u32 = SMW(wb + L::PARK + 9);
+            rng.has32 = SMW(wbL + L::PARK + 8); rng.u32 = SMW(wbL + L::PARK + 9);
         }
     }
 
     CDA_TICK(8);   // reward/done
+    const int wbL = (int)(fresh_tid_x() >> 5) * L::WORDS;   // (as inside the loop: not the entry-time copy)
     // ---- store: header, accounts, pool prefix
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
-        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)k.tape_px, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, SMW(wb + L::PARK + 10), SMW(wb + L::PARK + 11));
-        const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wb + L::PARK]);
-        *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)k.nb, (unsigned)k.na, SMW(wb + L::PARK + 8), SMW(wb + L::PARK + 9));
+        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)k.tape_px, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, SMW(wbL + L::PARK + 10), SMW(wbL + L::PARK + 11));
+        const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wbL + L::PARK]);
+        *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)k.nb, (unsigned)k.na, SMW(wbL + L::PARK + 8), SMW(wbL + L::PARK + 9));
         *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(pk[0], pk[1]);
         *reinterpret_cast<ulonglong2 *>(hdr + 16) = make_ulonglong2(pk[2], pk[3]);
     }

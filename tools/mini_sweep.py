@@ -34,7 +34,19 @@ def run(A, M, mix, steps=50, prewarm=150):
     hot = e0.elapsed_time(e1) / steps
     st = int(env.status().max().item()); env.close()
     return "%%dx%%d %%s: %%6.1f us (%%5.1f M/s) hot %%6.1f us (%%5.1f M/s) st %%d" %% (A, M, mix[:6], ms * 1e3, M / ms / 1e3, hot * 1e3, M / hot / 1e3, st)
-print("%%-14s" %% os.environ["TAG"], " | ".join(run(*w) for w in ((4, 4096, "limit_market"), (8, 8192, "modify_heavy"), (4, 32768, "limit_market"))), flush=True)
+def roll(A, M, T):
+    env = cda.VecCDAEnv(dict(num_of_agents=A, max_step=1 << 30), num_markets=M)
+    env.reset(seed=1000)
+    env.rollout_random(128, policy_seed=1); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(4): env.rollout_random(T, policy_seed=2 + r)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 4
+    st = int(env.status().max().item()); env.close()
+    return "rollout %%dx%%d T=%%d: %%5.1f M/s st %%d" %% (A, M, T, M * T / ms / 1e3, st)
+print("%%-14s" %% os.environ["TAG"], " | ".join(run(*w) for w in ((4, 4096, "limit_market"), (8, 8192, "modify_heavy"), (4, 32768, "limit_market"))),
+      "|", roll(4, 4096, 64), "|", roll(4, 32768, 64), flush=True)
 ''' % ROOT
 for spec in sys.argv[1:]:          # name[:ENV=VAL,ENV=VAL]
     name, _, envs = spec.partition(":")
