@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             SMW(wbL + L::SNAP + b + l) = __float_as_uint(pn);
             SMW(wbL + L::SNAP + b + CDA_K_ROWS + l) = __float_as_uint(sn);
             SMW(wbL + L::TOPK + lane) = (unsigned)myP;                          // frozen raw top-K for the next step's _set_price
-            hdr[20 + lane] = (unsigned)myP;
+            hdr[20 + (fresh_tid_x() & 31u)] = (unsigned)myP;   // (fresh lane index: reusing the entry-time &hdr[20 + lane] would keep that pointer spilled across the whole step)
         } else if (lane < 22) {
             double x = Mid; bool live = true;
             if (lane == 21) {
