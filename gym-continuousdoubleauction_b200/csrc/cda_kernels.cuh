@@ -26,13 +26,11 @@
 #include "cda_zig_tables.cuh"
 
 #define CDA_FULL 0xffffffffu
-#ifndef CDA_SCAN_MODE
-#define CDA_SCAN_MODE 1
-#endif
-#if CDA_SCAN_MODE == 1
 #define CDA_SCAN_PRAGMA _Pragma("unroll 1")
-#else
-#define CDA_SCAN_PRAGMA
+#ifndef CDA_BEST_CACHE
+#define CDA_BEST_CACHE 1      /* 1: the best price of each side is cached (seeded from the header, maintained by append / remove): a scan only
+                                 after an order AT the best price was removed.  (Defined HERE, above its first use: until r02e the switch sat
+                                 below pool_best(), which therefore always scanned.) */
 #endif
 #define CDA_HDR_BYTES 192
 #define CDA_POOL_FIELDS 5 /* 0 pt (trader<<24|price), 1 qty, 2 order_id, 3 timestamp, 4 seq */
@@ -197,10 +195,6 @@ __device__ __forceinline__ long long rng_integers(CdaRng &r, long long lo, long 
 // G_r = 1 + A + ... + A^(r-1).  Row r = {A^r hi, A^r lo, G_r hi, G_r lo}; filled by cda_create.
 // Lets lane a evaluate "its" draw of the sequential numpy stream without waiting for lanes < a.
 __device__ unsigned long long cda_pcg_jump[CDA_MAX_AGENTS + 1][4];   // global (lane-indexed reads; see cda_zig_tables.cuh)
-#ifndef CDA_JUMP_SMEM
-#define CDA_JUMP_SMEM 1       /* 1: every warp loads the A+1 jump-ahead rows it can need at kernel entry and keeps them in shared memory (the load
-                                 latency then overlaps the header / action fetch instead of sitting in front of the normal draws) */
-#endif
 extern __shared__ __align__(128) unsigned smw[];
 // jump_w: word index of the warp's copy of the table in smw, or -1: read the table in global memory
 __device__ __forceinline__ void rng_jump(const CdaRng &g, int r, int jump_w, unsigned long long &shi, unsigned long long &slo) {
@@ -370,20 +364,11 @@ template <int CAP> __device__ __forceinline__ int pool_best_scan(const CdaMkt<CA
     const int n = k.count(side);
     if (n == 0) return -1;
     unsigned loc = side == 0 ? 0u : 0xffffffffu;
-#if CDA_SCAN_MODE == 2
-    const int nt = (n - k.lane + 31) >> 5;
-#pragma unroll
-    for (int it = 0; it < CAP / 32; ++it) {
-        const unsigned p = it < nt ? (SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) : loc;
-        loc = side == 0 ? max(loc, p) : min(loc, p);
-    }
-#else
     CDA_SCAN_PRAGMA
     for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
         const unsigned p = SMW(pt) & CDA_PRICE_MASK;
         loc = side == 0 ? max(loc, p) : min(loc, p);
     }
-#endif
     return (int)(side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc));
 }
 // best price of a side through the cache (a scan only after an order AT the best price was removed)
@@ -401,21 +386,10 @@ template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> 
     int pt = k.side_w(side) + k.lane;
     const int n = k.count(side);
     unsigned bk = 0xffffffffu; int bi = -1;
-#if CDA_SCAN_MODE == 2
-    const int nt = (n - k.lane + 31) >> 5;
-#pragma unroll
-    for (int it = 0; it < CAP / 32; ++it) {
-        if (it < nt && (SMW(pt + it * CDA_TILE_WORDS) & mask) == want) {
-            const unsigned kk = SMW(pt + it * CDA_TILE_WORDS + field * 32);
-            if (kk < bk) { bk = kk; bi = k.lane + 32 * it; }
-        }
-    }
-#else
     CDA_SCAN_PRAGMA
     for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
         if ((SMW(pt) & mask) == want) { const unsigned kk = SMW(pt + field * 32); if (kk < bk) { bk = kk; bi = i; } }
     }
-#endif
     const unsigned mk = __reduce_min_sync(CDA_FULL, bk);
     if (mk == 0xffffffffu) return -1;
     const unsigned b = __ballot_sync(CDA_FULL, bk == mk);
@@ -424,11 +398,13 @@ template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> 
 // ordertree.py:70-77 remove_order_by_id: dense pool => move the last entry into the hole
 template <int CAP> __device__ __forceinline__ void pool_remove(CdaMkt<CAP> &k, int side, int idx) {
     const int last = k.count(side) - 1;
+#if CDA_BEST_CACHE
     {   // best-price cache: an order leaving the best level may empty it -> unknown; an emptied side -> -1
         const int cb = k.cached_best(side);
         if (last == 0) k.set_best(side, -1);
         else if (cb >= 0 && (int)(SMW(k.side_w(side) + CDA_EOFF(idx)) & CDA_PRICE_MASK) == cb) k.set_best(side, -2);
     }
+#endif
     __syncwarp();
     if (idx != last && k.lane < CDA_POOL_FIELDS) {
         const int f = k.side_w(side) + k.lane * 32;
@@ -443,10 +419,12 @@ template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, i
     const int n = k.count(side);
     if (n >= CAP) { k.raise(CDA_ST_POOL_OVERFLOW); return false; }
     const unsigned seq = k.seqctr++;
+#if CDA_BEST_CACHE
     {   // best-price cache: a better (or first) price becomes the best; unknown stays unknown
         const int cb = k.cached_best(side);
         if (cb == -1 || (cb >= 0 && (side == 0 ? (int)price > cb : (int)price < cb))) k.set_best(side, (int)price);
     }
+#endif
     __syncwarp();
     if (k.lane < CDA_POOL_FIELDS) {
         const unsigned v = k.lane == 0 ? (((unsigned)trader << 24) | price) : k.lane == 1 ? qty : k.lane == 2 ? oid : k.lane == 3 ? ts : seq;
@@ -589,23 +567,6 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 #else
 #define CDA_TICK(i) do {} while (0)
 #endif
-#ifndef CDA_BEST_CACHE
-#define CDA_BEST_CACHE 1
-#endif
-#ifndef CDA_PREFETCH_TABLES
-#define CDA_PREFETCH_TABLES 0
-#endif
-#ifndef CDA_EARLY_ACCT
-#define CDA_EARLY_ACCT 0      /* 1: load the accounts at kernel entry; 0 (measured best once spills were gone): after the normal draws (the RNG phase is the
-                                 register-pressure peak: values loaded before it get spilled, and the spill store has
-                                 to wait for the load, exposing its latency) */
-#endif
-#ifndef CDA_BULK_STORE
-#define CDA_BULK_STORE 1      /* 1: write the whole live pool prefix back with cp.async.bulk (measured 4 % faster), 0: dirty tiles with plain stores */
-#endif
-#ifndef CDA_FUSED_TOPK
-#define CDA_FUSED_TOPK 1      /* 1: the top-K sweep handles the bid and the ask side in one loop body (independent chains overlap) */
-#endif
 /* registers per lane for the old-snapshot prefetch (covers n_hist <= 4): five 128-B chunks when the output row is cut at the 128-B
    boundaries of its destination (routed outputs: PCIe / NVLink write transactions), four when chunk 0 starts at the row start */
 #define CDA_HIST_PREFETCH (ROUTED ? 5 : 4)
@@ -632,34 +593,13 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const int cbar_w = actb + 5 * WARPS * A;           // (16-B aligned: 20*A words)
     // the RNG tables are indexed by data that arrives ~2 us into the kernel: start pulling them into L1 now
     // (L1 is cold at every launch; without this the ziggurat / jump-ahead reads wait a full L2 or HBM round trip)
-#if CDA_PREFETCH_TABLES == 1
-    prefetch_l1(lane < 16 ? reinterpret_cast<const char *>(cda_zig_wi) + lane * 128 : reinterpret_cast<const char *>(cda_zig_ki) + (lane - 16) * 128);
-    if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
-#elif CDA_PREFETCH_TABLES == 2   /* one warp per CTA */
-    if (warp == 0) {
-        prefetch_l1(lane < 16 ? reinterpret_cast<const char *>(cda_zig_wi) + lane * 128 : reinterpret_cast<const char *>(cda_zig_ki) + (lane - 16) * 128);
-        if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
-    }
-#elif CDA_PREFETCH_TABLES == 4   /* ONE CTA pulls the ziggurat tables into L2 (they are evicted whenever something streams through L2 between
-                                    steps; the draws ~2 us later then miss L1 into L2 instead of into HBM) */
-    if (blockIdx.x == 0) {
-        const char *t = warp == 0 ? reinterpret_cast<const char *>(cda_zig_wi) : warp == 1 ? reinterpret_cast<const char *>(cda_zig_ki) : reinterpret_cast<const char *>(cda_zig_fi);
-        if (warp < 3 && lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + lane * 128));
-    }
-#elif CDA_PREFETCH_TABLES == 3   /* only the jump-ahead rows (always the same few lines) */
-    if (lane * 128 < (A + 1) * 32) prefetch_l1(reinterpret_cast<const char *>(cda_pcg_jump) + lane * 128);
-#endif
     // this warp's copy of the jump-ahead rows 0..A: loaded NOW, stored to shared memory just before the normal draws (by then the
     // load has landed: nothing waits for it).  It lives in the tail of the decoded-action tile (u32[32][3], of which 3A words are
     // used): no extra shared memory, so 7 CTAs per SM still fit; with more than 8 agents it does not fit and the draws read
     // the table in global memory.
-#if CDA_JUMP_SMEM
     const bool jump_sm = ((3 * A + 3) & ~3) + 8 * (A + 1) <= 96;
     ulonglong2 jrow = make_ulonglong2(0ULL, 0ULL);   // lane j < 2(A+1): 16-byte piece j of the table (row j/2: A^r for even j, G_r for odd j)
     if (jump_sm && lane < 2 * (A + 1)) jrow = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + lane);
-#else
-    const bool jump_sm = false;
-#endif
     if (!ROLLOUT && p.act_tma) {
         if (threadIdx.x == 0) {
             const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w * 4u;
@@ -723,7 +663,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const uint4 h0 = *reinterpret_cast<const uint4 *>(hdr + 0);
     const uint4 h1 = *reinterpret_cast<const uint4 *>(hdr + 4);
     const uint4 h2 = *reinterpret_cast<const uint4 *>(hdr + 8);
-    const uint2 hb = *reinterpret_cast<const uint2 *>(hdr + 40);     // best bid / best ask after the previous step (0 = none)
 
     if (lane < 2 * CDA_K_ROWS) SMW(wb + L::TOPK + lane) = tk0;
     __syncwarp();
@@ -747,7 +686,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     k.tape_px = (int)h1.x;
     k.fills_base = p.fills; k.mkt = m;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
-    k.bestb = k.nb ? (hb.x ? (int)hb.x : -2) : -1; k.besta = k.na ? (hb.y ? (int)hb.y : -2) : -1;
+    k.bestb = -2; k.besta = -2;
 
     // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
@@ -805,13 +744,12 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         if (a_pcode < 0 || a_pcode >= CDA_K_ROWS) a_pcode = 0;
         if (a_poff < 0 || a_poff > 2) a_poff = 1;
         const unsigned present = __ballot_sync(CDA_FULL, lane < A && a_cat >= 0);
+        SMW(wb + L::ORDER + lane) = (unsigned)a_cat;   // parked across the draws (the register-pressure peak); the order tile is free until the shuffle
         CDA_TICK(10);  // actions arrived
-#if CDA_JUMP_SMEM
         if (!ROLLOUT || it == 0) {
             if (jump_sm && lane < 2 * (A + 1)) *reinterpret_cast<ulonglong2 *>(&smw[wb + L::ACT + ((3 * A + 3) & ~3) + 4 * lane]) = jrow;
             __syncwarp();
         }
-#endif
         // one standard-normal draw per PRESENT agent, in agent order, pass agents included (:311-339).
         // Lane a jumps the LCG ahead by (its rank + 1) steps and evaluates its own draw; this is the sequential
         // stream as long as every draw returns from the first ziggurat test (98.8 % each).
@@ -856,6 +794,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         if ((present >> lane) & 1u) z = __longlong_as_double((long long)(((unsigned long long)SMW(zw + 1) << 32) | SMW(zw)));
         __syncwarp();   // every lane has its draw back before the tile receives the decoded actions
         CDA_TICK(11);  // draws done
+        a_cat = (int)SMW(wb + L::ORDER + lane);
         const int a_side = a_cat <= 0 ? -1 : (a_cat <= 4 ? 0 : 1);
         const int a_type = a_cat <= 0 ? 0 : ((a_cat - 1) & 3);
         long long a_size = 0; int a_price = -1;
@@ -917,6 +856,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         CDA_TICK(3);   // pool + account tiles landed
 
         // ================= do_actions: action_helper.py:201-239 =============================
+        {   // best-price cache: seeded from level 0 of the frozen pre-step top-K (0 = that side was empty), here rather than at kernel
+            // entry / across rollout steps so that it occupies registers only while the book is being worked on
+            const unsigned b0 = SMW(wb + L::TOPK), a0 = SMW(wb + L::TOPK + CDA_K_ROWS);
+            k.bestb = k.nb ? (b0 ? (int)b0 : -2) : -1; k.besta = k.na ? (a0 ? (int)a0 : -2) : -1;
+        }
         for (int q = 0; q < n_act; ++q) {
             const int t = __shfl_sync(CDA_FULL, ord, q);
             const unsigned ts_ = SMW(wb + L::ACT + 3 * t);
@@ -939,7 +883,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         __syncwarp();
         if (lane < 2 * CDA_K_ROWS) SMW(wb + L::VOL + lane) = 0;
         __syncwarp();
-#if CDA_FUSED_TOPK
         // Both sides go through ONE loop body per pass: the bid chain and the ask chain are independent, so their
         // shared-memory loads, the four redux.or and the rank arithmetic overlap instead of running back to back
         // (the kernel is bound by dependent-issue latency at 7 warps per scheduler, not by issue slots).
@@ -1015,60 +958,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 prev = P;
             }
         }
-#else
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-            const int pt = k.side_w(side) + lane;            // this lane's column of every tile
-            const int n = k.count(side);
-            if (n == 0) continue;
-            const int nt = (n - lane + 31) >> 5;              // tiles in which this lane owns a live order
-            const unsigned B = (unsigned)pool_best(k, side);      // usually cached by the matching phase
-            unsigned mlo = 0, mhi = 0; bool far = false;
-            CDA_SCAN_PRAGMA
-            for (int it = 0; it < nt; ++it) {
-                const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK;
-                const unsigned d = side == 0 ? B - pp : pp - B;
-                if (d < 32) mlo |= 1u << d; else if (d < 64) mhi |= 1u << (d - 32); else far = true;
-            }
-            mlo = __reduce_or_sync(CDA_FULL, mlo); mhi = __reduce_or_sync(CDA_FULL, mhi);
-            const bool far_any = __any_sync(CDA_FULL, far);
-            const int nlo = __popc(mlo), nlev = nlo + __popc(mhi);
-            CDA_SCAN_PRAGMA
-            for (int it = 0; it < nt; ++it) {
-                const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK;
-                const unsigned d = side == 0 ? B - pp : pp - B;
-                if (d < 64) {
-                    const int rank = d < 32 ? __popc(mlo & ((1u << d) - 1u)) : nlo + __popc(mhi & ((1u << (d - 32)) - 1u));
-                    if (rank < CDA_K_ROWS) {      // every order of a level writes the same price: benign same-value race
-                        atomicAdd(&smw[wb + L::VOL + side * CDA_K_ROWS + rank], SMW(pt + it * CDA_TILE_WORDS + 32));
-                        SMW(wb + L::LPX + side * CDA_K_ROWS + rank) = pp;
-                    }
-                }
-            }
-            __syncwarp();
-            const int li = lane - side * CDA_K_ROWS;
-            if (li >= 0 && li < CDA_K_ROWS && li < nlev) { myP = (int)SMW(wb + L::LPX + lane); myV = SMW(wb + L::VOL + lane); }
-            if (nlev < CDA_K_ROWS && far_any) {        // levels further than 64 ticks from the best: generic search
-                unsigned prev = side == 0 ? B - 63u : B + 63u;
-                for (int lv = nlev; lv < CDA_K_ROWS; ++lv) {
-                    unsigned l2 = side == 0 ? 0u : 0xffffffffu;
-                    _Pragma("unroll 1")
-                    for (int it = 0; it < nt; ++it) {
-                        const unsigned pp = SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK;
-                        if (side == 0 ? pp < prev : pp > prev) l2 = side == 0 ? max(l2, pp) : min(l2, pp);
-                    }
-                    const unsigned P = side == 0 ? __reduce_max_sync(CDA_FULL, l2) : __reduce_min_sync(CDA_FULL, l2);
-                    if (P == (side == 0 ? 0u : 0xffffffffu)) break;
-                    unsigned s = 0;
-                    _Pragma("unroll 1")
-                    for (int it = 0; it < nt; ++it) if ((SMW(pt + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) == P) s += SMW(pt + it * CDA_TILE_WORDS + 32);
-                    const unsigned V = __reduce_add_sync(CDA_FULL, s);
-                    if (lane == side * CDA_K_ROWS + lv) { myP = (int)P; myV = V; }
-                    prev = P;
-                }
-            }
-        }
-#endif
         // ---- fetch the older snapshots of the stacked observation (state_helper.py:88-90); latency hides behind
         //      mark-to-market and the observation math.  Lane mapping: the output row of market m starts 32-B
         //      aligned (672-B rows), so element e is handled by lane (e + mis) & 31 of chunk (e + mis) >> 5, where
@@ -1259,7 +1148,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         g_prev[lane] = nav_prev_carry; g_max[lane] = nav_max_carry; g_pos[lane] = (int)ac.pos; g_ntr[lane] = ac.ntr;
         g_ctr[lane] = ac.ctr;
     }
-#if CDA_BULK_STORE
     fence_proxy_async();
     __syncwarp();
     {
@@ -1271,20 +1159,6 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             bulk_wait_read0();
         }
     }
-#else
-    // ---- pool write-back: only the tiles this launch modified, as plain coalesced 128-B stores (fire and
-    //      forget: nothing to wait for, unlike a bulk store whose source smem must outlive the read)
-    __syncwarp();
-#pragma unroll 1
-    for (unsigned dm = k.dirty; dm; dm &= dm - 1) {
-        const int b = __ffs(dm) - 1, side = b >> 3, tile = b & 7;
-        if (tile * 32 >= k.count(side)) continue;               // tile fell off the live prefix
-        const int sw = k.side_w(side) + tile * CDA_TILE_WORDS + lane;
-        unsigned *gw = gpool + side * (CDA_POOL_FIELDS * CAP) + tile * CDA_TILE_WORDS + lane;
-#pragma unroll
-        for (int f = 0; f < CDA_POOL_FIELDS; ++f) gw[f * 32] = SMW(sw + f * 32);
-    }
-#endif
     CDA_TICK(9);   // state stored
 #ifdef CDA_PROFILE_PHASES
     { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); if (lane == 0 && p.prof) p.prof[(size_t)m * 16 + 13] = gt; }   // warp end (ns)
