@@ -40,6 +40,16 @@ CASES = [
     ("nhist2_a5_absent", dict(num_of_agents=5, n_hist=2), 5004, 80, "uniform", 0.25),
     ("nhist6_a3_fixed_anchor", dict(num_of_agents=3, n_hist=6, initial_price_min=50, initial_price_max=50), 6005, 64, "limit_market", 0.0),
     ("trunc_a4_maxstep10", dict(num_of_agents=4, max_step=10), 7006, 12, "uniform", 0.0),
+    # configuration corners (added after the first set; existing fixtures are never rewritten unless --force)
+    ("single_agent_a1", dict(num_of_agents=1), 8007, 64, "uniform", 0.0),                      # self-trades only, no permutation draw
+    ("two_agents_a2", dict(num_of_agents=2), 8108, 80, "limit_market", 0.0),
+    ("sixteen_agents_a16", dict(num_of_agents=16), 8209, 48, "uniform", 0.0),                  # capacity-256 kernel
+    ("tick5_a4", dict(num_of_agents=4, tick_size=5), 8310, 80, "uniform", 0.0),                # integral tick != 1
+    ("sizes_a4", dict(num_of_agents=4, min_size=3, mkt_max_size=20, limit_size_multiple=4), 8411, 80, "uniform", 0.0),
+    ("reward_coeffs_a4", dict(num_of_agents=4, order_penalty=0.3, trade_penalty=0.01, drawdown_penalty=0.5, passive_bonus=0.25,
+                              loss_multiplier=2.0), 8512, 80, "limit_market", 0.0),
+    ("low_anchor_a4", dict(num_of_agents=4, initial_price_min=1, initial_price_max=3), 8613, 80, "uniform", 0.0),   # prices clamp at one tick
+    ("high_anchor_a4", dict(num_of_agents=4, initial_price_min=4000, initial_price_max=5000, init_cash=50_000_000), 8714, 80, "modify_heavy", 0.0),
 ]
 
 
@@ -104,16 +114,20 @@ def appendix_d_case():
 def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    force = "--force" in sys.argv
     for name, cfg_over, seed, T, mix, absent in CASES:
+        if os.path.exists(os.path.join(outdir, f"traj_{name}.npz")) and not force:
+            continue
         A = cfg_over.get("num_of_agents", 4)
         acts = gen_actions(np.random.default_rng(seed + 7), T, A, mix, absent)
         out = run_case(cfg_over, seed, acts)
         np.savez_compressed(os.path.join(outdir, f"traj_{name}.npz"), **out)
         print(name, "T", T, "fills", out["fills"].shape[0], "time", out["scalars"][-1, 0])
-    cfg, seed, acts = appendix_d_case()
-    out = run_case(cfg, seed, acts)
-    np.savez_compressed(os.path.join(outdir, "traj_appendix_d.npz"), **out)
-    print("appendix_d rewards:\n", out["reward"])
+    if force or not os.path.exists(os.path.join(outdir, "traj_appendix_d.npz")):
+        cfg, seed, acts = appendix_d_case()
+        out = run_case(cfg, seed, acts)
+        np.savez_compressed(os.path.join(outdir, "traj_appendix_d.npz"), **out)
+        print("appendix_d rewards:\n", out["reward"])
 
 
 if __name__ == "__main__":
