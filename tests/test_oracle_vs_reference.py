@@ -73,3 +73,22 @@ def test_reset_seed_none_continues_stream():
         ro, rr, _, _ = ref.step(*[x[t] for x in acts]); oo, orw, _, _ = orc.step(*[x[t][None] for x in acts])
     assert np.array_equal(ro, oo[0])
     assert_dump_equal(ref.dump(), orc.dump(0))
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_random_configurations(case):
+    """Configuration fuzz: agents, tick, size limits, cash, anchor range, history depth, reward coefficients and the
+    action mix are all drawn at random (seeded); the oracle must track the reference bit for bit on each."""
+    rng = np.random.default_rng(9000 + case)
+    A = int(rng.integers(1, 9))
+    lo = int(rng.choice([1, 3, 10, 250, 3000]))
+    extra = dict(
+        tick_size=int(rng.choice([1, 1, 2, 5])), n_hist=int(rng.integers(1, 7)),
+        min_size=int(rng.integers(1, 4)), mkt_max_size=int(rng.choice([10, 40, 100])), limit_size_multiple=int(rng.choice([1, 3, 10])),
+        init_cash=int(rng.choice([2_000, 50_000, 1_000_000, 80_000_000])),
+        initial_price_min=lo, initial_price_max=lo + int(rng.integers(0, 60)),
+        order_penalty=float(rng.choice([0.0, 0.1, 0.7])), trade_penalty=float(rng.choice([0.0, 0.05])),
+        drawdown_penalty=float(rng.choice([0.0, 0.2, 1.0])), passive_bonus=float(rng.choice([0.0, 0.1])),
+        loss_multiplier=float(rng.choice([1.0, 1.5, 3.0])))
+    mix = str(rng.choice(["uniform", "limit_market", "modify_heavy"]))
+    run(9100 + case, A, 90, mix, extra, absent=float(rng.choice([0.0, 0.0, 0.2])))
