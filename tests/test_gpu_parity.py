@@ -279,8 +279,6 @@ def test_host_window_needs_reset_first():
     env.close()
 
 
-@pytest.mark.skipif(not os.environ.get("CDA_GPU_FUZZ"), reason="configuration fuzz CUDA vs oracle: written at the end of round 1, after the "
-                    "GPU budget was spent — set CDA_GPU_FUZZ=1 to run it (DESIGN.md section 9, item 2)")
 @pytest.mark.parametrize("case", range(12))
 def test_random_configurations_gpu_vs_oracle(case):
     """The configuration fuzz of tests/test_oracle_vs_reference.py::test_random_configurations, CUDA env against the oracle."""
