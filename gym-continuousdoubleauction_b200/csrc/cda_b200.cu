@@ -144,6 +144,11 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     if (cap == 0) cap = cfg->num_agents <= 8 ? 160 : 256;
     if (cap != 64 && cap != 128 && cap != 160 && cap != 192 && cap != 256) return CDA_EINVAL;
     if (cfg->fill_capacity < 0 || cfg->fill_capacity > 1024) return CDA_EINVAL;
+    {   // the cold-path kernels (reset window / ring fill, info gather) index with 32-bit ints: one handle takes at most
+        // INT_MAX / max(2 * n_hist * 42, 15 * A) markets (6.39 M with the defaults, 48 GB of state); shard beyond that
+        const long long per = std::max<long long>(2LL * cfg->n_hist * CDA_SNAPSHOT_DIM, 15LL * cfg->num_agents);
+        if ((long long)num_markets * per > 2147483647LL) return CDA_EINVAL;
+    }
     CUDA_TRY(cudaSetDevice(device));
     CdaEnv *e = new (std::nothrow) CdaEnv();
     if (!e) return CDA_ENOMEM;

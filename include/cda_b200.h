@@ -87,7 +87,11 @@ enum CdaInfoField {
     CDA_INFO__COUNT
 };
 
-/* continuousDoubleAuctionEnv.__init__ (continuousDoubleAuction_env.py:27-119), for M markets. */
+/* continuousDoubleAuctionEnv.__init__ (continuousDoubleAuction_env.py:27-119), for M markets.
+ * One handle takes at most INT_MAX / max(2*n_hist*42, 15*num_agents) markets (6.39 M with the defaults, 48 GB of
+ * state): CDA_EINVAL beyond that — shard the markets over several handles / GPUs.
+ * Host buffers handed to the cda_step_host* / window / ring calls are looked up ONCE per distinct pointer (pinned +
+ * mapped?) and the answer is cached in the handle: keep a buffer pinned for as long as the handle may see its address. */
 int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv **out);
 int cda_destroy(CdaEnv *env);
 

@@ -55,3 +55,29 @@ def test_strerror_and_build_info():
     L = _native.lib()
     assert b"sm_100a" in L.cda_build_info()
     assert L.cda_strerror(-1) and L.cda_strerror(0) == b"ok"
+
+
+def _cfg(**kw):
+    d = dict(num_agents=4, n_hist=4, max_step=64, tick_size=1, init_cash=1_000_000, min_size=1, mkt_max_size=100,
+             limit_size_multiple=10, initial_price_min=10, initial_price_max=100, order_capacity=0, fill_capacity=0,
+             order_penalty=0.1, trade_penalty=0.05, drawdown_penalty=0.2, passive_bonus=0.1, loss_multiplier=1.5)
+    d.update(kw)
+    return _native.CdaConfig(**d)
+
+
+def test_create_rejects_bad_configurations_before_touching_cuda():
+    """Argument validation is the first thing cda_create does: CDA_EINVAL (-1) comes back without a GPU."""
+    L = _native.lib()
+    h = ctypes.c_void_p()
+    bad = [dict(num_agents=0), dict(num_agents=33), dict(n_hist=0), dict(n_hist=17), dict(tick_size=0), dict(init_cash=0),
+           dict(max_step=0), dict(initial_price_min=0), dict(initial_price_min=50, initial_price_max=49), dict(mkt_max_size=0),
+           dict(limit_size_multiple=0), dict(order_capacity=100), dict(fill_capacity=2000)]
+    for kw in bad:
+        c = _cfg(**kw)
+        assert L.cda_create(ctypes.byref(c), 16, 0, ctypes.byref(h)) == -1, kw
+        assert not h.value
+    c = _cfg()
+    assert L.cda_create(ctypes.byref(c), 0, 0, ctypes.byref(h)) == -1                 # no markets
+    assert L.cda_create(ctypes.byref(c), 7_000_000, 0, ctypes.byref(h)) == -1         # beyond the 32-bit indexing limit of the cold paths
+    assert L.cda_create(None, 16, 0, ctypes.byref(h)) == -1
+    assert L.cda_step(None, *([None] * 10)) == -1 and L.cda_step_window(None, None, 3, 1) == -1
