@@ -81,3 +81,25 @@ def test_create_rejects_bad_configurations_before_touching_cuda():
     assert L.cda_create(ctypes.byref(c), 7_000_000, 0, ctypes.byref(h)) == -1         # beyond the 32-bit indexing limit of the cold paths
     assert L.cda_create(None, 16, 0, ctypes.byref(h)) == -1
     assert L.cda_step(None, *([None] * 10)) == -1 and L.cda_step_window(None, None, 3, 1) == -1
+
+
+def test_single_step_kernels_stay_spill_free_and_within_the_one_wave_register_budget():
+    """Performance invariants of the headline shape, checked on the built binary: 72 registers are what 28
+    warps per SM allow (4096 markets = one wave on 148 SMs), and the single-step bodies of the default order capacity must
+    not spill — a spilled value reloaded late in the step is an L2 round trip in this kernel (measured 2.8 % for one reload)."""
+    import shutil
+    import subprocess
+    import pytest
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    cda.build()
+    txt = subprocess.run([tool, "--dump-resource-usage", _native.SO_PATH], capture_output=True, text=True).stdout
+    usage = dict(re.findall(r"Function (\S+):\s*\n\s*(REG:\d+ STACK:\d+)", txt))
+    step = {k: v for k, v in usage.items() if "cda_step_kernel" in k}
+    assert len(step) == 15                                         # 5 capacities x {device step, routed step, rollout}
+    for name, res in step.items():
+        reg, stack = (int(x) for x in re.findall(r"\d+", res))
+        assert reg <= 72, (name, res)
+        if "ILi160ELi4ELb0E" in name:                              # single-step bodies (device and routed) of the default capacity
+            assert stack == 0, (name, res)
