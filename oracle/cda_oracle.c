@@ -28,6 +28,7 @@
 #include <string.h>
 
 #include "np_rng.h"
+#include "dec28.h"
 
 #define ORC_K 10          /* k_rows  (config/tunable_constants.json: observation_layout) */
 #define ORC_SNAP 42       /* book_rows*k_rows + extra_dim */
@@ -39,6 +40,7 @@
 #define ORC_ST_FILL_OVERFLOW 1u
 #define ORC_ST_BAD_SIZE 2u
 #define ORC_ST_BAD_ACTION 4u
+#define ORC_ST_LEDGER_MISMATCH 8u   /* decimal_ledger mode: a Decimal(28) value is not within 1e-9 of its exact-integer twin */
 
 typedef struct {
     int32_t num_agents, n_hist, max_step, tick;
@@ -46,6 +48,8 @@ typedef struct {
     int32_t min_size, mkt_max_size, limit_size_multiple;
     int32_t price_lo, price_hi; /* initial_price_min / initial_price_max (inclusive) */
     double order_penalty, trade_penalty, drawdown_penalty, passive_bonus, loss_multiplier;
+    int32_t decimal_ledger; /* 1: ALSO keep the money fields as Decimal(prec 28) exactly like the reference (dec28.h) and take the
+                               cash-gate / bankruptcy / high-water-mark decisions on them; 0 (default): exact int64 ledger only */
 } OrcConfig;
 
 /* ---- orderbook/order.py:4-36, orderlist.py, ordertree.py ---------------------------------- */
@@ -82,6 +86,8 @@ typedef struct {
     int32_t num_trades, num_trades_step, num_passive_fills_step, order_step_placed, num_rejected_step;
     int32_t is_pass;
     double reward, terms[5], drawdown;
+    int32_t dl;                                                   /* copy of cfg.decimal_ledger */
+    dec d_cash, d_hold, d_pv, d_vwap, d_nav, d_prev_nav, d_max_nav; /* the reference's Decimal fields (decimal_ledger mode) */
 } OrcAcct;
 
 typedef struct {
@@ -192,11 +198,31 @@ static void tree_remove(OrcTree *t, int oi) {
 
 /* ---------------- ledger: account.py:124-231, cash_processor.py, calculate.py --------------- */
 /* party: 0 = init_party, 1 = counter_party.  side: 0 bid, 1 ask (that party's side). */
+#define DI(x) dec_from_i64((int64_t)(x))
 static void cash_increase(OrcAcct *a, int party, int64_t v) { /* cash_processor.py:31-36 */
     if (party == 0) a->cash -= v; else a->hold -= v;
+    if (a->dl) { if (party == 0) a->d_cash = dec_sub(a->d_cash, DI(v)); else a->d_hold = dec_sub(a->d_hold, DI(v)); }
 }
 static void cash_decrease(OrcAcct *a, int party, int64_t v) { /* cash_processor.py:38-45 */
     if (party == 0) a->cash += v; else { a->cash += v; a->hold -= v; a->cash += v; }
+    if (a->dl) {
+        if (party == 0) a->d_cash = dec_add(a->d_cash, DI(v));
+        else { a->d_cash = dec_add(a->d_cash, DI(v)); a->d_hold = dec_sub(a->d_hold, DI(v)); a->d_cash = dec_add(a->d_cash, DI(v)); }
+    }
+}
+/* escrow moves with exact integer values: cash_processor.py:15-29 (dir = +1: cash -> hold), :55-62 / :85-97 (dir = -1: hold -> cash;
+ * the reference subtracts from cash_on_hold first, then adds to cash) */
+static void escrow_move(OrcAcct *a, int64_t v, int dir) {
+    if (dir > 0) { a->cash -= v; a->hold += v; } else { a->hold -= v; a->cash += v; }
+    if (a->dl) {
+        if (dir > 0) { a->d_cash = dec_sub(a->d_cash, DI(v)); a->d_hold = dec_add(a->d_hold, DI(v)); }
+        else { a->d_hold = dec_sub(a->d_hold, DI(v)); a->d_cash = dec_add(a->d_cash, DI(v)); }
+    }
+}
+/* calculate.py:24-33 cal_profit + "position_val = raw_val + profit" on the Decimal fields */
+static void dl_set_pv(OrcAcct *a, int is_long, dec raw, dec mkt) {
+    dec profit = is_long ? dec_sub(mkt, raw) : dec_sub(raw, mkt);
+    a->d_pv = dec_add(raw, profit);
 }
 /* account.py:135-149 _covered: position_val = raw + profit; cash += position_val - mkt_val */
 static int64_t acct_covered(OrcAcct *a, int is_long, int64_t price) {
@@ -206,6 +232,12 @@ static int64_t acct_covered(OrcAcct *a, int is_long, int64_t price) {
     a->pv = raw + profit;
     a->cash += a->pv - mkt; /* cash_processor.py:47-53 size_zero_cash_transfer */
     a->pv = 0; a->C = 0;
+    if (a->dl) {
+        dec draw = dec_mul(DI(ap), a->d_vwap), dmkt = DI(mkt);
+        dl_set_pv(a, is_long, draw, dmkt);
+        a->d_cash = dec_add(a->d_cash, dec_sub(a->d_pv, dmkt));
+        a->d_pv = dec_zero(); a->d_vwap = dec_zero();
+    }
     return mkt;
 }
 static void acct_size_increase(OrcAcct *a, int is_long, int party, int64_t q, int64_t price, int64_t tv) {
@@ -215,6 +247,10 @@ static void acct_size_increase(OrcAcct *a, int is_long, int party, int64_t q, in
     a->C += tv;
     int64_t raw = a->C, mkt = total * price;
     a->pv = raw + (is_long ? mkt - raw : raw - mkt);
+    if (a->dl) {
+        a->d_vwap = dec_div(dec_add(dec_mul(DI(ap), a->d_vwap), DI(tv)), DI(total));
+        dl_set_pv(a, is_long, dec_mul(DI(total), a->d_vwap), DI(mkt));
+    }
     cash_increase(a, party, tv);
 }
 static void acct_size_decrease(OrcAcct *a, int is_long, int party, int64_t q, int64_t price, int64_t tv) {
@@ -225,6 +261,10 @@ static void acct_size_decrease(OrcAcct *a, int is_long, int party, int64_t q, in
         a->C -= tv; /* VWAP' = (|pos|*VWAP - tv)/left */
         int64_t raw = a->C, mkt = left * price;
         a->pv = raw + (is_long ? mkt - raw : raw - mkt);
+        if (a->dl) {
+            a->d_vwap = dec_div(dec_sub(dec_mul(DI(ap), a->d_vwap), DI(tv)), DI(left));
+            dl_set_pv(a, is_long, dec_mul(DI(left), a->d_vwap), DI(mkt));
+        }
     } else {
         acct_covered(a, is_long, price);
     }
@@ -238,6 +278,7 @@ static void acct_covered_side_chg(OrcAcct *a, int is_long, int party, int64_t q,
     int64_t new_size = q - ap;
     a->pv = new_size * price;
     a->C = new_size * price; /* VWAP = price */
+    if (a->dl) { a->d_pv = DI(new_size * price); a->d_vwap = DI(price); }
     cash_increase(a, party, a->pv);
 }
 /* account.py:215-231 process_acc */
@@ -255,6 +296,7 @@ static void orc_process_acc(OrcAcct *a, int party, int side, int64_t q, int64_t 
         else acct_covered_side_chg(a, 0, party, q, price);
     } else { /* account.py:173-176 _neutral */
         a->pv += tv; a->C = tv;
+        if (a->dl) { a->d_pv = dec_add(a->d_pv, DI(tv)); a->d_vwap = DI(price); }
         cash_increase(a, party, tv);
     }
     /* account.py:196-213 _update_net_position */
@@ -267,7 +309,13 @@ static void orc_mtm(OrcAcct *a, int64_t p) {
     a->pv = a->C + profit;
     a->prev_nav = a->nav;
     a->nav = a->cash + a->hold + a->pv;
-    if (a->nav > a->max_nav) a->max_nav = a->nav;
+    if (!a->dl) { if (a->nav > a->max_nav) a->max_nav = a->nav; return; }
+    dec diff = a->pos >= 0 ? dec_sub(DI(p), a->d_vwap) : dec_sub(a->d_vwap, DI(p));   /* calculate.py:44-45 */
+    dec dprofit = dec_mul(DI(ap), diff);
+    a->d_pv = dec_add(dec_mul(DI(ap), a->d_vwap), dprofit);
+    a->d_prev_nav = a->d_nav;
+    a->d_nav = dec_add(dec_add(a->d_cash, a->d_hold), a->d_pv);                        /* calculate.py:12 */
+    if (dec_cmp(a->d_nav, a->d_max_nav) > 0) { a->d_max_nav = a->d_nav; a->max_nav = a->nav; }
 }
 
 /* ---------------- matching: orderbook.py:61-194 -------------------------------------------- */
@@ -353,7 +401,7 @@ static int get_order_id(OrcTree *t, int trader, int type, int64_t price) {
 
 /* trader.py:108-151 _order_approved */
 static int order_approved(OrcMarket *mk, OrcAcct *a, int side, int64_t size, int is_market, int64_t price) {
-    if (a->nav <= 0) return 0;
+    if (a->dl ? dec_sign(a->d_nav) <= 0 : a->nav <= 0) return 0;
     int64_t opening;
     if ((side == 0 && a->pos >= 0) || (side == 1 && a->pos <= 0)) opening = size;
     else { int64_t ap = a->pos < 0 ? -a->pos : a->pos; opening = size - ap; if (opening < 0) opening = 0; }
@@ -364,6 +412,7 @@ static int order_approved(OrcMarket *mk, OrcAcct *a, int side, int64_t size, int
         if (opp->n_levels > 0) est = side == 0 ? opp->levels[0].price : opp->levels[opp->n_levels - 1].price;
         else est = mk->tape_nonempty ? mk->tape_last : 1;
     } else est = price;
+    if (a->dl) return dec_cmp(a->d_cash, DI(opening * est)) >= 0;   /* on the Decimal cash, residues included */
     return a->cash >= opening * est;
 }
 
@@ -377,7 +426,7 @@ static void process_trades(OrcMarket *mk, int f0, int self_id) {
             orc_process_acc(&mk->acc[f->maker], 1, 1 - f->taker_side, f->qty, f->price);
             orc_process_acc(&mk->acc[self_id], 0, f->taker_side, f->qty, f->price);
         } else { /* cash_processor.py:55-62 init_is_counter_cash_transfer */
-            mk->acc[self_id].hold -= tv; mk->acc[self_id].cash += tv;
+            escrow_move(&mk->acc[self_id], tv, -1);
         }
     }
 }
@@ -421,14 +470,14 @@ static void place_order(OrcEnv *e, OrcMarket *mk, int id, int type, int side, in
             rq = process_limit(mk, side, size, price, id, mk->next_order_id, mk->time); rp = price;
         } else {
             OrcOrder *o = &own->orders[oi];
-            int64_t ov = o->price * o->qty; a->hold -= ov; a->cash += ov; /* cancel_cash_transfer */
+            int64_t ov = o->price * o->qty; escrow_move(a, ov, -1); /* cancel_cash_transfer */
             modify_order(mk, side, oi, price, size, &rp, &rq);
         }
     } else if (type == 2) { /* trader.py:205-217 */
         int oi = get_order_id(own, id, 2, price);
         if (oi >= 0) {
             OrcOrder *o = &own->orders[oi];
-            int64_t ov = o->price * o->qty; a->hold -= ov; a->cash += ov;
+            int64_t ov = o->price * o->qty; escrow_move(a, ov, -1);
             modify_order(mk, side, oi, price, size, &rp, &rq);
         }
     } else { /* trader.py:237-252 */
@@ -438,11 +487,11 @@ static void place_order(OrcEnv *e, OrcMarket *mk, int id, int type, int side, in
             int64_t ov = o->price * o->qty;
             mk->time++; /* orderbook.py:196-208 */
             tree_remove(own, oi);
-            a->hold -= ov; a->cash += ov;
+            escrow_move(a, ov, -1);
         }
     }
     if (mk->n_fills > f0) process_trades(mk, f0, id);
-    if (rq > 0) { int64_t v = rp * rq; a->cash -= v; a->hold += v; } /* cash_processor.py:15-29 */
+    if (rq > 0) escrow_move(a, rp * rq, +1); /* cash_processor.py:15-29 */
     (void)e;
 }
 
@@ -494,6 +543,8 @@ static void market_reset(OrcEnv *e, OrcMarket *mk, int reseed, uint64_t seed) {
         OrcAcct *a = &mk->acc[i];
         memset(a, 0, sizeof(*a));
         a->cash = a->nav = a->prev_nav = a->max_nav = c->init_cash;
+        a->dl = c->decimal_ledger;
+        if (a->dl) a->d_cash = a->d_nav = a->d_prev_nav = a->d_max_nav = DI(c->init_cash);
     }
     float snap[ORC_SNAP];
     set_agg_lob(e, mk, snap); /* state_helper.py:66-78 */
@@ -567,9 +618,14 @@ static void market_step(OrcEnv *e, OrcMarket *mk, const int32_t *cat, const floa
     for (int i = 0; i < A; ++i) { /* reward_helper.py:35-103 ; done_helper.py:3-18 */
         OrcAcct *a = &mk->acc[i];
         double nav_change = (double)(a->nav - a->prev_nav);
-        double nav_term = nav_change * (nav_change < 0 ? c->loss_multiplier : 1.0);
         int64_t ddi = a->max_nav - a->nav; if (ddi < 0) ddi = 0;
         double dd = (double)ddi;
+        if (a->dl) {   /* float(nav - prev_nav), float(max(0, max_nav - nav)) on the Decimal fields */
+            nav_change = dec_to_double(dec_sub(a->d_nav, a->d_prev_nav));
+            dec ddd = dec_sub(a->d_max_nav, a->d_nav);
+            dd = dec_sign(ddd) > 0 ? dec_to_double(ddd) : 0.0;
+        }
+        double nav_term = nav_change * (nav_change < 0 ? c->loss_multiplier : 1.0);
         volatile double t0 = nav_term;
         volatile double t1 = -(c->order_penalty * (double)a->order_step_placed);
         volatile double t2 = -(c->trade_penalty * (double)a->num_trades_step);
@@ -580,7 +636,7 @@ static void market_step(OrcEnv *e, OrcMarket *mk, const int32_t *cat, const floa
         a->reward = r; a->drawdown = dd;
         a->terms[0] = t0; a->terms[1] = t1; a->terms[2] = t2; a->terms[3] = t3; a->terms[4] = t4;
         reward[i] = r;
-        if (a->nav <= 0) mk->done_mask |= (1u << i);
+        if (a->dl ? dec_sign(a->d_nav) <= 0 : a->nav <= 0) mk->done_mask |= (1u << i);
     }
     uint32_t all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
     *term = (mk->done_mask & all) == all;            /* done_helper.py:20-55 */
@@ -695,6 +751,13 @@ void orc_dump_accounts(void *h, int m, int64_t *out) {
     for (int i = 0; i < e->cfg.num_agents; ++i) {
         const OrcAcct *a = &k->acc[i]; int64_t *o = out + i * 14;
         o[0] = a->cash; o[1] = a->hold; o[2] = a->pv; o[3] = a->C; o[4] = a->nav; o[5] = a->prev_nav; o[6] = a->max_nav;
+        if (a->dl) {   /* the Decimal twins, to the nearest integer (what ref_runner does with the reference's fields); they must agree */
+            int64_t ap = a->pos < 0 ? -a->pos : a->pos;
+            int64_t dv[7] = {dec_to_i64_nearest(a->d_cash), dec_to_i64_nearest(a->d_hold), dec_to_i64_nearest(a->d_pv),
+                             dec_to_i64_nearest(dec_mul(DI(ap), a->d_vwap)), dec_to_i64_nearest(a->d_nav),
+                             dec_to_i64_nearest(a->d_prev_nav), dec_to_i64_nearest(a->d_max_nav)};
+            for (int j = 0; j < 7; ++j) { if (dv[j] != o[j]) k->status |= ORC_ST_LEDGER_MISMATCH; o[j] = dv[j]; }
+        }
         o[7] = a->pos; o[8] = a->num_trades; o[9] = a->num_trades_step; o[10] = a->num_passive_fills_step;
         o[11] = a->order_step_placed; o[12] = a->num_rejected_step; o[13] = a->is_pass;
     }
@@ -728,5 +791,24 @@ void orc_test_stream(uint64_t seed, int n, const int32_t *ops, double *outn, int
         if (ops[i] == 0) outn[i] = orc_standard_normal(&r);
         else if (ops[i] == -1) outn[i] = (double)orc_integers(&r, lo, hi);
         else { int p[ORC_MAX_AGENTS]; orc_permutation(&r, ops[i], p); for (int k = 0; k < ops[i]; ++k) outp[32 * i + k] = p[k]; }
+    }
+}
+
+/* dec28.h test entry: op is one of  + - * / (divide) c (compare: result "-1", "0" or "1"); operands and result are decimal strings */
+void orc_dec_op(char op, const char *a, const char *b, char *out, int cap) {
+    dec x = dec_from_str(a), y = dec_from_str(b), r;
+    if (op == 'c') { snprintf(out, (size_t)cap, "%d", dec_cmp(x, y)); return; }
+    r = op == '+' ? dec_add(x, y) : op == '-' ? dec_sub(x, y) : op == '*' ? dec_mul(x, y) : dec_div(x, y);
+    dec_to_str(r, out, (size_t)cap);
+}
+double orc_dec_to_double(const char *a) { return dec_to_double(dec_from_str(a)); }
+/* decimal_ledger mode: the seven Decimal fields of every agent of market m as strings, 48 bytes each:
+ * cash, cash_on_hold, position_val, VWAP, nav, prev_nav, max_nav (account.py:12-53) */
+void orc_dump_accounts_dec(void *h, int m, char *out /*[A][7][48]*/) {
+    OrcEnv *e = (OrcEnv *)h; OrcMarket *k = &e->mk[m];
+    for (int i = 0; i < e->cfg.num_agents; ++i) {
+        const OrcAcct *a = &k->acc[i];
+        const dec f[7] = {a->d_cash, a->d_hold, a->d_pv, a->d_vwap, a->d_nav, a->d_prev_nav, a->d_max_nav};
+        for (int j = 0; j < 7; ++j) dec_to_str(f[j], out + ((size_t)i * 7 + j) * 48, 48);
     }
 }

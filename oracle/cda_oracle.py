@@ -30,13 +30,13 @@ class OrcConfig(ctypes.Structure):
         ("price_lo", ctypes.c_int32), ("price_hi", ctypes.c_int32),
         ("order_penalty", ctypes.c_double), ("trade_penalty", ctypes.c_double),
         ("drawdown_penalty", ctypes.c_double), ("passive_bonus", ctypes.c_double),
-        ("loss_multiplier", ctypes.c_double),
+        ("loss_multiplier", ctypes.c_double), ("decimal_ledger", ctypes.c_int32),
     ]
 
 
 def build(force=False):
     """Compile the oracle with gcc (no-op when up to date)."""
-    srcs = [os.path.join(_HERE, f) for f in ("cda_oracle.c", "np_rng.h", "zig_tables.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("cda_oracle.c", "np_rng.h", "zig_tables.h", "dec28.h")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
         return _SO
@@ -65,7 +65,10 @@ def _p(a):
 class OracleEnv:
     """M independent markets stepped on the CPU by the C oracle (tensor-style API)."""
 
-    def __init__(self, config=None, num_markets=1):
+    def __init__(self, config=None, num_markets=1, decimal_ledger=False):
+        """decimal_ledger=True: the oracle ALSO keeps the reference's Decimal(prec 28) money fields (oracle/dec28.h) and decides the
+        cash gate / bankruptcy / high-water mark on them — reproduces the reference even where its ~1e-24 VWAP residues
+        flip a `cash >= order value` test at exact equality (the exact-integer ledger, default, is what the CUDA env runs)."""
         cfg = dict(DEFAULTS)
         cfg.update(config or {})
         self.cfg = cfg
@@ -80,7 +83,7 @@ class OracleEnv:
                       int(cfg["limit_size_multiple"]), int(cfg["initial_price_min"]),
                       int(cfg["initial_price_max"]), float(cfg["order_penalty"]),
                       float(cfg["trade_penalty"]), float(cfg["drawdown_penalty"]),
-                      float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]))
+                      float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]), 1 if decimal_ledger else 0)
         self._L = lib()
         self._h = self._L.orc_create(ctypes.byref(c), self.M)
         if not self._h:
@@ -89,6 +92,16 @@ class OracleEnv:
         self.reward = np.zeros((self.M, self.A), np.float64)
         self.terminated = np.zeros(self.M, np.uint8)
         self.truncated = np.zeros(self.M, np.uint8)
+
+    def dump_decimal(self, m=0):
+        """decimal_ledger mode: {field: [Decimal per agent]} of market m — the reference's own Decimal values, residues included."""
+        from decimal import Decimal
+        buf = ctypes.create_string_buffer(self.A * 7 * 48)
+        self._L.orc_dump_accounts_dec(ctypes.c_void_p(self._h), int(m), buf)
+        names = ("cash", "cash_on_hold", "position_val", "VWAP", "nav", "prev_nav", "max_nav")
+        raw = buf.raw
+        get = lambda i, j: Decimal(raw[(i * 7 + j) * 48:(i * 7 + j + 1) * 48].split(b"\0", 1)[0].decode())
+        return {n: [get(i, j) for i in range(self.A)] for j, n in enumerate(names)}
 
     def __del__(self):
         if getattr(self, "_h", None):

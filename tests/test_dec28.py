@@ -1,0 +1,67 @@
+"""oracle/dec28.h (the Decimal(prec 28, ROUND_HALF_EVEN) arithmetic of the oracle's optional decimal ledger) against Python's own
+`decimal` — the library the reference's ledger runs on (envs/account/*.py)."""
+import ctypes
+import random
+from decimal import Decimal, getcontext
+
+import pytest
+
+from oracle import cda_oracle
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = cda_oracle.lib()
+    lib.orc_dec_op.argtypes = [ctypes.c_char, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    lib.orc_dec_to_double.argtypes = [ctypes.c_char_p]
+    lib.orc_dec_to_double.restype = ctypes.c_double
+    return lib
+
+
+def rand_dec(rng):
+    kind = rng.random()
+    if kind < 0.25:                                   # ledger-like integers
+        return Decimal(rng.randrange(-10**rng.randrange(1, 12), 10**rng.randrange(1, 12)))
+    if kind < 0.5:                                    # integer plus a residue of the size the reference's VWAP division leaves
+        return Decimal(rng.randrange(0, 10**9)) + Decimal(rng.randrange(-999, 999)).scaleb(-rng.randrange(18, 27))
+    digits = rng.randrange(1, 29)
+    return Decimal(rng.randrange(-10**digits, 10**digits)).scaleb(rng.randrange(-30, 12))
+
+
+def test_four_operations_and_compare_match_python_decimal(L):
+    assert getcontext().prec == 28
+    rng = random.Random(12345)
+    out = ctypes.create_string_buffer(96)
+    n = 0
+    for _ in range(6000):
+        a, b = rand_dec(rng), rand_dec(rng)
+        for op, f in (("+", lambda: a + b), ("-", lambda: a - b), ("*", lambda: a * b), ("/", lambda: a / b)):
+            if op == "/" and b == 0:
+                continue
+            L.orc_dec_op(op.encode(), str(a).encode(), str(b).encode(), out, 96)
+            assert Decimal(out.value.decode()) == f(), (op, a, b, out.value)
+            n += 1
+        L.orc_dec_op(b"c", str(a).encode(), str(b).encode(), out, 96)
+        assert int(out.value) == (a > b) - (a < b)
+    assert n > 20000
+
+
+def test_rounding_corners(L):
+    out = ctypes.create_string_buffer(96)
+    cases = [("+", "9999999999999999999999999999", "0.5"), ("+", "9999999999999999999999999999", "0.4999999"),
+             ("+", "1000000000000000000000000000.5", "0"), ("-", "1", "1e-40"), ("-", "1e10", "1e-30"),
+             ("/", "1", "3"), ("/", "2", "3"), ("/", "129", "6"), ("/", "64", "3"), ("*", "21.33333333333333333333333333", "3"),
+             ("*", "0.6666666666666666666666666667", "3"), ("+", "395.999999999999999999999999", "1e-24"),
+             ("-", "1000000", "0.000000000000000000000049999"), ("/", "1e-30", "7"), ("*", "-99999999999999", "99999999999999")]
+    for op, a, b in cases:
+        A, B = Decimal(a), Decimal(b)
+        want = A + B if op == "+" else A - B if op == "-" else A * B if op == "*" else A / B
+        L.orc_dec_op(op.encode(), a.encode(), b.encode(), out, 96)
+        assert Decimal(out.value.decode()) == want, (op, a, b, out.value, want)
+
+
+def test_to_float_is_correctly_rounded(L):
+    rng = random.Random(7)
+    for _ in range(3000):
+        a = rand_dec(rng)
+        assert L.orc_dec_to_double(str(a).encode()) == float(a), a
