@@ -28,7 +28,12 @@
 #include <string.h>
 
 #include "np_rng.h"
+#ifdef ORC_DEC128
+#include "dec128.h"   /* fixed-width (unsigned __int128) form of the same arithmetic: the shape of the future device ledger */
+#else
 #include "dec28.h"
+static int dec_range_errors = 0;
+#endif
 
 #define ORC_K 10          /* k_rows  (config/tunable_constants.json: observation_layout) */
 #define ORC_SNAP 42       /* book_rows*k_rows + extra_dim */
@@ -757,6 +762,7 @@ void orc_dump_accounts(void *h, int m, int64_t *out) {
                              dec_to_i64_nearest(dec_mul(DI(ap), a->d_vwap)), dec_to_i64_nearest(a->d_nav),
                              dec_to_i64_nearest(a->d_prev_nav), dec_to_i64_nearest(a->d_max_nav)};
             for (int j = 0; j < 7; ++j) { if (dv[j] != o[j]) k->status |= ORC_ST_LEDGER_MISMATCH; o[j] = dv[j]; }
+            if (dec_range_errors) k->status |= ORC_ST_LEDGER_MISMATCH;   /* dec128.h: an operation did not fit 128 bits */
         }
         o[7] = a->pos; o[8] = a->num_trades; o[9] = a->num_trades_step; o[10] = a->num_passive_fills_step;
         o[11] = a->order_step_placed; o[12] = a->num_rejected_step; o[13] = a->is_pass;
@@ -802,6 +808,7 @@ void orc_dec_op(char op, const char *a, const char *b, char *out, int cap) {
     dec_to_str(r, out, (size_t)cap);
 }
 double orc_dec_to_double(const char *a) { return dec_to_double(dec_from_str(a)); }
+int orc_dec_range_errors(void) { return dec_range_errors; }
 /* decimal_ledger mode: the seven Decimal fields of every agent of market m as strings, 48 bytes each:
  * cash, cash_on_hold, position_val, VWAP, nav, prev_nav, max_nav (account.py:12-53) */
 void orc_dump_accounts_dec(void *h, int m, char *out /*[A][7][48]*/) {

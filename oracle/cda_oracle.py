@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libcda_oracle.so")
+_SO128 = os.path.join(_HERE, "_build", "libcda_oracle_dec128.so")   # decimal ledger on unsigned __int128 (dec128.h)
 
 DEFAULTS = dict(  # config/env_defaults.json of the reference (standalone defaults)
     num_of_agents=4, init_cash=1_000_000, tick_size=1, max_step=64, n_hist=4,
@@ -36,26 +37,27 @@ class OrcConfig(ctypes.Structure):
 
 def build(force=False):
     """Compile the oracle with gcc (no-op when up to date)."""
-    srcs = [os.path.join(_HERE, f) for f in ("cda_oracle.c", "np_rng.h", "zig_tables.h", "dec28.h")]
-    if (not force and os.path.exists(_SO)
-            and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
+    srcs = [os.path.join(_HERE, f) for f in ("cda_oracle.c", "np_rng.h", "zig_tables.h", "dec28.h", "dec128.h")]
+    if (not force and os.path.exists(_SO) and os.path.exists(_SO128)
+            and all(min(os.path.getmtime(_SO), os.path.getmtime(_SO128)) >= os.path.getmtime(s) for s in srcs)):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(dec128=False):
+    """dec128=True: the build whose decimal ledger runs on unsigned __int128 (oracle/dec128.h)."""
+    if dec128 not in _libs:
         build()
-        _lib = ctypes.CDLL(_SO)
-        _lib.orc_create.restype = ctypes.c_void_p
-        _lib.orc_create.argtypes = [ctypes.POINTER(OrcConfig), ctypes.c_int]
-        _lib.orc_destroy.argtypes = [ctypes.c_void_p]
-    return _lib
+        L = ctypes.CDLL(_SO128 if dec128 else _SO)
+        L.orc_create.restype = ctypes.c_void_p
+        L.orc_create.argtypes = [ctypes.POINTER(OrcConfig), ctypes.c_int]
+        L.orc_destroy.argtypes = [ctypes.c_void_p]
+        _libs[dec128] = L
+    return _libs[dec128]
 
 
 def _p(a):
@@ -65,7 +67,7 @@ def _p(a):
 class OracleEnv:
     """M independent markets stepped on the CPU by the C oracle (tensor-style API)."""
 
-    def __init__(self, config=None, num_markets=1, decimal_ledger=False):
+    def __init__(self, config=None, num_markets=1, decimal_ledger=False, dec128=False):
         """decimal_ledger=True: the oracle ALSO keeps the reference's Decimal(prec 28) money fields (oracle/dec28.h) and decides the
         cash gate / bankruptcy / high-water mark on them — reproduces the reference even where its ~1e-24 VWAP residues
         flip a `cash >= order value` test at exact equality (the exact-integer ledger, default, is what the CUDA env runs)."""
@@ -84,7 +86,7 @@ class OracleEnv:
                       int(cfg["initial_price_max"]), float(cfg["order_penalty"]),
                       float(cfg["trade_penalty"]), float(cfg["drawdown_penalty"]),
                       float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]), 1 if decimal_ledger else 0)
-        self._L = lib()
+        self._L = lib(dec128)
         self._h = self._L.orc_create(ctypes.byref(c), self.M)
         if not self._h:
             raise ValueError("orc_create rejected the config")

@@ -23,12 +23,12 @@ def gen(rng, T, A, mix, absent=0.0):
             rng.integers(0, 10, (T, A)).astype(np.int32), rng.integers(0, 3, (T, A)).astype(np.int32))
 
 
-def run(seed, A, T, mix, extra=None, absent=0.0, decimal_ledger=False):
+def run(seed, A, T, mix, extra=None, absent=0.0, decimal_ledger=False, dec128=False):
     """decimal_ledger: the oracle keeps the reference's Decimal(28) fields too and must reproduce them EXACTLY (residues included)."""
     from oracle.ref_runner import ReferenceMarket
     cfg = dict(num_of_agents=A, init_cash=1_000_000, max_step=T + 5, n_hist=4)
     cfg.update(extra or {})
-    ref, orc = ReferenceMarket(cfg), OracleEnv(cfg, 1, decimal_ledger=decimal_ledger)
+    ref, orc = ReferenceMarket(cfg), OracleEnv(cfg, 1, decimal_ledger=decimal_ledger, dec128=dec128)
     assert np.array_equal(ref.reset(seed=seed), orc.reset(seeds=[seed])[0])
     acts = gen(np.random.default_rng(seed + 7), T, A, mix, absent)
     for t in range(T):
@@ -133,14 +133,17 @@ def test_decimal_ledger_reproduces_the_reference_where_the_exact_ledger_cannot()
     """Same trajectory as the known divergence above, oracle in decimal_ledger mode (oracle/dec28.h): every Decimal field of every
     agent equals the reference's at every step — residues included — so the refused order is refused here too and the whole
     250-step trajectory is identical, rewards bit for bit."""
-    run(61018, 7, 250, "modify_heavy",
-        dict(init_cash=3000, n_hist=2, tick_size=3, min_size=1, mkt_max_size=10, limit_size_multiple=3, initial_price_min=3,
-             initial_price_max=21), decimal_ledger=True)
+    for dec128 in (False, True):
+        run(61018, 7, 250, "modify_heavy",
+            dict(init_cash=3000, n_hist=2, tick_size=3, min_size=1, mkt_max_size=10, limit_size_multiple=3, initial_price_min=3,
+                 initial_price_max=21), decimal_ledger=True, dec128=dec128)
 
 
+@pytest.mark.parametrize("dec128", [False, True], ids=["digits", "u128"])
 @pytest.mark.parametrize("case", range(8))
-def test_decimal_ledger_low_cash_configurations(case):
-    """Low-cash fuzz (the cash gate binds all the time) with the Decimal(28) twin ledger compared field by field."""
+def test_decimal_ledger_low_cash_configurations(case, dec128):
+    """Low-cash fuzz (the cash gate binds all the time) with the Decimal(28) twin ledger compared field by field; once on the
+    digit-array arithmetic (dec28.h), once on the fixed-width unsigned __int128 form the device port will use (dec128.h)."""
     rng = np.random.default_rng(50000 + case)
     A = int(rng.integers(2, 9))
     lo = int(rng.choice([3, 10, 37, 250, 999]))
@@ -149,4 +152,4 @@ def test_decimal_ledger_low_cash_configurations(case):
                  init_cash=int(rng.choice([300, 1_000, 3_000, 7_777, 20_000, 100_000])),
                  initial_price_min=lo, initial_price_max=lo + int(rng.integers(0, 30)))
     mix = str(rng.choice(["uniform", "limit_market", "modify_heavy"]))
-    run(70000 + case, A, 150, mix, extra, absent=float(rng.choice([0.0, 0.1])), decimal_ledger=True)
+    run(70000 + case, A, 150, mix, extra, absent=float(rng.choice([0.0, 0.1])), decimal_ledger=True, dec128=dec128)
