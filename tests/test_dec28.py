@@ -65,3 +65,34 @@ def test_to_float_is_correctly_rounded(L):
     for _ in range(3000):
         a = rand_dec(rng)
         assert L.orc_dec_to_double(str(a).encode()) == float(a), a
+
+
+def test_fixed_width_form_matches_python_decimal_on_ledger_shaped_operands():
+    """oracle/dec128.h (unsigned __int128 coefficients — the form meant for the device ledger): exact on the operand shapes the
+    ledger produces (money +- residue, sizes and prices as the short factor / divisor), and it COUNTS what does not fit 128
+    bits instead of returning a wrong digit."""
+    lib = cda_oracle.lib(dec128=True)
+    lib.orc_dec_op.argtypes = [ctypes.c_char, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    rng = random.Random(99)
+    out = ctypes.create_string_buffer(96)
+
+    def money():
+        v = Decimal(rng.randrange(-10**rng.randrange(1, 11), 10**rng.randrange(1, 11)))
+        if rng.random() < 0.7:                          # a full-precision value: integer part + residue down to 28 significant digits
+            v = (v + Decimal(rng.randrange(-10**6, 10**6)).scaleb(-rng.randrange(16, 27))) * 1
+        return v
+
+    def small():
+        return Decimal(rng.randrange(1, 10**rng.randrange(1, 7)))
+
+    before = lib.orc_dec_range_errors()
+    for _ in range(6000):
+        a, b, k = money(), money(), small()
+        for op, x, y, want in (("+", a, b, a + b), ("-", a, b, a - b), ("*", k, a, k * a), ("/", a, k, a / k)):
+            lib.orc_dec_op(op.encode(), str(x).encode(), str(y).encode(), out, 96)
+            assert Decimal(out.value.decode()) == want, (op, x, y, out.value, want)
+        lib.orc_dec_op(b"c", str(a).encode(), str(b).encode(), out, 96)
+        assert int(out.value) == (a > b) - (a < b)
+    assert lib.orc_dec_range_errors() == before         # everything above fitted
+    lib.orc_dec_op(b"*", b"1234567890123456789012345678", b"9876543210987654321098765432", out, 96)
+    assert lib.orc_dec_range_errors() == before + 1     # 28 x 28 digits does not: reported, not mis-rounded
