@@ -809,6 +809,7 @@ void orc_dec_op(char op, const char *a, const char *b, char *out, int cap) {
 }
 double orc_dec_to_double(const char *a) { return dec_to_double(dec_from_str(a)); }
 int orc_dec_range_errors(void) { return dec_range_errors; }
+void orc_dec_reset_range_errors(void) { dec_range_errors = 0; }
 /* decimal_ledger mode: the seven Decimal fields of every agent of market m as strings, 48 bytes each:
  * cash, cash_on_hold, position_val, VWAP, nav, prev_nav, max_nav (account.py:12-53) */
 void orc_dump_accounts_dec(void *h, int m, char *out /*[A][7][48]*/) {

@@ -87,6 +87,8 @@ class OracleEnv:
                       float(cfg["trade_penalty"]), float(cfg["drawdown_penalty"]),
                       float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]), 1 if decimal_ledger else 0)
         self._L = lib(dec128)
+        if decimal_ledger:
+            self._L.orc_dec_reset_range_errors()   # (a process-wide counter of dec128.h; an env reports it through its status word)
         self._h = self._L.orc_create(ctypes.byref(c), self.M)
         if not self._h:
             raise ValueError("orc_create rejected the config")

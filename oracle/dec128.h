@@ -4,10 +4,11 @@
  * device ledger of DESIGN.md section 9 item 0 will take — nvcc supports unsigned __int128 in device code — validated
  * here first, on the CPU, inside the oracle (build with -DORC_DEC128) against the reference's own Decimal fields.
  *
- * Every operation computes the EXACT result in 128 bits and rounds once.  That needs the aligned operands of an addition,
- * and the scaled dividend of a division, to stay below 10^38 (< 2^127): true for ledger values (money below ~1e10 with
- * at most 28 significant digits, divisors = position sizes).  An operation that would not fit raises `dec_range_errors`
- * instead of returning a wrong digit (the oracle turns that into a status bit).
+ * Every operation rounds ONCE, from the exact result: additions are exact for every pair of operands (aligned in 128 bits
+ * when they fit, otherwise on a 30-digit window with a sticky bit); a product needs digits(a) + digits(b) <= 38 and a
+ * quotient a divisor of at most 9 digits — true for the ledger, where one factor is always a size or a price.  A
+ * product or quotient that would not fit raises `dec_range_errors` instead of returning a wrong digit (the oracle turns
+ * that into a status bit).
  * ===================================================================================== */
 #ifndef CDA_DEC128_H
 #define CDA_DEC128_H
@@ -68,20 +69,21 @@ static dec dec_add(dec a, dec b) {
     if (a.exp < b.exp) { dec t = a; a = b; b = t; }            /* a has the larger exponent */
     int diff = a.exp - b.exp;
     int na = dec_ndigits(a.c);
-    if (na + diff > 38) {                                       /* try again with the zeros stripped */
-        a = dec_strip(a); b = dec_strip(b);
-        if (a.exp < b.exp) { dec t = a; a = b; b = t; }
-        diff = a.exp - b.exp; na = dec_ndigits(a.c);
-        int nb = dec_ndigits(b.c);
-        if (na + diff > 38) {
-            if (a.exp + na > b.exp + nb + 2 * DEC_P) return a;  /* b is far below a's last digit */
-            ++dec_range_errors; return a;
-        }
+    if (na + diff <= 38) {                                      /* the aligned operands fit: exact sum, one rounding */
+        u128 x = a.c * dec_pow10(diff), y = b.c;
+        if (a.sign == b.sign) return dec_round_u128(a.sign, x + y, b.exp, 0);
+        if (x == y) return dec_zero();
+        return x > y ? dec_round_u128(a.sign, x - y, b.exp, 0) : dec_round_u128(b.sign, y - x, b.exp, 0);
     }
-    u128 x = a.c * dec_pow10(diff), y = b.c;
-    if (a.sign == b.sign) return dec_round_u128(a.sign, x + y, b.exp, 0);
-    if (x == y) return dec_zero();
-    return x > y ? dec_round_u128(a.sign, x - y, b.exp, 0) : dec_round_u128(b.sign, y - x, b.exp, 0);
+    /* b lies (partly) below the 28-digit window of a (na + diff > 38 implies |b| < |a| * 1e-10): widen a to 30 digits (two
+     * guard digits), cut b at that position and keep what was cut as a sticky bit.  With a fraction 0 < f < 1 cut off,
+     * a' + b' + f rounds like (a' + b', sticky) and a' - b' - f like (a' - b' - 1, sticky). */
+    int t = 30 - na, shift = diff - t;
+    u128 x = a.c * dec_pow10(t), y = 0; int sticky;
+    if (shift > 38) sticky = 1;
+    else { u128 p = dec_pow10(shift); y = b.c / p; sticky = (b.c % p) != 0; }
+    u128 r = a.sign == b.sign ? x + y : x - y - (sticky ? 1 : 0);
+    return dec_round_u128(a.sign, r, a.exp - t, sticky);
 }
 static dec dec_sub(dec a, dec b) { return dec_add(a, dec_neg(b)); }
 

@@ -52,12 +52,17 @@ def test_rounding_corners(L):
              ("+", "1000000000000000000000000000.5", "0"), ("-", "1", "1e-40"), ("-", "1e10", "1e-30"),
              ("/", "1", "3"), ("/", "2", "3"), ("/", "129", "6"), ("/", "64", "3"), ("*", "21.33333333333333333333333333", "3"),
              ("*", "0.6666666666666666666666666667", "3"), ("+", "395.999999999999999999999999", "1e-24"),
-             ("-", "1000000", "0.000000000000000000000049999"), ("/", "1e-30", "7"), ("*", "-99999999999999", "99999999999999")]
+             ("-", "1000000", "0.000000000000000000000049999"), ("/", "1e-30", "7"), ("*", "-99999999999999", "99999999999999"),
+             ("+", "-11", "-7142857142857142857142857143e-54"), ("-", "10", "1e-40"), ("-", "1", "5e-29"), ("+", "1", "5e-28"),
+             ("+", "1", "5.000000000000000000000000001e-28"), ("-", "1e10", "4.9999999999999999999999999999e-18")]
+    L128 = cda_oracle.lib(dec128=True)
+    L128.orc_dec_op.argtypes = L.orc_dec_op.argtypes
     for op, a, b in cases:
         A, B = Decimal(a), Decimal(b)
         want = A + B if op == "+" else A - B if op == "-" else A * B if op == "*" else A / B
-        L.orc_dec_op(op.encode(), a.encode(), b.encode(), out, 96)
-        assert Decimal(out.value.decode()) == want, (op, a, b, out.value, want)
+        for lib in (L, L128):                           # digit arrays and the fixed-width form
+            lib.orc_dec_op(op.encode(), a.encode(), b.encode(), out, 96)
+            assert Decimal(out.value.decode()) == want, (op, a, b, out.value, want)
 
 
 def test_to_float_is_correctly_rounded(L):
@@ -85,10 +90,15 @@ def test_fixed_width_form_matches_python_decimal_on_ledger_shaped_operands():
     def small():
         return Decimal(rng.randrange(1, 10**rng.randrange(1, 7)))
 
+    def tiny():                                          # far below the other operand's 28-digit window, down to irrelevance
+        return Decimal(rng.randrange(-10**28, 10**28)).scaleb(-rng.randrange(30, 90))
+
     before = lib.orc_dec_range_errors()
     for _ in range(6000):
-        a, b, k = money(), money(), small()
-        for op, x, y, want in (("+", a, b, a + b), ("-", a, b, a - b), ("*", k, a, k * a), ("/", a, k, a / k)):
+        a, b, k, e = money(), money(), small(), tiny()
+        s_ = Decimal(rng.randrange(-99, 99))
+        for op, x, y, want in (("+", a, b, a + b), ("-", a, b, a - b), ("*", k, a, k * a), ("/", a, k, a / k),
+                               ("+", a, e, a + e), ("-", a, e, a - e), ("-", e, a, e - a), ("+", s_, e, s_ + e), ("-", s_, e, s_ - e)):
             lib.orc_dec_op(op.encode(), str(x).encode(), str(y).encode(), out, 96)
             assert Decimal(out.value.decode()) == want, (op, x, y, out.value, want)
         lib.orc_dec_op(b"c", str(a).encode(), str(b).encode(), out, 96)
