@@ -91,9 +91,10 @@ typedef struct {
     int32_t num_trades, num_trades_step, num_passive_fills_step, order_step_placed, num_rejected_step;
     int32_t is_pass;
     double reward, terms[5], drawdown;
-    int32_t dl;                                                   /* copy of cfg.decimal_ledger */
-    dec d_cash, d_hold, d_pv, d_vwap, d_nav, d_prev_nav, d_max_nav; /* the reference's Decimal fields (decimal_ledger mode) */
+    struct OrcDec *d;   /* decimal_ledger mode: the reference's Decimal fields of this account (kept OUT of this struct so that the
+                           default build of the CPU baseline steps exactly the memory it always did); NULL otherwise */
 } OrcAcct;
+typedef struct OrcDec { dec cash, hold, pv, vwap, nav, prev_nav, max_nav; } OrcDec;
 
 typedef struct {
     OrcTree bids, asks;
@@ -114,6 +115,7 @@ typedef struct {
     OrcConfig cfg;
     int M;
     OrcMarket *mk;
+    OrcDec *dec;   /* [M][ORC_MAX_AGENTS] Decimal twins (decimal_ledger mode), else NULL */
 } OrcEnv;
 
 /* ---------------- tree primitives ---------------------------------------------------------- */
@@ -206,28 +208,28 @@ static void tree_remove(OrcTree *t, int oi) {
 #define DI(x) dec_from_i64((int64_t)(x))
 static void cash_increase(OrcAcct *a, int party, int64_t v) { /* cash_processor.py:31-36 */
     if (party == 0) a->cash -= v; else a->hold -= v;
-    if (a->dl) { if (party == 0) a->d_cash = dec_sub(a->d_cash, DI(v)); else a->d_hold = dec_sub(a->d_hold, DI(v)); }
+    if (a->d) { if (party == 0) a->d->cash = dec_sub(a->d->cash, DI(v)); else a->d->hold = dec_sub(a->d->hold, DI(v)); }
 }
 static void cash_decrease(OrcAcct *a, int party, int64_t v) { /* cash_processor.py:38-45 */
     if (party == 0) a->cash += v; else { a->cash += v; a->hold -= v; a->cash += v; }
-    if (a->dl) {
-        if (party == 0) a->d_cash = dec_add(a->d_cash, DI(v));
-        else { a->d_cash = dec_add(a->d_cash, DI(v)); a->d_hold = dec_sub(a->d_hold, DI(v)); a->d_cash = dec_add(a->d_cash, DI(v)); }
+    if (a->d) {
+        if (party == 0) a->d->cash = dec_add(a->d->cash, DI(v));
+        else { a->d->cash = dec_add(a->d->cash, DI(v)); a->d->hold = dec_sub(a->d->hold, DI(v)); a->d->cash = dec_add(a->d->cash, DI(v)); }
     }
 }
 /* escrow moves with exact integer values: cash_processor.py:15-29 (dir = +1: cash -> hold), :55-62 / :85-97 (dir = -1: hold -> cash;
  * the reference subtracts from cash_on_hold first, then adds to cash) */
 static void escrow_move(OrcAcct *a, int64_t v, int dir) {
     if (dir > 0) { a->cash -= v; a->hold += v; } else { a->hold -= v; a->cash += v; }
-    if (a->dl) {
-        if (dir > 0) { a->d_cash = dec_sub(a->d_cash, DI(v)); a->d_hold = dec_add(a->d_hold, DI(v)); }
-        else { a->d_hold = dec_sub(a->d_hold, DI(v)); a->d_cash = dec_add(a->d_cash, DI(v)); }
+    if (a->d) {
+        if (dir > 0) { a->d->cash = dec_sub(a->d->cash, DI(v)); a->d->hold = dec_add(a->d->hold, DI(v)); }
+        else { a->d->hold = dec_sub(a->d->hold, DI(v)); a->d->cash = dec_add(a->d->cash, DI(v)); }
     }
 }
 /* calculate.py:24-33 cal_profit + "position_val = raw_val + profit" on the Decimal fields */
 static void dl_set_pv(OrcAcct *a, int is_long, dec raw, dec mkt) {
     dec profit = is_long ? dec_sub(mkt, raw) : dec_sub(raw, mkt);
-    a->d_pv = dec_add(raw, profit);
+    a->d->pv = dec_add(raw, profit);
 }
 /* account.py:135-149 _covered: position_val = raw + profit; cash += position_val - mkt_val */
 static int64_t acct_covered(OrcAcct *a, int is_long, int64_t price) {
@@ -237,11 +239,11 @@ static int64_t acct_covered(OrcAcct *a, int is_long, int64_t price) {
     a->pv = raw + profit;
     a->cash += a->pv - mkt; /* cash_processor.py:47-53 size_zero_cash_transfer */
     a->pv = 0; a->C = 0;
-    if (a->dl) {
-        dec draw = dec_mul(DI(ap), a->d_vwap), dmkt = DI(mkt);
+    if (a->d) {
+        dec draw = dec_mul(DI(ap), a->d->vwap), dmkt = DI(mkt);
         dl_set_pv(a, is_long, draw, dmkt);
-        a->d_cash = dec_add(a->d_cash, dec_sub(a->d_pv, dmkt));
-        a->d_pv = dec_zero(); a->d_vwap = dec_zero();
+        a->d->cash = dec_add(a->d->cash, dec_sub(a->d->pv, dmkt));
+        a->d->pv = dec_zero(); a->d->vwap = dec_zero();
     }
     return mkt;
 }
@@ -252,9 +254,9 @@ static void acct_size_increase(OrcAcct *a, int is_long, int party, int64_t q, in
     a->C += tv;
     int64_t raw = a->C, mkt = total * price;
     a->pv = raw + (is_long ? mkt - raw : raw - mkt);
-    if (a->dl) {
-        a->d_vwap = dec_div(dec_add(dec_mul(DI(ap), a->d_vwap), DI(tv)), DI(total));
-        dl_set_pv(a, is_long, dec_mul(DI(total), a->d_vwap), DI(mkt));
+    if (a->d) {
+        a->d->vwap = dec_div(dec_add(dec_mul(DI(ap), a->d->vwap), DI(tv)), DI(total));
+        dl_set_pv(a, is_long, dec_mul(DI(total), a->d->vwap), DI(mkt));
     }
     cash_increase(a, party, tv);
 }
@@ -266,9 +268,9 @@ static void acct_size_decrease(OrcAcct *a, int is_long, int party, int64_t q, in
         a->C -= tv; /* VWAP' = (|pos|*VWAP - tv)/left */
         int64_t raw = a->C, mkt = left * price;
         a->pv = raw + (is_long ? mkt - raw : raw - mkt);
-        if (a->dl) {
-            a->d_vwap = dec_div(dec_sub(dec_mul(DI(ap), a->d_vwap), DI(tv)), DI(left));
-            dl_set_pv(a, is_long, dec_mul(DI(left), a->d_vwap), DI(mkt));
+        if (a->d) {
+            a->d->vwap = dec_div(dec_sub(dec_mul(DI(ap), a->d->vwap), DI(tv)), DI(left));
+            dl_set_pv(a, is_long, dec_mul(DI(left), a->d->vwap), DI(mkt));
         }
     } else {
         acct_covered(a, is_long, price);
@@ -283,7 +285,7 @@ static void acct_covered_side_chg(OrcAcct *a, int is_long, int party, int64_t q,
     int64_t new_size = q - ap;
     a->pv = new_size * price;
     a->C = new_size * price; /* VWAP = price */
-    if (a->dl) { a->d_pv = DI(new_size * price); a->d_vwap = DI(price); }
+    if (a->d) { a->d->pv = DI(new_size * price); a->d->vwap = DI(price); }
     cash_increase(a, party, a->pv);
 }
 /* account.py:215-231 process_acc */
@@ -301,7 +303,7 @@ static void orc_process_acc(OrcAcct *a, int party, int side, int64_t q, int64_t 
         else acct_covered_side_chg(a, 0, party, q, price);
     } else { /* account.py:173-176 _neutral */
         a->pv += tv; a->C = tv;
-        if (a->dl) { a->d_pv = dec_add(a->d_pv, DI(tv)); a->d_vwap = DI(price); }
+        if (a->d) { a->d->pv = dec_add(a->d->pv, DI(tv)); a->d->vwap = DI(price); }
         cash_increase(a, party, tv);
     }
     /* account.py:196-213 _update_net_position */
@@ -314,13 +316,13 @@ static void orc_mtm(OrcAcct *a, int64_t p) {
     a->pv = a->C + profit;
     a->prev_nav = a->nav;
     a->nav = a->cash + a->hold + a->pv;
-    if (!a->dl) { if (a->nav > a->max_nav) a->max_nav = a->nav; return; }
-    dec diff = a->pos >= 0 ? dec_sub(DI(p), a->d_vwap) : dec_sub(a->d_vwap, DI(p));   /* calculate.py:44-45 */
+    if (!a->d) { if (a->nav > a->max_nav) a->max_nav = a->nav; return; }
+    dec diff = a->pos >= 0 ? dec_sub(DI(p), a->d->vwap) : dec_sub(a->d->vwap, DI(p));   /* calculate.py:44-45 */
     dec dprofit = dec_mul(DI(ap), diff);
-    a->d_pv = dec_add(dec_mul(DI(ap), a->d_vwap), dprofit);
-    a->d_prev_nav = a->d_nav;
-    a->d_nav = dec_add(dec_add(a->d_cash, a->d_hold), a->d_pv);                        /* calculate.py:12 */
-    if (dec_cmp(a->d_nav, a->d_max_nav) > 0) { a->d_max_nav = a->d_nav; a->max_nav = a->nav; }
+    a->d->pv = dec_add(dec_mul(DI(ap), a->d->vwap), dprofit);
+    a->d->prev_nav = a->d->nav;
+    a->d->nav = dec_add(dec_add(a->d->cash, a->d->hold), a->d->pv);                        /* calculate.py:12 */
+    if (dec_cmp(a->d->nav, a->d->max_nav) > 0) { a->d->max_nav = a->d->nav; a->max_nav = a->nav; }
 }
 
 /* ---------------- matching: orderbook.py:61-194 -------------------------------------------- */
@@ -406,7 +408,7 @@ static int get_order_id(OrcTree *t, int trader, int type, int64_t price) {
 
 /* trader.py:108-151 _order_approved */
 static int order_approved(OrcMarket *mk, OrcAcct *a, int side, int64_t size, int is_market, int64_t price) {
-    if (a->dl ? dec_sign(a->d_nav) <= 0 : a->nav <= 0) return 0;
+    if (a->d ? dec_sign(a->d->nav) <= 0 : a->nav <= 0) return 0;
     int64_t opening;
     if ((side == 0 && a->pos >= 0) || (side == 1 && a->pos <= 0)) opening = size;
     else { int64_t ap = a->pos < 0 ? -a->pos : a->pos; opening = size - ap; if (opening < 0) opening = 0; }
@@ -417,7 +419,7 @@ static int order_approved(OrcMarket *mk, OrcAcct *a, int side, int64_t size, int
         if (opp->n_levels > 0) est = side == 0 ? opp->levels[0].price : opp->levels[opp->n_levels - 1].price;
         else est = mk->tape_nonempty ? mk->tape_last : 1;
     } else est = price;
-    if (a->dl) return dec_cmp(a->d_cash, DI(opening * est)) >= 0;   /* on the Decimal cash, residues included */
+    if (a->d) return dec_cmp(a->d->cash, DI(opening * est)) >= 0;   /* on the Decimal cash, residues included */
     return a->cash >= opening * est;
 }
 
@@ -548,8 +550,11 @@ static void market_reset(OrcEnv *e, OrcMarket *mk, int reseed, uint64_t seed) {
         OrcAcct *a = &mk->acc[i];
         memset(a, 0, sizeof(*a));
         a->cash = a->nav = a->prev_nav = a->max_nav = c->init_cash;
-        a->dl = c->decimal_ledger;
-        if (a->dl) a->d_cash = a->d_nav = a->d_prev_nav = a->d_max_nav = DI(c->init_cash);
+        if (e->dec) {
+            a->d = &e->dec[(size_t)(mk - e->mk) * ORC_MAX_AGENTS + i];
+            memset(a->d, 0, sizeof(*a->d));
+            a->d->cash = a->d->nav = a->d->prev_nav = a->d->max_nav = DI(c->init_cash);
+        }
     }
     float snap[ORC_SNAP];
     set_agg_lob(e, mk, snap); /* state_helper.py:66-78 */
@@ -625,9 +630,9 @@ static void market_step(OrcEnv *e, OrcMarket *mk, const int32_t *cat, const floa
         double nav_change = (double)(a->nav - a->prev_nav);
         int64_t ddi = a->max_nav - a->nav; if (ddi < 0) ddi = 0;
         double dd = (double)ddi;
-        if (a->dl) {   /* float(nav - prev_nav), float(max(0, max_nav - nav)) on the Decimal fields */
-            nav_change = dec_to_double(dec_sub(a->d_nav, a->d_prev_nav));
-            dec ddd = dec_sub(a->d_max_nav, a->d_nav);
+        if (a->d) {   /* float(nav - prev_nav), float(max(0, max_nav - nav)) on the Decimal fields */
+            nav_change = dec_to_double(dec_sub(a->d->nav, a->d->prev_nav));
+            dec ddd = dec_sub(a->d->max_nav, a->d->nav);
             dd = dec_sign(ddd) > 0 ? dec_to_double(ddd) : 0.0;
         }
         double nav_term = nav_change * (nav_change < 0 ? c->loss_multiplier : 1.0);
@@ -641,7 +646,7 @@ static void market_step(OrcEnv *e, OrcMarket *mk, const int32_t *cat, const floa
         a->reward = r; a->drawdown = dd;
         a->terms[0] = t0; a->terms[1] = t1; a->terms[2] = t2; a->terms[3] = t3; a->terms[4] = t4;
         reward[i] = r;
-        if (a->dl ? dec_sign(a->d_nav) <= 0 : a->nav <= 0) mk->done_mask |= (1u << i);
+        if (a->d ? dec_sign(a->d->nav) <= 0 : a->nav <= 0) mk->done_mask |= (1u << i);
     }
     uint32_t all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
     *term = (mk->done_mask & all) == all;            /* done_helper.py:20-55 */
@@ -655,13 +660,14 @@ void *orc_create(const OrcConfig *cfg, int M) {
     OrcEnv *e = (OrcEnv *)calloc(1, sizeof(OrcEnv));
     e->cfg = *cfg; e->M = M;
     e->mk = (OrcMarket *)calloc((size_t)M, sizeof(OrcMarket));
+    if (cfg->decimal_ledger) e->dec = (OrcDec *)calloc((size_t)M * ORC_MAX_AGENTS, sizeof(OrcDec));
     for (int m = 0; m < M; ++m) { tree_init(&e->mk[m].bids); tree_init(&e->mk[m].asks); }
     return e;
 }
 void orc_destroy(void *h) {
     OrcEnv *e = (OrcEnv *)h;
     for (int m = 0; m < e->M; ++m) { tree_free(&e->mk[m].bids); tree_free(&e->mk[m].asks); }
-    free(e->mk); free(e);
+    free(e->mk); free(e->dec); free(e);
 }
 /* seeds: NULL => keep every stream (reset(seed=None)); mask: NULL => all markets. */
 void orc_reset(void *h, const uint64_t *seeds, const uint8_t *mask, float *obs) {
@@ -756,11 +762,11 @@ void orc_dump_accounts(void *h, int m, int64_t *out) {
     for (int i = 0; i < e->cfg.num_agents; ++i) {
         const OrcAcct *a = &k->acc[i]; int64_t *o = out + i * 14;
         o[0] = a->cash; o[1] = a->hold; o[2] = a->pv; o[3] = a->C; o[4] = a->nav; o[5] = a->prev_nav; o[6] = a->max_nav;
-        if (a->dl) {   /* the Decimal twins, to the nearest integer (what ref_runner does with the reference's fields); they must agree */
+        if (a->d) {   /* the Decimal twins, to the nearest integer (what ref_runner does with the reference's fields); they must agree */
             int64_t ap = a->pos < 0 ? -a->pos : a->pos;
-            int64_t dv[7] = {dec_to_i64_nearest(a->d_cash), dec_to_i64_nearest(a->d_hold), dec_to_i64_nearest(a->d_pv),
-                             dec_to_i64_nearest(dec_mul(DI(ap), a->d_vwap)), dec_to_i64_nearest(a->d_nav),
-                             dec_to_i64_nearest(a->d_prev_nav), dec_to_i64_nearest(a->d_max_nav)};
+            int64_t dv[7] = {dec_to_i64_nearest(a->d->cash), dec_to_i64_nearest(a->d->hold), dec_to_i64_nearest(a->d->pv),
+                             dec_to_i64_nearest(dec_mul(DI(ap), a->d->vwap)), dec_to_i64_nearest(a->d->nav),
+                             dec_to_i64_nearest(a->d->prev_nav), dec_to_i64_nearest(a->d->max_nav)};
             for (int j = 0; j < 7; ++j) { if (dv[j] != o[j]) k->status |= ORC_ST_LEDGER_MISMATCH; o[j] = dv[j]; }
             if (dec_range_errors) k->status |= ORC_ST_LEDGER_MISMATCH;   /* dec128.h: an operation did not fit 128 bits */
         }
@@ -816,7 +822,7 @@ void orc_dump_accounts_dec(void *h, int m, char *out /*[A][7][48]*/) {
     OrcEnv *e = (OrcEnv *)h; OrcMarket *k = &e->mk[m];
     for (int i = 0; i < e->cfg.num_agents; ++i) {
         const OrcAcct *a = &k->acc[i];
-        const dec f[7] = {a->d_cash, a->d_hold, a->d_pv, a->d_vwap, a->d_nav, a->d_prev_nav, a->d_max_nav};
+        const dec f[7] = {a->d->cash, a->d->hold, a->d->pv, a->d->vwap, a->d->nav, a->d->prev_nav, a->d->max_nav};
         for (int j = 0; j < 7; ++j) dec_to_str(f[j], out + ((size_t)i * 7 + j) * 48, 48);
     }
 }
