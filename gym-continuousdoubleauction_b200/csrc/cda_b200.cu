@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "cda_kernels.cuh"
+#include "cda_dec128.cuh"
 
 #ifndef CDA_WARPS_PER_CTA
 #define CDA_WARPS_PER_CTA 4
@@ -709,5 +710,67 @@ int32_t cda_num_markets(const CdaEnv *e) { return e ? e->M : 0; }
 int32_t cda_obs_dim(const CdaEnv *e) { return e ? e->dev.W : 0; }
 int32_t cda_order_capacity(const CdaEnv *e) { return e ? e->dev.cap : 0; }
 int64_t cda_kernel_launches(const CdaEnv *e) { return e ? e->launches : 0; }
+
+// ---- cda_dec128.cuh test entries (the Decimal(28) arithmetic of the future device ledger; not on any product path) --------
+static CdaDec dec_parse(const char *s) {
+    int sign = 0; if (*s == '-') { sign = 1; ++s; } else if (*s == '+') ++s;
+    cda_u128 x = 0; int exp = 0, seen_pt = 0, nd = 0, sticky = 0;
+    for (; *s && *s != 'e' && *s != 'E'; ++s) {
+        if (*s == '.') { seen_pt = 1; continue; }
+        if (nd < 38) { x = x * 10 + (unsigned)(*s - '0'); if (x) ++nd; if (seen_pt) --exp; }
+        else { sticky |= *s != '0'; if (!seen_pt) ++exp; }
+    }
+    if (*s == 'e' || *s == 'E') exp += atoi(s + 1);
+    return cda_dec_round(sign, x, exp, sticky);
+}
+static void dec_format(CdaDec a, char *out, int cap) {
+    if (a.c == 0) { snprintf(out, (size_t)cap, "0"); return; }
+    char t[48]; int n = 0; cda_u128 x = a.c;
+    while (x) { t[n++] = (char)('0' + (int)(x % 10)); x /= 10; }
+    int p = 0;
+    if (a.sign && p + 1 < cap) out[p++] = '-';
+    while (n && p + 1 < cap) out[p++] = t[--n];
+    snprintf(out + p, (size_t)(cap - p), "e%d", a.exp);
+}
+__host__ __device__ static inline CdaDec dec_apply(int op, CdaDec a, CdaDec b, int *err) {
+    switch (op) {
+        case '+': return cda_dec_add(a, b);
+        case '-': return cda_dec_sub(a, b);
+        case '*': return cda_dec_mul(a, b, err);
+        case '/': return cda_dec_div(a, b, err);
+        default: { CdaDec r = cda_dec_zero(); const int c = cda_dec_cmp(a, b); r.c = c ? 1 : 0; r.sign = c < 0; return r; }   // 'c': -1 / 0 / +1
+    }
+}
+__global__ void cda_dec_selftest_kernel(int op, int n, const CdaDec *a, const CdaDec *b, CdaDec *out, int *err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int e = 0;
+    out[i] = dec_apply(op, a[i], b[i], &e);
+    if (e) atomicAdd(err, e);
+}
+int cda_debug_dec_op(int32_t op, const char *a, const char *b, char *out, int32_t cap, int32_t *range_err) {
+    if (!a || !b || !out || cap < 48) return CDA_EINVAL;
+    int e = 0;
+    dec_format(dec_apply(op, dec_parse(a), dec_parse(b), &e), out, cap);
+    if (range_err) *range_err = e;
+    return CDA_OK;
+}
+int cda_debug_dec_op_device(int32_t op, int32_t n, const char *const *a, const char *const *b, char *out, int32_t cap, int32_t *range_err) {
+    if (!a || !b || !out || n < 1 || cap < 48) return CDA_EINVAL;
+    std::vector<CdaDec> ha((size_t)n), hb((size_t)n), ho((size_t)n);
+    for (int i = 0; i < n; ++i) { ha[i] = dec_parse(a[i]); hb[i] = dec_parse(b[i]); }
+    CdaDec *da = nullptr, *db = nullptr, *dout = nullptr; int *derr = nullptr, herr = 0;
+    const size_t bytes = (size_t)n * sizeof(CdaDec);
+    CUDA_TRY(cudaMalloc(&da, bytes)); CUDA_TRY(cudaMalloc(&db, bytes)); CUDA_TRY(cudaMalloc(&dout, bytes)); CUDA_TRY(cudaMalloc(&derr, sizeof(int)));
+    CUDA_TRY(cudaMemcpy(da, ha.data(), bytes, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(db, hb.data(), bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(derr, 0, sizeof(int)));
+    cda_dec_selftest_kernel<<<(n + 127) / 128, 128>>>(op, n, da, db, dout, derr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(ho.data(), dout, bytes, cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(derr);
+    for (int i = 0; i < n; ++i) dec_format(ho[i], out + (size_t)i * cap, cap);
+    if (range_err) *range_err = herr;
+    return CDA_OK;
+}
 
 }  // extern "C"

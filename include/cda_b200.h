@@ -224,7 +224,16 @@ int32_t cda_num_markets(const CdaEnv *env);
 int32_t cda_record_bytes(const CdaEnv *env);   /* size of one packed result record of cda_step_host_window */
 int32_t cda_obs_dim(const CdaEnv *env);
 int32_t cda_order_capacity(const CdaEnv *env);
-int64_t cda_kernel_launches(const CdaEnv *env); /* kernels launched by this handle so far */
+int64_t cda_kernel_launches(const CdaEnv *env);
+
+/* Test entries for csrc/cda_dec128.cuh — Decimal(prec 28, ROUND_HALF_EVEN) arithmetic on fixed-width integers, the form the
+ * reference's Decimal ledger (envs/account/account.py:124-231, calculate.py:5-55) will take on the device.
+ * op: '+', '-', '*', '/' or 'c' (compare: "-1e0" / "0" / "1e0"); operands and results are decimal strings ("-396e0",
+ * "3.5e-24"); result slots are `cap` (>= 48) bytes each.  *range_err counts products / quotients outside the 128-bit domain.
+ * cda_debug_dec_op runs the HOST compilation of the header, cda_debug_dec_op_device the DEVICE one (n operand pairs, one
+ * thread each).  Neither is on a product path. */
+int cda_debug_dec_op(int32_t op, const char *a, const char *b, char *out, int32_t cap, int32_t *range_err);
+int cda_debug_dec_op_device(int32_t op, int32_t n, const char *const *a, const char *const *b, char *out, int32_t cap, int32_t *range_err); /* kernels launched by this handle so far */
 const char *cda_strerror(int code);
 const char *cda_last_cuda_error(void);
 const char *cda_build_info(void);

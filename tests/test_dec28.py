@@ -106,3 +106,59 @@ def test_fixed_width_form_matches_python_decimal_on_ledger_shaped_operands():
     assert lib.orc_dec_range_errors() == before         # everything above fitted
     lib.orc_dec_op(b"*", b"1234567890123456789012345678", b"9876543210987654321098765432", out, 96)
     assert lib.orc_dec_range_errors() == before + 1     # 28 x 28 digits does not: reported, not mis-rounded
+
+
+def _ledger_operands(rng, n):
+    def money():
+        v = Decimal(rng.randrange(-10**rng.randrange(1, 11), 10**rng.randrange(1, 11)))
+        if rng.random() < 0.7:
+            v = (v + Decimal(rng.randrange(-10**6, 10**6)).scaleb(-rng.randrange(16, 27))) * 1
+        return v
+    out = []
+    for _ in range(n):
+        a, b = money(), money()
+        k = Decimal(rng.randrange(1, 10**rng.randrange(1, 7)))
+        e = Decimal(rng.randrange(-10**28, 10**28)).scaleb(-rng.randrange(30, 90))
+        out += [("+", a, b), ("-", a, b), ("*", k, a), ("/", a, k), ("+", a, e), ("-", a, e), ("-", e, a), ("c", a, b), ("c", a, a + e)]
+    return out
+
+
+def _want(op, x, y):
+    if op == "c":
+        return Decimal((x > y) - (x < y))
+    return x + y if op == "+" else x - y if op == "-" else x * y if op == "*" else x / y
+
+
+def test_product_header_host_side_matches_python_decimal():
+    """csrc/cda_dec128.cuh (the header the device ledger will use), HOST compilation, through the C-ABI test entry."""
+    from gym_continuousdoubleauction_b200 import _native
+    L = _native.lib()
+    out = ctypes.create_string_buffer(64)
+    err = ctypes.c_int32(0)
+    rng = random.Random(4242)
+    for op, x, y in _ledger_operands(rng, 3000):
+        assert L.cda_debug_dec_op(ord(op), str(x).encode(), str(y).encode(), out, 64, ctypes.byref(err)) == 0
+        assert err.value == 0 and Decimal(out.value.decode()) == _want(op, x, y), (op, x, y, out.value)
+    L.cda_debug_dec_op(ord("*"), b"1234567890123456789012345678", b"9876543210987654321098765432", out, 64, ctypes.byref(err))
+    assert err.value == 1                                  # outside the 128-bit domain: reported
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not __import__("os").environ.get("CDA_GPU_DEC_TEST"), reason="device compilation of cda_dec128.cuh: written after the "
+                    "round's GPU budget was spent — set CDA_GPU_DEC_TEST=1 to run it (DESIGN.md section 9, item 0)")
+def test_product_header_device_side_matches_python_decimal():
+    from gym_continuousdoubleauction_b200 import _native
+    L = _native.lib()
+    rng = random.Random(777)
+    cases = _ledger_operands(rng, 500)
+    for op in "+-*/c":
+        sel = [(x, y) for o, x, y in cases if o == op]
+        n = len(sel)
+        A = (ctypes.c_char_p * n)(*[str(x).encode() for x, _ in sel])
+        B = (ctypes.c_char_p * n)(*[str(y).encode() for _, y in sel])
+        out = ctypes.create_string_buffer(64 * n)
+        err = ctypes.c_int32(0)
+        assert L.cda_debug_dec_op_device(ord(op), n, A, B, out, 64, ctypes.byref(err)) == 0 and err.value == 0
+        for i, (x, y) in enumerate(sel):
+            got = out.raw[64 * i:64 * (i + 1)].split(b"\0", 1)[0].decode()
+            assert Decimal(got) == _want(op, x, y), (op, x, y, got)
