@@ -14,6 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("CDA_B200_LIB") or os.path.join(CSRC, "libcda_b200.so")   # CDA_B200_LIB: a variant build (tools/variant_bench.py)
 SOURCES = ("cda_b200.cu", "cda_kernels.cuh", "cda_zig_tables.cuh", "cda_dec128.cuh")
 HEADER = os.path.join(_ROOT, "include", "cda_b200.h")
+TESTING_HEADER = os.path.join(_ROOT, "include", "cda_b200_testing.h")   # test / measurement entries (not product ABI)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
@@ -47,15 +48,16 @@ EXPORTS = (
     "cda_gather_create", "cda_gather_connect", "cda_step_gather", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_record_bytes", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
-    "cda_seed_to_pcg64", "cda_debug_phase_buffer", "cda_debug_dec_op", "cda_debug_dec_op_device",
+    "cda_seed_to_pcg64", "cda_gather_parity", "cda_status_flag", "cda_status_flag_clear",
 )
+TESTING_EXPORTS = ("cda_debug_phase_buffer", "cda_debug_dec_op", "cda_debug_dec_op_device", "cda_debug_set_window_mode")
 
 
 def needs_build():
     if not os.path.exists(SO_PATH):
         return True
     t = os.path.getmtime(SO_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER, TESTING_HEADER]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -128,6 +130,10 @@ def lib():
         sig(name, None, ctypes.c_char_p)
     sig("cda_strerror", [i32], ctypes.c_char_p)
     sig("cda_seed_to_pcg64", [u64, ctypes.POINTER(u64)])
+    sig("cda_gather_parity", [vp], i32)
+    sig("cda_status_flag", [vp], ctypes.POINTER(ctypes.c_uint32))
+    sig("cda_status_flag_clear", [vp])
+    sig("cda_debug_set_window_mode", [i32], None)
     sig("cda_debug_phase_buffer", None, ctypes.c_void_p)
     sig("cda_debug_dec_op", [i32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, ctypes.POINTER(i32)])
     sig("cda_debug_dec_op_device", [i32, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, i32, ctypes.POINTER(i32)])

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "cda_kernels.cuh"
+#include "cda_b200_testing.h"
 #include "cda_dec128.cuh"
 
 #ifndef CDA_WARPS_PER_CTA
@@ -28,6 +29,13 @@ static thread_local char g_cuda_err[256] = "";
             return CDA_ECUDA;                                                                   \
         }                                                                                       \
     } while (0)
+
+// Every entry point that launches or copies runs on the handle's device and leaves the caller's current device as it was.
+struct DevGuard {
+    int prev = -1; bool switched = false;
+    explicit DevGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess; }
+    ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 struct CdaEnv {
     CdaConfig cfg;
@@ -51,6 +59,8 @@ struct CdaEnv {
     int act_tma;               // CDA_ACT_TMA (default 1): stage the action rows with cp.async.bulk
     double zc_fraction;        // share of the obs rows the kernel writes straight to host memory (the rest is DMA'd)   // same for the action block (kernel reads pinned host memory)
     long long launches;
+    unsigned *status_host, *status_dev;   // one mapped pinned word: any step kernel that ends with a non-zero sticky market status stores 1 here
+    int g_parity;                          // fused all-gather: half of the double-buffered gather region the NEXT cda_step_gather writes
     size_t smem_bytes;
     int host_ctas, dev_ctas;   // resident CTAs per SM for the host paths / the device path (0 = as many as fit)
 };
@@ -150,7 +160,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
         const long long per = std::max<long long>(2LL * cfg->n_hist * CDA_SNAPSHOT_DIM, 15LL * cfg->num_agents);
         if ((long long)num_markets * per > 2147483647LL) return CDA_EINVAL;
     }
-    CUDA_TRY(cudaSetDevice(device));
+    DevGuard guard(device);
+    { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != device) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaSetDevice(%d) failed", device); cudaGetLastError(); return CDA_ECUDA; } }
     CdaEnv *e = new (std::nothrow) CdaEnv();
     if (!e) return CDA_ENOMEM;
     memset(e, 0, sizeof(*e));
@@ -183,6 +194,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     // caller's host buffers are laid out the same way)
     if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4 + MA * 8 + (size_t)num_markets * 2);
     if (err == cudaSuccess) err = cudaMalloc(&e->s_rec, (size_t)num_markets * (((size_t)d.A * 8 + 8 + 63) / 64 * 64));
+    if (err == cudaSuccess) err = cudaHostAlloc(reinterpret_cast<void **>(&e->status_host), 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess) { *e->status_host = 0; err = cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->status_dev), e->status_host, 0); }
     if (err != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc failed: %s", cudaGetErrorString(err));
         cda_destroy(e);
@@ -227,7 +240,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
 
 int cda_destroy(CdaEnv *e) {
     if (!e) return CDA_OK;
-    cudaSetDevice(e->device);
+    DevGuard guard(e->device);
+    if (e->status_host) cudaFreeHost(e->status_host);
     if (e->g_connected) for (int g = 0; g < e->g_world; ++g) if (g != e->g_rank && e->g_peer[g]) cudaIpcCloseMemHandle(e->g_peer[g]);
     cudaFree(e->g_local);
     cudaFree(e->state); cudaFree(e->fills); cudaFree(e->fill_counts);
@@ -239,6 +253,7 @@ int cda_destroy(CdaEnv *e) {
 int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *d_obs, void *stream) {
     if (!e) return CDA_EINVAL;
     if (!d_seeds && !e->was_reset) return CDA_ESTATE;   // reset(seed=None) needs an existing stream
+    DevGuard guard(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 128, grid = (e->M + threads - 1) / threads;
     cda_reset_kernel<<<grid, threads, 0, st>>>(e->dev, e->state, e->M, (const unsigned long long *)d_seeds, d_mask, d_obs);
@@ -252,6 +267,7 @@ int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *
 static unsigned long long *g_prof = nullptr;
 static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st, bool host_path = false) {
     p.cfg = e->dev; p.state = e->state; p.M = e->M;
+    p.status_flag = e->status_dev;
     if (!p.obs_hi) p.obs_split = e->M;   // no split: every row goes to p.obs
     if (!p.obs_stride) p.obs_stride = e->dev.W;
     if (!p.reward_stride) p.reward_stride = e->dev.A;
@@ -274,6 +290,7 @@ int cda_step(CdaEnv *e, const int32_t *d_category, const float *d_size_mean, con
              const int32_t *d_price, const int32_t *d_price_offset, float *d_obs, double *d_reward,
              uint8_t *d_terminated, uint8_t *d_truncated, void *stream) {
     if (!e || !d_category || !d_size_mean || !d_size_sigma || !d_price || !d_price_offset) return CDA_EINVAL;
+    DevGuard guard(e->device);
     if (!e->was_reset) return CDA_ESTATE;
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
@@ -286,6 +303,7 @@ int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean
                   const int32_t *h_price, const int32_t *h_price_offset, float *h_obs, double *h_reward,
                   uint8_t *h_terminated, uint8_t *h_truncated, void *stream) {
     if (!e || !h_category || !h_size_mean || !h_size_sigma || !h_price || !h_price_offset) return CDA_EINVAL;
+    DevGuard guard(e->device);
     if (!e->was_reset) return CDA_ESTATE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t MA = (size_t)e->M * e->dev.A;
@@ -370,6 +388,7 @@ int cda_step_host(CdaEnv *e, const int32_t *h_category, const float *h_size_mean
     return CDA_OK;
 }
 
+static int g_dbg_window = getenv("CDA_DEBUG_WINDOW") ? atoi(getenv("CDA_DEBUG_WINDOW")) : 0;   // timing experiments (tools/): see step_window_impl
 static void *mapped_alias(const void *h) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
@@ -381,6 +400,7 @@ int cda_step_host_ring(CdaEnv *e, const int32_t *h_category, const float *h_size
                        const int32_t *h_price, const int32_t *h_price_offset, float *h_ring, double *h_reward,
                        uint8_t *h_terminated, uint8_t *h_truncated, int64_t ring_pos, void *stream) {
     if (!e || !h_category || !h_size_mean || !h_size_sigma || !h_price || !h_price_offset || !h_ring || !h_reward || !h_terminated || !h_truncated) return CDA_EINVAL;
+    DevGuard guard(e->device);
     if (!e->was_reset) return CDA_ESTATE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t MA = (size_t)e->M * e->dev.A;
@@ -410,6 +430,7 @@ int cda_step_host_ring(CdaEnv *e, const int32_t *h_category, const float *h_size
 
 int cda_reset_host_ring(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_ring, void *stream) {
     if (!e || !h_ring) return CDA_EINVAL;
+    DevGuard guard(e->device);
     void *dr = mapped_alias(h_ring);
     if (!dr) return CDA_EINVAL;
     int rc = cda_reset(e, d_seeds, d_mask, nullptr, stream);
@@ -428,6 +449,7 @@ static int step_window_impl(CdaEnv *e, const int32_t *h_category, const float *h
                             const int32_t *h_price, const int32_t *h_price_offset, bool market_major, float *h_window, int32_t slots, int32_t pos,
                             void *h_records, bool inline_rec, int32_t sync, void *stream) {
     if (!e || !h_category || !h_size_mean || !h_size_sigma || !h_price || !h_price_offset || !h_window || !h_records) return CDA_EINVAL;
+    DevGuard guard(e->device);
     const int H = e->dev.n_hist, A = e->dev.A;
     if (slots < H || pos < H - 1 || pos >= slots) return CDA_EINVAL;
     if (inline_rec && (pos + 1 >= slots || 2 * A + 2 > CDA_SNAPSHOT_DIM)) return CDA_EINVAL;
@@ -445,8 +467,9 @@ static int step_window_impl(CdaEnv *e, const int32_t *h_category, const float *h
     }
     // timing experiments only (tools/e2e_timeline.py): 1 = reuse the actions already staged on the device (no input
     // transfer after the first call), 2 = keep the outputs on the device (no output transfer), 3 = both
-    static const int dbg = getenv("CDA_DEBUG_WINDOW") ? atoi(getenv("CDA_DEBUG_WINDOW")) : 0;
+    const int dbg = g_dbg_window;
     static int dbg_calls = 0;
+    if (!(dbg & 1)) dbg_calls = 0;
     const bool dbg_skip_in = (dbg & 1) && dbg_calls++ > 0, dbg_dev_out = (dbg & 2) != 0;
     if (dbg & 1) zi = nullptr;
     CdaStepParams p;
@@ -542,6 +565,7 @@ int cda_step_window(CdaEnv *e, const int32_t *h_action_block, int32_t pos, int32
 
 int cda_reset_host_window(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream) {
     if (!e || !h_window || slots < e->dev.n_hist) return CDA_EINVAL;
+    DevGuard guard(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = cda_reset(e, d_seeds, d_mask, nullptr, stream);
     if (rc) return rc;
@@ -562,6 +586,7 @@ int cda_reset_host_window(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_m
 int cda_rollout_random(CdaEnv *e, int32_t num_steps, uint64_t policy_seed, float *d_obs, double *d_reward,
                        uint8_t *d_terminated, uint8_t *d_truncated, void *stream) {
     if (!e || num_steps < 1) return CDA_EINVAL;
+    DevGuard guard(e->device);
     if (!e->was_reset) return CDA_ESTATE;
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
@@ -570,13 +595,20 @@ int cda_rollout_random(CdaEnv *e, int32_t num_steps, uint64_t policy_seed, float
     return step_common(e, p, (cudaStream_t)stream);
 }
 
+static size_t cda_gather_half_bytes_(int M, int world, int W, int A) {
+    const size_t rows = (size_t)world * M;
+    return (rows * ((size_t)W * 4 + (size_t)A * 8 + 2) + 255) / 256 * 256;
+}
 int cda_gather_create(CdaEnv *e, int32_t world, int32_t rank, void *ipc_handle_out64, void **d_local_buf, uint64_t *bytes) {
     if (!e || world < 1 || world > CDA_MAX_PEERS || rank < 0 || rank >= world || !ipc_handle_out64) return CDA_EINVAL;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    CUDA_TRY(cudaSetDevice(e->device));
+    DevGuard guard(e->device);
     if (e->g_local) return CDA_EINVAL;
     const size_t rows = (size_t)world * e->M;
-    e->g_bytes = rows * ((size_t)e->dev.W * 4 + (size_t)e->dev.A * 8 + 2);
+    // TWO halves, written alternately: a rank one step ahead stores step t+1 into the other half while slower ranks still read
+    // step t (the per-step cross-rank barrier keeps every rank within one step of the others)
+    e->g_bytes = 2 * cda_gather_half_bytes_(e->M, world, e->dev.W, e->dev.A);
+    e->g_parity = 0;
     CUDA_TRY(cudaMalloc(&e->g_local, e->g_bytes));
     CUDA_TRY(cudaMemset(e->g_local, 0, e->g_bytes));
     cudaIpcMemHandle_t h;
@@ -590,7 +622,7 @@ int cda_gather_create(CdaEnv *e, int32_t world, int32_t rank, void *ipc_handle_o
 
 int cda_gather_connect(CdaEnv *e, const void *all_handles) {
     if (!e || !e->g_local || !all_handles) return CDA_EINVAL;
-    CUDA_TRY(cudaSetDevice(e->device));
+    DevGuard guard(e->device);
     for (int g = 0; g < e->g_world; ++g) {
         if (g == e->g_rank) { e->g_peer[g] = e->g_local; continue; }
         cudaIpcMemHandle_t h;
@@ -606,12 +638,15 @@ int cda_gather_connect(CdaEnv *e, const void *all_handles) {
 int cda_step_gather(CdaEnv *e, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
                     const int32_t *d_price, const int32_t *d_price_offset, void *stream) {
     if (!e || !d_category || !d_size_mean || !d_size_sigma || !d_price || !d_price_offset) return CDA_EINVAL;
+    DevGuard guard(e->device);
     if (!e->was_reset || !e->g_connected) return CDA_ESTATE;
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
     p.cat = d_category; p.mean = d_size_mean; p.sigma = d_size_sigma; p.pcode = d_price; p.poff = d_price_offset;
     p.gather_world = e->g_world; p.gather_row0 = e->g_rank * e->M; p.gather_rows = e->g_world * e->M;
-    for (int g = 0; g < e->g_world; ++g) p.gather_peer[g] = e->g_peer[g];
+    const size_t half = e->g_bytes / 2;
+    for (int g = 0; g < e->g_world; ++g) p.gather_peer[g] = e->g_peer[g] + (size_t)e->g_parity * half;
+    e->g_parity ^= 1;
     // non-null markers so the epilogue runs (the destinations come from gather_peer)
     p.obs = reinterpret_cast<float *>(e->g_local); p.reward = reinterpret_cast<double *>(e->g_local);
     p.term = e->g_local; p.trunc = e->g_local;
@@ -620,6 +655,7 @@ int cda_step_gather(CdaEnv *e, const int32_t *d_category, const float *d_size_me
 
 int cda_get_info(CdaEnv *e, int32_t field, int64_t *d_out, void *stream) {
     if (!e || !d_out || field < 0 || field >= CDA_INFO__COUNT) return CDA_EINVAL;
+    DevGuard guard(e->device);
     const int n = field == CDA_INFO_MARKET ? e->M : e->M * e->dev.A;
     const int threads = 256, grid = (n + threads - 1) / threads;
     cda_info_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, field, (long long *)d_out);
@@ -630,6 +666,7 @@ int cda_get_info(CdaEnv *e, int32_t field, int64_t *d_out, void *stream) {
 
 int cda_get_info_all(CdaEnv *e, int64_t *d_out, void *stream) {
     if (!e || !d_out) return CDA_EINVAL;
+    DevGuard guard(e->device);
     const int n = CDA_INFO_MARKET * e->M * e->dev.A + e->M;
     const int threads = 256, grid = (n + threads - 1) / threads;
     cda_info_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, -1, (long long *)d_out);
@@ -640,6 +677,7 @@ int cda_get_info_all(CdaEnv *e, int64_t *d_out, void *stream) {
 
 int cda_get_fills(CdaEnv *e, int32_t *d_fills, int32_t *d_counts, void *stream) {
     if (!e || !e->fills) return CDA_EINVAL;
+    DevGuard guard(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_fills) CUDA_TRY(cudaMemcpyAsync(d_fills, e->fills, (size_t)e->M * e->dev.fill_cap * CDA_FILL_WORDS * 4, cudaMemcpyDeviceToDevice, st));
     if (d_counts) CUDA_TRY(cudaMemcpyAsync(d_counts, e->fill_counts, (size_t)e->M * 4, cudaMemcpyDeviceToDevice, st));
@@ -649,7 +687,7 @@ int cda_get_fills(CdaEnv *e, int32_t *d_fills, int32_t *d_counts, void *stream) 
 int cda_dump_market(CdaEnv *e, int32_t market, int64_t *h_bids, int64_t *h_asks, int64_t *h_bids_map,
                     int64_t *h_asks_map, int32_t max_rows, int32_t *h_counts, uint64_t *h_rng6) {
     if (!e || market < 0 || market >= e->M || !h_counts) return CDA_EINVAL;
-    CUDA_TRY(cudaSetDevice(e->device));
+    DevGuard guard(e->device);
     std::vector<unsigned char> blk(e->dev.stride);
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(blk.data(), e->state + (size_t)market * e->dev.stride, e->dev.stride, cudaMemcpyDeviceToHost));
@@ -686,6 +724,7 @@ int cda_dump_market(CdaEnv *e, int32_t market, int64_t *h_bids, int64_t *h_asks,
     return CDA_OK;
 }
 
+void cda_debug_set_window_mode(int32_t mode) { g_dbg_window = mode; }
 // debug builds (-DCDA_PROFILE_PHASES): returns the device buffer of 16 per-phase cycle sums (allocated on first call)
 unsigned long long *cda_debug_phase_buffer(void) {
 #ifdef CDA_PROFILE_PHASES
@@ -696,15 +735,20 @@ unsigned long long *cda_debug_phase_buffer(void) {
 size_t cda_state_bytes(const CdaEnv *e) { return e ? e->state_bytes : 0; }
 int cda_save_state(CdaEnv *e, void *h_dst, void *stream) {
     if (!e || !h_dst) return CDA_EINVAL;
+    DevGuard guard(e->device);
     CUDA_TRY(cudaMemcpyAsync(h_dst, e->state, e->state_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return CDA_OK;
 }
 int cda_load_state(CdaEnv *e, const void *h_src, void *stream) {
     if (!e || !h_src) return CDA_EINVAL;
+    DevGuard guard(e->device);
     CUDA_TRY(cudaMemcpyAsync(e->state, h_src, e->state_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     e->was_reset = true;
     return CDA_OK;
 }
+int32_t cda_gather_parity(const CdaEnv *e) { return e ? (e->g_parity ^ 1) : 0; }   // half written by the LAST cda_step_gather
+const volatile uint32_t *cda_status_flag(const CdaEnv *e) { return e ? e->status_host : nullptr; }
+int cda_status_flag_clear(CdaEnv *e) { if (!e) return CDA_EINVAL; *e->status_host = 0; return CDA_OK; }
 int32_t cda_record_bytes(const CdaEnv *e) { return e ? (int32_t)(((size_t)e->dev.A * 8 + 8 + 63) / 64 * 64) : 0; }
 int32_t cda_num_markets(const CdaEnv *e) { return e ? e->M : 0; }
 int32_t cda_obs_dim(const CdaEnv *e) { return e ? e->dev.W : 0; }

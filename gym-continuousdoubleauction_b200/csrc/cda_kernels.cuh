@@ -91,6 +91,7 @@ struct CdaStepParams {
     // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
     int gather_world, gather_row0, gather_rows;
     unsigned char *gather_peer[CDA_MAX_PEERS];
+    unsigned *status_flag;            // mapped pinned host word: set to 1 by any market that ends the step with a non-zero sticky status
 };
 
 // ------------------------------------ numpy-exact RNG --------------------------------------
@@ -1136,7 +1137,9 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     // ---- store: header, accounts, pool prefix
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
-        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)k.tape_px, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, SMW(wbL + L::PARK + 10), SMW(wbL + L::PARK + 11));
+        const unsigned stv = SMW(wbL + L::PARK + 11);
+        if (stv) *p.status_flag = 1u;   // (rare) lets the host notice a sticky status without a gather
+        *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)k.tape_px, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, SMW(wbL + L::PARK + 10), stv);
         const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wbL + L::PARK]);
         *reinterpret_cast<uint4 *>(hdr + 8) = make_uint4((unsigned)k.nb, (unsigned)k.na, SMW(wbL + L::PARK + 8), SMW(wbL + L::PARK + 9));
         *reinterpret_cast<ulonglong2 *>(hdr + 12) = make_ulonglong2(pk[0], pk[1]);

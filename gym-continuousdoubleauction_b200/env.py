@@ -183,7 +183,7 @@ class continuousDoubleAuctionEnv(_Base):
         self.drawdown_penalty, self.passive_bonus = float(cfg["drawdown_penalty"]), float(cfg["passive_bonus"])
         self.loss_multiplier = float(cfg["loss_multiplier"])
         self._vec = VecCDAEnv(cfg, num_markets=1, device=int(self.config.get("device", 0)),
-                              order_capacity=int(self.config.get("order_capacity", 0)), fill_capacity=64)
+                              order_capacity=int(self.config.get("order_capacity", 0)), fill_capacity=int(self.config.get("fill_capacity", 64)))
         agent_ids = [f"agent_{i}" for i in range(self.num_of_agents)]
         self._agent_ids = set(agent_ids)
         self.agents = list(agent_ids)
@@ -252,7 +252,7 @@ class continuousDoubleAuctionEnv(_Base):
         self.best_ask = float(mk[2]) if mk[2] > 0 else None
         self.spread = (self.best_ask - self.best_bid) if (self.best_bid is not None and self.best_ask is not None) else None
         self._vec_status = int(mk[7])
-        if self._vec_status:
+        if self._vec_status & 29:                                  # fatal bits only: a fill-LOG overflow (bit 2) leaves book and ledger exact
             self._vec.check_status()
         next_states = {a: o for a in self.agents}                 # one shared array, like the reference
         rewards = {a: float(rew[0, i]) for i, a in enumerate(self.agents)}

@@ -15,6 +15,7 @@ from .config import SNAPSHOT_DIM, resolve
 
 STATUS_BITS = {1: "order pool overflow", 2: "fill log overflow", 4: "bad action",
                8: "price out of range", 16: "bad order size"}
+FATAL_STATUS = 1 | 4 | 8 | 16      # the reference calls sys.exit() / corrupts nothing here; bit 2 only truncates the per-step fill LOG
 
 
 def _ptr(t):
@@ -22,7 +23,16 @@ def _ptr(t):
 
 
 class VecCDAEnv:
-    def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0):
+    def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0, status_policy="raise"):
+        """status_policy: what step*/reset* do when a market carries a sticky status bit (see STATUS_BITS; noticed through a
+        pinned flag word the step kernel sets, i.e. at the first call after the offending step has completed — no launch and
+        no synchronisation while all markets are clean): "raise" RuntimeError on pool overflow / bad action / price range /
+        bad size (book and ledger of that market no longer follow the reference), "warn" once per bit, or "ignore".
+        A fill-log overflow (bit 2) only truncates the per-step log — book and ledger stay exact — and never raises."""
+        if status_policy not in ("raise", "warn", "ignore"):
+            raise ValueError("status_policy must be 'raise', 'warn' or 'ignore'")
+        self.status_policy = status_policy
+        self._status_warned = 0
         if not torch.cuda.is_available():
             raise RuntimeError("VecCDAEnv needs a CUDA device (sm_100a); there is no CPU fallback")
         cfg = resolve(config)
@@ -44,6 +54,7 @@ class VecCDAEnv:
         h = ctypes.c_void_p()
         _native.check(self._L.cda_create(ctypes.byref(c), self.M, self.device.index, ctypes.byref(h)))
         self._h = h
+        self._status_flag = self._L.cda_status_flag(h)          # POINTER(c_uint32) into pinned host memory
         self.fill_capacity = int(fill_capacity)
         self.order_capacity = self._L.cda_order_capacity(h)
         with torch.cuda.device(self.device):
@@ -68,23 +79,56 @@ class VecCDAEnv:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # ------------------------------------------------------------------ sticky status
+    def _poll_status(self):
+        """Called by every step / reset entry: free while all markets are clean (one read of a pinned host word)."""
+        if self._status_flag[0] and self.status_policy != "ignore":
+            self._on_status()
+
+    def _on_status(self):
+        self._L.cda_status_flag_clear(self._h)
+        bits = 0
+        for v in torch.unique(self.status()).cpu().tolist():
+            bits |= int(v)
+        names = ", ".join(v for b, v in STATUS_BITS.items() if bits & b)
+        if (bits & FATAL_STATUS) and self.status_policy == "raise":
+            raise RuntimeError("cda_b200 market status: " + names + " (the affected markets no longer follow the reference; "
+                               "reset them, raise order_capacity, or construct the env with status_policy='warn')")
+        new = bits & ~self._status_warned
+        if new:
+            import warnings
+            warnings.warn("cda_b200 market status: " + ", ".join(v for b, v in STATUS_BITS.items() if new & b))
+            self._status_warned |= new
+
     # ------------------------------------------------------------------ reset
-    def reset(self, seed=None, mask=None):
-        """seed: None (keep every market's stream, reference `reset(seed=None)`), an int (market m
-        is seeded with seed + m), or a length-M sequence/tensor of per-market integer seeds.
-        mask: optional bool/uint8 [M] selecting the markets to reset.  Returns obs [M, W]."""
+    def _seed_mask_tensors(self, seed, mask):
+        """seed: None | int (market m gets seed + m) | one non-negative integer per market; mask: None | bool/uint8 [M].
+        Returns device tensors (u64 bits as int64 [M] or None, uint8 [M] or None) — the ONE place the reset paths convert
+        and validate their arguments (cda_reset_kernel indexes seeds[m] / mask[m] for every market)."""
         seeds_t = None
         if seed is not None:
             if isinstance(seed, (int, np.integer)):
+                if int(seed) < 0:
+                    raise ValueError("seed must be non-negative")
                 seeds = np.arange(self.M, dtype=np.uint64) + np.uint64(seed)
             else:
-                seeds = np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed).astype(np.uint64)
-                if seeds.shape != (self.M,):
-                    raise ValueError("seed must be None, an int, or one seed per market")
+                raw = np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed)
+                if raw.shape != (self.M,) or raw.dtype.kind not in "iu" or (raw.dtype.kind == "i" and (raw < 0).any()):
+                    raise ValueError("seed must be None, a non-negative int, or one non-negative integer seed per market")
+                seeds = raw.astype(np.uint64)
             seeds_t = torch.from_numpy(seeds.view(np.int64)).to(self.device)
         mask_t = None
         if mask is not None:
             mask_t = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+            if mask_t.shape != (self.M,):
+                raise ValueError("mask must have one entry per market")
+        return seeds_t, mask_t
+
+    def reset(self, seed=None, mask=None):
+        """seed: None (keep every market's stream, reference `reset(seed=None)`), an int (market m
+        is seeded with seed + m), or a length-M sequence/tensor of per-market integer seeds.
+        mask: optional bool/uint8 [M] selecting the markets to reset.  Returns obs [M, W]."""
+        seeds_t, mask_t = self._seed_mask_tensors(seed, mask)
         _native.check(self._L.cda_reset(self._h, _ptr(seeds_t), _ptr(mask_t), _ptr(self.obs), self._stream()))
         return self.obs
 
@@ -98,6 +142,8 @@ class VecCDAEnv:
             if t.dtype != dt or not t.is_cuda or not t.is_contiguous() or t.numel() != self.M * self.A:
                 raise ValueError("actions must be contiguous CUDA tensors [M, A] of int32/float32")
         obs, rew, term, trunc = out if out is not None else (self.obs, self.reward, self.terminated, self.truncated)
+        if self._status_flag[0]:
+            self._poll_status()
         _native.check(self._L.cda_step(self._h, _ptr(category), _ptr(size_mean), _ptr(size_sigma), _ptr(price),
                                        _ptr(price_offset), _ptr(obs), _ptr(rew), _ptr(term), _ptr(trunc),
                                        self._stream()))
@@ -150,6 +196,8 @@ class VecCDAEnv:
         reads it in place (mapped pinned memory) and writes obs/reward/flags into this env's pinned
         output block; returns numpy views of that block."""
         p = self._ensure_pinned()
+        if self._status_flag[0]:
+            self._poll_status()
         base = action_block.data_ptr()
         n = self.M * self.A * 4
         vp = ctypes.c_void_p
@@ -180,12 +228,7 @@ class VecCDAEnv:
     def reset_host_ring(self, seed=None, mask=None):
         """reset() for the ring host path: returns the stacked observation as a view of the pinned ring."""
         self._ensure_ring()
-        seeds_t = None
-        if seed is not None:
-            seeds = (np.arange(self.M, dtype=np.uint64) + np.uint64(seed)) if isinstance(seed, (int, np.integer)) \
-                else np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed).astype(np.uint64)
-            seeds_t = torch.from_numpy(seeds.view(np.int64)).to(self.device)
-        mask_t = None if mask is None else torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        seeds_t, mask_t = self._seed_mask_tensors(seed, mask)
         _native.check(self._L.cda_reset_host_ring(self._h, _ptr(seeds_t), _ptr(mask_t), self._ring_ptrs[0], self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
         return self._ring_view()
@@ -247,12 +290,7 @@ class VecCDAEnv:
     def reset_host_window(self, seed=None, mask=None):
         """reset() for the window host path: returns the stacked observation as a view of the pinned window."""
         self._ensure_window()
-        seeds_t = None
-        if seed is not None:
-            seeds = (np.arange(self.M, dtype=np.uint64) + np.uint64(seed)) if isinstance(seed, (int, np.integer)) \
-                else np.asarray(seed.cpu() if isinstance(seed, torch.Tensor) else seed).astype(np.uint64)
-            seeds_t = torch.from_numpy(seeds.view(np.int64)).to(self.device)
-        mask_t = None if mask is None else torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        seeds_t, mask_t = self._seed_mask_tensors(seed, mask)
         stream = self._stream()
         _native.check(self._L.cda_reset_host_window(self._h, _ptr(seeds_t), _ptr(mask_t), self._win_ptrs[0], self.WINDOW_SLOTS, stream))
         # tight-loop form: buffers + the CURRENT stream are bound once; step_host_window then makes a 4-argument call
@@ -286,11 +324,15 @@ class VecCDAEnv:
         if rc:
             _native.check(rc)
         self._win_pos = pos
+        if self._status_flag[0]:
+            self._poll_status()
         return self._win_views[pos]
 
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""
         p = self._ensure_pinned()
+        if self._status_flag[0]:
+            self._poll_status()
         _native.check(self._L.cda_step_host(self._h, _ptr(p["cat"]), _ptr(p["mean"]), _ptr(p["sigma"]), _ptr(p["price"]),
                                             _ptr(p["off"]), _ptr(p["obs"]), _ptr(p["reward"]), _ptr(p["term"]),
                                             _ptr(p["trunc"]), self._stream()))
@@ -321,18 +363,26 @@ class VecCDAEnv:
             def __init__(s, p, n):
                 s.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
         raw = torch.as_tensor(_Raw(ptr.value, nbytes.value), device=self.device)
-        o_b, r_b = rows * self.W * 4, rows * self.A * 8
-        self._gather = (raw[:o_b].view(torch.float32).view(rows, self.W), raw[o_b:o_b + r_b].view(torch.float64).view(rows, self.A),
-                        raw[o_b + r_b:o_b + r_b + rows], raw[o_b + r_b + rows:o_b + r_b + 2 * rows])
+        o_b, r_b, half = rows * self.W * 4, rows * self.A * 8, nbytes.value // 2
+        # two halves written alternately (cda_b200.h): a faster rank's step t+1 lands in the other half while this rank reads step t
+        self._gather_halves = [
+            (raw[k:k + o_b].view(torch.float32).view(rows, self.W), raw[k + o_b:k + o_b + r_b].view(torch.float64).view(rows, self.A),
+             raw[k + o_b + r_b:k + o_b + r_b + rows], raw[k + o_b + r_b + rows:k + o_b + r_b + 2 * rows]) for k in (0, half)]
+        self._gather = self._gather_halves[0]
         self._gather_raw = raw
         dist.barrier(group=group)
         return self._gather
 
     def step_gather(self, category, size_mean, size_sigma, price, price_offset):
-        """cda_step whose epilogue writes this rank's rows into every rank's gather buffer (P2P stores).
-        Order the consumers with a cross-rank barrier (e.g. a 1-element all-reduce on the same stream)."""
-        _native.check(self._L.cda_step_gather(self._h, _ptr(category), _ptr(size_mean), _ptr(size_sigma), _ptr(price),
-                                              _ptr(price_offset), self._stream()))
+        """cda_step whose epilogue writes this rank's rows into every rank's gather buffer (P2P stores over NVLink).
+        Returns (obs f32[G*M,W], reward f64[G*M,A], terminated u8[G*M], truncated u8[G*M]) views of the half of THIS rank's
+        double-buffered gather region that this step fills.  Make ONE cross-rank barrier (e.g. a 1-element all-reduce on the
+        same stream) after the call before consuming them; they stay valid until the call after next (the other half takes the
+        next step), so no second "consumers are done" barrier is needed."""
+        with torch.cuda.device(self.device):
+            _native.check(self._L.cda_step_gather(self._h, _ptr(category), _ptr(size_mean), _ptr(size_sigma), _ptr(price),
+                                                  _ptr(price_offset), self._stream()))
+        self._gather = self._gather_halves[self._L.cda_gather_parity(self._h)]
         return self._gather
 
     # ------------------------------------------------------------------ fused random rollout
@@ -365,11 +415,15 @@ class VecCDAEnv:
     def status(self):
         return self.info("market")[:, 7]
 
-    def check_status(self):
-        """Raise if any market carries a sticky status bit (the reference would have sys.exit()ed)."""
+    def check_status(self, include_fill_log=False):
+        """Raise if any market carries a FATAL sticky status bit (pool overflow, bad action, price range, bad size: the
+        reference would have sys.exit()ed or kept an order this library dropped).  A fill-log overflow (bit 2) only truncates
+        the per-step fill log — book and ledger stay exact — and is reported only when include_fill_log=True."""
         bits = 0
         for v in torch.unique(self.status()).cpu().tolist():
             bits |= int(v)
+        if not include_fill_log:
+            bits &= FATAL_STATUS
         if bits:
             raise RuntimeError("cda_b200 market status: " + ", ".join(v for b, v in STATUS_BITS.items() if bits & b))
         return 0

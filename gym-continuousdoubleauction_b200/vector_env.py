@@ -125,7 +125,7 @@ class VectorCDAEnv:
             raise RuntimeError("lazy info read after a later step()/reset(): the device state has moved on")
         if self._gathered[0] != step_id:
             info = {k: v.cpu().numpy() for k, v in self._vec.info_all().items()}
-            if int(info["market"][:, 7].max()):
+            if int(np.bitwise_or.reduce(info["market"][:, 7])) & 29:
                 self._vec.check_status()
             self._gathered = (step_id, info)
         return self._gathered[1]

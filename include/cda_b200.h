@@ -188,12 +188,17 @@ int cda_rollout_random(CdaEnv *env, int32_t num_steps, uint64_t policy_seed, flo
  * cda_gather_connect maps every peer's buffer.  cda_step_gather is cda_step whose epilogue stores each
  * market's outputs straight into ALL G buffers (P2P stores over NVLink/NVSwitch), so the transfer overlaps
  * the matching work of other warps and no separate collective moves the data.  The caller orders the
- * consumers with any tiny cross-rank barrier (e.g. a 1-element NCCL all-reduce) after the call. */
+ * consumers with any tiny cross-rank barrier (e.g. a 1-element NCCL all-reduce) after the call.
+ * The buffer is DOUBLE-BUFFERED: it holds two such blocks (each rounded up to 256 B; *bytes covers both) and consecutive
+ * cda_step_gather calls write them alternately, so a rank that is one step ahead never overwrites rows a slower rank is still
+ * reading (the per-step barrier keeps the ranks within one step of each other: no second, consumer-done barrier is needed).
+ * cda_gather_parity() = index (0/1) of the block the LAST cda_step_gather wrote; block k starts at byte k * (*bytes / 2). */
 #define CDA_MAX_PEERS 8
 int cda_gather_create(CdaEnv *env, int32_t world, int32_t rank, void *ipc_handle_out64, void **d_local_buf, uint64_t *bytes);
 int cda_gather_connect(CdaEnv *env, const void *all_ipc_handles /* [world][64] */);
 int cda_step_gather(CdaEnv *env, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
                     const int32_t *d_price, const int32_t *d_price_offset, void *stream);
+int32_t cda_gather_parity(const CdaEnv *env);
 
 /* Lazy info (info_helper.py:30-116): gathers one field for all markets into d_out. */
 int cda_get_info(CdaEnv *env, int32_t field, int64_t *d_out, void *stream);
@@ -224,22 +229,18 @@ int32_t cda_num_markets(const CdaEnv *env);
 int32_t cda_record_bytes(const CdaEnv *env);   /* size of one packed result record of cda_step_host_window */
 int32_t cda_obs_dim(const CdaEnv *env);
 int32_t cda_order_capacity(const CdaEnv *env);
-int64_t cda_kernel_launches(const CdaEnv *env);
+int64_t cda_kernel_launches(const CdaEnv *env);   /* kernels launched by this handle so far */
 
-/* Test entries for csrc/cda_dec128.cuh — Decimal(prec 28, ROUND_HALF_EVEN) arithmetic on fixed-width integers, the form the
- * reference's Decimal ledger (envs/account/account.py:124-231, calculate.py:5-55) will take on the device.
- * op: '+', '-', '*', '/' or 'c' (compare: "-1e0" / "0" / "1e0"); operands and results are decimal strings ("-396e0",
- * "3.5e-24"); result slots are `cap` (>= 48) bytes each.  *range_err counts products / quotients outside the 128-bit domain.
- * cda_debug_dec_op runs the HOST compilation of the header, cda_debug_dec_op_device the DEVICE one (n operand pairs, one
- * thread each).  Neither is on a product path. */
-int cda_debug_dec_op(int32_t op, const char *a, const char *b, char *out, int32_t cap, int32_t *range_err);
-int cda_debug_dec_op_device(int32_t op, int32_t n, const char *const *a, const char *const *b, char *out, int32_t cap, int32_t *range_err); /* kernels launched by this handle so far */
+/* Sticky-status early warning (the reference calls sys.exit() where this library sets a per-market status bit): a pinned host
+ * word that every step kernel sets to 1 when ANY market ends the step with a non-zero status.  Reading it costs nothing (no
+ * launch, no synchronisation; it reflects the steps that have completed so far), so a host loop can poll it after every step
+ * and only then pay for the precise per-market gather (cda_get_info(CDA_INFO_MARKET), column 7).  cda_status_flag_clear re-arms it. */
+const volatile uint32_t *cda_status_flag(const CdaEnv *env);
+int cda_status_flag_clear(CdaEnv *env);
+
 const char *cda_strerror(int code);
 const char *cda_last_cuda_error(void);
 const char *cda_build_info(void);
-
-/* Debug builds only (-DCDA_PROFILE_PHASES): device buffer of 16 per-phase cycle sums, else NULL. */
-unsigned long long *cda_debug_phase_buffer(void);
 
 /* Host-side helper: the PCG64 state numpy gives for `seed` (state_hi, state_lo, inc_hi, inc_lo). */
 void cda_seed_to_pcg64(uint64_t seed, uint64_t out[4]);

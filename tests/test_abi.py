@@ -9,8 +9,8 @@ from gym_continuousdoubleauction_b200 import _native
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "cda_b200.h")).read()
+def declared_symbols(header="cda_b200.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(cda_[a-z0-9_]+)\s*\(", txt)))
 
@@ -23,6 +23,9 @@ def test_library_builds_and_exports_every_declared_symbol():
     missing = [s for s in syms if not hasattr(L, s)]
     assert not missing, missing
     assert sorted(_native.EXPORTS) == syms
+    assert not [s for s in syms if "debug" in s]                       # test entries live in their own header
+    tsyms = declared_symbols("cda_b200_testing.h")
+    assert sorted(_native.TESTING_EXPORTS) == tsyms and not [s for s in tsyms if not hasattr(L, s)]
 
 
 def test_host_side_seeding_matches_numpy():

@@ -47,9 +47,12 @@ def _worker(rank, world, port, M, T, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+WORLD = int(os.environ.get("CDA_TEST_WORLD", "0")) or min(8, max(2, torch.cuda.device_count()))   # every GPU of the box (2, 4 or 8)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or torch.cuda.device_count() < WORLD, reason="needs >= 2 GPUs (CDA_TEST_WORLD of them)")
 def test_peer_gather_equals_nccl_allgather_and_single_process():
-    world, M, T = 2, 256, 12
+    world, M, T = WORLD, 256, 12
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -34,7 +34,7 @@ def test_pool_overflow_sets_sticky_status_and_raises():
     """64-order capacity, 8 agents stacking limit bids at distinct ghost levels: the reference would
     keep growing; we flag the market (sticky) instead of corrupting it."""
     env = cda.VecCDAEnv(dict(num_of_agents=8, max_step=100000, initial_price_min=5000, initial_price_max=5000),
-                        num_markets=2, order_capacity=64)
+                        num_markets=2, order_capacity=64, status_policy="ignore")
     env.reset(seed=1)
     M, A = 2, 8
     g = torch.Generator(device="cuda"); g.manual_seed(0)
@@ -54,11 +54,44 @@ def test_pool_overflow_sets_sticky_status_and_raises():
 
 
 def test_bad_action_sets_status_not_crash():
-    env = cda.VecCDAEnv(dict(num_of_agents=4), num_markets=1)
+    env = cda.VecCDAEnv(dict(num_of_agents=4), num_markets=1, status_policy="ignore")
     env.reset(seed=1)
     z = lambda v, dt: torch.full((1, 4), v, dtype=dt, device="cuda")
     env.step(z(11, torch.int32), z(0.0, torch.float32), z(0.0, torch.float32), z(3, torch.int32), z(1, torch.int32))
     assert int(env.status()[0].item()) & 4
+    env.close()
+
+
+def test_status_flag_makes_step_raise_without_being_asked():
+    """a pool overflow must not pass silently.  Default policy: the first step() after the offending step has
+    completed raises (the kernel sets a pinned flag word; polling it costs nothing while every market is clean)."""
+    env = cda.VecCDAEnv(dict(num_of_agents=8, max_step=100000, initial_price_min=5000, initial_price_max=5000),
+                        num_markets=2, order_capacity=64)
+    env.reset(seed=1)
+    M, A = 2, 8
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    with pytest.raises(RuntimeError, match="order pool overflow"):
+        for t in range(200):
+            cat = torch.full((M, A), 2, dtype=torch.int32, device="cuda")
+            z = torch.zeros((M, A), dtype=torch.float32, device="cuda")
+            env.step(cat, z, z, torch.randint(0, 10, (M, A), device="cuda", generator=g, dtype=torch.int32),
+                     torch.randint(0, 3, (M, A), device="cuda", generator=g, dtype=torch.int32))
+            torch.cuda.synchronize()
+    env.close()
+
+
+def test_fill_log_overflow_is_not_fatal_in_the_dict_adapter():
+    """one aggressive order sweeping more resting orders than the fill log holds truncates the LOG only; the dict
+    adapter (fill_capacity 2 here) keeps stepping and its ledger stays exact (NAV conserved)."""
+    env = cda.continuousDoubleAuctionEnv(dict(num_of_agents=4, max_step=1000, initial_price_min=50, initial_price_max=50, fill_capacity=2))
+    env.reset(seed=3)
+    one = lambda c, m=0.0: {"category": c, "size_mean": np.array([m], np.float32), "size_sigma": np.array([0.0], np.float32), "price": 0, "price_offset": 1}
+    for p in range(3):      # three makers rest one small ask each at the same ghost level, in three steps
+        env.step({f"agent_{p}": one(6, 0.0)})                     # size_mean 0 -> one unit each, all at the same price
+    _, _, _, _, infos = env.step({"agent_3": one(1, 1.0)})       # a market buy of 50.5 -> 51 units sweeps all three
+    assert len(env.fills()) == 2 and env._vec_status & 2          # log truncated, flagged ...
+    env.step({"agent_0": one(0)})                                 # ... and the env keeps going
+    assert sum(int(infos[a]["NAV"]) for a in env.agents) == 4 * 1_000_000
     env.close()
 
 
