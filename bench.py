@@ -46,6 +46,19 @@ def b_alg(A):
     return 1986 + 188 * A
 
 
+# The reference itself (unmodified Python env.step through the gymnasium/ray stub) measured in the build container, step-only,
+# one core: it cannot travel to the GPU box, so its number is quoted beside the C port's.
+PY_REFERENCE = {"value": 2181.0, "unit": "env-steps/s", "cores": 1, "config": "A=4, uniform actions, 1 market per env object",
+                "source": "BASELINE.md section 2 (Xeon 2.1 GHz, Python 3.12.3, numpy 2.3.5); 18,700 env-steps/s on 8 cores / 8 processes"}
+
+
+def workload_config(workload, A, M, world, mix):
+    """The `config` object of BOTH arms: identical keys and values (the driver compares them)."""
+    return {"workload": workload, "agents": A, "markets_per_gpu": M, "markets_total": world * M, "mix": mix,
+            "seeds": "1000 + global market id", "prewarm_steps": "books populated before timing (GPU arm: --prewarm, CPU arm: 64)",
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB write) unless --no-l2-flush; CPU arm: n/a"}
+
+
 def env_config(A):
     return dict(num_of_agents=A, init_cash=1_000_000, max_step=1 << 30, n_hist=4, tick_size=1,
                 initial_price_min=10, initial_price_max=100, min_size=1, mkt_max_size=100,
@@ -118,7 +131,7 @@ def cpu_path(A, M, mix, seconds_target, threads):
         steps += chunk
         if spent >= seconds_target / 3.0:
             break
-    return {"value": M * steps / spent, "unit": UNIT, "cores": threads, "kind": "port",
+    return {"python_reference": PY_REFERENCE, "value": M * steps / spent, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{steps} steps x {M} markets x {A} agents ({mix}), {spent:.2f} s wall stepping, C oracle of the reference algorithm, "
                       f"{threads} threads (one slice of markets per thread, no barriers)",
             "seconds": spent, "steps": steps}
@@ -152,11 +165,13 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(per), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64 ledger / f64 obs math / f32 obs", "data": "synthetic",
-        "config": {"workload": args.workload, "agents": A, "markets": Mtot, "mix": mix,
-                   "note": "reference is pure Python and cannot travel to the GPU box; this arm times the C oracle "
-                           "(port of the reference algorithm, pinned bit-exact to it) on all host threads"},
+        "config": workload_config(args.workload, A, M, world, mix),
+        "details": {"note": "the reference is pure Python and cannot travel to the GPU box; this arm times the C oracle "
+                            "(port of the reference algorithm, pinned bit-exact to it) on all host threads",
+                    "python_reference": PY_REFERENCE},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{len(per)} x {inner} steps x {Mtot} markets x {A} agents ({mix})"},
+                         "sample": f"{len(per)} x {inner} steps x {Mtot} markets x {A} agents ({mix})",
+                         "python_reference": PY_REFERENCE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -252,7 +267,8 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    if rank == 0:          # ONE sampler per job: rank 0's GPU (every rank running its own nvidia-smi loop perturbs the host paths)
+        sampler.start()
     launches0 = env.kernel_launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
@@ -331,8 +347,9 @@ def main():
         for _ in range(400):
             dev_step()
         torch.cuda.synchronize()
-    clocks = sampler.stop()   # sampled across the device-timed, L2-hot, end-to-end regions + 0.6 s of sustained stepping
-    clocks["window"] = "value + L2-hot + e2e regions + 0.6 s sustained stepping"
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the device-timed, L2-hot, end-to-end regions + 0.6 s of sustained stepping
+    if clocks is not None:
+        clocks["window"] = "value + L2-hot + e2e regions + 0.6 s sustained stepping (rank 0's GPU)"
 
     # ------------------------------------------------------------------ optional obs all-gather
     ag = None
@@ -392,13 +409,17 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = b_alg(A) * M / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(args.workload)
+        if traffic is not None:
+            traffic_source = ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed ncu --set full "
+                              "capture profiles/" + str(tj.get(args.workload + "__source")))
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
+                "traffic": traffic, "traffic_source": traffic_source, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6.65 TB/s",
                 "kernel": "cda_step_kernel", "kernel_ms": kern_ms, "alg_bytes_per_market_step": b_alg(A),
                 "l2_hot_kernel_ms": hot_ms, "l2_hot_achieved": b_alg(A) * M / (hot_ms * 1e-3) / 1e9}
     cpu = None
@@ -408,12 +429,12 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64 ledger / int32 book / f64 obs+reward math, f32 obs out", "data": "synthetic",
-        "config": {"workload": args.workload, "agents": A, "markets_per_gpu": M, "markets_total": world * M, "mix": mix,
-                   "order_capacity": env.order_capacity, "prewarm_steps": args.prewarm,
-                   "l2": "flushed between timed steps (256 MiB write)" if not args.no_l2_flush else "not flushed",
-                   "rng": "numpy-exact PCG64+ziggurat on device", "seeds": "1000 + global market id",
-                   "agent_steps_per_s": value * A, "status_bits": status_bits,
-                   "value_l2_hot": world * M / (hot_ms * 1e-3)},
+        "impl": "cda_b200",
+        "config": workload_config(args.workload, A, M, world, mix),
+        "details": {"order_capacity": env.order_capacity, "prewarm_steps": args.prewarm,
+                    "l2": "flushed between timed steps (256 MiB write)" if not args.no_l2_flush else "not flushed",
+                    "rng": "numpy-exact PCG64+ziggurat on device", "agent_steps_per_s": value * A, "status_bits": status_bits,
+                    "value_l2_hot": world * M / (hot_ms * 1e-3)},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     if ag:

@@ -48,6 +48,7 @@ struct CdaEnv {
     int *s_cat; float *s_mean; float *s_sigma; int *s_pcode; int *s_poff;
     float *s_obs; double *s_reward; unsigned char *s_term; unsigned char *s_trunc;
     unsigned char *s_rec;      // packed result records [M][A*8+8] (window host path)
+    float *s_plane;            // device staging of one output plane (cda_step_planes fallback when the host plane is not mapped)
     bool was_reset;
     // fused all-gather
     int g_world, g_rank; unsigned char *g_local; size_t g_bytes; unsigned char *g_peer[CDA_MAX_PEERS]; bool g_connected;
@@ -245,7 +246,7 @@ int cda_destroy(CdaEnv *e) {
     if (e->g_connected) for (int g = 0; g < e->g_world; ++g) if (g != e->g_rank && e->g_peer[g]) cudaIpcCloseMemHandle(e->g_peer[g]);
     cudaFree(e->g_local);
     cudaFree(e->state); cudaFree(e->fills); cudaFree(e->fill_counts);
-    cudaFree(e->s_cat); cudaFree(e->s_obs); cudaFree(e->s_rec);
+    cudaFree(e->s_cat); cudaFree(e->s_obs); cudaFree(e->s_rec); cudaFree(e->s_plane);
     delete e;
     return CDA_OK;
 }
@@ -563,6 +564,51 @@ int cda_step_window(CdaEnv *e, const int32_t *h_action_block, int32_t pos, int32
                             e->w_window, e->w_slots, pos, e->w_records, (flags & CDA_WIN_INLINE_RECORD) != 0, flags & CDA_WIN_SYNC, e->w_stream);
 }
 
+// ---- dense plane output (see include/cda_b200.h): one aligned cell per market and step, consecutive markets contiguous -------------
+int cda_step_planes(CdaEnv *e, const int32_t *h_action_block, float *h_plane, int32_t cell_words, int32_t flags, void *stream) {
+    if (!e || !h_action_block || !h_plane) return CDA_EINVAL;
+    DevGuard guard(e->device);
+    const int A = e->dev.A;
+    if (cell_words < CDA_SNAPSHOT_DIM + 2 * A + 2 || (cell_words & 1)) return CDA_EINVAL;
+    if (!e->was_reset) return CDA_ESTATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool mm = (flags & CDA_WIN_MARKET_MAJOR) != 0;
+    const size_t MA = (size_t)e->M * A, fstep = mm ? (size_t)A * 4 : MA * 4;
+    if (e->zi_host != h_action_block) { e->zi_host = h_action_block; e->zi_dev = e->zerocopy_in ? mapped_alias(h_action_block) : nullptr; }
+    if (e->zc_host != h_plane) { e->zc_host = h_plane; e->zc_dev = e->zerocopy ? mapped_alias(h_plane) : nullptr; }
+    const char *zi = reinterpret_cast<const char *>(e->zi_dev);
+    float *zp = reinterpret_cast<float *>(e->zc_dev);
+    if (!zi) { CUDA_TRY(cudaMemcpyAsync(e->s_cat, h_action_block, MA * 20, cudaMemcpyHostToDevice, st)); zi = reinterpret_cast<const char *>(e->s_cat); }
+    if (!zp && !e->s_plane) CUDA_TRY(cudaMalloc(&e->s_plane, (size_t)e->M * 64 * 4 > (size_t)e->M * cell_words * 4 ? (size_t)e->M * 64 * 4 : (size_t)e->M * cell_words * 4));
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cat = reinterpret_cast<const int *>(zi); p.mean = reinterpret_cast<const float *>(zi + fstep); p.sigma = reinterpret_cast<const float *>(zi + 2 * fstep);
+    p.pcode = reinterpret_cast<const int *>(zi + 3 * fstep); p.poff = reinterpret_cast<const int *>(zi + 4 * fstep);
+    if (mm) { p.act_mstride = 5 * A; p.act_packed = 1; }
+    p.ring_out = zp ? zp : e->s_plane; p.ring_stride = cell_words; p.ring_slot = 0; p.ring_mirror = 0; p.rec_inline = 1; p.ring_pad = cell_words;
+    int rc = step_common(e, p, st, true);
+    if (rc) return rc;
+    if (!zp) CUDA_TRY(cudaMemcpyAsync(h_plane, e->s_plane, (size_t)e->M * cell_words * 4, cudaMemcpyDeviceToHost, st));   // ONE contiguous copy
+    if (flags & CDA_WIN_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+    return CDA_OK;
+}
+
+int cda_reset_planes(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_planes, int32_t slots, int32_t cell_words, int32_t pos, void *stream) {
+    if (!e || !h_planes || slots < e->dev.n_hist || cell_words < CDA_SNAPSHOT_DIM || pos < 0 || pos >= slots) return CDA_EINVAL;
+    DevGuard guard(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cda_reset(e, d_seeds, d_mask, nullptr, stream);
+    if (rc) return rc;
+    float *zp = reinterpret_cast<float *>(mapped_alias(h_planes));
+    if (!zp) return CDA_EINVAL;                 // cold path: the plane ring must be pinned + mapped
+    const int n = e->M * e->dev.W, threads = 256;
+    cda_emit_planes_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(e->dev, e->state, e->M, zp, slots, cell_words, pos);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CDA_OK;
+}
+
 int cda_reset_host_window(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream) {
     if (!e || !h_window || slots < e->dev.n_hist) return CDA_EINVAL;
     DevGuard guard(e->device);
@@ -733,6 +779,12 @@ unsigned long long *cda_debug_phase_buffer(void) {
     return g_prof;
 }
 size_t cda_state_bytes(const CdaEnv *e) { return e ? e->state_bytes : 0; }
+int cda_state_layout(const CdaEnv *e, int32_t out[8]) {
+    if (!e || !out) return CDA_EINVAL;
+    out[0] = (int32_t)e->dev.stride; out[1] = (int32_t)e->dev.off_acct; out[2] = (int32_t)e->dev.off_hist; out[3] = (int32_t)e->dev.off_pool;
+    out[4] = e->dev.cap; out[5] = e->dev.A; out[6] = e->dev.n_hist; out[7] = CDA_HDR_BYTES;
+    return CDA_OK;
+}
 int cda_save_state(CdaEnv *e, void *h_dst, void *stream) {
     if (!e || !h_dst) return CDA_EINVAL;
     DevGuard guard(e->device);

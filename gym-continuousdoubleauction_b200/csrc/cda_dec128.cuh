@@ -1,18 +1,21 @@
 // cda_dec128.cuh — Decimal(prec 28, ROUND_HALF_EVEN) add / sub / mul / div / compare on fixed-width integers, host + device.
 //
-// NOT USED BY THE STEP KERNEL YET.  The reference keeps money as Python `decimal.Decimal` (envs/account/account.py:124-231,
-// calculate.py:5-55, cash_processor.py:15-97, agent/trader.py:108-151); its VWAP divisions leave ~1e-24 residues in cash /
-// NAV, and a `cash >= order value` test at EXACT equality is decided by the residue's sign — the one place where the exact
-// integer ledger of the kernel can disagree with the reference.  Reproducing that needs the reference's
-// arithmetic itself: value = (-1)^sign * c * 10^exp with c < 10^28 in an unsigned __int128, every operation computed exactly
-// in 128 bits and rounded ONCE.  This header is that arithmetic in the form the device ledger will use; it is the same
-// algorithm as oracle/dec128.h, which reproduces the reference's Decimal fields exactly inside the oracle (700 fuzzed
-// configurations).  The host side of THIS file is pinned against Python's decimal through cda_debug_dec_op
-// (tests/test_dec28.py); the device side is compiled (cda_dec_selftest_kernel) and waits for its GPU test.
+// The reference keeps money as Python `decimal.Decimal` (envs/account/account.py:124-231, calculate.py:5-55,
+// cash_processor.py:15-97, agent/trader.py:108-151); its VWAP divisions leave ~1e-24 residues in cash / NAV, and a
+// `cash >= order value` test at EXACT equality is decided by the residue's sign — the one place where an exact integer ledger
+// can disagree with the reference.  Reproducing that needs the reference's arithmetic itself:
+// value = (-1)^sign * c * 10^exp with c < 10^28 in an unsigned __int128, every operation computed exactly in 128 bits and
+// rounded ONCE.  This header is that arithmetic; the device twin ledger (cda_twin.cuh) is built on it.  It is the same algorithm
+// as oracle/dec128.h, which reproduces the reference's Decimal fields exactly inside the oracle (700 fuzzed configurations).
+// The host compilation of THIS file is pinned against Python's decimal through cda_debug_dec_op, the device compilation
+// through cda_debug_dec_op_device (tests/test_dec28.py).
 //
-// Domain: additions are exact for all operands; a product needs digits(a) + digits(b) <= 38 and a quotient a divisor of
-// at most 9 digits (in the ledger one factor is always a size or a price).  Outside it `*range_err` is incremented and the
-// result is not to be used.
+// Domain: additions are exact for all operands; a product needs digits(a) + digits(b) <= 38 and a quotient a divisor below
+// 2^32 (in the ledger one factor is always a size or a price).  Outside it `*range_err` is incremented and the result is not to
+// be used.
+//
+// Speed (device): no 128-bit division anywhere — powers of ten come from a table, digit counts from the bit length, and every
+// quotient is a chain of (64-bit / 32-bit) steps done with one FP64 multiply and an exact integer fix-up.
 #pragma once
 #include <stdint.h>
 
@@ -22,21 +25,110 @@ struct CdaDec { cda_u128 c; int exp; int sign; };   // c == 0 <=> zero (sign 0)
 #define CDA_DEC_P 28
 #if defined(__CUDACC__)
 #define CDA_HD __host__ __device__ __forceinline__
+#define CDA_TAB __device__ const
 #else
 #define CDA_HD inline
+#define CDA_TAB static const
 #endif
 
-CDA_HD cda_u128 cda_dec_pow10(int k) {               // 0 <= k <= 38; no table: shared by host and device, off the hot path
-    cda_u128 r = 1, b = 10;
-    for (; k; k >>= 1, b *= b) if (k & 1) r *= b;
-    return r;
+#define CDA_POW10_ROWS \
+    {0x0000000000000000ULL, 0x0000000000000001ULL}, \
+    {0x0000000000000000ULL, 0x000000000000000aULL}, \
+    {0x0000000000000000ULL, 0x0000000000000064ULL}, \
+    {0x0000000000000000ULL, 0x00000000000003e8ULL}, \
+    {0x0000000000000000ULL, 0x0000000000002710ULL}, \
+    {0x0000000000000000ULL, 0x00000000000186a0ULL}, \
+    {0x0000000000000000ULL, 0x00000000000f4240ULL}, \
+    {0x0000000000000000ULL, 0x0000000000989680ULL}, \
+    {0x0000000000000000ULL, 0x0000000005f5e100ULL}, \
+    {0x0000000000000000ULL, 0x000000003b9aca00ULL}, \
+    {0x0000000000000000ULL, 0x00000002540be400ULL}, \
+    {0x0000000000000000ULL, 0x000000174876e800ULL}, \
+    {0x0000000000000000ULL, 0x000000e8d4a51000ULL}, \
+    {0x0000000000000000ULL, 0x000009184e72a000ULL}, \
+    {0x0000000000000000ULL, 0x00005af3107a4000ULL}, \
+    {0x0000000000000000ULL, 0x00038d7ea4c68000ULL}, \
+    {0x0000000000000000ULL, 0x002386f26fc10000ULL}, \
+    {0x0000000000000000ULL, 0x016345785d8a0000ULL}, \
+    {0x0000000000000000ULL, 0x0de0b6b3a7640000ULL}, \
+    {0x0000000000000000ULL, 0x8ac7230489e80000ULL}, \
+    {0x0000000000000005ULL, 0x6bc75e2d63100000ULL}, \
+    {0x0000000000000036ULL, 0x35c9adc5dea00000ULL}, \
+    {0x000000000000021eULL, 0x19e0c9bab2400000ULL}, \
+    {0x000000000000152dULL, 0x02c7e14af6800000ULL}, \
+    {0x000000000000d3c2ULL, 0x1bcecceda1000000ULL}, \
+    {0x0000000000084595ULL, 0x161401484a000000ULL}, \
+    {0x000000000052b7d2ULL, 0xdcc80cd2e4000000ULL}, \
+    {0x00000000033b2e3cULL, 0x9fd0803ce8000000ULL}, \
+    {0x00000000204fce5eULL, 0x3e25026110000000ULL}, \
+    {0x00000001431e0faeULL, 0x6d7217caa0000000ULL}, \
+    {0x0000000c9f2c9cd0ULL, 0x4674edea40000000ULL}, \
+    {0x0000007e37be2022ULL, 0xc0914b2680000000ULL}, \
+    {0x000004ee2d6d415bULL, 0x85acef8100000000ULL}, \
+    {0x0000314dc6448d93ULL, 0x38c15b0a00000000ULL}, \
+    {0x0001ed09bead87c0ULL, 0x378d8e6400000000ULL}, \
+    {0x0013426172c74d82ULL, 0x2b878fe800000000ULL}, \
+    {0x00c097ce7bc90715ULL, 0xb34b9f1000000000ULL}, \
+    {0x0785ee10d5da46d9ULL, 0x00f436a000000000ULL}, \
+    {0x4b3b4ca85a86c47aULL, 0x098a224000000000ULL}
+static const unsigned long long cda_pow10_host[39][2] = { CDA_POW10_ROWS };
+#if defined(__CUDACC__)
+__device__ const unsigned long long cda_pow10_dev[39][2] = { CDA_POW10_ROWS };
+#endif
+
+CDA_HD cda_u128 cda_dec_pow10(int k) {               // 0 <= k <= 38
+#if defined(__CUDA_ARCH__)
+    return ((cda_u128)cda_pow10_dev[k][0] << 64) | cda_pow10_dev[k][1];
+#else
+    return ((cda_u128)cda_pow10_host[k][0] << 64) | cda_pow10_host[k][1];
+#endif
 }
-CDA_HD int cda_dec_ndigits(cda_u128 x) {             // 0 for x == 0
-    int n = 0;
-    cda_u128 p = 1;
-    while (n < 38 && x >= p) { p *= 10; ++n; }       // p = 10^n
-    if (n == 38 && x >= p) return 39;
-    return n;
+CDA_HD int cda_dec_bitlen(cda_u128 x) {
+    const unsigned long long hi = (unsigned long long)(x >> 64), lo = (unsigned long long)x;
+#if defined(__CUDA_ARCH__)
+    return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
+#else
+    return hi ? 128 - __builtin_clzll(hi) : (lo ? 64 - __builtin_clzll(lo) : 0);
+#endif
+}
+CDA_HD int cda_dec_ndigits(cda_u128 x) {             // 0 for x == 0; 39 for x >= 10^38
+    const int t = (cda_dec_bitlen(x) * 1233) >> 12;  // floor(bits * log10 2), exact for bits <= 128 (checked exhaustively)
+    if (t >= 38) return x >= cda_dec_pow10(38) ? 39 : 38;
+    return t + (x >= cda_dec_pow10(t) ? 1 : 0);
+}
+// n / d and n % d for d < 2^32, n < d * 2^32 (one step of a long division): FP64 estimate (error <= 1), exact integer fix-up
+CDA_HD unsigned cda_div64_32(unsigned long long n, unsigned d, unsigned *rem) {
+#if defined(__CUDA_ARCH__)
+    long long q = (long long)__double2ull_rz(__ull2double_rz(n) * __drcp_rn((double)d));
+    long long r = (long long)(n - (unsigned long long)q * d);
+    if (r < 0) { --q; r += d; }
+    if (r < 0) { --q; r += d; }
+    if (r >= (long long)d) { ++q; r -= d; }
+    if (r >= (long long)d) { ++q; r -= d; }
+    *rem = (unsigned)r;
+    return (unsigned)q;
+#else
+    *rem = (unsigned)(n % d);
+    return (unsigned)(n / d);
+#endif
+}
+// x / d, remainder in *rem, for 0 < d < 2^32
+CDA_HD cda_u128 cda_u128_divmod_small(cda_u128 x, unsigned d, unsigned *rem) {
+    const unsigned long long hi = (unsigned long long)(x >> 64), lo = (unsigned long long)x;
+    unsigned r = 0;
+    const unsigned q3 = cda_div64_32(hi >> 32, d, &r);
+    const unsigned q2 = cda_div64_32(((unsigned long long)r << 32) | (hi & 0xffffffffULL), d, &r);
+    const unsigned q1 = cda_div64_32(((unsigned long long)r << 32) | (lo >> 32), d, &r);
+    const unsigned q0 = cda_div64_32(((unsigned long long)r << 32) | (lo & 0xffffffffULL), d, &r);
+    *rem = r;
+    return ((cda_u128)(((unsigned long long)q3 << 32) | q2) << 64) | (((unsigned long long)q1 << 32) | q0);
+}
+// x / 10^k for 0 <= k <= 38 (chunks of nine digits); the remainder is x - q * 10^k (the caller multiplies back: exact and cheap)
+CDA_HD cda_u128 cda_u128_div_pow10(cda_u128 x, int k) {
+    unsigned r;
+    while (k >= 9) { x = cda_u128_divmod_small(x, 1000000000u, &r); k -= 9; }
+    if (k > 0) x = cda_u128_divmod_small(x, (unsigned)cda_dec_pow10(k), &r);
+    return x;
 }
 CDA_HD CdaDec cda_dec_zero() { CdaDec r; r.c = 0; r.exp = 0; r.sign = 0; return r; }
 
@@ -47,9 +139,9 @@ CDA_HD CdaDec cda_dec_round(int sign, cda_u128 x, int exp, int sticky) {
     const int nd = cda_dec_ndigits(x);
     if (nd > CDA_DEC_P) {
         int k = nd - CDA_DEC_P;
-        const cda_u128 p = cda_dec_pow10(k), half = p / 2;
-        cda_u128 q = x / p;
-        const cda_u128 rem = x % p;
+        const cda_u128 p = cda_dec_pow10(k), half = p >> 1;
+        cda_u128 q = cda_u128_div_pow10(x, k);
+        const cda_u128 rem = x - q * p;
         if (rem > half || (rem == half && (sticky || (q & 1)))) ++q;
         if (q == cda_dec_pow10(CDA_DEC_P)) { q = cda_dec_pow10(CDA_DEC_P - 1); ++k; }
         x = q; exp += k;
@@ -57,13 +149,24 @@ CDA_HD CdaDec cda_dec_round(int sign, cda_u128 x, int exp, int sticky) {
     r.c = x; r.exp = exp; r.sign = sign;
     return r;
 }
-CDA_HD CdaDec cda_dec_from_i64(long long v) {
-    const int sign = v < 0;
-    const unsigned long long u = sign ? (unsigned long long)(-(v + 1)) + 1ULL : (unsigned long long)v;
-    return cda_dec_round(sign, (cda_u128)u, 0, 0);
+CDA_HD CdaDec cda_dec_from_i64(long long v) {        // |v| < 2^63 < 10^19: never rounded
+    CdaDec r;
+    r.sign = v < 0;
+    r.c = (cda_u128)(r.sign ? (unsigned long long)(-(v + 1)) + 1ULL : (unsigned long long)v);
+    r.exp = 0;
+    if (r.c == 0) r.sign = 0;
+    return r;
 }
 CDA_HD CdaDec cda_dec_neg(CdaDec a) { if (a.c) a.sign ^= 1; return a; }
-CDA_HD CdaDec cda_dec_strip(CdaDec a) { while (a.c && a.c % 10 == 0) { a.c /= 10; ++a.exp; } return a; }
+CDA_HD CdaDec cda_dec_strip(CdaDec a) {              // value-preserving: drop trailing zeros of the coefficient
+    while (a.c) {
+        unsigned r;
+        const cda_u128 q = cda_u128_divmod_small(a.c, 10u, &r);
+        if (r) break;
+        a.c = q; ++a.exp;
+    }
+    return a;
+}
 
 CDA_HD CdaDec cda_dec_add(CdaDec a, CdaDec b) {
     if (a.c == 0) return b;
@@ -82,7 +185,7 @@ CDA_HD CdaDec cda_dec_add(CdaDec a, CdaDec b) {
     const int t = 30 - na, shift = diff - t;
     const cda_u128 x = a.c * cda_dec_pow10(t);
     cda_u128 y = 0; int sticky = 1;
-    if (shift <= 38) { const cda_u128 p = cda_dec_pow10(shift); y = b.c / p; sticky = (b.c % p) != 0; }
+    if (shift <= 38) { const cda_u128 p = cda_dec_pow10(shift); y = cda_u128_div_pow10(b.c, shift); sticky = (b.c - y * p) != 0; }
     const cda_u128 r = a.sign == b.sign ? x + y : x - y - (sticky ? 1 : 0);
     return cda_dec_round(a.sign, r, a.exp - t, sticky);
 }
@@ -96,14 +199,16 @@ CDA_HD CdaDec cda_dec_mul(CdaDec a, CdaDec b, int *range_err) {
     }
     return cda_dec_round(a.sign ^ b.sign, a.c * b.c, a.exp + b.exp, 0);
 }
-// a / b, b != 0 with at most 9 significant digits: dividend scaled to 38 digits, quotient >= 29 digits + sticky remainder
+// a / b, b != 0 with a coefficient below 2^32 after stripping: dividend scaled to 38 digits, quotient >= 29 digits + sticky remainder
 CDA_HD CdaDec cda_dec_div(CdaDec a, CdaDec b, int *range_err) {
     if (a.c == 0) return cda_dec_zero();
     b = cda_dec_strip(b);
     const int nb = cda_dec_ndigits(b.c), na = cda_dec_ndigits(a.c), k = 38 - na;
-    if (na + k - nb < CDA_DEC_P + 1) { ++*range_err; return cda_dec_zero(); }
+    if (na + k - nb < CDA_DEC_P + 1 || (b.c >> 32) != 0) { ++*range_err; return cda_dec_zero(); }
     const cda_u128 x = a.c * cda_dec_pow10(k);
-    return cda_dec_round(a.sign ^ b.sign, x / b.c, a.exp - k - b.exp, (x % b.c) != 0);
+    unsigned rem;
+    const cda_u128 q = cda_u128_divmod_small(x, (unsigned)b.c, &rem);
+    return cda_dec_round(a.sign ^ b.sign, q, a.exp - k - b.exp, rem != 0);
 }
 CDA_HD int cda_dec_cmp(CdaDec a, CdaDec b) {          // -1, 0, +1 (the sign of a rounded difference is the sign of the exact one)
     const CdaDec d = cda_dec_sub(a, b);

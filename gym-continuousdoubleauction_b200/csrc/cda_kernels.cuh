@@ -88,6 +88,8 @@ struct CdaStepParams {
     int reward_stride, flag_stride;   // doubles between markets' reward rows (A when dense); bytes between markets' flags (1 when dense)
     float *ring_out; int ring_slot;   // host ring / window: newest snapshot only, at slot ring_slot of row m (+ a mirror copy n_hist slots later)
     int ring_stride, ring_mirror;     // floats per market row of ring_out; 1 = also write the mirror copy
+    int ring_pad;                     // > 0: the cell written at ring_slot is padded with zeros to this many words (dense plane output: a market's
+                                      //      snapshot + record fill one aligned 256-B cell, so every store is a whole 128-B line)
     // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
     int gather_world, gather_row0, gather_rows;
     unsigned char *gather_peer[CDA_MAX_PEERS];
@@ -1094,10 +1096,12 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 nw += 2 * A + 2;
                 __syncwarp();
             }
+            const int nw_data = nw;
+            if (p.ring_pad > nw) nw = p.ring_pad;
             float *rg = o_ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
             for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < nw; cc += 32) {
                 if (cc < 0) continue;
-                const float v = __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wbL + L::SNAP + cc) : SMW(wbL + L::ACT + cc - CDA_SNAPSHOT_DIM));
+                const float v = cc >= nw_data ? 0.f : __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wbL + L::SNAP + cc) : SMW(wbL + L::ACT + cc - CDA_SNAPSHOT_DIM));
                 rg[cc] = v;
                 if (o_ring_mirror && cc < CDA_SNAPSHOT_DIM) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
             }
@@ -1221,6 +1225,19 @@ __global__ void cda_emit_obs_kernel(CdaDevCfg cfg, const unsigned char *state, i
     const unsigned t_step = reinterpret_cast<const unsigned *>(blk)[3];
     const float *g_hist = reinterpret_cast<const float *>(blk + cfg.off_hist);
     dst[(size_t)m * stride + e] = g_hist[((t_step + (unsigned)j) % (unsigned)cfg.n_hist) * CDA_SNAPSHOT_DIM + cc];
+}
+
+// dense plane ring (cda_step_planes): the n_hist most recent snapshots of every market go to the planes ending at slot `pos`
+// (plane (pos - n_hist + 1 + j) mod slots receives the j-th oldest), cell m of each plane.  Cold path (reset / attach).
+__global__ void cda_emit_planes_kernel(CdaDevCfg cfg, const unsigned char *state, int M, float *planes, int slots, int cell, int pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * cfg.W) return;
+    const int m = i / cfg.W, e = i - m * cfg.W, j = e / CDA_SNAPSHOT_DIM, cc = e - j * CDA_SNAPSHOT_DIM;
+    const unsigned char *blk = state + (size_t)m * cfg.stride;
+    const unsigned t_step = reinterpret_cast<const unsigned *>(blk)[3];
+    const float *g_hist = reinterpret_cast<const float *>(blk + cfg.off_hist);
+    const int slot = ((pos - cfg.n_hist + 1 + j) % slots + slots) % slots;
+    planes[((size_t)slot * M + m) * cell + cc] = g_hist[((t_step + (unsigned)j) % (unsigned)cfg.n_hist) * CDA_SNAPSHOT_DIM + cc];
 }
 
 // fill every slot of the mirrored host ring of the selected markets with their current newest snapshot

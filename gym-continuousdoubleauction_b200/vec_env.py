@@ -22,6 +22,38 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class StackedPlanes:
+    """Stacked observation of every market as n_hist zero-copy [M, 42] views (oldest snapshot first) of the pinned plane ring.
+    Indexing / np.asarray() give the reference's layout: obs[m] is the f32[n_hist*42] vector of market m (a copy)."""
+    __slots__ = ("planes",)
+
+    def __init__(self, planes):
+        self.planes = planes
+
+    @property
+    def shape(self):
+        return (self.planes[0].shape[0], len(self.planes) * SNAPSHOT_DIM)
+
+    def stacked(self, out=None):
+        M, W = self.shape
+        out = np.empty((M, W), np.float32) if out is None else out
+        for j, p in enumerate(self.planes):
+            out[:, j * SNAPSHOT_DIM:(j + 1) * SNAPSHOT_DIM] = p
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.stacked()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) == 2 and isinstance(idx[0], (int, np.integer)) and isinstance(idx[1], (int, np.integer)):
+            j, c = divmod(int(idx[1]) % self.shape[1], SNAPSHOT_DIM)
+            return self.planes[j][idx[0], c]
+        if isinstance(idx, (int, np.integer)):
+            return np.concatenate([p[idx] for p in self.planes])
+        return self.stacked()[idx]
+
+
 class VecCDAEnv:
     def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0, status_policy="raise"):
         """status_policy: what step*/reset* do when a market carries a sticky status bit (see STATUS_BITS; noticed through a
@@ -328,6 +360,68 @@ class VecCDAEnv:
             self._poll_status()
         return self._win_views[pos]
 
+    # ---- dense plane ring: each step's output is ONE contiguous, line-aligned region (the host path that scales to 8 GPUs / node)
+    PLANE_SLOTS = 8
+    PLANE_CELL_WORDS = 64          # 256-B cell per market and step: 42-float snapshot | reward f64[A] | terminated | truncated | zero pad
+
+    def _ensure_planes(self):
+        if getattr(self, "_planes", None) is None:
+            M, A, S = self.M, self.A, self.PLANE_SLOTS
+            need = SNAPSHOT_DIM + 2 * A + 2
+            cell = self.PLANE_CELL_WORDS if self.PLANE_CELL_WORDS >= need and self.PLANE_CELL_WORDS % 2 == 0 else (need + 31) // 32 * 32
+            self._plane_cell = cell
+            self._planes = torch.zeros((S, M, cell), dtype=torch.float32, pin_memory=True)
+            pn = self._planes.numpy()
+            self._planes_np = pn
+            self._plane_ptrs = [self._planes[s].data_ptr() for s in range(S)]
+            cb = cell * 4
+            self._plane_snap = [pn[s, :, :SNAPSHOT_DIM] for s in range(S)]                                     # [M, 42] view per slot
+            self._plane_out = [(np.ndarray((M, A), np.float64, pn, (s * M * cell + SNAPSHOT_DIM) * 4, (cb, 8)),
+                                np.ndarray((M,), np.uint8, pn, (s * M * cell + SNAPSHOT_DIM) * 4 + 8 * A, (cb,)),
+                                np.ndarray((M,), np.uint8, pn, (s * M * cell + SNAPSHOT_DIM) * 4 + 8 * A + 1, (cb,))) for s in range(S)]
+            self._plane_pos = None
+        return self._planes
+
+    def _plane_stack(self):
+        """The stacked observation as n_hist [M, 42] views, oldest snapshot first."""
+        S, H = self.PLANE_SLOTS, self.n_hist
+        return StackedPlanes([self._plane_snap[(self._plane_pos - H + 1 + j) % S] for j in range(H)])
+
+    def reset_host_planes(self, seed=None, mask=None):
+        """reset() for the dense-plane host path (see include/cda_b200.h cda_step_planes): returns a StackedPlanes."""
+        self._ensure_planes()
+        if self.PLANE_SLOTS < self.n_hist + 1:
+            raise ValueError("PLANE_SLOTS must exceed n_hist")
+        seeds_t, mask_t = self._seed_mask_tensors(seed, mask)
+        pos = self._plane_pos if self._plane_pos is not None else self.n_hist - 1
+        _native.check(self._L.cda_reset_planes(self._h, _ptr(seeds_t), _ptr(mask_t), ctypes.c_void_p(self._plane_ptrs[0]), self.PLANE_SLOTS,
+                                               self._plane_cell, pos, self._stream()))
+        self._plane_pos = pos
+        self._plane_stream = self._stream()
+        return self._plane_stack()
+
+    def attach_host_planes(self):
+        """Start (or re-synchronise) the plane ring from the device state without resetting any market."""
+        return self.reset_host_planes(seed=None, mask=np.zeros(self.M, dtype=np.uint8))
+
+    def step_host_planes(self, action_block, sync=True, market_major=True):
+        """Dense-plane host path.  `action_block`: ONE pinned int32 tensor, [M, 5, A] (market_major) or [5, M, A], read in place by
+        the kernel.  Returns (StackedPlanes obs, reward f64[M, A], terminated u8[M], truncated u8[M]) — views of the pinned plane
+        ring, valid until PLANE_SLOTS - n_hist further steps have been made.  `np.asarray(obs)` / `obs.stacked()` materialises the
+        contiguous f32[M, n_hist*42] array (one host copy); `obs.planes` are the n_hist zero-copy [M, 42] views, oldest first."""
+        pos = self._plane_pos
+        if pos is None:
+            raise RuntimeError("call reset_host_planes() before step_host_planes()")
+        pos = (pos + 1) % self.PLANE_SLOTS
+        rc = self._L.cda_step_planes(self._h, action_block.data_ptr(), self._plane_ptrs[pos], self._plane_cell,
+                                     (1 if sync else 0) | (2 if market_major else 0), self._plane_stream)
+        if rc:
+            _native.check(rc)
+        self._plane_pos = pos
+        if self._status_flag[0]:
+            self._poll_status()
+        return (self._plane_stack(),) + self._plane_out[pos]
+
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""
         p = self._ensure_pinned()
@@ -462,6 +556,51 @@ class VecCDAEnv:
             nf = int(n[m].item())
             out["n_fills"] = nf
             out["fills"] = f[m, :min(nf, self.fill_capacity)].cpu().numpy()
+        return out
+
+    def dump_all(self, markets=None):
+        """Canonical dumps (same schema as dump()) of many markets from ONE checkpoint copy, parsed on the host with the layout
+        cda_state_layout() reports — what the full-size parity tests use (dump() costs ~20 launches per market)."""
+        lay = (ctypes.c_int32 * 8)()
+        _native.check(self._L.cda_state_layout(self._h, lay))
+        stride, off_acct, off_hist, off_pool, cap, A = (int(lay[i]) for i in range(6))
+        raw = self.state_dict()["state"].numpy().reshape(self.M, stride)
+        hdr = raw[:, :192].view(np.uint32)
+        acc = np.ascontiguousarray(raw[:, off_acct:off_acct + 60 * A])
+        i64 = acc[:, :48 * A].view(np.int64).reshape(self.M, 6, A)                  # cash hold cost nav prev max
+        pos = acc[:, 48 * A:52 * A].view(np.int32).astype(np.int64)
+        ntr = acc[:, 52 * A:56 * A].view(np.uint32).astype(np.int64)
+        ctr = acc[:, 56 * A:60 * A].view(np.uint32).astype(np.int64)
+        pool = np.ascontiguousarray(raw[:, off_pool:off_pool + 2 * 5 * cap * 4]).view(np.uint32).reshape(self.M, 2, cap // 32, 5, 32)
+        fills = counts = None
+        if self.fill_capacity:
+            f, n = self.fills()
+            fills, counts = f.cpu().numpy(), n.cpu().numpy()
+        out = {}
+        for m in (range(self.M) if markets is None else markets):
+            h = hdr[m]
+            d = {"time": int(h[0]), "next_order_id": int(h[1]), "t_step": int(h[3]), "last_price": int(np.int32(h[4])), "done_mask": int(h[6]),
+                 "status": int(h[7]), "best_bid": int(np.int32(h[40])), "best_ask": int(np.int32(h[41])),
+                 "rng": np.array([(int(h[13]) << 32) | int(h[12]), (int(h[15]) << 32) | int(h[14]), (int(h[17]) << 32) | int(h[16]),
+                                  (int(h[19]) << 32) | int(h[18]), int(h[10]), int(h[11])], dtype=np.uint64)}
+            for side, name in ((0, "bids"), (1, "asks")):
+                n = int(h[8 + side])
+                fl = pool[m, side].transpose(1, 0, 2).reshape(5, cap)[:, :n].astype(np.int64)   # field-major, live prefix
+                price, trader = fl[0] & 0xffffff, fl[0] >> 24
+                order = np.lexsort((fl[4], -price if side == 0 else price))                    # priority: price, then insertion seq
+                d[name] = np.stack([price, fl[1], trader, fl[2], fl[3]], axis=1)[order]
+                d[name + "_map"] = fl[2][np.argsort(fl[4], kind="stable")]
+            tape = bool(h[5] & 1)
+            lp = d["last_price"]
+            ap = np.abs(pos[m])
+            pv = np.where(pos[m] >= 0, ap * lp, 2 * i64[m, 2] - ap * lp) if tape else np.zeros(A, np.int64)
+            c = ctr[m]
+            d["accounts"] = np.stack([i64[m, 0], i64[m, 1], pv, i64[m, 2], i64[m, 3], i64[m, 4], i64[m, 5], pos[m], ntr[m], c & 0xfff,
+                                      (c >> 12) & 0xfff, (c >> 24) & 1, (c >> 25) & 1, (c >> 26) & 1], axis=1)
+            if fills is not None:
+                d["n_fills"] = int(counts[m])
+                d["fills"] = fills[m, :min(int(counts[m]), self.fill_capacity)]
+            out[m] = d
         return out
 
     # ------------------------------------------------------------------ checkpoint

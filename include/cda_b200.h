@@ -173,6 +173,22 @@ int cda_reset_host_window(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d
 int cda_window_bind(CdaEnv *env, float *h_window, int32_t slots, void *h_records, void *stream);
 int cda_step_window(CdaEnv *env, const int32_t *h_action_block, int32_t pos, int32_t flags);
 
+/* Host path with a DENSE PLANE RING — the end-to-end path that scales on a multi-GPU node.
+ * The sliding window above keeps every market's stack contiguous, at the price of scattering each step's output over M rows
+ * (one 168 + 8(A+1)-byte piece per 5 KB row: every market touches its own page and 3-4 partial cache lines of host memory).  On a
+ * node where 8 GPUs store into one host that is what saturates first (profiles/r03b_diag8_split.txt: the output leg grows from
+ * 12 to 57 us per step between 1 and 8 active GPUs while the input leg and the kernels do not change).  Here the host keeps
+ *     h_planes f32[slots][M][cell_words]   (pinned + mapped; cell_words even, >= 42 + 2A + 2, e.g. 64 = one aligned 256-B cell)
+ * and step t stores, for every market m, the newest snapshot followed by the result record { double reward[A]; uint8_t terminated,
+ * truncated; pad } into cell m of plane (t mod slots), zero-padded to the cell size: ONE contiguous, line-aligned M*cell region per
+ * step (two whole 128-B stores per market), no per-market pages, nothing is ever re-sent.  The stacked observation of market m is
+ * the n_hist cells  h_planes[(pos-n_hist+1 .. pos) mod slots][m][0..41]  (oldest first) — a strided [M][n_hist][42] view, not one
+ * contiguous row: a consumer that needs f32[M][168] contiguous makes that one copy itself (uploads can take the planes as they are).
+ * `h_plane` in cda_step_planes is the address of plane `pos` (h_planes + pos*M*cell_words); flags: CDA_WIN_SYNC, CDA_WIN_MARKET_MAJOR.
+ * cda_reset_planes resets the selected markets and (re)writes the n_hist planes ending at `pos` for every market. */
+int cda_step_planes(CdaEnv *env, const int32_t *h_action_block, float *h_plane, int32_t cell_words, int32_t flags, void *stream);
+int cda_reset_planes(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_planes, int32_t slots, int32_t cell_words, int32_t pos, void *stream);
+
 /* Fused T-step rollout with the on-device uniform random policy (the RandomRLModule /
  * CDA_rand.py workload: category U{0..8}, price U{0..9}, offset U{0..2}, mean U(-1,1), sigma U(0,1),
  * gym_continuousDoubleAuction/train/model/model_handler.py:38-78).  Policy draws come from a
@@ -222,6 +238,14 @@ int cda_dump_market(CdaEnv *env, int32_t market, int64_t *h_bids, int64_t *h_ask
 /* Device-state checkpoint (the reference has none). */
 size_t cda_state_bytes(const CdaEnv *env);
 int cda_save_state(CdaEnv *env, void *h_dst, void *stream);
+/* Layout of one market's block inside the checkpoint (bytes): out = { stride, off_accounts, off_snapshot_ring, off_order_pool,
+ * order_capacity, num_agents, n_hist, header_bytes }.  Market m starts at m * stride.  Header words (u32): 0 time, 1 next_order_id,
+ * 2 insertion counter, 3 t_step, 4 last_price, 5 flags (bit 0: tape non-empty), 6 done_mask, 7 status, 8 n_bid, 9 n_ask,
+ * 10 rng.has_uint32, 11 rng.uinteger, 12..19 PCG64 state_hi, state_lo, inc_hi, inc_lo (u64 each), 20..39 raw top-K prices, 40 best_bid,
+ * 41 best_ask.  Accounts: cash, hold, cost_basis, nav, prev_nav, max_nav (i64[A] each), position (i32[A]), num_trades (u32[A]),
+ * step counters (u32[A]: trades[0:12) passive[12:24) placed[24] rejected[25] is_pass[26]).  Order pool: u32[2 sides][cap/32][5][32],
+ * fields trader<<24|price, qty, order_id, timestamp, insertion seq; live orders are entries 0..n-1 of their side, unsorted. */
+int cda_state_layout(const CdaEnv *env, int32_t out[8]);
 int cda_load_state(CdaEnv *env, const void *h_src, void *stream);
 
 /* Introspection */

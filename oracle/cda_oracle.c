@@ -683,8 +683,30 @@ void orc_reset(void *h, const uint64_t *seeds, const uint8_t *mask, float *obs) 
  * orc_rollout runs T consecutive steps (actions [T][M][A]); markets are independent, so each
  * thread owns a contiguous slice of markets and runs all T steps on it without barriers — the
  * reference's best case (one env per process, N processes).  Outputs hold the LAST step. */
+/* Uniform random policy of the fused device rollout (cda_rollout_random): the shape of the reference's RandomRLModule
+ * (train/model/model_handler.py:38-78: category U{0..8}, price U{0..9}, price_offset U{0..2}, size_mean U(-1,1), size_sigma U(0,1)) drawn
+ * from a counter-based generator keyed by (policy_seed, market, t_step, agent) — NOT from the env stream, which stays numpy-exact.
+ * Restated here so that the device rollout has a CPU twin: same actions, then the ordinary market_step. */
+static uint64_t orc_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+static void orc_policy_actions(uint64_t seed, int m, uint32_t t_step, int A, int32_t *cat, float *mean, float *sigma, int32_t *pcode, int32_t *poff) {
+    for (int a = 0; a < A; ++a) {
+        const uint64_t h = orc_splitmix64(seed ^ orc_splitmix64(((uint64_t)m << 32) ^ ((uint64_t)t_step * 64ULL + (uint64_t)a)));
+        cat[a] = (int32_t)(((h & 0xffffu) * 9u) >> 16);
+        pcode[a] = (int32_t)((((h >> 16) & 0xffffu) * 10u) >> 16);
+        poff[a] = (int32_t)((((h >> 32) & 0xffffu) * 3u) >> 16);
+        const uint64_t h2 = orc_splitmix64(h);
+        mean[a] = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
+        sigma[a] = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
+    }
+}
 typedef struct {
     OrcEnv *e; int m0, m1, T;
+    int policy; uint64_t policy_seed;   /* policy != 0: actions come from orc_policy_actions instead of the arrays */
     const int32_t *cat; const float *mean; const float *sigma; const int32_t *pcode; const int32_t *poff;
     float *obs; double *reward; uint8_t *term; uint8_t *trunc;
 } OrcJob;
@@ -692,15 +714,23 @@ static void *orc_job_run(void *arg) {
     OrcJob *j = (OrcJob *)arg; OrcEnv *e = j->e;
     const int A = e->cfg.num_agents, W = e->cfg.n_hist * ORC_SNAP;
     const size_t MA = (size_t)e->M * A;
-    for (int t = 0; t < j->T; ++t)
-        for (int m = j->m0; m < j->m1; ++m) {
+    /* market-outer, time-inner: a market's state stays in the core's cache for all T steps (markets are independent, so the order
+     * of (t, m) pairs does not matter; this is the CPU path's best case and keeps it from slowing down as M grows) */
+    for (int m = j->m0; m < j->m1; ++m)
+        for (int t = 0; t < j->T; ++t) {
             size_t o = (size_t)t * MA + (size_t)m * A, r = (size_t)m * A;
+            if (j->policy) {
+                int32_t pc[ORC_MAX_AGENTS], pp[ORC_MAX_AGENTS], po[ORC_MAX_AGENTS]; float pm[ORC_MAX_AGENTS], ps[ORC_MAX_AGENTS];
+                orc_policy_actions(j->policy_seed, m, (uint32_t)e->mk[m].t_step, A, pc, pm, ps, pp, po);
+                market_step(e, &e->mk[m], pc, pm, ps, pp, po, j->obs + (size_t)m * W, j->reward + r, j->term + m, j->trunc + m);
+                continue;
+            }
             market_step(e, &e->mk[m], j->cat + o, j->mean + o, j->sigma + o, j->pcode + o, j->poff + o,
                         j->obs + (size_t)m * W, j->reward + r, j->term + m, j->trunc + m);
         }
     return NULL;
 }
-void orc_rollout(void *h, int T, const int32_t *cat, const float *mean, const float *sigma, const int32_t *pcode,
+static void orc_rollout_impl(void *h, int T, int policy, uint64_t policy_seed, const int32_t *cat, const float *mean, const float *sigma, const int32_t *pcode,
                  const int32_t *poff, float *obs, double *reward, uint8_t *term, uint8_t *trunc, int nthreads) {
     OrcEnv *e = (OrcEnv *)h;
     if (nthreads < 1) nthreads = 1;
@@ -709,7 +739,7 @@ void orc_rollout(void *h, int T, const int32_t *cat, const float *mean, const fl
     OrcJob jobs[256]; pthread_t th[256];
     for (int k = 0; k < nthreads; ++k) {
         OrcJob *j = &jobs[k];
-        j->e = e; j->T = T;
+        j->e = e; j->T = T; j->policy = policy; j->policy_seed = policy_seed;
         j->m0 = (int)((int64_t)e->M * k / nthreads); j->m1 = (int)((int64_t)e->M * (k + 1) / nthreads);
         j->cat = cat; j->mean = mean; j->sigma = sigma; j->pcode = pcode; j->poff = poff;
         j->obs = obs; j->reward = reward; j->term = term; j->trunc = trunc;
@@ -717,6 +747,14 @@ void orc_rollout(void *h, int T, const int32_t *cat, const float *mean, const fl
     if (nthreads == 1) { orc_job_run(&jobs[0]); return; }
     for (int k = 0; k < nthreads; ++k) pthread_create(&th[k], NULL, orc_job_run, &jobs[k]);
     for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+}
+void orc_rollout(void *h, int T, const int32_t *cat, const float *mean, const float *sigma, const int32_t *pcode,
+                 const int32_t *poff, float *obs, double *reward, uint8_t *term, uint8_t *trunc, int nthreads) {
+    orc_rollout_impl(h, T, 0, 0, cat, mean, sigma, pcode, poff, obs, reward, term, trunc, nthreads);
+}
+/* T steps of every market under the uniform random policy (CPU twin of cda_rollout_random); outputs hold the LAST step */
+void orc_rollout_random(void *h, int T, uint64_t policy_seed, float *obs, double *reward, uint8_t *term, uint8_t *trunc, int nthreads) {
+    orc_rollout_impl(h, T, 1, policy_seed, NULL, NULL, NULL, NULL, NULL, obs, reward, term, trunc, nthreads);
 }
 void orc_step(void *h, const int32_t *cat, const float *mean, const float *sigma, const int32_t *pcode,
               const int32_t *poff, float *obs, double *reward, uint8_t *term, uint8_t *trunc, int nthreads) {

@@ -140,6 +140,12 @@ class OracleEnv:
                             _p(self.reward), _p(self.terminated), _p(self.truncated), int(nthreads))
         return self.obs, self.reward, self.terminated, self.truncated
 
+    def rollout_random(self, num_steps, policy_seed=0, nthreads=1):
+        """CPU twin of VecCDAEnv.rollout_random: the same counter-based uniform policy, then the ordinary step."""
+        self._L.orc_rollout_random(ctypes.c_void_p(self._h), int(num_steps), ctypes.c_uint64(policy_seed), _p(self.obs), _p(self.reward),
+                                   _p(self.terminated), _p(self.truncated), int(nthreads))
+        return self.obs, self.reward, self.terminated, self.truncated
+
     # ---- canonical state dump (same schema as ref_runner.dump_reference and the GPU env) ----
     def dump(self, m=0):
         h = ctypes.c_void_p(self._h)

@@ -28,6 +28,11 @@ def test_reference_arm_line():
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"] == "cfg3_limit_market_4x4096" and line["gpu_launches"] == 0
+    # both arms print the SAME config object (the driver compares them): rebuild the GPU arm's from the same helper
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.workload_config("cfg3_limit_market_4x4096", 4, 64, 1, "limit_market")
+    assert cb["python_reference"]["value"] == 2181.0 and cb["python_reference"]["cores"] == 1
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -44,7 +49,8 @@ def test_committed_gpu_bench_line_has_the_contract_keys():
     assert line["metric"].split(" (")[0] in _baseline_metric() and line["unit"] == "env-steps/s"
     assert line["n_gpus"] == 1 and line["gpu_launches"] == line["steps"] > 0 and line["warmup"] >= 3
     assert line["config"]["workload"] == "cfg3_limit_market_4x4096" and "model" not in line["config"]
-    assert "flushed" in line["config"]["l2"] and line["config"]["status_bits"] == 0
+    det = line.get("details", line["config"])                                   # (r01 lines kept these under config)
+    assert "flushed" in line["config"]["l2"] and det["status_bits"] == 0
     e = line["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 * 4 * 20 and e["d2h_bytes_per_step"] > 4096 * 168
     assert e["value"] < line["value"]                                   # measured through the host API, not a copy of `value`

@@ -80,6 +80,78 @@ def test_config2_uniform_4x1024_bit_exact():
     env.close()
 
 
+def _full_size(A, M, T, mix, seed):
+    """BASELINE-size run: obs / reward / flags compared at EVERY step for EVERY market, and every market's book, order-map order,
+    ledger, fill log and RNG state at three points of the run (oracle on all host threads; GPU side parsed from one checkpoint)."""
+    cfg = base_cfg(num_of_agents=A)
+    env = cda.VecCDAEnv(cfg, num_markets=M, fill_capacity=32)
+    orc = OracleEnv(cfg, M)
+    seeds = np.arange(M, dtype=np.uint64) + np.uint64(seed)
+    assert np.array_equal(env.reset(seed=seeds).cpu().numpy(), orc.reset(seeds=seeds))
+    acts = make_actions(seed + 1, T, M, A, mix)
+    nthreads = os.cpu_count() or 8
+    for t in range(T):
+        og, rg, teg, trg = env.step(*[torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts])
+        oc, rc, tec, trc = orc.step(*[a[t] for a in acts], nthreads=nthreads)
+        assert np.abs(og.cpu().numpy().astype(np.float64) - oc).max() <= OBS_TOL, f"t={t}"
+        assert np.abs(rg.cpu().numpy() - rc).max() <= REW_TOL, f"t={t}"
+        assert np.array_equal(teg.cpu().numpy(), tec) and np.array_equal(trg.cpu().numpy(), trc), f"t={t}"
+        if t in (T // 3, 2 * T // 3, T - 1):
+            dumps = env.dump_all()
+            for m in range(M):
+                assert_dump_equal(dumps[m], orc.dump(m), ctx=f"t={t} m={m}")
+    assert (env.status().cpu().numpy() == 0).all()
+    env.close()
+
+
+def test_config3_full_size_4x4096_limit_market_every_market():
+    """BASELINE config 3 at its full size (it was only checked at 256 markets)."""
+    _full_size(4, 4096, 96, "limit_market", 1000)
+
+
+def test_config4_full_size_8x8192_modify_heavy_every_market():
+    """BASELINE config 4 at its full size."""
+    _full_size(8, 8192, 64, "modify_heavy", 3000)
+
+
+def test_dump_all_equals_dump():
+    """dump_all() (host-side parse of one checkpoint through cda_state_layout) == dump() (per-field device gathers)."""
+    cfg = base_cfg()
+    env = cda.VecCDAEnv(cfg, num_markets=24, fill_capacity=32)
+    env.reset(seed=77)
+    acts = make_actions(5, 60, 24, 4, "uniform")
+    for t in range(60):
+        env.step(*[torch.from_numpy(np.ascontiguousarray(a[t])).cuda() for a in acts])
+    dumps = env.dump_all()
+    for m in range(24):
+        assert_dump_equal(dumps[m], env.dump(m), ctx=f"m={m}")
+        assert dumps[m]["status"] == 0
+    env.close()
+
+
+@pytest.mark.parametrize("A,M,T", [(4, 1024, 200), (8, 256, 120), (3, 64, 90)])
+def test_fused_random_rollout_equals_oracle_policy_twin(A, M, T):
+    """cda_rollout_random (T steps in ONE launch, on-device uniform policy) against the oracle's twin of that policy stream
+    (oracle/cda_oracle.c orc_rollout_random): last-step obs / reward / flags and every market's book, ledger and RNG state."""
+    cfg = base_cfg(num_of_agents=A)
+    env = cda.VecCDAEnv(cfg, num_markets=M)
+    orc = OracleEnv(cfg, M)
+    seeds = np.arange(M, dtype=np.uint64) + np.uint64(4242)
+    env.reset(seed=seeds); orc.reset(seeds=seeds)
+    done = 0
+    for chunk in (1, 7, T - 8):                                   # launches of different lengths continue one trajectory
+        og, rg, teg, trg = env.rollout_random(chunk, policy_seed=99)
+        oc, rc, tec, trc = orc.rollout_random(chunk, policy_seed=99, nthreads=os.cpu_count() or 8)
+        done += chunk
+        assert np.abs(og.cpu().numpy().astype(np.float64) - oc).max() <= OBS_TOL, f"after {done} steps"
+        assert np.abs(rg.cpu().numpy() - rc).max() <= REW_TOL
+        assert np.array_equal(teg.cpu().numpy(), tec) and np.array_equal(trg.cpu().numpy(), trc)
+        dumps = env.dump_all()
+        for m in range(M):
+            assert_dump_equal(dumps[m], orc.dump(m), ctx=f"after {done} steps, m={m}", fills=False)
+    env.close()
+
+
 def test_uniform_small_every_step_dump():
     run_pair(base_cfg(), M=8, T=150, mix="uniform", seed=11, dump_every=1, dump_markets=range(8))
 
@@ -267,6 +339,41 @@ def test_host_window_view_equals_stacked_obs_across_wraps_and_masked_reset(n_his
         seen_trunc |= bool(tr2.any())
         prev = o1.copy()
     assert seen_trunc or T < 50
+    assert (e2.status().cpu().numpy() == 0).all()
+    e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("n_hist,A,market_major,cell", [(4, 4, True, 64), (4, 4, False, 52), (1, 4, True, 64), (6, 8, True, 64), (3, 24, True, 0), (4, 6, True, 64)])
+def test_host_planes_equal_stacked_obs_across_ring_wraps_and_masked_reset(n_hist, A, market_major, cell):
+    """cda_step_planes stores, per step, every market's newest snapshot + result record into ONE dense plane of a pinned ring;
+    the n_hist most recent planes must equal the ordinary host path's stacked observation bit for bit (np.asarray(obs), obs[m],
+    obs[m, e]) and the record views its reward / flags — across ring wraps, per-market resets and truncation."""
+    cfg = base_cfg(n_hist=n_hist, num_of_agents=A, max_step=50)
+    M, T = 96, 70
+    cda.VecCDAEnv.PLANE_SLOTS, cda.VecCDAEnv.PLANE_CELL_WORDS = max(8, n_hist + 2), cell or 64
+    e1 = cda.VecCDAEnv(cfg, num_markets=M); e2 = cda.VecCDAEnv(cfg, num_markets=M)
+    cda.VecCDAEnv.PLANE_SLOTS, cda.VecCDAEnv.PLANE_CELL_WORDS = 8, 64
+    e2.PLANE_SLOTS, e2.PLANE_CELL_WORDS = max(8, n_hist + 2), cell or 64
+    o1 = e1.reset(seed=11).cpu().numpy(); o2 = e2.reset_host_planes(seed=11)
+    assert o2.shape == (M, n_hist * 42) and np.array_equal(o1, np.asarray(o2))
+    blk = _pinned_block(make_actions(6, T, M, A, "uniform"), T, M, A)
+    blk_mm = blk.permute(0, 2, 1, 3).contiguous().pin_memory()
+    seen_trunc = False
+    for t in range(T):
+        if t in (7, 28, 29, 60):
+            mask = (np.arange(M) % 3 == t % 3).astype(np.uint8)
+            a = e1.reset(seed=None, mask=mask).cpu().numpy(); b = np.asarray(e2.reset_host_planes(seed=None, mask=mask))
+            assert np.array_equal(a[mask == 1], b[mask == 1])
+            if t > 0:
+                assert np.array_equal(prev[mask == 0], b[mask == 0])
+        o1, r1, te1, tr1 = e1.step_host_block(blk[t])
+        o2, r2, te2, tr2 = e2.step_host_planes(blk_mm[t] if market_major else blk[t], market_major=market_major)
+        assert np.array_equal(o1, np.asarray(o2)), f"t={t}"
+        assert np.array_equal(o1[5], o2[5]) and o1[M - 1, n_hist * 42 - 1] == o2[M - 1, n_hist * 42 - 1] and o1[3, 0] == o2[3, 0]
+        assert r2.shape == (M, A) and np.array_equal(r1, r2) and np.array_equal(te1, te2) and np.array_equal(tr1, tr2), f"t={t}"
+        seen_trunc |= bool(tr2.any())
+        prev = o1.copy()
+    assert seen_trunc
     assert (e2.status().cpu().numpy() == 0).all()
     e1.close(); e2.close()
 

@@ -82,8 +82,8 @@ def main():
     M, A, T = 4096, 4, 300
     acts = make_actions(7 + rank, T, M, A, "limit_market")
 
-    def make_env():
-        env = cda.VecCDAEnv(dict(num_of_agents=A, max_step=1 << 30), num_markets=M, device=local)
+    def make_env(planes=False):
+        env = cda.VecCDAEnv(dict(num_of_agents=A, max_step=1 << 30), num_markets=M, device=local, status_policy="ignore")   # (the no-input timing mode replays one action block: books overflow)
         env.reset(seed=np.arange(M, dtype=np.uint64) + np.uint64(1000 + rank * M))
         dev = [torch.from_numpy(a).cuda() for a in acts]
         for i in range(200):
@@ -93,7 +93,10 @@ def main():
             pin[:, :, f].copy_(torch.from_numpy(acts[f]))
         for f in (1, 2):
             pin[:, :, f].view(torch.float32).copy_(torch.from_numpy(acts[f]))
-        env.attach_host_window()
+        if planes:
+            env.attach_host_planes()
+        else:
+            env.attach_host_window()
         torch.cuda.synchronize()
         return env, dev, [pin[i] for i in range(T)]
 
@@ -117,6 +120,26 @@ def main():
         for i in range(K):
             env.step_host_window(blocks[(20 + i) % T], market_major=True, sync=(i % 50 == 49))
         torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / K * 1e6
+
+    def t_planes(env, dev, blocks):
+        for i in range(20):
+            env.step_host_planes(blocks[i])
+        t0 = time.perf_counter()
+        for i in range(K):
+            o, r, te, tr = env.step_host_planes(blocks[(20 + i) % T])
+            _ = float(r[0, 0]) + float(o[M - 1, env.W - 1])
+        return (time.perf_counter() - t0) / K * 1e6
+
+    def t_planes_stacked(env, dev, blocks):      # ... plus the consumer's copy into a contiguous [M, 168] array
+        buf = np.empty((M, env.W), np.float32)
+        for i in range(20):
+            env.step_host_planes(blocks[i])
+        t0 = time.perf_counter()
+        for i in range(K):
+            o, r, te, tr = env.step_host_planes(blocks[(20 + i) % T])
+            o.stacked(out=buf)
+            _ = float(r[0, 0]) + float(buf[M - 1, env.W - 1])
         return (time.perf_counter() - t0) / K * 1e6
 
     def t_dev_sync(env, dev, blocks):
@@ -149,24 +172,74 @@ def main():
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         results[(n, name)] = float(v[0])
         if rank == 0:
-            print(f"n_active={n:<2d} {name:<10s} {float(v[0]):8.1f} us/step  -> {n * M / float(v[0]):7.1f} M env-steps/s aggregate", flush=True)
+            print(f"n_active={n:<2d} {name:<16s} {float(v[0]):8.1f} us/step  -> {n * M / float(v[0]):7.1f} M env-steps/s aggregate", flush=True)
 
-    ns = [n for n in (1, 2, 4, 8) if n <= world]
-    for n in ns:
-        for name, fn in (("full", t_full), ("nosync", t_nosync), ("dev_sync", t_dev_sync), ("full_smi", t_full_smi)):
-            run_variant(name, fn, (env, dev, blocks), n)
-    # NUMA-local variant: pin to the GPU's node, re-create env + pinned buffers
-    env.close()
-    cpus = node_cpus(node) if node >= 0 else None
-    if cpus:
-        os.sched_setaffinity(0, set(cpus) & set(aff) or set(aff))
-    env2 = make_env()
-    for n in ns:
-        run_variant("full_numa", t_full, env2, n)
-        run_variant("dev_sync_numa", t_dev_sync, env2, n)
-    if rank == 0:
-        print("== efficiency of `full` vs n=1:", {n: round(results[(1, "full")] / results[(n, "full")], 3) for n in ns})
-        print("== efficiency of `full_numa` vs n=1:", {n: round(results[(1, "full_numa")] / results[(n, "full_numa")], 3) for n in ns})
+    L = env._L
+    quick = os.environ.get("DIAG_SPLIT", "0") == "1"
+    ns = [n for n in ((1, 8) if quick else (1, 2, 4, 8)) if n <= world]
+
+    def with_mode(mode, fn):
+        def g(*a):
+            L.cda_debug_set_window_mode(mode)
+            try:
+                return fn(*a)
+            finally:
+                L.cda_debug_set_window_mode(0)
+        return g
+
+    if os.environ.get("DIAG_LAYOUT", "0") == "1":
+        # output layout: window row pitch (slots) vs the dense plane ring
+        ns = [n for n in (1, 2, 4, 8) if n <= world]
+        for n in ns:
+            run_variant("window32", t_full, (env, dev, blocks), n)
+        env.close()
+        for slots in (16, 8):
+            cda.VecCDAEnv.WINDOW_SLOTS = slots
+            e2 = make_env()
+            for n in ns:
+                run_variant(f"window{slots}", t_full, e2, n)
+            e2[0].close()
+        cda.VecCDAEnv.WINDOW_SLOTS = 32
+        for cell in (64, 52):
+            cda.VecCDAEnv.PLANE_CELL_WORDS = cell
+            e2 = make_env(planes=True)
+            for n in ns:
+                run_variant(f"planes{cell}", t_planes, e2, n)
+                if cell == 64:
+                    run_variant("planes64+copy", t_planes_stacked, e2, n)
+            e2[0].close()
+    elif quick:
+        # which direction is the limiter?  (timing modes of the window path: bit 0 = no input transfer, bit 1 = no output transfer)
+        for n in ns:
+            for name, fn in (("full", t_full), ("no_in", with_mode(1, t_full)), ("no_out", with_mode(2, t_full)), ("no_io", with_mode(3, t_full)),
+                             ("nosync", t_nosync), ("nosync_no_in", with_mode(1, t_nosync)), ("nosync_no_out", with_mode(2, t_nosync))):
+                run_variant(name, fn, (env, dev, blocks), n)
+        env.close()
+        for tag, ev in (("in_dma", {"CDA_ZEROCOPY_IN": "0"}), ("out_dma", {"CDA_ZEROCOPY": "0"}), ("io_dma", {"CDA_ZEROCOPY_IN": "0", "CDA_ZEROCOPY": "0"})):
+            os.environ.update(ev)
+            e2 = make_env()
+            for k in ev:
+                del os.environ[k]
+            for n in ns:
+                run_variant(tag, t_full, e2, n)
+                run_variant(tag + "_nosync", t_nosync, e2, n)
+            e2[0].close()
+    else:
+        for n in ns:
+            for name, fn in (("full", t_full), ("nosync", t_nosync), ("dev_sync", t_dev_sync), ("full_smi", t_full_smi)):
+                run_variant(name, fn, (env, dev, blocks), n)
+        # NUMA-local variant: pin to the GPU's node, re-create env + pinned buffers
+        env.close()
+        cpus = node_cpus(node) if node >= 0 else None
+        if cpus:
+            os.sched_setaffinity(0, set(cpus) & set(aff) or set(aff))
+        env2 = make_env()
+        for n in ns:
+            run_variant("full_numa", t_full, env2, n)
+            run_variant("dev_sync_numa", t_dev_sync, env2, n)
+        if rank == 0:
+            print("== efficiency of `full` vs n=1:", {n: round(results[(1, "full")] / results[(n, "full")], 3) for n in ns})
+            print("== efficiency of `full_numa` vs n=1:", {n: round(results[(1, "full_numa")] / results[(n, "full_numa")], 3) for n in ns})
     dist.barrier()
     dist.destroy_process_group()
 
