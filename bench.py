@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--ref-inner", type=int, default=64, help="env steps per reference-arm bench step (amortises the thread start-up of the CPU path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--decimal-ledger", type=int, default=0, help="0 (VecCDAEnv's default): exact int64 ledger; 1: also carry the reference's Decimal(28) residues "
+                    "(deferred twin: decides exact-equality ties like the reference; identical results on this workload)")
     ap.add_argument("--allgather", action="store_true", help="N>1: also time an NCCL all-gather of obs/reward per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -218,7 +220,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    env = cda.VecCDAEnv(env_config(A), num_markets=M, device=local)
+    env = cda.VecCDAEnv(env_config(A), num_markets=M, device=local, decimal_ledger=bool(args.decimal_ledger))
     # markets are keyed by GLOBAL market id so results do not depend on the GPU count
     gseeds = np.arange(M, dtype=np.uint64) + np.uint64(1000 + rank * M)
     env.reset(seed=gseeds)
@@ -431,7 +433,7 @@ def main():
         "dtype": "int64 ledger / int32 book / f64 obs+reward math, f32 obs out", "data": "synthetic",
         "impl": "cda_b200",
         "config": workload_config(args.workload, A, M, world, mix),
-        "details": {"order_capacity": env.order_capacity, "prewarm_steps": args.prewarm,
+        "details": {"order_capacity": env.order_capacity, "prewarm_steps": args.prewarm, "decimal_ledger": bool(args.decimal_ledger),
                     "l2": "flushed between timed steps (256 MiB write)" if not args.no_l2_flush else "not flushed",
                     "rng": "numpy-exact PCG64+ziggurat on device", "agent_steps_per_s": value * A, "status_bits": status_bits,
                     "value_l2_hot": world * M / (hot_ms * 1e-3)},

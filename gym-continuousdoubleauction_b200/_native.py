@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("CDA_B200_LIB") or os.path.join(CSRC, "libcda_b200.so")   # CDA_B200_LIB: a variant build (tools/variant_bench.py)
-SOURCES = ("cda_b200.cu", "cda_kernels.cuh", "cda_zig_tables.cuh", "cda_dec128.cuh")
+SOURCES = ("cda_b200.cu", "cda_kernels.cuh", "cda_zig_tables.cuh", "cda_dec128.cuh", "cda_twin.cuh")
 HEADER = os.path.join(_ROOT, "include", "cda_b200.h")
 TESTING_HEADER = os.path.join(_ROOT, "include", "cda_b200_testing.h")   # test / measurement entries (not product ABI)
 
@@ -31,7 +31,7 @@ class CdaConfig(ctypes.Structure):
         ("order_capacity", ctypes.c_int32), ("fill_capacity", ctypes.c_int32),
         ("order_penalty", ctypes.c_double), ("trade_penalty", ctypes.c_double),
         ("drawdown_penalty", ctypes.c_double), ("passive_bonus", ctypes.c_double),
-        ("loss_multiplier", ctypes.c_double),
+        ("loss_multiplier", ctypes.c_double), ("decimal_ledger", ctypes.c_int32), ("reserved_", ctypes.c_int32),
     ]
 
 
@@ -48,9 +48,9 @@ EXPORTS = (
     "cda_gather_create", "cda_gather_connect", "cda_step_gather", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_record_bytes", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
-    "cda_seed_to_pcg64", "cda_state_layout", "cda_gather_parity", "cda_status_flag", "cda_status_flag_clear",
+    "cda_seed_to_pcg64", "cda_state_layout", "cda_twin_sync", "cda_gather_parity", "cda_status_flag", "cda_status_flag_clear",
 )
-TESTING_EXPORTS = ("cda_debug_phase_buffer", "cda_debug_dec_op", "cda_debug_dec_op_device", "cda_debug_set_window_mode")
+TESTING_EXPORTS = ("cda_debug_phase_buffer", "cda_debug_dec_op", "cda_debug_dec_op_device", "cda_debug_set_window_mode", "cda_debug_restart_count")
 
 
 def needs_build():
@@ -133,10 +133,12 @@ def lib():
     sig("cda_strerror", [i32], ctypes.c_char_p)
     sig("cda_seed_to_pcg64", [u64, ctypes.POINTER(u64)])
     sig("cda_state_layout", [vp, ctypes.POINTER(i32)])
+    sig("cda_twin_sync", [vp, vp, vp])
     sig("cda_gather_parity", [vp], i32)
     sig("cda_status_flag", [vp], ctypes.POINTER(ctypes.c_uint32))
     sig("cda_status_flag_clear", [vp])
     sig("cda_debug_set_window_mode", [i32], None)
+    sig("cda_debug_restart_count", None, i64)
     sig("cda_debug_phase_buffer", None, ctypes.c_void_p)
     sig("cda_debug_dec_op", [i32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, ctypes.POINTER(i32)])
     sig("cda_debug_dec_op_device", [i32, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, i32, ctypes.POINTER(i32)])

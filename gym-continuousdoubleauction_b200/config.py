@@ -36,7 +36,7 @@ def env_defaults():
 def resolve(config):
     """Merge a (possibly partial) env config dict over the defaults; validate like the reference."""
     cfg = env_defaults()
-    unknown = [k for k in (config or {}) if k not in cfg and k not in ("num_markets", "device", "order_capacity", "fill_capacity")]
+    unknown = [k for k in (config or {}) if k not in cfg and k not in ("num_markets", "device", "order_capacity", "fill_capacity", "decimal_ledger")]
     cfg.update(config or {})
     if float(cfg["tick_size"]) != int(cfg["tick_size"]) or int(cfg["tick_size"]) < 1:
         raise ValueError("cda_b200 supports integral tick_size >= 1 only "

@@ -61,6 +61,7 @@ struct CdaEnv {
     double zc_fraction;        // share of the obs rows the kernel writes straight to host memory (the rest is DMA'd)   // same for the action block (kernel reads pinned host memory)
     long long launches;
     unsigned *status_host, *status_dev;   // one mapped pinned word: any step kernel that ends with a non-zero sticky market status stores 1 here
+    int twin_steps, twin_every;            // decimal_ledger: steps since the last journal flush; flush cadence (CDA_TWIN_FLUSH_STEPS, $CDA_TWIN_FLUSH overrides: measurements)
     int g_parity;                          // fused all-gather: half of the double-buffered gather region the NEXT cda_step_gather writes
     size_t smem_bytes;
     int host_ctas, dev_ctas;   // resident CTAs per SM for the host paths / the device path (0 = as many as fit)
@@ -78,7 +79,7 @@ static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStre
     // per-warp tiles, then the CTA's action tile u32[5][WARPS][A] and its mbarrier
     //     then one 16-B aligned account tile (60*A bytes) per warp
     size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
-                  (size_t)CDA_WARPS_PER_CTA * (((15 * e->dev.A + 3) & ~3) * 4);
+                  (size_t)CDA_WARPS_PER_CTA * (16 * e->dev.A * 4);
     if (ctas_per_sm > 0) {
         const size_t per_sm = 233472, pad = per_sm / (size_t)(ctas_per_sm + 1) - 1024 + 256;   // ctas_per_sm + 1 CTAs no longer fit
         if (pad > smem && pad <= 232448 - 1024) smem = pad;
@@ -180,9 +181,16 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     d.c_passive = cfg->passive_bonus; d.c_loss = cfg->loss_multiplier;
     d.W = cfg->n_hist * CDA_SNAPSHOT_DIM;
     d.off_acct = CDA_HDR_BYTES;
-    d.off_hist = align_up(d.off_acct + (unsigned)d.A * 60u, 16);
+    d.off_hist = align_up(d.off_acct + (unsigned)d.A * 64u, 16);
     d.off_pool = align_up(d.off_hist + (unsigned)d.W * 4u, 16);
-    d.stride = align_up(d.off_pool + 2u * CDA_POOL_FIELDS * (unsigned)cap * 4u, 128);
+    unsigned end = d.off_pool + 2u * CDA_POOL_FIELDS * (unsigned)cap * 4u;
+    d.dec = cfg->decimal_ledger ? 1 : 0;
+    if (d.dec) {   // Decimal twins + event journals behind the pool (cda_twin.cuh): 64 + 8 * CDA_JRN_E bytes per agent
+        d.off_twin = align_up(end, 64);
+        d.off_jrn = d.off_twin + (unsigned)d.A * CDA_TWIN_BYTES;
+        end = d.off_jrn + (unsigned)d.A * CDA_JRN_E * 8u;
+    }
+    d.stride = align_up(end, 128);
     e->state_bytes = (size_t)d.stride * (size_t)num_markets;
     const size_t MA = (size_t)num_markets * d.A;
     cudaError_t err = cudaMalloc(&e->state, e->state_bytes);
@@ -232,6 +240,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
         const char *hcs = getenv("CDA_HOST_CTAS"), *dcs = getenv("CDA_DEV_CTAS");
         e->host_ctas = hcs ? atoi(hcs) : 0;
         e->dev_ctas = dcs ? atoi(dcs) : 0;
+        const char *tf = getenv("CDA_TWIN_FLUSH");
+        e->twin_every = tf && atoi(tf) > 0 ? atoi(tf) : CDA_TWIN_FLUSH_STEPS;
         const char *zf = getenv("CDA_ZC_FRACTION");
         e->zc_fraction = zf ? atof(zf) : 0.25;   // SM stores to host reach ~25 GB/s but overlap the kernel; the copy engine does ~53 GB/s after it   // measured: kernel reading the pinned action block beats a separate H2D copy by ~10 us
     }
@@ -265,6 +275,14 @@ int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *
     return CDA_OK;
 }
 
+static int twin_flush(CdaEnv *e, cudaStream_t st) {
+    const int n = e->M * e->dev.A, threads = 128;
+    cda_twin_flush_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(e->dev, e->state, e->M, e->status_dev);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    e->twin_steps = 0;
+    return CDA_OK;
+}
 static unsigned long long *g_prof = nullptr;
 static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st, bool host_path = false) {
     p.cfg = e->dev; p.state = e->state; p.M = e->M;
@@ -279,11 +297,18 @@ static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st, bool host_p
     p.fills = e->fills; p.fill_counts = e->fill_counts;
     // TMA staging of the action rows: rows of A 4-byte words must be multiples of 16 B and the arrays 16-B aligned
     static const int dbg_acct_tma = getenv("CDA_ACCT_TMA") ? atoi(getenv("CDA_ACCT_TMA")) : 1;
-    p.acct_tma = dbg_acct_tma && (e->dev.A % 4) == 0;
+    p.acct_tma = dbg_acct_tma;   // the account block is 64 * A bytes: a multiple of 16 for every A
     p.act_tma = e->act_tma && p.num_steps == 0 && (e->dev.A % 4) == 0 &&
                 (((uintptr_t)p.cat | (uintptr_t)p.mean | (uintptr_t)p.sigma | (uintptr_t)p.pcode | (uintptr_t)p.poff) & 15) == 0;
     CUDA_TRY(launch_step_any(e, p, st, host_path ? e->host_ctas : e->dev_ctas));
     e->launches++;
+    if (e->dev.dec) {   // deferred Decimal twin: replay the event journals every CDA_TWIN_FLUSH_STEPS steps (one thread per agent, same stream)
+        e->twin_steps += p.num_steps > 0 ? p.num_steps : 1;
+        if (e->twin_steps >= e->twin_every) {
+            int rc = twin_flush(e, st);
+            if (rc) return rc;
+        }
+    }
     return CDA_OK;
 }
 
@@ -637,8 +662,17 @@ int cda_rollout_random(CdaEnv *e, int32_t num_steps, uint64_t policy_seed, float
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
     p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated;
-    p.num_steps = num_steps; p.policy_seed = policy_seed;
-    return step_common(e, p, (cudaStream_t)stream);
+    p.policy_seed = policy_seed;
+    // decimal_ledger: the journals are flushed between launches, so a long rollout runs as chunks of at most CDA_TWIN_FLUSH_STEPS steps
+    const int chunk = e->dev.dec ? std::min(e->twin_every, CDA_TWIN_FLUSH_STEPS) : num_steps;
+    for (int done = 0; done < num_steps;) {
+        CdaStepParams q = p;
+        q.num_steps = std::min(chunk, num_steps - done);
+        int rc = step_common(e, q, (cudaStream_t)stream);
+        if (rc) return rc;
+        done += q.num_steps;
+    }
+    return CDA_OK;
 }
 
 static size_t cda_gather_half_bytes_(int M, int world, int W, int A) {
@@ -771,6 +805,11 @@ int cda_dump_market(CdaEnv *e, int32_t market, int64_t *h_bids, int64_t *h_asks,
 }
 
 void cda_debug_set_window_mode(int32_t mode) { g_dbg_window = mode; }
+int64_t cda_debug_restart_count(void) {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, cda_debug_restarts, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (int64_t)v;
+}
 // debug builds (-DCDA_PROFILE_PHASES): returns the device buffer of 16 per-phase cycle sums (allocated on first call)
 unsigned long long *cda_debug_phase_buffer(void) {
 #ifdef CDA_PROFILE_PHASES
@@ -778,11 +817,25 @@ unsigned long long *cda_debug_phase_buffer(void) {
 #endif
     return g_prof;
 }
+int cda_twin_sync(CdaEnv *e, int64_t *d_out, void *stream) {
+    if (!e) return CDA_EINVAL;
+    if (!e->dev.dec) return d_out ? CDA_EINVAL : CDA_OK;
+    DevGuard guard(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = twin_flush(e, st);
+    if (rc || !d_out) return rc;
+    const int n = e->M * e->dev.A, threads = 128;
+    cda_twin_dump_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(e->dev, e->state, e->M, (long long *)d_out);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return CDA_OK;
+}
 size_t cda_state_bytes(const CdaEnv *e) { return e ? e->state_bytes : 0; }
-int cda_state_layout(const CdaEnv *e, int32_t out[8]) {
+int cda_state_layout(const CdaEnv *e, int32_t out[12]) {
     if (!e || !out) return CDA_EINVAL;
     out[0] = (int32_t)e->dev.stride; out[1] = (int32_t)e->dev.off_acct; out[2] = (int32_t)e->dev.off_hist; out[3] = (int32_t)e->dev.off_pool;
     out[4] = e->dev.cap; out[5] = e->dev.A; out[6] = e->dev.n_hist; out[7] = CDA_HDR_BYTES;
+    out[8] = e->dev.dec; out[9] = (int32_t)e->dev.off_twin; out[10] = (int32_t)e->dev.off_jrn; out[11] = CDA_JRN_E;
     return CDA_OK;
 }
 int cda_save_state(CdaEnv *e, void *h_dst, void *stream) {

@@ -25,10 +25,10 @@ struct CdaDec { cda_u128 c; int exp; int sign; };   // c == 0 <=> zero (sign 0)
 #define CDA_DEC_P 28
 #if defined(__CUDACC__)
 #define CDA_HD __host__ __device__ __forceinline__
-#define CDA_TAB __device__ const
+#define CDA_HDN __host__ __device__ __noinline__ inline   /* the arithmetic proper: real calls, or one replay is 50 k instructions */
 #else
 #define CDA_HD inline
-#define CDA_TAB static const
+#define CDA_HDN inline
 #endif
 
 #define CDA_POW10_ROWS \
@@ -76,6 +76,34 @@ static const unsigned long long cda_pow10_host[39][2] = { CDA_POW10_ROWS };
 __device__ const unsigned long long cda_pow10_dev[39][2] = { CDA_POW10_ROWS };
 #endif
 
+// 10^k for k <= 19, normalised (shifted left until its top bit is set), with the Moller-Granlund reciprocal floor((2^128 - 1) / d) - 2^64
+// of the normalised divisor and the shift: a 128-bit / 10^k quotient is then two multiply-high steps instead of a long division
+#define CDA_MG10_ROWS \
+    {0x8000000000000000ULL, 0xffffffffffffffffULL, 63ULL}, \
+    {0xa000000000000000ULL, 0x9999999999999999ULL, 60ULL}, \
+    {0xc800000000000000ULL, 0x47ae147ae147ae14ULL, 57ULL}, \
+    {0xfa00000000000000ULL, 0x0624dd2f1a9fbe76ULL, 54ULL}, \
+    {0x9c40000000000000ULL, 0xa36e2eb1c432ca57ULL, 50ULL}, \
+    {0xc350000000000000ULL, 0x4f8b588e368f0846ULL, 47ULL}, \
+    {0xf424000000000000ULL, 0x0c6f7a0b5ed8d36bULL, 44ULL}, \
+    {0x9896800000000000ULL, 0xad7f29abcaf48578ULL, 40ULL}, \
+    {0xbebc200000000000ULL, 0x5798ee2308c39df9ULL, 37ULL}, \
+    {0xee6b280000000000ULL, 0x12e0be826d694b2eULL, 34ULL}, \
+    {0x9502f90000000000ULL, 0xb7cdfd9d7bdbab7dULL, 30ULL}, \
+    {0xba43b74000000000ULL, 0x5fd7fe17964955fdULL, 27ULL}, \
+    {0xe8d4a51000000000ULL, 0x19799812dea11197ULL, 24ULL}, \
+    {0x9184e72a00000000ULL, 0xc25c268497681c26ULL, 20ULL}, \
+    {0xb5e620f480000000ULL, 0x6849b86a12b9b01eULL, 17ULL}, \
+    {0xe35fa931a0000000ULL, 0x203af9ee756159b2ULL, 14ULL}, \
+    {0x8e1bc9bf04000000ULL, 0xcd2b297d889bc2b6ULL, 10ULL}, \
+    {0xb1a2bc2ec5000000ULL, 0x70ef54646d496892ULL, 7ULL}, \
+    {0xde0b6b3a76400000ULL, 0x2725dd1d243aba0eULL, 4ULL}, \
+    {0x8ac7230489e80000ULL, 0xd83c94fb6d2ac34aULL, 0ULL}
+static const unsigned long long cda_mg10_host[20][3] = { CDA_MG10_ROWS };
+#if defined(__CUDACC__)
+__device__ const unsigned long long cda_mg10_dev[20][3] = { CDA_MG10_ROWS };
+#endif
+
 CDA_HD cda_u128 cda_dec_pow10(int k) {               // 0 <= k <= 38
 #if defined(__CUDA_ARCH__)
     return ((cda_u128)cda_pow10_dev[k][0] << 64) | cda_pow10_dev[k][1];
@@ -113,7 +141,7 @@ CDA_HD unsigned cda_div64_32(unsigned long long n, unsigned d, unsigned *rem) {
 #endif
 }
 // x / d, remainder in *rem, for 0 < d < 2^32
-CDA_HD cda_u128 cda_u128_divmod_small(cda_u128 x, unsigned d, unsigned *rem) {
+CDA_HDN cda_u128 cda_u128_divmod_small(cda_u128 x, unsigned d, unsigned *rem) {
     const unsigned long long hi = (unsigned long long)(x >> 64), lo = (unsigned long long)x;
     unsigned r = 0;
     const unsigned q3 = cda_div64_32(hi >> 32, d, &r);
@@ -123,17 +151,48 @@ CDA_HD cda_u128 cda_u128_divmod_small(cda_u128 x, unsigned d, unsigned *rem) {
     *rem = r;
     return ((cda_u128)(((unsigned long long)q3 << 32) | q2) << 64) | (((unsigned long long)q1 << 32) | q0);
 }
-// x / 10^k for 0 <= k <= 38 (chunks of nine digits); the remainder is x - q * 10^k (the caller multiplies back: exact and cheap)
-CDA_HD cda_u128 cda_u128_div_pow10(cda_u128 x, int k) {
-    unsigned r;
-    while (k >= 9) { x = cda_u128_divmod_small(x, 1000000000u, &r); k -= 9; }
-    if (k > 0) x = cda_u128_divmod_small(x, (unsigned)cda_dec_pow10(k), &r);
+CDA_HD unsigned long long cda_umulhi64(unsigned long long a, unsigned long long b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (unsigned long long)(((cda_u128)a * b) >> 64);
+#endif
+}
+// (u1 * 2^64 + u0) / d for a normalised d (top bit set), u1 < d, with v = floor((2^128 - 1) / d) - 2^64 (Moller & Granlund 2011, alg. 4)
+CDA_HD unsigned long long cda_div2by1(unsigned long long u1, unsigned long long u0, unsigned long long d, unsigned long long v, unsigned long long *rem) {
+    unsigned long long q0 = v * u1, q1 = cda_umulhi64(v, u1);
+    const unsigned long long s0 = q0 + u0;
+    q1 += u1 + (s0 < q0 ? 1ULL : 0ULL) + 1ULL;
+    q0 = s0;
+    unsigned long long r = u0 - q1 * d;
+    if (r > q0) { --q1; r += d; }
+    if (r >= d) { ++q1; r -= d; }
+    *rem = r;
+    return q1;
+}
+// x / 10^k for 0 <= k <= 38; the remainder is x - q * 10^k (the caller multiplies back: exact and cheap)
+CDA_HDN cda_u128 cda_u128_div_pow10(cda_u128 x, int k) {
+    while (k > 0) {
+        const int j = k > 19 ? 19 : k;
+        k -= j;
+#if defined(__CUDA_ARCH__)
+        const unsigned long long d = cda_mg10_dev[j][0], v = cda_mg10_dev[j][1]; const int s = (int)cda_mg10_dev[j][2];
+#else
+        const unsigned long long d = cda_mg10_host[j][0], v = cda_mg10_host[j][1]; const int s = (int)cda_mg10_host[j][2];
+#endif
+        const unsigned long long hi = (unsigned long long)(x >> 64), lo = (unsigned long long)x;
+        const unsigned long long x2 = s ? hi >> (64 - s) : 0ULL, x1 = s ? (hi << s) | (lo >> (64 - s)) : hi, x0 = lo << s;
+        unsigned long long r;
+        const unsigned long long qh = cda_div2by1(x2, x1, d, v, &r);
+        const unsigned long long ql = cda_div2by1(r, x0, d, v, &r);
+        x = ((cda_u128)qh << 64) | ql;
+    }
     return x;
 }
 CDA_HD CdaDec cda_dec_zero() { CdaDec r; r.c = 0; r.exp = 0; r.sign = 0; return r; }
 
 // x * 10^exp (+ sticky: something non-zero beyond x) -> 28 significant digits, half to even
-CDA_HD CdaDec cda_dec_round(int sign, cda_u128 x, int exp, int sticky) {
+CDA_HDN CdaDec cda_dec_round(int sign, cda_u128 x, int exp, int sticky) {
     CdaDec r = cda_dec_zero();
     if (x == 0) return r;
     const int nd = cda_dec_ndigits(x);
@@ -158,7 +217,12 @@ CDA_HD CdaDec cda_dec_from_i64(long long v) {        // |v| < 2^63 < 10^19: neve
     return r;
 }
 CDA_HD CdaDec cda_dec_neg(CdaDec a) { if (a.c) a.sign ^= 1; return a; }
-CDA_HD CdaDec cda_dec_strip(CdaDec a) {              // value-preserving: drop trailing zeros of the coefficient
+CDA_HDN CdaDec cda_dec_strip(CdaDec a) {              // value-preserving: drop trailing zeros of the coefficient
+    while (a.c && (a.c >> 64) == 0) {               // (the common case, a divisor that is a position size: plain 64-bit arithmetic)
+        const unsigned long long c = (unsigned long long)a.c;
+        if (c % 10ULL) return a;
+        a.c = c / 10ULL; ++a.exp;
+    }
     while (a.c) {
         unsigned r;
         const cda_u128 q = cda_u128_divmod_small(a.c, 10u, &r);
@@ -168,7 +232,7 @@ CDA_HD CdaDec cda_dec_strip(CdaDec a) {              // value-preserving: drop t
     return a;
 }
 
-CDA_HD CdaDec cda_dec_add(CdaDec a, CdaDec b) {
+CDA_HDN CdaDec cda_dec_add(CdaDec a, CdaDec b) {
     if (a.c == 0) return b;
     if (b.c == 0) return a;
     if (a.exp < b.exp) { const CdaDec t = a; a = b; b = t; }   // a has the larger exponent
@@ -191,7 +255,7 @@ CDA_HD CdaDec cda_dec_add(CdaDec a, CdaDec b) {
 }
 CDA_HD CdaDec cda_dec_sub(CdaDec a, CdaDec b) { return cda_dec_add(a, cda_dec_neg(b)); }
 
-CDA_HD CdaDec cda_dec_mul(CdaDec a, CdaDec b, int *range_err) {
+CDA_HDN CdaDec cda_dec_mul(CdaDec a, CdaDec b, int *range_err) {
     if (a.c == 0 || b.c == 0) return cda_dec_zero();
     if (cda_dec_ndigits(a.c) + cda_dec_ndigits(b.c) > 38) {
         a = cda_dec_strip(a); b = cda_dec_strip(b);
@@ -200,7 +264,7 @@ CDA_HD CdaDec cda_dec_mul(CdaDec a, CdaDec b, int *range_err) {
     return cda_dec_round(a.sign ^ b.sign, a.c * b.c, a.exp + b.exp, 0);
 }
 // a / b, b != 0 with a coefficient below 2^32 after stripping: dividend scaled to 38 digits, quotient >= 29 digits + sticky remainder
-CDA_HD CdaDec cda_dec_div(CdaDec a, CdaDec b, int *range_err) {
+CDA_HDN CdaDec cda_dec_div(CdaDec a, CdaDec b, int *range_err) {
     if (a.c == 0) return cda_dec_zero();
     b = cda_dec_strip(b);
     const int nb = cda_dec_ndigits(b.c), na = cda_dec_ndigits(a.c), k = 38 - na;

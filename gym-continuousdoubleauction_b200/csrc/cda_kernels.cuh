@@ -24,6 +24,7 @@
 
 #include "cda_b200.h"
 #include "cda_zig_tables.cuh"
+#include "cda_twin.cuh"
 
 #define CDA_FULL 0xffffffffu
 #define CDA_SCAN_PRAGMA _Pragma("unroll 1")
@@ -44,7 +45,8 @@
 // Per-market block in HBM (stride bytes, 128-B aligned), see DESIGN.md "Data layout":
 //   [0,192)            header words (below)
 //   [off_acct, ...)    accounts, SoA inside the market: cash[A] hold[A] cost[A] nav[A] prev_nav[A]
-//                      max_nav[A] (i64), pos[A] (i32), num_trades[A] (u32), stepctr[A] (u32)
+//                      max_nav[A] (i64), pos[A] (i32), num_trades[A] (u32), stepctr[A] (u32), twin flags[A] (u32): 64*A bytes
+//   [off_twin, ...)    decimal_ledger only: CdaTwinStored[A] (64 B each), then the event journals u64[A][CDA_JRN_E] (cda_twin.cuh)
 //   [off_hist, ...)    snapshot ring  f32[n_hist][42]
 //   [off_pool, ...)    order pool     u32[2 sides][cap/32 tiles][5 fields][32]  ("blocked SoA": the live
 //                      prefix of a side is ONE contiguous run of whole tiles => one bulk copy per side,
@@ -64,6 +66,8 @@ struct CdaDevCfg {
     double c_order, c_trade, c_dd, c_passive, c_loss;
     unsigned off_acct, off_hist, off_pool, stride;
     int W;                    // n_hist * 42
+    int dec;                  // 1: decimal_ledger — the deferred Decimal(28) twin of cda_twin.cuh decides exact-equality ties like the reference
+    unsigned off_twin, off_jrn;
 };
 
 struct CdaStepParams {
@@ -289,7 +293,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 struct CdaAcct {
     long long cash, hold, cost, nav, pos;
     unsigned ntr;
-    unsigned ctr;   // per-step counters, packed as stored: trades[0:12) passive[12:24) placed[24] rejected[25] is_pass[26]
+    unsigned ctr;   // per-step counters, packed as stored: trades[0:12) passive[12:24) placed[24] rejected[25] is_pass[26]; bit 27: this agent's
+                    // Decimal cash carries a residue ("tracked": every cash movement is journaled, cda_twin.cuh) — copied from the twin flags
 };
 // account.py:215-231 process_acc with the ledger restated on integers (cost = |pos|*VWAP):
 //   open/increase: cost += q*p (account.py:124-133, :173-176); decrease: cost -= q*p (:151-157);
@@ -336,7 +341,8 @@ struct CdaSmemLayout {
     static constexpr int ORDER = LPX + 2 * CDA_K_ROWS;               // u32[32] shuffled execution order
     static constexpr int ACT = ORDER + 32;                           // u32[32][3] decoded actions: type|side<<8, size, price
     static constexpr int PARK = ACT + 96;                            // 10 words: parked PCG64 state (+2 pad)
-    static constexpr int BAR = PARK + 12;                            // mbarrier (8-B aligned)
+    static constexpr int TIE = PARK + 12;                            // u32[8] decimal_ledger: restart count | answers << 8, then up to 7 parked tie answers
+    static constexpr int BAR = TIE + 8;                              // mbarrier (8-B aligned)
     static constexpr int WORDS = ((BAR + 2 + 3) / 4) * 4;            // keep 16-B alignment of the next tile
     static constexpr int BYTES = WORDS * 4;
     static_assert(BAR % 2 == 0, "mbarrier must be 8-B aligned");
@@ -354,6 +360,7 @@ struct CdaMkt {
     int tape_nonempty, tape_px;
     int lane;
     int *fills_base; int fill_cap, n_fills, mkt;   // fill log: row = fills_base + mkt * fill_cap * 8 (computed when a fill happens)
+    int twf_w;           // decimal_ledger: word index (smw) of THIS lane's twin-flags word, -1 = ledger off / not an agent lane
     __device__ __forceinline__ int side_w(int side) const { return pool_w + side * (CDA_POOL_FIELDS * CAP); }
     __device__ __forceinline__ int count(int side) const { return side ? na : nb; }
     __device__ __forceinline__ void set_count(int side, int v) { if (side) na = v; else nb = v; }
@@ -361,6 +368,69 @@ struct CdaMkt {
     __device__ __forceinline__ int cached_best(int side) const { return side ? besta : bestb; }
     __device__ __forceinline__ void set_best(int side, int v) { if (side) besta = v; else bestb = v; }
 };
+
+// ---- decimal_ledger: journal appends (cda_twin.cuh).  Executed by the lane that owns the account, only when k.twf_w >= 0.
+#define CDA_TRACKED_BIT (1u << 27)
+template <int CAP> __device__ __forceinline__ void twin_log(const CdaMkt<CAP> &k, const CdaStepParams &p, unsigned long long ev) {
+    unsigned twf = SMW(k.twf_w);
+    unsigned jn = twf & CDA_TWF_JN_MASK;
+    unsigned char *blk = p.state + (size_t)k.mkt * p.cfg.stride;
+    unsigned long long *jr = reinterpret_cast<unsigned long long *>(blk + p.cfg.off_jrn) + k.lane * CDA_JRN_E;
+    // No call in here (this sits inside the matching loop).  The journal cannot fill up in normal operation: the host replays it every
+    // CDA_TWIN_FLUSH_STEPS steps (~0.7 events per agent and step at the BASELINE fill rates, CDA_JRN_E fit); an agent that does
+    // overflow it is flagged (CDA_ST_DEC_RANGE: its residues are no longer exact), never silently wrong.
+    if (jn >= CDA_JRN_E) { SMW(k.twf_w) = twf | CDA_TWF_RANGE; return; }
+    jr[jn] = ev;
+    SMW(k.twf_w) = (twf & ~CDA_TWF_JN_MASK) | (jn + 1u);
+}
+// ---- ties that only the Decimal twin can decide: DETERMINISTIC RE-EXECUTION WITH PARKED ANSWERS -------------------------------------
+// A call to the 128-bit arithmetic anywhere inside the step body costs the hot path its register allocation (measured: 0 -> 440
+// bytes of spill), so the step body contains none.  Nothing a step does is committed to global memory before its epilogue, so when a
+// warp meets a tie it (1) parks a request {what, who, operands, journal length so far}, (2) leaves the step body, (3) at the TOP LEVEL
+// of the kernel — no live values — replays the agent's journal up to that point WITHOUT storing it (cda_twin_query) and parks the
+// answer in a small per-warp table, and (4) runs the launch's steps for this market again from the state in global memory.  The
+// re-execution is deterministic, reaches the same tie, finds the answer and carries on.  Keys: gate tie (step, action slot), NAV tie
+// (step, agent).  Cost: one extra pass for that one market, about once per 10^5..10^6 agent-steps on low-cash configurations.
+__device__ unsigned long long cda_debug_restarts = 0ULL;   // tie-resolution passes made by all step kernels so far (cda_debug_restart_count)
+#define CDA_TIE_SLOTS 7
+#define CDA_TIE_KEY_GATE(it, q) (0x10000u | ((unsigned)(it) << 8) | (unsigned)(q))
+#define CDA_TIE_KEY_NAV(it, a) (0x20000u | ((unsigned)(it) << 8) | (unsigned)(a))
+// answer for `key` (2 bits) or -1; tie_w[0] = restarts | n << 8, tie_w[1..] = key << 2 | answer
+__device__ __forceinline__ int tie_lookup(int tie_w, unsigned key) {
+    const int n = (int)((SMW(tie_w) >> 8) & 0xffu);
+    for (int i = 0; i < n && i < CDA_TIE_SLOTS; ++i) { const unsigned w = SMW(tie_w + 1 + i); if ((w >> 2) == key) return (int)(w & 3u); }
+    return n >= CDA_TIE_SLOTS ? 2 : -1;   // table full (flagged CDA_ST_DEC_RANGE by the resolver): decide like the integers do, so that the passes terminate
+}
+// pure query on a COPY of the twin: replays jn journal entries, stores nothing.  mode 1: code of (cash - a0); mode 2: code of nav at price
+// a2 with integer cash a0 and cash_on_hold a1.  Codes: 1 greater / positive, 2 equal / zero, 3 less / negative; bit 2 = range error.
+__device__ __noinline__ unsigned cda_twin_query(const CdaTwinStored *st, const unsigned long long *jr, int jn, int mode, long long a0, long long a1, long long a2) {
+    CdaTwin t;
+    cda_twin_load(t, st);
+    for (int i = 0; i < jn; ++i) cda_twin_apply(t, jr[i]);
+    cda_twin_settle(t);
+    int c;
+    if (mode == 1) c = t.tracked ? cda_dec_cmp(t.cash, CDA_DI(a0)) : 0;
+    else c = cda_twin_nav_sign(t, a0, a1, a2);
+    return (c > 0 ? 1u : c == 0 ? 2u : 3u) | (t.err ? 4u : 0u);
+}
+// a fill on this lane's account: FILL event; a fill that COVERS the position (flat or flip) is where a residue can enter cash
+// (account.py:135-149), so from there on this agent's cash is tracked: CASHSYNC carries the (still exact) integer cash
+template <int CAP> __device__ __forceinline__ void twin_log_fill(const CdaMkt<CAP> &k, const CdaStepParams &p, CdaAcct &a, int party, int side, unsigned q, int px) {
+    const long long ap = a.pos < 0 ? -a.pos : a.pos;
+    if (a.pos != 0 && ((a.pos > 0) != (side == 0)) && ap <= (long long)q && !(a.ctr & CDA_TRACKED_BIT)) {
+        twin_log(k, p, cda_ev_value(CDA_EV_CASHSYNC, a.cash));
+        a.ctr |= CDA_TRACKED_BIT;
+        SMW(k.twf_w) |= CDA_TWF_TRACKED;
+    }
+    twin_log(k, p, cda_ev_fill(party, side, q, (unsigned)px));
+}
+#define CDA_TWIN_ST(p, mkt, lane) (reinterpret_cast<CdaTwinStored *>((p).state + (size_t)(mkt) * (p).cfg.stride + (p).cfg.off_twin) + (lane))
+#define CDA_TWIN_JR(p, mkt, lane) (reinterpret_cast<unsigned long long *>((p).state + (size_t)(mkt) * (p).cfg.stride + (p).cfg.off_jrn) + (lane) * CDA_JRN_E)
+// nav > 0 as the reference's Decimal sees it (a zero integer NAV defers to the sign recorded at the last mark-to-market)
+template <int CAP> __device__ __forceinline__ bool nav_positive(const CdaMkt<CAP> &k, long long nav) {
+    if (nav != 0 || k.twf_w < 0) return nav > 0;
+    return ((SMW(k.twf_w) >> CDA_TWF_NAVSIGN_SHIFT) & 3u) == 1u;   // recorded by the mark-to-market that produced the zero
+}
 
 template <int CAP> __device__ __forceinline__ int pool_best_scan(const CdaMkt<CAP> &k, int side) {
     int pt = k.side_w(side) + k.lane;
@@ -442,15 +512,19 @@ template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, i
 // trader.py:49-106 place_order as ONE straight-line flow with a single matching loop (keeps the
 // SASS small enough for the instruction cache).  All arguments are warp-uniform.
 // type: 0 market, 1 limit, 2 modify, 3 cancel.   `ac` is this lane's account.
+// Returns true when the gate hit an exact-equality tie that only the Decimal twin can decide and no answer is parked for it yet
+// (decimal_ledger; nothing has been changed): the trader's lane has parked the gated value in req_w, the caller leaves the step body.
+// tie_w: the warp's answer table; tie_key: this action's key; req_w: two scratch words for the value.
 template <int CAP>
-__device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, int type, int side, long long size, int price) {
+__device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams &p, CdaAcct &ac, int t, int type, int side, long long size, int price,
+                                            int tie_w, unsigned tie_key, int req_w) {
     const int opp = side ^ 1;
     const bool is_t = k.lane == t;
     // ---- trader.py:108-151 _order_approved (on the trader's lane; market orders need the best opposite quote)
     int best_opp = -1;
     if (type == 0) best_opp = pool_best(k, opp);
     int ok_l = 0;
-    if (is_t && ac.nav > 0) {
+    if (is_t && nav_positive(k, ac.nav)) {
         long long opening;
         if ((side == 0 && ac.pos >= 0) || (side == 1 && ac.pos <= 0)) opening = size;
         else { const long long ap = ac.pos < 0 ? -ac.pos : ac.pos; opening = size - ap; if (opening < 0) opening = 0; }
@@ -458,11 +532,18 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
         else {
             const long long est = type == 0 ? (best_opp > 0 ? best_opp : (k.tape_nonempty ? k.tape_px : 1)) : price;
             ok_l = ac.cash >= opening * est;
+            if ((ac.ctr & CDA_TRACKED_BIT) && ac.cash == opening * est) {   // the Decimal residue decides (about 1 agent-step in 10^5 at low cash)
+                const int ans = tie_lookup(tie_w, tie_key);
+                if (ans >= 0) ok_l = ans != 3;             // cash >= value unless the Decimal cash is smaller
+                else { const long long v = opening * est; SMW(req_w) = (unsigned)v; SMW(req_w + 1) = (unsigned)((unsigned long long)v >> 32); ok_l = 2; }
+            }
         }
     }
-    if (!__shfl_sync(CDA_FULL, ok_l, t)) { if (is_t) ac.ctr |= 1u << 25; return; }
+    ok_l = __shfl_sync(CDA_FULL, ok_l, t);
+    if (ok_l == 2) return true;
+    if (!ok_l) { if (is_t) ac.ctr |= 1u << 25; return false; }
     if (type <= 1 && is_t) ac.ctr |= 1u << 24;                          // trader.py:75-76
-    if (size <= 0 && type <= 1) { k.raise(CDA_ST_BAD_SIZE); return; }  // reference: sys.exit in process_order
+    if (size <= 0 && type <= 1) { k.raise(CDA_ST_BAD_SIZE); return false; }  // reference: sys.exit in process_order
 
     // ---- trader.py:254-287 _get_order_ID: limit/cancel = first in order_map order at that price (min seq);
     //      modify = oldest timestamp at any price
@@ -472,7 +553,7 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
         const unsigned want = type == 2 ? ((unsigned)t << 24) : (((unsigned)t << 24) | (unsigned)price);
         idx = pool_argmin(k, side, mask, want, type == 2 ? 3 : 4);
     }
-    if (type >= 2 && idx < 0) return;                                    // nothing to modify / cancel: no book op
+    if (type >= 2 && idx < 0) return false;                              // nothing to modify / cancel: no book op
 
     unsigned oid;
     if (idx >= 0) {
@@ -480,16 +561,22 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
         const int pl = k.side_w(side) + CDA_EOFF(idx);
         const unsigned op = SMW(pl) & CDA_PRICE_MASK, oq = SMW(pl + 32);
         oid = SMW(pl + 64);
-        if (is_t) { const long long ov = (long long)op * oq; ac.hold -= ov; ac.cash += ov; }
+        if (is_t) {
+            const long long ov = (long long)op * oq; ac.hold -= ov; ac.cash += ov;
+            if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, ov));
+        }
         k.time++;                                                        // orderbook.py:196-200, :212-215
-        if (type == 3) { pool_remove(k, side, idx); return; }
+        if (type == 3) { pool_remove(k, side, idx); return false; }
         if ((unsigned)price == op && (unsigned long long)size <= oq) {   // orderbook.py:245-248 in place
             __syncwarp();
             if (k.lane == 0) { SMW(pl + 32) = (unsigned)size; SMW(pl + 96) = k.time; }
             k.touch(side, idx);
             __syncwarp();
-            if (is_t) { const long long v = (long long)price * size; ac.cash -= v; ac.hold += v; }
-            return;
+            if (is_t) {
+                const long long v = (long long)price * size; ac.cash -= v; ac.hold += v;
+                if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, -v));
+            }
+            return false;
         }
         pool_remove(k, side, idx);                                       // orderbook.py:250-266 re-process, same id
     } else {
@@ -537,16 +624,24 @@ __device__ __forceinline__ void place_order(CdaMkt<CAP> &k, CdaAcct &ac, int t, 
         }
         k.n_fills++;
         if (maker != t) {                     // trader.py:311-322: counter party, then initiator (disjoint lanes)
-            if (k.lane == maker || is_t) acct_fill(ac, is_t ? 0 : 1, is_t ? side : opp, traded, P);
+            if (k.lane == maker || is_t) {
+                if (k.twf_w >= 0) twin_log_fill(k, p, ac, is_t ? 0 : 1, is_t ? side : opp, traded, P);
+                acct_fill(ac, is_t ? 0 : 1, is_t ? side : opp, traded, P);
+            }
         } else if (is_t) {                    // cash_processor.py:55-62 self-trade: escrow back to cash
             const long long tv = (long long)traded * P;
             ac.hold -= tv; ac.cash += tv;
+            if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, tv));
         }
     }
     // ---- residue rests (orderbook.py:174-191) and is escrowed (cash_processor.py:15-29); market remainder dropped
     if (type != 0 && qty > 0 && pool_append(k, side, (unsigned)price, qty, t, oid, k.time)) {
-        if (is_t) { const long long v = (long long)price * qty; ac.cash -= v; ac.hold += v; }
+        if (is_t) {
+            const long long v = (long long)price * qty; ac.cash -= v; ac.hold += v;
+            if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, -v));
+        }
     }
+    return false;
 }
 
 // counter-based generator for the fused random-policy rollout (NOT the env stream)
@@ -577,7 +672,40 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 template <int CAP, int WARPS, bool ROLLOUT, bool ROUTED>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
     using L = CdaSmemLayout<CAP>;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // ---- CTA prologue (its values die here: nothing defined above `restart` may be live across the resolve block's call) ----
+        // action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A] array) behind one
+        // CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns 20 sector-sized PCIe reads per CTA into
+        // 5 requests (ONE for a market-major block) issued at the very start of the kernel.
+        const int A0 = p.cfg.A, actb0 = WARPS * L::WORDS, cbar_w0 = actb0 + 5 * WARPS * A0;
+        if (!ROLLOUT && p.act_tma) {
+            if (threadIdx.x == 0) {
+                const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w0 * 4u;
+                const int m0 = blockIdx.x * WARPS, nm = min(WARPS, p.M - m0);
+                const unsigned fb = (unsigned)(nm * A0) * 4u;
+                mbar_init(cbar, 1);
+                mbar_expect_tx(cbar, 5u * fb);
+                const unsigned dst = smem_u32(smw) + (unsigned)actb0 * 4u, fs = (unsigned)(WARPS * A0) * 4u;
+                const size_t so = (size_t)m0 * p.act_mstride;
+                if (p.act_packed) bulk_g2s(dst, p.cat + so, 5u * fb, cbar);   // tile = u32[markets][5][A]
+                else {                                                        // tile = u32[5][WARPS][A]
+                    bulk_g2s(dst, p.cat + so, fb, cbar);
+                    bulk_g2s(dst + fs, p.mean + so, fb, cbar);
+                    bulk_g2s(dst + 2u * fs, p.sigma + so, fb, cbar);
+                    bulk_g2s(dst + 3u * fs, p.pcode + so, fb, cbar);
+                    bulk_g2s(dst + 4u * fs, p.poff + so, fb, cbar);
+                }
+            }
+        }
+        __syncthreads();                                   // mbarrier initialised before any warp goes on
+        if ((int)(blockIdx.x * WARPS + (threadIdx.x >> 5)) >= p.M) return;
+        if ((threadIdx.x & 31) == 0) smw[(threadIdx.x >> 5) * L::WORDS + L::TIE] = 0u;  // decimal_ledger: no restart yet, no parked answers
+        __syncwarp();
+    }
+    // decimal_ledger: a tie only the Decimal twin can decide makes the warp leave the step body (`goto resolve`, nothing committed),
+    // answer it at the bottom of the kernel and come back HERE to run this launch's steps for its market again (see tie_lookup)
+restart:;
+  {
+    const int warp = (int)(fresh_tid_x() >> 5), lane = (int)(fresh_tid_x() & 31u);   // (fresh reads: not the prologue's copies kept alive across `resolve`)
     const int m = blockIdx.x * WARPS + warp;
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
@@ -589,41 +717,15 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     const int o_obs_split = ROUTED ? p.obs_split : p.M, o_ring_mirror = ROUTED ? p.ring_mirror : 0;
     float *const o_ring_out = ROUTED ? p.ring_out : nullptr;
     const int o_obs_stride = ROUTED ? p.obs_stride : cfg.W, o_reward_stride = ROUTED ? p.reward_stride : A, o_flag_stride = ROUTED ? p.flag_stride : 1;
-    // ---- action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A]
-    //      array) behind one CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns
-    //      20 sector-sized PCIe reads per CTA into 5 requests issued at the very start of the kernel.
     const int actb = WARPS * L::WORDS;                 // word index of the CTA's action tile: u32[5][WARPS][A], then the mbarrier
     const int cbar_w = actb + 5 * WARPS * A;           // (16-B aligned: 20*A words)
-    // the RNG tables are indexed by data that arrives ~2 us into the kernel: start pulling them into L1 now
-    // (L1 is cold at every launch; without this the ziggurat / jump-ahead reads wait a full L2 or HBM round trip)
-    // this warp's copy of the jump-ahead rows 0..A: loaded NOW, stored to shared memory just before the normal draws (by then the
+    // this warp's copy of the PCG jump-ahead rows 0..A: loaded NOW, stored to shared memory just before the normal draws (by then the
     // load has landed: nothing waits for it).  It lives in the tail of the decoded-action tile (u32[32][3], of which 3A words are
     // used): no extra shared memory, so 7 CTAs per SM still fit; with more than 8 agents it does not fit and the draws read
     // the table in global memory.
     const bool jump_sm = ((3 * A + 3) & ~3) + 8 * (A + 1) <= 96;
     ulonglong2 jrow = make_ulonglong2(0ULL, 0ULL);   // lane j < 2(A+1): 16-byte piece j of the table (row j/2: A^r for even j, G_r for odd j)
     if (jump_sm && lane < 2 * (A + 1)) jrow = __ldg(reinterpret_cast<const ulonglong2 *>(&cda_pcg_jump[0][0]) + lane);
-    if (!ROLLOUT && p.act_tma) {
-        if (threadIdx.x == 0) {
-            const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w * 4u;
-            const int m0 = blockIdx.x * WARPS, nm = min(WARPS, p.M - m0);
-            const unsigned fb = (unsigned)(nm * A) * 4u;
-            mbar_init(cbar, 1);
-            mbar_expect_tx(cbar, 5u * fb);
-            const unsigned dst = smem_u32(smw) + (unsigned)actb * 4u, fs = (unsigned)(WARPS * A) * 4u;
-            const size_t so = (size_t)m0 * p.act_mstride;
-            if (p.act_packed) bulk_g2s(dst, p.cat + so, 5u * fb, cbar);   // tile = u32[markets][5][A]
-            else {                                                        // tile = u32[5][WARPS][A]
-                bulk_g2s(dst, p.cat + so, fb, cbar);
-                bulk_g2s(dst + fs, p.mean + so, fb, cbar);
-                bulk_g2s(dst + 2u * fs, p.sigma + so, fb, cbar);
-                bulk_g2s(dst + 3u * fs, p.pcode + so, fb, cbar);
-                bulk_g2s(dst + 4u * fs, p.poff + so, fb, cbar);
-            }
-        }
-    }
-    __syncthreads();                                   // mbarrier initialised (and the jump rows stored) before any warp goes on
-    if (m >= p.M) return;
 #ifdef CDA_PROFILE_PHASES
     long long tprev = clock64();
     { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); if (lane == 0 && p.prof) { p.prof[(size_t)m * 16 + 12] = gt; unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.prof[(size_t)m * 16 + 14] = sm; } }   // warp start (ns), SM id
@@ -641,22 +743,22 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     long long *g_cash = reinterpret_cast<long long *>(blk + cfg.off_acct); \
     long long *g_hold = g_cash + A, *g_cost = g_cash + 2 * A, *g_nav = g_cash + 3 * A, *g_prev = g_cash + 4 * A, *g_max = g_cash + 5 * A; \
     int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A); \
-    unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A; \
-    (void)g_hold; (void)g_cost; (void)g_nav; (void)g_prev; (void)g_max; (void)g_pos; (void)g_ntr; (void)g_ctr;
+    unsigned *g_ntr = reinterpret_cast<unsigned *>(g_pos + A), *g_ctr = g_ntr + A, *g_twf = g_ctr + A; \
+    (void)g_hold; (void)g_cost; (void)g_nav; (void)g_prev; (void)g_max; (void)g_pos; (void)g_ntr; (void)g_ctr; (void)g_twf;
     CdaAcct ac = CdaAcct{0, 0, 0, 0, 0, 0, 0};
-    // ---- account tile: the market's whole account block (cash hold cost nav prev_nav max_nav i64[A], pos ntr ctr
-    //      u32[A]: 60*A contiguous bytes) goes global -> shared with ONE bulk copy issued before anything else; the
+    // ---- account tile: the market's whole account block (cash hold cost nav prev_nav max_nav i64[A], pos ntr ctr twf
+    //      u32[A]: 64*A contiguous bytes) goes global -> shared with ONE bulk copy issued before anything else; the
     //      lanes pick their fields out of shared memory when do_actions / mark-to-market need them, so no register
     //      holds an account value across the decode / RNG phases and no global-load latency is exposed later.
     //      The warp's mbarrier counts two arrivals: this copy and the order-pool copy issued once the header is here.
-    const int acct_w = cbar_w + 4 + warp * ((15 * A + 3) & ~3);      // word index of this warp's account tile (16-B aligned)
+    const int acct_w = cbar_w + 4 + warp * (16 * A);                 // word index of this warp's account tile (16-B aligned)
     if (lane == 0) {
-        mbar_init(bar, 2);
-        if (p.acct_tma) { mbar_expect_tx(bar, 60u * (unsigned)A); bulk_g2s(smem_u32(smw) + (unsigned)acct_w * 4u, blk + cfg.off_acct, 60u * (unsigned)A, bar); }
+        if ((SMW(wb + L::TIE) & 0xffu) == 0u) mbar_init(bar, 2);      // (a restarted pass uses the barrier's next phase)
+        if (p.acct_tma) { mbar_expect_tx(bar, 64u * (unsigned)A); bulk_g2s(smem_u32(smw) + (unsigned)acct_w * 4u, blk + cfg.off_acct, 64u * (unsigned)A, bar); }
     }
-    if (!p.acct_tma) {   // A % 4 != 0: same tile, filled by plain loads
+    if (!p.acct_tma) {   // (debug switch) same tile, filled by plain loads
         const unsigned *ga = reinterpret_cast<const unsigned *>(blk + cfg.off_acct);
-        for (int i = lane; i < 15 * A; i += 32) SMW(acct_w + i) = ga[i];
+        for (int i = lane; i < 16 * A; i += 32) SMW(acct_w + i) = ga[i];
         __syncwarp();
         if (lane == 0) mbar_arrive(bar);
     }
@@ -690,6 +792,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     k.fills_base = p.fills; k.mkt = m;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
     k.bestb = -2; k.besta = -2;
+    k.twf_w = (cfg.dec && lane < A) ? acct_w + 15 * A + lane : -1;
 
     // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
@@ -846,7 +949,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         __syncwarp();
 
         CDA_TICK(2);   // shuffle done
-        if (!waited) { mbar_wait(bar, 0); waited = true; }
+        if (!waited) { mbar_wait(bar, SMW(wb + L::TIE) & 1u); waited = true; }
         {   // this lane's account, out of the account tile.  In a multi-step rollout the tile is also where the
                                              // accounts live BETWEEN steps (written back at the end of every step): nothing account-related is
                                              // carried in registers across the decode / RNG phases of the next step.  Unconditional loads (lanes
@@ -855,6 +958,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
             ac.cash = sq[al]; ac.hold = sq[A + al]; ac.cost = sq[2 * A + al]; ac.nav = sq[3 * A + al];
             ac.pos = (int)SMW(acct_w + 12 * A + al); ac.ntr = SMW(acct_w + 13 * A + al);
+            if (k.twf_w >= 0 && (SMW(k.twf_w) & CDA_TWF_TRACKED)) ac.ctr |= CDA_TRACKED_BIT;
         }
         CDA_TICK(3);   // pool + account tiles landed
 
@@ -869,13 +973,46 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             const unsigned ts_ = SMW(wb + L::ACT + 3 * t);
             const long long size = (long long)SMW(wb + L::ACT + 3 * t + 1);
             const int price = (int)SMW(wb + L::ACT + 3 * t + 2);
-            place_order(k, ac, t, (int)(ts_ & 0xffu), (int)(ts_ >> 8), size, price);
+            if (place_order(k, p, ac, t, (int)(ts_ & 0xffu), (int)(ts_ >> 8), size, price, wb + L::TIE, CDA_TIE_KEY_GATE(it, q), wb + L::SNAP)) {
+                // gate tie without an answer (decimal_ledger, rare): request = {mode 1, value, -, -, key} in this lane's slot of the pool tile
+                // (the pool is reloaded by the next pass), then leave
+                const int rq = wb + L::POOL + 8 * lane;
+                SMW(rq) = lane == t ? 1u : 0u;
+                if (lane == t) { SMW(rq + 1) = SMW(wb + L::SNAP); SMW(rq + 2) = SMW(wb + L::SNAP + 1); SMW(rq + 6) = CDA_TIE_KEY_GATE(it, q); }
+                goto resolve;
+            }
         }
 
         CDA_TICK(4);   // do_actions done
         // mark-to-market needs max_nav / prev_nav from the state block: issue those loads now, do the top-K sweep
         // (which does not depend on the accounts), then mark to market
         const int last_price = k.tape_px;              // exchg_helper.py:62-63 (the snapshot's midpoint fallback reads it)
+        // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
+        // (the new NAV right here — few values are live, which matters for the rare tie below; prev_nav / max_nav follow after the sweep)
+        if (k.tape_nonempty) {
+            if (lane < A) {
+                const long long ap = ac.pos < 0 ? -ac.pos : ac.pos;
+                const long long pv = ac.pos >= 0 ? ap * last_price : 2 * ac.cost - ap * last_price;
+                ac.nav = ac.cash + ac.hold + pv;
+            }
+            // decimal_ledger: an integer NAV of exactly 0 — the Decimal NAV's sign decides bankruptcy and the next gate (done_helper.py,
+            // trader.py:112).  Answer parked by an earlier pass -> record it in the twin flags; none yet -> park the request and leave.
+            if (cfg.dec && __any_sync(CDA_FULL, lane < A && ac.nav == 0)) {
+                int code = -2;                                   // -2: no tie on this lane
+                if (lane < A && ac.nav == 0) code = tie_lookup(wb + L::TIE, CDA_TIE_KEY_NAV(it, lane));
+                if (__any_sync(CDA_FULL, code == -1)) {
+                    const int rq = wb + L::POOL + 8 * lane;
+                    SMW(rq) = code == -1 ? 2u : 0u;
+                    if (code == -1) {
+                        SMW(rq + 1) = (unsigned)ac.cash; SMW(rq + 2) = (unsigned)((unsigned long long)ac.cash >> 32);
+                        SMW(rq + 3) = (unsigned)ac.hold; SMW(rq + 4) = (unsigned)((unsigned long long)ac.hold >> 32);
+                        SMW(rq + 5) = (unsigned)last_price; SMW(rq + 6) = CDA_TIE_KEY_NAV(it, lane);
+                    }
+                    goto resolve;
+                }
+                if (code >= 0) SMW(k.twf_w) = (SMW(k.twf_w) & ~(3u << CDA_TWF_NAVSIGN_SHIFT)) | ((unsigned)code << CDA_TWF_NAVSIGN_SHIFT);
+            }
+        }
 
         // ================= set_agg_LOB: state_helper.py:113-214 =============================
         // Top-K levels per side in ONE sweep: the distinct prices within 64 ticks of the best form
@@ -986,21 +1123,15 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 if (e >= 0 && e < W_old) { int ri = first + e; if (ri >= cfg.W) ri -= cfg.W; hv[q] = g_hist[ri]; }
             }
         }
-        // ================= mark_to_mkt: exchg_helper.py:56-66, calculate.py:35-55 ===========
-        long long ld_max = 0, ld_prev = 0;
+        // ---- mark_to_mkt, second half (calculate.py:49-51): prev_nav = the NAV before this step's mark-to-market, max_nav = high-water mark.
+        //      The old values still sit in the account tile (the new NAV was computed right after do_actions, see above).
+        long long nav_prev = 0, nav_max = 0;
         if (lane < A) {
             const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
-            ld_prev = sq[4 * A + lane]; ld_max = sq[5 * A + lane];
+            nav_max = sq[5 * A + lane];
+            nav_prev = k.tape_nonempty ? sq[3 * A + lane] : sq[4 * A + lane];   // never marked yet: keep the stored value
+            if (k.tape_nonempty && ac.nav > nav_max) nav_max = ac.nav;
         }
-        long long nav_prev = ac.nav, nav_max = ld_max;   // calculate.py:49-51
-        if (k.tape_nonempty) {
-            if (lane < A) {
-                const long long ap = ac.pos < 0 ? -ac.pos : ac.pos;
-                const long long pv = ac.pos >= 0 ? ap * last_price : 2 * ac.cost - ap * last_price;
-                ac.nav = ac.cash + ac.hold + pv;
-                if (ac.nav > nav_max) nav_max = ac.nav;
-            }
-        } else nav_prev = ld_prev;   // never marked yet: keep the stored value
         nav_max_carry = nav_max; nav_prev_carry = nav_prev;
         CDA_TICK(5);   // top-K levels + mtm done
         const int best_bid = __shfl_sync(CDA_FULL, myP, 0), best_ask = __shfl_sync(CDA_FULL, myP, CDA_K_ROWS);
@@ -1024,7 +1155,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             SMW(wbL + L::SNAP + b + l) = __float_as_uint(pn);
             SMW(wbL + L::SNAP + b + CDA_K_ROWS + l) = __float_as_uint(sn);
             SMW(wbL + L::TOPK + lane) = (unsigned)myP;                          // frozen raw top-K for the next step's _set_price
-            hdr[20 + (fresh_tid_x() & 31u)] = (unsigned)myP;   // (fresh lane index: reusing the entry-time &hdr[20 + lane] would keep that pointer spilled across the whole step)
+            if (!ROLLOUT || last_it) hdr[20 + (fresh_tid_x() & 31u)] = (unsigned)myP;   // (fresh lane index: reusing the entry-time &hdr[20 + lane] would keep that pointer spilled across the whole step)
         } else if (lane < 22) {
             double x = Mid; bool live = true;
             if (lane == 21) {
@@ -1081,7 +1212,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                     for (int g = 0; g < o_gather_world; ++g) *reinterpret_cast<double *>(p.gather_peer[g] + off) = r;
                 } else p.reward[(size_t)m * o_reward_stride + lane] = r;
             }
-            broke = ac.nav <= 0;
+            broke = !nav_positive(k, ac.nav);
             if (o_rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wbL + L::ACT + 2 * lane) = (unsigned)rb; SMW(wbL + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
         }
         const unsigned done_mask = SMW(wbL + L::PARK + 10) | __ballot_sync(CDA_FULL, broke);
@@ -1119,7 +1250,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
             if (p.fill_counts) p.fill_counts[m] = k.n_fills;
-            hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask;
+            hdr[40] = (unsigned)best_bid; hdr[41] = (unsigned)best_ask;   // (inside `last_it`: a restarted rollout pass must find the header untouched)
         }
         t_step++;
         __syncwarp();
@@ -1139,6 +1270,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     CDA_TICK(8);   // reward/done
     const int wbL = (int)(fresh_tid_x() >> 5) * L::WORDS;   // (as inside the loop: not the entry-time copy)
     // ---- store: header, accounts, pool prefix
+    if (cfg.dec) {   // a Decimal operation left the 128-bit domain (sizes / prices far beyond the reference's ranges): sticky status
+        const bool re = k.twf_w >= 0 && (SMW(k.twf_w) & CDA_TWF_RANGE);
+        if (__any_sync(CDA_FULL, re)) k.raise(CDA_ST_DEC_RANGE);
+        __syncwarp();
+    }
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
         const unsigned stv = SMW(wbL + L::PARK + 11);
@@ -1154,6 +1290,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         g_cash[lane] = ac.cash; g_hold[lane] = ac.hold; g_cost[lane] = ac.cost; g_nav[lane] = ac.nav;
         g_prev[lane] = nav_prev_carry; g_max[lane] = nav_max_carry; g_pos[lane] = (int)ac.pos; g_ntr[lane] = ac.ntr;
         g_ctr[lane] = ac.ctr;
+        if (k.twf_w >= 0) {
+            const unsigned twf = SMW(k.twf_w);
+            g_twf[lane] = twf & ~CDA_TWF_RANGE;
+        }
     }
     fence_proxy_async();
     __syncwarp();
@@ -1170,6 +1310,31 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
 #ifdef CDA_PROFILE_PHASES
     { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); if (lane == 0 && p.prof) p.prof[(size_t)m * 16 + 13] = gt; }   // warp end (ns)
 #endif
+    return;
+  }
+resolve:
+    // ---- decimal_ledger, rare: answer the parked tie requests with the Decimal twin (the ONLY place the step kernel calls the 128-bit
+    //      arithmetic: top level, nothing live), park the answers, run the launch's steps for this market again
+    {
+        const int wbR = (int)(fresh_tid_x() >> 5) * L::WORDS, lnR = (int)(fresh_tid_x() & 31u);
+        const int mR = blockIdx.x * WARPS + (int)(fresh_tid_x() >> 5);
+        const int rq = wbR + L::POOL + 8 * lnR;
+        __syncwarp();
+        const unsigned mode = SMW(rq);
+        if (mode) {
+            const long long a0 = (long long)(((unsigned long long)SMW(rq + 2) << 32) | SMW(rq + 1)), a1 = (long long)(((unsigned long long)SMW(rq + 4) << 32) | SMW(rq + 3));
+            const int twfR = WARPS * L::WORDS + 5 * WARPS * p.cfg.A + 4 + (int)(fresh_tid_x() >> 5) * (16 * p.cfg.A) + 15 * p.cfg.A + lnR;   // this lane's twin flags (account tile)
+            const unsigned r = cda_twin_query(CDA_TWIN_ST(p, mR, lnR), CDA_TWIN_JR(p, mR, lnR), (int)(SMW(twfR) & CDA_TWF_JN_MASK), (int)mode, a0, a1, (long long)(int)SMW(rq + 5));
+            const unsigned idx = (atomicAdd(&smw[wbR + L::TIE], 0x100u) >> 8) & 0xffu;
+            unsigned *hdrR = reinterpret_cast<unsigned *>(p.state + (size_t)mR * p.cfg.stride);
+            if (idx < CDA_TIE_SLOTS) SMW(wbR + L::TIE + 1 + idx) = (SMW(rq + 6) << 2) | (r & 3u);
+            if (idx >= CDA_TIE_SLOTS || (r & 4u)) { atomicOr(hdrR + 7, CDA_ST_DEC_RANGE); *p.status_flag = 1u; }   // table full / out of the 128-bit domain: flagged
+        }
+        __syncwarp();
+        if (lnR == 0) { const unsigned w = SMW(wbR + L::TIE); SMW(wbR + L::TIE) = (w & ~0xffu) | ((w + 1u) & 0xffu); atomicAdd(&cda_debug_restarts, 1ULL); }
+        __syncwarp();
+    }
+    goto restart;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1202,7 +1367,11 @@ __global__ void cda_reset_kernel(CdaDevCfg cfg, unsigned char *state, int M, con
         g_cash[3 * A + a] = cfg.init_cash; g_cash[4 * A + a] = cfg.init_cash; g_cash[5 * A + a] = cfg.init_cash;
     }
     int *g_pos = reinterpret_cast<int *>(g_cash + 6 * A);
-    for (int a = 0; a < 3 * A; ++a) g_pos[a] = 0;
+    for (int a = 0; a < 4 * A; ++a) g_pos[a] = 0;                                         // position, num_trades, step counters, twin flags
+    if (cfg.dec) {                                                                         // Decimal twin: VWAP 0, cash untracked, empty journal
+        unsigned long long *tw = reinterpret_cast<unsigned long long *>(blk + cfg.off_twin);
+        for (int a = 0; a < A * (CDA_TWIN_BYTES / 8); ++a) tw[a] = 0ULL;
+    }
     // empty-book snapshot (state_helper.py:66-78, :163-175): zeros, log(anchor), 0
     float *g_hist = reinterpret_cast<float *>(blk + cfg.off_hist);
     double Mid = (double)anchor; if (Mid <= 0) Mid = 100.0;
@@ -1250,6 +1419,36 @@ __global__ void cda_ring_fill_kernel(CdaDevCfg cfg, const unsigned char *state, 
     if (mask && !mask[m]) return;
     const float *g_hist = reinterpret_cast<const float *>(state + (size_t)m * cfg.stride + cfg.off_hist);
     ring[i] = g_hist[e % CDA_SNAPSHOT_DIM];   // slot 0 (all slots are equal right after a reset)
+}
+
+// ------------------------------------------------------------------------------------------
+// decimal_ledger: periodic journal replay, one THREAD per (market, agent) (cda_twin.cuh); runs between steps on the env's stream
+// ------------------------------------------------------------------------------------------
+__global__ void cda_twin_flush_kernel(CdaDevCfg cfg, unsigned char *state, int M, unsigned *status_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * cfg.A) return;
+    const int m = i / cfg.A, a = i - m * cfg.A;
+    unsigned char *blk = state + (size_t)m * cfg.stride;
+    unsigned *twfp = reinterpret_cast<unsigned *>(blk + cfg.off_acct) + 15 * cfg.A + a;
+    const unsigned twf = *twfp;
+    const int jn = (int)(twf & CDA_TWF_JN_MASK);
+    if (jn == 0) return;
+    const unsigned r = cda_twin_replay(reinterpret_cast<CdaTwinStored *>(blk + cfg.off_twin) + a,
+                                       reinterpret_cast<const unsigned long long *>(blk + cfg.off_jrn) + a * CDA_JRN_E, jn, 0, 0, 0, 0);
+    *twfp = (twf & ~(CDA_TWF_JN_MASK | CDA_TWF_TRACKED)) | ((r & 1u) ? CDA_TWF_TRACKED : 0u);
+    if (r & 2u) { atomicOr(reinterpret_cast<unsigned *>(blk) + 7, CDA_ST_DEC_RANGE); *status_flag = 1u; }
+}
+// the twins (after a flush) for inspection: out i64[M][A][8] = vwap lo, hi, exp, sign, cash lo, hi, exp | sign << 32, with word 7's
+// bit 40 = cash tracked and the position in word 3's upper half (see VecCDAEnv.decimal_fields)
+__global__ void cda_twin_dump_kernel(CdaDevCfg cfg, const unsigned char *state, int M, long long *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * cfg.A) return;
+    const int m = i / cfg.A, a = i - m * cfg.A;
+    const unsigned char *blk = state + (size_t)m * cfg.stride;
+    const CdaTwinStored *s = reinterpret_cast<const CdaTwinStored *>(blk + cfg.off_twin) + a;
+    long long *o = out + (size_t)i * 8;
+    o[0] = (long long)s->vwap_lo; o[1] = (long long)s->vwap_hi; o[2] = s->vwap_exp; o[3] = (long long)(unsigned)s->vwap_sign | ((long long)s->pos << 32);
+    o[4] = (long long)s->cash_lo; o[5] = (long long)s->cash_hi; o[6] = s->cash_exp; o[7] = (long long)(unsigned)s->cash_sign | ((long long)(s->flags & 1u) << 40);
 }
 
 // ------------------------------------------------------------------------------------------

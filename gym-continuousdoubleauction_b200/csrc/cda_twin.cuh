@@ -12,11 +12,12 @@
 //   * per agent, the twin state is { Decimal VWAP, Decimal cash (only while it carries a residue: "tracked"), position } as of the
 //     last flush, plus a JOURNAL of the ledger events since then (8 bytes each: FILL {party, side, qty, price}, and — only while cash is
 //     tracked — ESCROW {signed value} / CASHSYNC {integer cash});
-//   * the step kernel only APPENDS events (a few instructions on the two lanes of a fill);
+//   * the step kernel only APPENDS events (a few instructions on the two lanes of a fill; no call inside the matching loop);
 //   * cda_twin_flush_kernel replays the journals with one THREAD per (market, agent) — 32 active lanes per warp instead of two — every
 //     CDA_TWIN_FLUSH_STEPS steps, on the same stream, between steps;
 //   * when a tie does occur (about one agent-step in 10^5..10^6 on low-cash configurations, never seen at the default cash), the
-//     trader's lane replays its own journal on the spot (cold, out-of-line) and reads the sign.
+//     step leaves its action loop, the trader's lane replays its own journal (cold, out of line) and the action is retried with the
+//     answer.
 // position_val and nav are pure functions of (cash, hold, |position|, VWAP, last price) — the reference recomputes position_val from
 // VWAP at every fill and every mark-to-market (calculate.py:24-55) and never accumulates it — so they are derived on demand.
 // The replay mirrors oracle/cda_oracle.c's decimal_ledger mode operation for operation (same order of additions: rounding depends
@@ -24,9 +25,10 @@
 #pragma once
 #include "cda_dec128.cuh"
 
-#define CDA_JRN_E 32                 /* journal entries per agent (8 bytes each) */
+#define CDA_JRN_E 48                 /* journal entries per agent (8 bytes each) */
+#define CDA_JRN_RESERVE 16           /* entries kept free for ONE step (an agent in more fills than this in one step is flagged) */
 #define CDA_TWIN_BYTES 64            /* twin state per agent */
-#define CDA_TWIN_FLUSH_STEPS 12      /* host-side flush cadence (steps); a full journal is flushed on the spot */
+#define CDA_TWIN_FLUSH_STEPS 10      /* host-side replay cadence (steps): ~7 events per agent at the BASELINE fill rates, 32 fit */
 // twin-flags word per agent (u32 in the accounts block, persistent): journal length, cash tracked, sign of a zero-integer NAV
 #define CDA_TWF_JN_MASK 0xffu
 #define CDA_TWF_TRACKED 0x100u
@@ -64,42 +66,50 @@ CDA_HD void cda_twin_store(const CdaTwin &t, CdaTwinStored *s) {
 #define CDA_DI(x) cda_dec_from_i64((long long)(x))
 CDA_HD void cda_twin_cash_add(CdaTwin &t, long long v) { if (t.tracked) t.cash = cda_dec_add(t.cash, CDA_DI(v)); }
 // account.py:135-149 _covered: position_val = raw + profit; cash += position_val - mkt_val (cash_processor.py:47-53); VWAP = 0
-CDA_HD long long cda_twin_covered(CdaTwin &t, int is_long, long long ap, long long price) {
+CDA_HDN long long cda_twin_covered(CdaTwin &t, int is_long, long long ap, long long price) {
     const long long mkt = ap * price;
-    const CdaDec draw = cda_dec_mul(CDA_DI(ap), t.vwap, &t.err), dmkt = CDA_DI(mkt);
-    const CdaDec profit = is_long ? cda_dec_sub(dmkt, draw) : cda_dec_sub(draw, dmkt);     // calculate.py:24-33
-    const CdaDec pv = cda_dec_add(draw, profit);
-    if (t.tracked) t.cash = cda_dec_add(t.cash, cda_dec_sub(pv, dmkt));
+    if (t.tracked) {                                           // (always, in the step kernel's protocol: CASHSYNC precedes a covering FILL)
+        const CdaDec draw = cda_dec_mul(CDA_DI(ap), t.vwap, &t.err), dmkt = CDA_DI(mkt);
+        const CdaDec profit = is_long ? cda_dec_sub(dmkt, draw) : cda_dec_sub(draw, dmkt);     // calculate.py:24-33
+        const CdaDec pv = cda_dec_add(draw, profit);
+        t.cash = cda_dec_add(t.cash, cda_dec_sub(pv, dmkt));
+    }
     t.vwap = cda_dec_zero();
     return mkt;
 }
-// account.py:215-231 process_acc on the Decimal fields; party 0 = init_party, 1 = counter_party; side 0 bid, 1 ask
-CDA_HD void cda_twin_fill(CdaTwin &t, int party, int side, long long q, long long price) {
+// account.py:215-231 process_acc on the Decimal fields; party 0 = init_party, 1 = counter_party; side 0 bid, 1 ask.
+// Written so that the expensive case — a VWAP update, increase or partial decrease alike — is ONE instruction stream (the replay kernel
+// runs 32 agents per warp: lanes in different branches serialise).
+CDA_HDN void cda_twin_fill(CdaTwin &t, int party, int side, long long q, long long price) {
     const long long tv = q * price, pos = t.pos, ap = pos < 0 ? -pos : pos;
+    const int is_long = pos > 0, same = (side == 0) == is_long;
+    t.pos = pos + (side == 0 ? q : -q);
+    if (pos != 0 && (same || ap > q)) {
+        // :124-133 _size_increase  VWAP' = (|pos| * VWAP + tv) / (|pos| + q);  :151-161 _size_decrease (left > 0)  VWAP' = (|pos| * VWAP - tv) / (|pos| - q)
+        const CdaDec raw = cda_dec_mul(CDA_DI(ap), t.vwap, &t.err);
+        t.vwap = cda_dec_div(cda_dec_add(raw, CDA_DI(same ? tv : -tv)), CDA_DI(same ? ap + q : ap - q), &t.err);
+        if (t.tracked) {                                       // cash_processor.py:31-45
+            if (same) { if (party == 0) cda_twin_cash_add(t, -tv); }
+            else { cda_twin_cash_add(t, tv); if (party == 1) cda_twin_cash_add(t, tv); }   // passive: cash += v, hold -= v, cash += v
+        }
+        return;
+    }
     if (pos == 0) {                                            // :173-176 _neutral
         t.vwap = CDA_DI(price);
-        if (party == 0) cda_twin_cash_add(t, -tv);             // cash_processor.py:31-36 (the passive side pays out of cash_on_hold)
-    } else {
-        const int is_long = pos > 0;
-        if ((side == 0) == is_long) {                          // :124-133 _size_increase
-            const long long total = ap + q;
-            t.vwap = cda_dec_div(cda_dec_add(cda_dec_mul(CDA_DI(ap), t.vwap, &t.err), CDA_DI(tv)), CDA_DI(total), &t.err);
-            if (party == 0) cda_twin_cash_add(t, -tv);
-        } else if (ap >= q) {                                  // :151-161 _size_decrease
-            const long long left = ap - q;
-            if (left > 0) t.vwap = cda_dec_div(cda_dec_sub(cda_dec_mul(CDA_DI(ap), t.vwap, &t.err), CDA_DI(tv)), CDA_DI(left), &t.err);
-            else cda_twin_covered(t, is_long, ap, price);
-            cda_twin_cash_add(t, tv);                          // cash_processor.py:38-45: initiator cash += v; passive cash += v, hold -= v, cash += v
-            if (party == 1) cda_twin_cash_add(t, tv);
-        } else {                                               // :163-171 _covered_side_chg
-            const long long mkt = cda_twin_covered(t, is_long, ap, price);
-            cda_twin_cash_add(t, mkt);
-            if (party == 1) cda_twin_cash_add(t, mkt);
-            t.vwap = CDA_DI(price);
-            if (party == 0) cda_twin_cash_add(t, -(q - ap) * price);
-        }
+        if (party == 0) cda_twin_cash_add(t, -tv);             // (the passive side pays out of cash_on_hold)
+        return;
     }
-    t.pos = pos + (side == 0 ? q : -q);
+    // the position is covered: flat (:151-161 with left == 0) or flipped (:163-171 _covered_side_chg)
+    const long long mkt = cda_twin_covered(t, is_long, ap, price);
+    if (ap == q) {
+        cda_twin_cash_add(t, tv);
+        if (party == 1) cda_twin_cash_add(t, tv);
+    } else {
+        cda_twin_cash_add(t, mkt);
+        if (party == 1) cda_twin_cash_add(t, mkt);
+        t.vwap = CDA_DI(price);
+        if (party == 0) cda_twin_cash_add(t, -(q - ap) * price);
+    }
 }
 CDA_HD void cda_twin_apply(CdaTwin &t, unsigned long long ev) {
     const unsigned long long tag = ev >> 62;
@@ -115,7 +125,7 @@ CDA_HD void cda_twin_settle(CdaTwin &t) {
     if (s.exp >= 0) t.tracked = 0;
 }
 // calculate.py:35-55 mark_to_mkt on the Decimal fields: the sign (-1, 0, +1) of nav = (cash + cash_on_hold) + position_val
-CDA_HD int cda_twin_nav_sign(CdaTwin &t, long long cash_int, long long hold, long long price) {
+CDA_HDN int cda_twin_nav_sign(CdaTwin &t, long long cash_int, long long hold, long long price) {
     const long long pos = t.pos, ap = pos < 0 ? -pos : pos;
     const CdaDec cash = t.tracked ? t.cash : CDA_DI(cash_int);
     const CdaDec diff = pos >= 0 ? cda_dec_sub(CDA_DI(price), t.vwap) : cda_dec_sub(t.vwap, CDA_DI(price));

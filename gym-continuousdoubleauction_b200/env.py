@@ -14,6 +14,8 @@ Differences, all documented in INTEGRATION.md:
     dict's iteration order, so pass dicts in agent order (RLlib does) for seed-level parity;
   * money is an exact int64 ledger: `info["NAV"]` is an integer string (the reference prints a
     Decimal with a ~1e-21 residue from its VWAP division; `Decimal(info["NAV"])` agrees to 1e-20).
+    The residues themselves are carried by the Decimal twin (`decimal_ledger`, on by default here):
+    they decide the rare exact-equality ties like the reference does; `decimal_fields()` shows them.
 """
 import os
 import warnings
@@ -183,7 +185,8 @@ class continuousDoubleAuctionEnv(_Base):
         self.drawdown_penalty, self.passive_bonus = float(cfg["drawdown_penalty"]), float(cfg["passive_bonus"])
         self.loss_multiplier = float(cfg["loss_multiplier"])
         self._vec = VecCDAEnv(cfg, num_markets=1, device=int(self.config.get("device", 0)),
-                              order_capacity=int(self.config.get("order_capacity", 0)), fill_capacity=int(self.config.get("fill_capacity", 64)))
+                              order_capacity=int(self.config.get("order_capacity", 0)), fill_capacity=int(self.config.get("fill_capacity", 64)),
+                              decimal_ledger=bool(self.config.get("decimal_ledger", True)))
         agent_ids = [f"agent_{i}" for i in range(self.num_of_agents)]
         self._agent_ids = set(agent_ids)
         self.agents = list(agent_ids)
@@ -264,6 +267,10 @@ class continuousDoubleAuctionEnv(_Base):
         truncateds["__all__"] = bool(trunc[0])
         self.t_step += 1
         return next_states, rewards, terminateds, truncateds, infos
+
+    def decimal_fields(self):
+        """The reference's Decimal money fields of this market, residues included (VecCDAEnv.decimal_fields)."""
+        return self._vec.decimal_fields([0])[0]
 
     def fills(self):
         """Trades of the last step (the reference's seq_trades), rows of

@@ -55,8 +55,15 @@ class StackedPlanes:
 
 
 class VecCDAEnv:
-    def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0, status_policy="raise"):
-        """status_policy: what step*/reset* do when a market carries a sticky status bit (see STATUS_BITS; noticed through a
+    def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0, status_policy="raise", decimal_ledger=False):
+        """decimal_ledger: besides the exact int64 ledger the env carries the reference's Decimal(prec 28) residues (VWAP and cash,
+        csrc/cda_twin.cuh: event journal + deferred replay, off the step's critical path), so that a cash gate or bankruptcy test that
+        lands on EXACT integer equality is decided like the reference's Decimal compare (agent/trader.py:108-151) — results are then
+        identical to the reference's unconditionally.  It costs a journal replay kernel every few steps (measured in DESIGN.md §4.3),
+        so the tensor API leaves it off by default: integers only, identical trajectories except at such ties (about one agent-step
+        in 10^5..10^6 when cash is of the order of single order values; none observed at the default cash of 10^6).  The dict
+        adapters (continuousDoubleAuctionEnv, VectorCDAEnv) — the drop-in surface — switch it on by default.
+        status_policy: what step*/reset* do when a market carries a sticky status bit (see STATUS_BITS; noticed through a
         pinned flag word the step kernel sets, i.e. at the first call after the offending step has completed — no launch and
         no synchronisation while all markets are clean): "raise" RuntimeError on pool overflow / bad action / price range /
         bad size (book and ledger of that market no longer follow the reference), "warn" once per bit, or "ignore".
@@ -82,7 +89,8 @@ class VecCDAEnv:
             int(cfg["min_size"]), int(cfg["mkt_max_size"]), int(cfg["limit_size_multiple"]),
             int(cfg["initial_price_min"]), int(cfg["initial_price_max"]), int(order_capacity),
             int(fill_capacity), float(cfg["order_penalty"]), float(cfg["trade_penalty"]),
-            float(cfg["drawdown_penalty"]), float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]))
+            float(cfg["drawdown_penalty"]), float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]), 1 if decimal_ledger else 0, 0)
+        self.decimal_ledger = bool(decimal_ledger)
         h = ctypes.c_void_p()
         _native.check(self._L.cda_create(ctypes.byref(c), self.M, self.device.index, ctypes.byref(h)))
         self._h = h
@@ -522,6 +530,46 @@ class VecCDAEnv:
             raise RuntimeError("cda_b200 market status: " + ", ".join(v for b, v in STATUS_BITS.items() if bits & b))
         return 0
 
+    def decimal_fields(self, markets=None):
+        """decimal_ledger: the reference's Decimal money fields of the given markets (default all), residues included, as
+        {market: {"cash": [Decimal]*A, "VWAP": [...], "cash_on_hold": [...], "position_val": [...], "nav": [...]}}.  cash and VWAP are
+        the device twin's values (after bringing the twins up to date); cash_on_hold is always an integer; position_val and nav are
+        derived with Python's decimal exactly as the reference's mark-to-market does (calculate.py:35-55) — the reference never
+        accumulates them, it recomputes them from VWAP at every fill and every mark-to-market."""
+        from decimal import Decimal, localcontext
+        if not self.decimal_ledger:
+            raise ValueError("construct the env with decimal_ledger=True")
+        buf = torch.empty((self.M, self.A, 8), dtype=torch.int64, device=self.device)
+        _native.check(self._L.cda_twin_sync(self._h, _ptr(buf), self._stream()))
+        tw = buf.cpu().numpy().view(np.uint64)
+        info = {k: v.cpu().numpy() for k, v in self.info_all().items()}
+
+        def dec(lo, hi, exp, sign):
+            c = (int(hi) << 64) | int(lo)
+            return Decimal((int(sign) & 1, tuple(int(ch) for ch in str(c)), int(np.int64(exp)))) if c else Decimal(0)
+        out = {}
+        with localcontext() as ctx:
+            ctx.prec = 28
+            for m in (range(self.M) if markets is None else markets):
+                tape = int(info["market"][m, 0]), bool(info["position_val"][m].any() or info["num_trades"][m].any())
+                d = {"cash": [], "VWAP": [], "cash_on_hold": [], "position_val": [], "nav": []}
+                for a in range(self.A):
+                    w = tw[m, a]
+                    vwap = dec(w[0], w[1], w[2], w[3] & np.uint64(0xffffffff))
+                    tracked = (int(w[7]) >> 40) & 1
+                    cash = dec(w[4], w[5], w[6], w[7] & np.uint64(0xffffffff)) if tracked else Decimal(int(info["cash"][m, a]))
+                    hold, pos, p = Decimal(int(info["cash_on_hold"][m, a])), int(info["net_position"][m, a]), Decimal(tape[0])
+                    ap = Decimal(abs(pos))
+                    if tape[1]:                                            # the tape is non-empty: marked to market every step
+                        diff = (p - vwap) if pos >= 0 else (vwap - p)
+                        pv = ap * vwap + ap * diff
+                    else:
+                        pv = Decimal(0)
+                    d["cash"].append(cash); d["VWAP"].append(vwap); d["cash_on_hold"].append(hold); d["position_val"].append(pv)
+                    d["nav"].append((cash + hold) + pv)
+                out[m] = d
+        return out
+
     def fills(self):
         if not self.fill_capacity:
             raise ValueError("construct the env with fill_capacity > 0 to log fills")
@@ -561,7 +609,7 @@ class VecCDAEnv:
     def dump_all(self, markets=None):
         """Canonical dumps (same schema as dump()) of many markets from ONE checkpoint copy, parsed on the host with the layout
         cda_state_layout() reports — what the full-size parity tests use (dump() costs ~20 launches per market)."""
-        lay = (ctypes.c_int32 * 8)()
+        lay = (ctypes.c_int32 * 12)()
         _native.check(self._L.cda_state_layout(self._h, lay))
         stride, off_acct, off_hist, off_pool, cap, A = (int(lay[i]) for i in range(6))
         raw = self.state_dict()["state"].numpy().reshape(self.M, stride)

@@ -62,7 +62,8 @@ class VectorCDAEnv:
         self.loss_multiplier = float(cfg["loss_multiplier"])
         self.agents = [f"agent_{i}" for i in range(self.num_of_agents)]
         self.possible_agents = list(self.agents)
-        self._vec = VecCDAEnv(cfg, num_markets=self.num_envs, device=device, order_capacity=order_capacity)
+        self._vec = VecCDAEnv(cfg, num_markets=self.num_envs, device=device, order_capacity=order_capacity,
+                              decimal_ledger=bool(self.config.get("decimal_ledger", True)))
         M, A = self.num_envs, self.num_of_agents
         # ONE pinned market-major action block i32[M][5][A]; the packers write straight into it
         self._blk = torch.empty((M, 5, A), dtype=torch.int32, pin_memory=True)

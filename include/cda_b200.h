@@ -49,6 +49,7 @@ extern "C" {
 #define CDA_ST_BAD_ACTION 4u      /* category/price/price_offset outside the action space */
 #define CDA_ST_PRICE_RANGE 8u     /* a price left [1, 2^24): outside the exactly-representable range */
 #define CDA_ST_BAD_SIZE 16u       /* order size <= 0 (reference: sys.exit in process_order) */
+#define CDA_ST_DEC_RANGE 32u      /* decimal_ledger: a Decimal(28) operation left the 128-bit domain (position >= 1e10 or a price beyond 2^24) */
 
 /* Mirrors the 17 env config keys (continuousDoubleAuction_env.py:35-53) that touch the hot path. */
 typedef struct CdaConfig {
@@ -62,6 +63,10 @@ typedef struct CdaConfig {
     int32_t order_capacity;      /* resting orders per side per market: 64, 128, 160, 192 or 256; 0 = auto (160 up to 8 agents, else 256) */
     int32_t fill_capacity;       /* fills logged per market per step (0 = no fill log) */
     double order_penalty, trade_penalty, drawdown_penalty, passive_bonus, loss_multiplier;
+    int32_t decimal_ledger;      /* 1: keep the reference's Decimal(prec 28) residues (deferred twin, csrc/cda_twin.cuh) so that a cash gate or a
+                                    bankruptcy test at EXACT integer equality is decided like the reference's Decimal compare
+                                    (agent/trader.py:108-151); 0: exact int64 ledger only (identical except at such ties) */
+    int32_t reserved_;
 } CdaConfig;
 
 typedef struct CdaEnv CdaEnv; /* opaque handle */
@@ -235,17 +240,23 @@ int cda_get_fills(CdaEnv *env, int32_t *d_fills, int32_t *d_counts, void *stream
 int cda_dump_market(CdaEnv *env, int32_t market, int64_t *h_bids, int64_t *h_asks, int64_t *h_bids_map,
                     int64_t *h_asks_map, int32_t max_rows, int32_t *h_counts, uint64_t *h_rng6);
 
+/* decimal_ledger: bring every agent's Decimal twin up to date (replays the event journals; the library does this by itself every few
+ * steps and on the spot whenever a decision needs it) and, optionally, copy the twins out: d_out i64[M][A][8] =
+ * { vwap coefficient lo, hi, exponent, sign | position << 32, cash coefficient lo, hi, exponent, sign | tracked << 40 } where a value is
+ * (-1)^sign * (hi * 2^64 + lo) * 10^exponent and `cash` is only meaningful while tracked (otherwise Decimal cash == integer cash). */
+int cda_twin_sync(CdaEnv *env, int64_t *d_out /* may be NULL */, void *stream);
+
 /* Device-state checkpoint (the reference has none). */
 size_t cda_state_bytes(const CdaEnv *env);
 int cda_save_state(CdaEnv *env, void *h_dst, void *stream);
 /* Layout of one market's block inside the checkpoint (bytes): out = { stride, off_accounts, off_snapshot_ring, off_order_pool,
- * order_capacity, num_agents, n_hist, header_bytes }.  Market m starts at m * stride.  Header words (u32): 0 time, 1 next_order_id,
+ * order_capacity, num_agents, n_hist, header_bytes, decimal_ledger, off_decimal_twins, off_event_journals, journal_entries }.  Market m starts at m * stride.  Header words (u32): 0 time, 1 next_order_id,
  * 2 insertion counter, 3 t_step, 4 last_price, 5 flags (bit 0: tape non-empty), 6 done_mask, 7 status, 8 n_bid, 9 n_ask,
  * 10 rng.has_uint32, 11 rng.uinteger, 12..19 PCG64 state_hi, state_lo, inc_hi, inc_lo (u64 each), 20..39 raw top-K prices, 40 best_bid,
  * 41 best_ask.  Accounts: cash, hold, cost_basis, nav, prev_nav, max_nav (i64[A] each), position (i32[A]), num_trades (u32[A]),
- * step counters (u32[A]: trades[0:12) passive[12:24) placed[24] rejected[25] is_pass[26]).  Order pool: u32[2 sides][cap/32][5][32],
+ * step counters (u32[A]: trades[0:12) passive[12:24) placed[24] rejected[25] is_pass[26]), Decimal-twin flags (u32[A]).  Order pool: u32[2 sides][cap/32][5][32],
  * fields trader<<24|price, qty, order_id, timestamp, insertion seq; live orders are entries 0..n-1 of their side, unsorted. */
-int cda_state_layout(const CdaEnv *env, int32_t out[8]);
+int cda_state_layout(const CdaEnv *env, int32_t out[12]);
 int cda_load_state(CdaEnv *env, const void *h_src, void *stream);
 
 /* Introspection */

@@ -26,6 +26,10 @@ unsigned long long *cda_debug_phase_buffer(void);
  * Process-wide; initialised from $CDA_DEBUG_WINDOW. */
 void cda_debug_set_window_mode(int32_t mode);
 
+/* decimal_ledger: how many tie-resolution passes (a market's steps re-executed with a parked answer, csrc/cda_kernels.cuh `resolve`) the step
+ * kernels of this process have made so far on the current device; -1 on error.  Synchronises. */
+int64_t cda_debug_restart_count(void);
+
 #ifdef __cplusplus
 }
 #endif
