@@ -60,6 +60,7 @@ struct CdaEnv {
     int act_tma;               // CDA_ACT_TMA (default 1): stage the action rows with cp.async.bulk
     double zc_fraction;        // share of the obs rows the kernel writes straight to host memory (the rest is DMA'd)   // same for the action block (kernel reads pinned host memory)
     long long launches;
+    unsigned *done_ctr; unsigned done_seq; int doorbell;   // completion doorbell (status_host[8] is the host word the kernel rings): CDA_DOORBELL=0 disables
     unsigned *status_host, *status_dev;   // one mapped pinned word: any step kernel that ends with a non-zero sticky market status stores 1 here
     int twin_steps, twin_every;            // decimal_ledger: steps since the last journal flush; flush cadence (CDA_TWIN_FLUSH_STEPS, $CDA_TWIN_FLUSH overrides: measurements)
     int g_parity;                          // fused all-gather: half of the double-buffered gather region the NEXT cda_step_gather writes
@@ -204,7 +205,9 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4 + MA * 8 + (size_t)num_markets * 2);
     if (err == cudaSuccess) err = cudaMalloc(&e->s_rec, (size_t)num_markets * (((size_t)d.A * 8 + 8 + 63) / 64 * 64));
     if (err == cudaSuccess) err = cudaHostAlloc(reinterpret_cast<void **>(&e->status_host), 64, cudaHostAllocMapped | cudaHostAllocPortable);
-    if (err == cudaSuccess) { *e->status_host = 0; err = cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->status_dev), e->status_host, 0); }
+    if (err == cudaSuccess) { memset(e->status_host, 0, 64); err = cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->status_dev), e->status_host, 0); }
+    if (err == cudaSuccess) err = cudaMalloc(&e->done_ctr, 64);
+    if (err == cudaSuccess) err = cudaMemset(e->done_ctr, 0, 64);
     if (err != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc failed: %s", cudaGetErrorString(err));
         cda_destroy(e);
@@ -240,6 +243,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
         const char *hcs = getenv("CDA_HOST_CTAS"), *dcs = getenv("CDA_DEV_CTAS");
         e->host_ctas = hcs ? atoi(hcs) : 0;
         e->dev_ctas = dcs ? atoi(dcs) : 0;
+        const char *db = getenv("CDA_DOORBELL");
+        e->doorbell = db ? atoi(db) : 1;
         const char *tf = getenv("CDA_TWIN_FLUSH");
         e->twin_every = tf && atoi(tf) > 0 ? atoi(tf) : CDA_TWIN_FLUSH_STEPS;
         const char *zf = getenv("CDA_ZC_FRACTION");
@@ -256,7 +261,7 @@ int cda_destroy(CdaEnv *e) {
     if (e->g_connected) for (int g = 0; g < e->g_world; ++g) if (g != e->g_rank && e->g_peer[g]) cudaIpcCloseMemHandle(e->g_peer[g]);
     cudaFree(e->g_local);
     cudaFree(e->state); cudaFree(e->fills); cudaFree(e->fill_counts);
-    cudaFree(e->s_cat); cudaFree(e->s_obs); cudaFree(e->s_rec); cudaFree(e->s_plane);
+    cudaFree(e->s_cat); cudaFree(e->s_obs); cudaFree(e->s_rec); cudaFree(e->s_plane); cudaFree(e->done_ctr);
     delete e;
     return CDA_OK;
 }
@@ -275,6 +280,19 @@ int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *
     return CDA_OK;
 }
 
+// Host side of the completion doorbell: spin on the pinned word the kernel's last warp writes (results are fenced before it); if it
+// does not ring within ~2 ms (a debugger, a preempted GPU) fall back to the stream synchronisation, which is always correct.
+static int doorbell_wait(CdaEnv *e, unsigned seq, cudaStream_t st) {
+    volatile unsigned *flag = e->status_host + 8;
+    for (int spin = 0; spin < 400000; ++spin) {
+        if (*flag == seq) return CDA_OK;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CDA_OK;
+}
 static int twin_flush(CdaEnv *e, cudaStream_t st) {
     const int n = e->M * e->dev.A, threads = 128;
     cda_twin_flush_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(e->dev, e->state, e->M, e->status_dev);
@@ -554,8 +572,11 @@ static int step_window_impl(CdaEnv *e, const int32_t *h_category, const float *h
         if (pos == H - 1) { p.obs = zw; p.obs_stride = wstride; }
         else { p.ring_out = zw; p.ring_stride = wstride; p.ring_slot = pos; p.ring_mirror = 0; }
     } else p.obs = e->s_obs;
+    const bool bell = zw && sync && e->doorbell && !(e->dev.dec && e->twin_steps + 1 >= e->twin_every);
+    if (bell) { p.done_ctr = e->done_ctr; p.done_flag = e->status_dev + 8; p.done_seq = ++e->done_seq; }
     int rc = step_common(e, p, st, true);
     if (rc) return rc;
+    if (bell) return doorbell_wait(e, p.done_seq, st);
     if (!zw && !dbg_dev_out) {
         const size_t dpitch = (size_t)wstride * 4, spitch = (size_t)e->dev.W * 4;
         if (pos == H - 1) CUDA_TRY(cudaMemcpy2DAsync(h_window, dpitch, e->s_obs, spitch, spitch, e->M, cudaMemcpyDeviceToHost, st));
@@ -611,9 +632,12 @@ int cda_step_planes(CdaEnv *e, const int32_t *h_action_block, float *h_plane, in
     p.pcode = reinterpret_cast<const int *>(zi + 3 * fstep); p.poff = reinterpret_cast<const int *>(zi + 4 * fstep);
     if (mm) { p.act_mstride = 5 * A; p.act_packed = 1; }
     p.ring_out = zp ? zp : e->s_plane; p.ring_stride = cell_words; p.ring_slot = 0; p.ring_mirror = 0; p.rec_inline = 1; p.ring_pad = cell_words;
+    const bool bell = zp && (flags & CDA_WIN_SYNC) && e->doorbell && !(e->dev.dec && e->twin_steps + 1 >= e->twin_every);   // (a replay kernel follows this step: synchronise)
+    if (bell) { p.done_ctr = e->done_ctr; p.done_flag = e->status_dev + 8; p.done_seq = ++e->done_seq; }
     int rc = step_common(e, p, st, true);
     if (rc) return rc;
     if (!zp) CUDA_TRY(cudaMemcpyAsync(h_plane, e->s_plane, (size_t)e->M * cell_words * 4, cudaMemcpyDeviceToHost, st));   // ONE contiguous copy
+    if (bell) return doorbell_wait(e, p.done_seq, st);
     if (flags & CDA_WIN_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
     return CDA_OK;
 }

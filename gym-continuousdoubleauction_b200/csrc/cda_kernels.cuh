@@ -97,6 +97,10 @@ struct CdaStepParams {
     // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
     int gather_world, gather_row0, gather_rows;
     unsigned char *gather_peer[CDA_MAX_PEERS];
+    // completion doorbell (host paths): every warp fences its output stores and counts itself on done_ctr (device memory); the last one
+    // resets the counter and stores done_seq to done_flag (mapped pinned host word), which the host polls instead of synchronising the
+    // stream: it sees the results a few microseconds before the driver sees the kernel retire
+    unsigned *done_ctr; unsigned *done_flag; unsigned done_seq;
     unsigned *status_flag;            // mapped pinned host word: set to 1 by any market that ends the step with a non-zero sticky status
 };
 
@@ -1304,6 +1308,15 @@ restart:;
             if (oa) bulk_s2g(gpool + CDA_POOL_FIELDS * CAP, sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, oa);
             bulk_commit();
             bulk_wait_read0();
+        }
+    }
+    if (ROUTED && p.done_flag) {
+        __threadfence_system();        // this warp's stores to host memory are visible before it counts itself
+        __syncwarp();
+        if (lane == 0 && atomicAdd(p.done_ctr, 1u) == (unsigned)p.M - 1u) {
+            *p.done_ctr = 0u;          // (every other warp has counted itself: the next launch starts from zero)
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(p.done_flag) = p.done_seq;
         }
     }
     CDA_TICK(9);   // state stored

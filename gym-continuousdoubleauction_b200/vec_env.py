@@ -370,13 +370,14 @@ class VecCDAEnv:
 
     # ---- dense plane ring: each step's output is ONE contiguous, line-aligned region (the host path that scales to 8 GPUs / node)
     PLANE_SLOTS = 8
-    PLANE_CELL_WORDS = 64          # 256-B cell per market and step: 42-float snapshot | reward f64[A] | terminated | truncated | zero pad
+    PLANE_CELL_WORDS = 0           # words per market and step: 42-float snapshot | reward f64[A] | terminated | truncated; 0 = exactly that (52 words for 4
+                                   # agents: bytes are what an 8-GPU node runs out of, profiles/r03f_e2e_scale_diag_8gpu_layout.txt), or a larger even size
 
     def _ensure_planes(self):
         if getattr(self, "_planes", None) is None:
             M, A, S = self.M, self.A, self.PLANE_SLOTS
             need = SNAPSHOT_DIM + 2 * A + 2
-            cell = self.PLANE_CELL_WORDS if self.PLANE_CELL_WORDS >= need and self.PLANE_CELL_WORDS % 2 == 0 else (need + 31) // 32 * 32
+            cell = self.PLANE_CELL_WORDS if self.PLANE_CELL_WORDS >= need and self.PLANE_CELL_WORDS % 2 == 0 else need + (need & 1)
             self._plane_cell = cell
             self._planes = torch.zeros((S, M, cell), dtype=torch.float32, pin_memory=True)
             pn = self._planes.numpy()
