@@ -195,7 +195,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--decimal-ledger", type=int, default=0, help="0 (VecCDAEnv's default): exact int64 ledger; 1: also carry the reference's Decimal(28) residues "
                     "(deferred twin: decides exact-equality ties like the reference; identical results on this workload)")
-    ap.add_argument("--allgather", action="store_true", help="N>1: also time an NCCL all-gather of obs/reward per step")
+    ap.add_argument("--allgather", action="store_true", help="(kept for compatibility: the config-5 all-gather mode is timed by default when N > 1)")
+    ap.add_argument("--no-allgather", action="store_true", help="N>1: skip the obs all-gather mode (NCCL baseline vs fused peer-memory gather)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -363,10 +364,10 @@ def main():
     if clocks is not None:
         clocks["window"] = "value + L2-hot + e2e regions + 0.6 s sustained stepping (rank 0's GPU)"
 
-    # ------------------------------------------------------------------ optional obs all-gather
+    # ------------------------------------------------------------------ obs all-gather (BASELINE config 5: one policy batch spans the GPUs)
     ag = None
-    if world > 1 and args.allgather:
-        # (a) baseline: step, then ONE NCCL all-gather of the packed obs|reward|flags block
+    if world > 1 and not args.no_allgather:
+        # (a) baseline: step, then ONE NCCL all-gather of the packed obs|reward|flags block (what a caller of torch.distributed does)
         blk_bytes = M * env.W * 4 + M * A * 8 + 2 * M
         loc = torch.empty(blk_bytes, dtype=torch.uint8, device=dev)
         outs = (loc[:M * env.W * 4].view(torch.float32).view(M, env.W), loc[M * env.W * 4:M * env.W * 4 + M * A * 8].view(torch.float64).view(M, A),
@@ -377,37 +378,37 @@ def main():
             k = step_ctr[0] % P; step_ctr[0] += 1
             env.step(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k], out=outs)
             dist.all_gather_into_tensor(allb, loc)
-        for i in range(5):
-            nccl_step()
-        torch.cuda.synchronize(); dist.barrier()
-        e0.record()
-        for i in range(args.steps):
-            nccl_step()
-        e1.record(); torch.cuda.synchronize()
-        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        # (b) fused: the step kernel's epilogue stores into every peer's gather buffer over NVLink; a 1-element
-        #     all-reduce orders the consumers
+
+        def timed_dev(fn):
+            for i in range(5):
+                fn()
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        tg = timed_dev(nccl_step)
+        # (b) fused: the step kernel's epilogue stores the newest snapshot + result record of every local market into EVERY rank's gather
+        #     window over NVLink and publishes a completion flag; a one-warp kernel waits for all ranks' flags: no NCCL call per step
         env.enable_peer_gather()
-        tiny = torch.zeros(1, device=dev)
 
         def fused_step():
             k = step_ctr[0] % P; step_ctr[0] += 1
             env.step_gather(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k])
-            dist.all_reduce(tiny)
-        for i in range(5):
-            fused_step()
-        torch.cuda.synchronize(); dist.barrier()
-        e0.record()
-        for i in range(args.steps):
-            fused_step()
-        e1.record(); torch.cuda.synchronize()
-        tf = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        ag = {"nccl_allgather": {"value": world * M * args.steps / (float(tg.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tg.item()) / args.steps,
-                                 "note": "step + one NCCL all_gather of the packed obs|reward|flags block per step, L2-hot"},
-              "fused_peer_gather": {"value": world * M * args.steps / (float(tf.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tf.item()) / args.steps,
-                                    "note": "cda_step_gather: kernel epilogue stores to all peers over NVLink (CUDA IPC) + 1-element all-reduce, L2-hot"}}
+        tf = timed_dev(fused_step)
+        cell = 4 * 42 + 8 * A + 2
+        ag = {"nccl_allgather": {"value": world * M * args.steps / (tg * 1e-3), "unit": UNIT, "ms_per_step": tg / args.steps,
+                                 "bytes_received_per_gpu_per_step": int((world - 1) * blk_bytes),
+                                 "note": "VecCDAEnv.step + one NCCL all_gather_into_tensor of the packed obs|reward|flags block per step, L2-hot"},
+              "fused_peer_gather": {"value": world * M * args.steps / (tf * 1e-3), "unit": UNIT, "ms_per_step": tf / args.steps,
+                                    "nvlink_bytes_sent_per_gpu_per_step": int((world - 1) * M * cell),
+                                    "note": "VecCDAEnv.step_gather: the kernel's epilogue stores the newest snapshot + record into every rank's gather window "
+                                            "(peer-mapped, NVLink) and publishes a completion flag; cda_gather_wait (one warp) orders the consumers; "
+                                            "obs = strided [G*M,168] view of the window; L2-hot"},
+              "fused_over_nccl": tg / tf}
 
     if rank != 0:
         if world > 1:

@@ -45,10 +45,10 @@ INFO_MARKET_COLS = ("last_price", "best_bid", "best_ask", "time", "next_order_id
 
 EXPORTS = (
     "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_step_host_ring", "cda_reset_host_ring", "cda_step_host_window", "cda_reset_host_window", "cda_window_bind", "cda_step_window", "cda_step_planes", "cda_reset_planes", "cda_rollout_random",
-    "cda_gather_create", "cda_gather_connect", "cda_step_gather", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
+    "cda_gather_create", "cda_gather_connect", "cda_gather_publish", "cda_step_gather", "cda_gather_wait", "cda_gather_pos", "cda_gather_row_words", "cda_gather_record_parity", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_record_bytes", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
-    "cda_seed_to_pcg64", "cda_state_layout", "cda_twin_sync", "cda_gather_parity", "cda_status_flag", "cda_status_flag_clear",
+    "cda_seed_to_pcg64", "cda_state_layout", "cda_twin_sync", "cda_status_flag", "cda_status_flag_clear",
 )
 TESTING_EXPORTS = ("cda_debug_phase_buffer", "cda_debug_dec_op", "cda_debug_dec_op_device", "cda_debug_set_window_mode", "cda_debug_restart_count")
 
@@ -134,7 +134,11 @@ def lib():
     sig("cda_seed_to_pcg64", [u64, ctypes.POINTER(u64)])
     sig("cda_state_layout", [vp, ctypes.POINTER(i32)])
     sig("cda_twin_sync", [vp, vp, vp])
-    sig("cda_gather_parity", [vp], i32)
+    sig("cda_gather_publish", [vp, vp])
+    sig("cda_gather_wait", [vp, vp])
+    sig("cda_gather_pos", [vp], i32)
+    sig("cda_gather_row_words", [vp], i32)
+    sig("cda_gather_record_parity", [vp], i32)
     sig("cda_status_flag", [vp], ctypes.POINTER(ctypes.c_uint32))
     sig("cda_status_flag_clear", [vp])
     sig("cda_debug_set_window_mode", [i32], None)

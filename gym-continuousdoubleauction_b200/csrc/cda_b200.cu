@@ -63,7 +63,7 @@ struct CdaEnv {
     unsigned *done_ctr; unsigned done_seq; int doorbell;   // completion doorbell (status_host[8] is the host word the kernel rings): CDA_DOORBELL=0 disables
     unsigned *status_host, *status_dev;   // one mapped pinned word: any step kernel that ends with a non-zero sticky market status stores 1 here
     int twin_steps, twin_every;            // decimal_ledger: steps since the last journal flush; flush cadence (CDA_TWIN_FLUSH_STEPS, $CDA_TWIN_FLUSH overrides: measurements)
-    int g_parity;                          // fused all-gather: half of the double-buffered gather region the NEXT cda_step_gather writes
+    int g_pos; unsigned g_seq;             // fused all-gather: slot of the newest snapshot in the gather windows; steps published so far
     size_t smem_bytes;
     int host_ctas, dev_ctas;   // resident CTAs per SM for the host paths / the device path (0 = as many as fit)
 };
@@ -98,7 +98,7 @@ static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStre
     }
     // routed outputs (host window / ring, packed or strided records, split rows, fused all-gather) take the full kernel; the plain
     // device step and the fused rollout take the body without that code
-    const bool routed = p.gather_world > 0 || p.ring_out || p.rec_inline || p.flag_pack || p.obs_hi || p.obs_split != e->M ||
+    const bool routed = p.rep_n > 1 || p.done_flag || p.ring_out || p.rec_inline || p.flag_pack || p.obs_hi || p.obs_split != e->M ||
                         p.obs_stride != e->dev.W || p.reward_stride != e->dev.A || p.flag_stride != 1;
     if (p.num_steps > 0) {
         if (routed) return cudaErrorInvalidValue;   // the rollout writes dense device arrays only
@@ -699,26 +699,27 @@ int cda_rollout_random(CdaEnv *e, int32_t num_steps, uint64_t policy_seed, float
     return CDA_OK;
 }
 
-static size_t cda_gather_half_bytes_(int M, int world, int W, int A) {
-    const size_t rows = (size_t)world * M;
-    return (rows * ((size_t)W * 4 + (size_t)A * 8 + 2) + 255) / 256 * 256;
-}
+// ---- fused step + all-gather over NVLink peer memory (include/cda_b200.h) ---------------------------------------------------------
+// Every rank owns a GATHER WINDOW  f32[world*M][CDA_GATHER_SLOTS][42]  (the sliding-window layout of the host path: a row's n_hist most
+// recent slots are its stacked observation, the result record rides behind the newest snapshot) followed by a flag array u32[64].
+// Row = CDA_GATHER_SLOTS snapshot slots, then TWO result records (step parity): a rank that is one step ahead writes the other record
+// and a different slot than the ones its peers' consumers are still reading.
+static int gather_row_words(const CdaEnv *e) { return (CDA_GATHER_SLOTS * CDA_SNAPSHOT_DIM + 2 * (2 * e->dev.A + 2) + 3) / 4 * 4; }
+static size_t gather_window_bytes(const CdaEnv *e, int world) { return (size_t)world * e->M * gather_row_words(e) * 4; }
+
 int cda_gather_create(CdaEnv *e, int32_t world, int32_t rank, void *ipc_handle_out64, void **d_local_buf, uint64_t *bytes) {
     if (!e || world < 1 || world > CDA_MAX_PEERS || rank < 0 || rank >= world || !ipc_handle_out64) return CDA_EINVAL;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (CDA_GATHER_SLOTS < 2 * e->dev.n_hist + 2) return CDA_EINVAL;
     DevGuard guard(e->device);
     if (e->g_local) return CDA_EINVAL;
-    const size_t rows = (size_t)world * e->M;
-    // TWO halves, written alternately: a rank one step ahead stores step t+1 into the other half while slower ranks still read
-    // step t (the per-step cross-rank barrier keeps every rank within one step of the others)
-    e->g_bytes = 2 * cda_gather_half_bytes_(e->M, world, e->dev.W, e->dev.A);
-    e->g_parity = 0;
+    e->g_bytes = gather_window_bytes(e, world) + 256;
     CUDA_TRY(cudaMalloc(&e->g_local, e->g_bytes));
     CUDA_TRY(cudaMemset(e->g_local, 0, e->g_bytes));
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, e->g_local));
     memcpy(ipc_handle_out64, &h, 64);
-    e->g_world = world; e->g_rank = rank; e->g_connected = false;
+    e->g_world = world; e->g_rank = rank; e->g_connected = false; e->g_seq = 0; e->g_pos = -1;
     if (d_local_buf) *d_local_buf = e->g_local;
     if (bytes) *bytes = e->g_bytes;
     return CDA_OK;
@@ -739,23 +740,77 @@ int cda_gather_connect(CdaEnv *e, const void *all_handles) {
     return CDA_OK;
 }
 
+// destinations of this rank's rows: its own window first (delta 0), then the peers'
+static void gather_targets(const CdaEnv *e, CdaStepParams &p) {
+    p.rep_n = e->g_world;
+    int n = 1;
+    p.rep_delta[0] = 0;
+    for (int g = 0; g < e->g_world; ++g) if (g != e->g_rank) p.rep_delta[n++] = (long long)(e->g_peer[g] - e->g_local);
+}
+
+int cda_gather_publish(CdaEnv *e, void *stream) {
+    if (!e) return CDA_EINVAL;
+    if (!e->was_reset || !e->g_connected) return CDA_ESTATE;
+    DevGuard guard(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = e->M * e->dev.W, threads = 256, wstride = gather_row_words(e);
+    for (int g = 0; g < e->g_world; ++g) {   // every market's current stack into slots 0..n_hist-1 of its row of every rank's window (cold path)
+        float *dst = reinterpret_cast<float *>(e->g_peer[g]) + (size_t)e->g_rank * e->M * wstride;
+        cda_emit_obs_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(e->dev, e->state, e->M, dst, wstride);
+    }
+    CUDA_TRY(cudaGetLastError());
+    e->launches += e->g_world;
+    e->g_pos = e->dev.n_hist - 1;
+    ++e->g_seq;
+    CUDA_TRY(cudaStreamSynchronize(st));     // the copies have landed in the peers' memory ...
+    const unsigned seq = e->g_seq;           // ... then this rank's flag in every window
+    for (int g = 0; g < e->g_world; ++g)
+        CUDA_TRY(cudaMemcpyAsync(e->g_peer[g] + gather_window_bytes(e, e->g_world) + 4 * e->g_rank, &seq, 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CDA_OK;
+}
+
 int cda_step_gather(CdaEnv *e, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
                     const int32_t *d_price, const int32_t *d_price_offset, void *stream) {
     if (!e || !d_category || !d_size_mean || !d_size_sigma || !d_price || !d_price_offset) return CDA_EINVAL;
     DevGuard guard(e->device);
-    if (!e->was_reset || !e->g_connected) return CDA_ESTATE;
+    if (!e->was_reset || !e->g_connected || e->g_pos < 0) return CDA_ESTATE;
+    const int H = e->dev.n_hist, A = e->dev.A, wstride = gather_row_words(e);
+    int pos = e->g_pos + 1;
+    if (pos >= CDA_GATHER_SLOTS) pos = H - 1;              // the window restarts: the whole stack is re-sent into slots 0..n_hist-1
     CdaStepParams p;
     memset(&p, 0, sizeof(p));
     p.cat = d_category; p.mean = d_size_mean; p.sigma = d_size_sigma; p.pcode = d_price; p.poff = d_price_offset;
-    p.gather_world = e->g_world; p.gather_row0 = e->g_rank * e->M; p.gather_rows = e->g_world * e->M;
-    const size_t half = e->g_bytes / 2;
-    for (int g = 0; g < e->g_world; ++g) p.gather_peer[g] = e->g_peer[g] + (size_t)e->g_parity * half;
-    e->g_parity ^= 1;
-    // non-null markers so the epilogue runs (the destinations come from gather_peer)
-    p.obs = reinterpret_cast<float *>(e->g_local); p.reward = reinterpret_cast<double *>(e->g_local);
-    p.term = e->g_local; p.trunc = e->g_local;
-    return step_common(e, p, (cudaStream_t)stream);
+    float *row0 = reinterpret_cast<float *>(e->g_local) + (size_t)e->g_rank * e->M * wstride;   // this rank's rows in its own window
+    gather_targets(e, p);
+    if (pos == H - 1) { p.obs = row0; p.obs_stride = wstride; }                                              // the whole stack
+    else { p.ring_out = row0; p.ring_stride = wstride; p.ring_slot = pos; p.ring_mirror = 0; }              // the newest snapshot only
+    {   // the result record of this step: record slot (seq & 1) behind the snapshot slots of the row
+        unsigned char *ir = reinterpret_cast<unsigned char *>(row0 + (size_t)CDA_GATHER_SLOTS * CDA_SNAPSHOT_DIM + (size_t)((e->g_seq + 1) & 1u) * (2 * A + 2));
+        p.reward = reinterpret_cast<double *>(ir); p.reward_stride = wstride / 2;
+        p.term = ir + (size_t)A * 8; p.trunc = p.term + 1; p.flag_stride = wstride * 4; p.flag_pack = 1;
+    }
+    // completion: the last warp publishes "step seq of rank r is in your window" to every rank's flag array
+    p.done_ctr = e->done_ctr; p.done_seq = ++e->g_seq;
+    p.done_flag = reinterpret_cast<unsigned *>(e->g_local + gather_window_bytes(e, e->g_world)) + e->g_rank;
+    int rc = step_common(e, p, (cudaStream_t)stream);
+    if (rc) return rc;
+    e->g_pos = pos;
+    return CDA_OK;
 }
+
+int cda_gather_wait(CdaEnv *e, void *stream) {
+    if (!e || !e->g_connected) return CDA_EINVAL;
+    DevGuard guard(e->device);
+    unsigned *flags = reinterpret_cast<unsigned *>(e->g_local + gather_window_bytes(e, e->g_world));
+    cda_gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, e->g_world, e->g_seq, flags + 32);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return CDA_OK;
+}
+int32_t cda_gather_pos(const CdaEnv *e) { return e ? e->g_pos : -1; }
+int32_t cda_gather_row_words(const CdaEnv *e) { return e ? gather_row_words(e) : 0; }
+int32_t cda_gather_record_parity(const CdaEnv *e) { return e ? (int32_t)(e->g_seq & 1u) : 0; }
 
 int cda_get_info(CdaEnv *e, int32_t field, int64_t *d_out, void *stream) {
     if (!e || !d_out || field < 0 || field >= CDA_INFO__COUNT) return CDA_EINVAL;
@@ -875,7 +930,6 @@ int cda_load_state(CdaEnv *e, const void *h_src, void *stream) {
     e->was_reset = true;
     return CDA_OK;
 }
-int32_t cda_gather_parity(const CdaEnv *e) { return e ? (e->g_parity ^ 1) : 0; }   // half written by the LAST cda_step_gather
 const volatile uint32_t *cda_status_flag(const CdaEnv *e) { return e ? e->status_host : nullptr; }
 int cda_status_flag_clear(CdaEnv *e) { if (!e) return CDA_EINVAL; *e->status_host = 0; return CDA_OK; }
 int32_t cda_record_bytes(const CdaEnv *e) { return e ? (int32_t)(((size_t)e->dev.A * 8 + 8 + 63) / 64 * 64) : 0; }

@@ -94,9 +94,12 @@ struct CdaStepParams {
     int ring_stride, ring_mirror;     // floats per market row of ring_out; 1 = also write the mirror copy
     int ring_pad;                     // > 0: the cell written at ring_slot is padded with zeros to this many words (dense plane output: a market's
                                       //      snapshot + record fill one aligned 256-B cell, so every store is a whole 128-B line)
-    // fused all-gather epilogue: outputs go to row (gather_row0 + m) of every peer's gather buffer
-    int gather_world, gather_row0, gather_rows;
-    unsigned char *gather_peer[CDA_MAX_PEERS];
+    // fused all-gather epilogue: every output store (obs row / newest snapshot + record / reward / flags / completion flag) is REPLICATED to
+    // rep_n destinations: the same address plus rep_delta[g] bytes (g = 0: the address itself).  The destinations are the ranks' gather
+    // windows, peer-mapped over NVLink (CUDA IPC), all laid out alike, so one base pointer (already offset to this rank's rows) and one
+    // byte delta per peer describe them all.  rep_n = 0 / 1: ordinary single-destination outputs.
+    int rep_n;
+    long long rep_delta[CDA_MAX_PEERS];
     // completion doorbell (host paths): every warp fences its output stores and counts itself on done_ctr (device memory); the last one
     // resets the counter and stores done_seq to done_flag (mapped pinned host word), which the host polls instead of synchronising the
     // stream: it sees the results a few microseconds before the driver sees the kernel retire
@@ -717,7 +720,7 @@ restart:;
     // ring, packed-record, split-row and fused all-gather paths execute is compiled out (720 of 4600 SASS instructions; the
     // kernel is several times larger than the 32 KB L1.5 instruction cache, and the smaller body measures 2-3 % faster once
     // the grid runs in more than one wave, when resident warps are spread over all phases of the step).
-    const int o_gather_world = ROUTED ? p.gather_world : 0, o_rec_inline = ROUTED ? p.rec_inline : 0, o_flag_pack = ROUTED ? p.flag_pack : 0;
+    const int o_rep_n = ROUTED && p.rep_n > 1 ? p.rep_n : 1, o_rec_inline = ROUTED ? p.rec_inline : 0, o_flag_pack = ROUTED ? p.flag_pack : 0;
     const int o_obs_split = ROUTED ? p.obs_split : p.M, o_ring_mirror = ROUTED ? p.ring_mirror : 0;
     float *const o_ring_out = ROUTED ? p.ring_out : nullptr;
     const int o_obs_stride = ROUTED ? p.obs_stride : cfg.W, o_reward_stride = ROUTED ? p.reward_stride : A, o_flag_stride = ROUTED ? p.flag_stride : 1;
@@ -1114,8 +1117,7 @@ restart:;
         const int wbL = (int)(fresh_tid_x() >> 5) * L::WORDS;
         float *orow = nullptr; int mis = 0;
         if (p.obs && last_it) {
-            orow = o_gather_world > 0 ? reinterpret_cast<float *>(p.gather_peer[0]) + (size_t)(p.gather_row0 + m) * cfg.W
-                                      : (m < o_obs_split ? p.obs : p.obs_hi) + (size_t)m * o_obs_stride;
+            orow = (m < o_obs_split ? p.obs : p.obs_hi) + (size_t)m * o_obs_stride;
             if (ROUTED) mis = (int)((reinterpret_cast<size_t>(orow) >> 2) & 31);
             // the ring holds exactly n_hist snapshots, so the stacked old part (oldest first) is ONE circular run of the ring
             // starting at the slot after the newest: element e lives at ring position (first + e) mod W — no division by 42
@@ -1177,10 +1179,10 @@ restart:;
         if (p.obs && last_it) {
             // one destination normally; with the fused all-gather, row (row0 + m) of EVERY peer's buffer
             // (plain stores to peer-mapped addresses: they travel over NVLink while other warps still match)
-            const int nd = o_gather_world > 0 ? o_gather_world : 1;
+            const int nd = o_rep_n;
 #pragma unroll 1
             for (int g = 0; g < nd; ++g) {
-                float *o = g == 0 ? orow : reinterpret_cast<float *>(p.gather_peer[g]) + (size_t)(p.gather_row0 + m) * cfg.W;
+                float *o = ROUTED ? reinterpret_cast<float *>(reinterpret_cast<char *>(orow) + p.rep_delta[g]) : orow;
 #pragma unroll
                 for (int q = 0; q < CDA_HIST_PREFETCH; ++q) {
                     const int e = lane + 32 * q - mis;
@@ -1211,10 +1213,9 @@ restart:;
             r = r + -(cfg.c_dd * (double)ddi);
             r = r + cfg.c_passive * (double)((ac.ctr >> 12) & 0xfffu);
             if (p.reward && last_it) {
-                if (o_gather_world > 0) {
-                    const size_t off = (size_t)p.gather_rows * cfg.W * 4 + ((size_t)(p.gather_row0 + m) * A + lane) * 8;
-                    for (int g = 0; g < o_gather_world; ++g) *reinterpret_cast<double *>(p.gather_peer[g] + off) = r;
-                } else p.reward[(size_t)m * o_reward_stride + lane] = r;
+                double *rp = p.reward + (size_t)m * o_reward_stride + lane;
+                *rp = r;
+                for (int g = 1; g < o_rep_n; ++g) *reinterpret_cast<double *>(reinterpret_cast<char *>(rp) + p.rep_delta[g]) = r;
             }
             broke = !nav_positive(k, ac.nav);
             if (o_rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wbL + L::ACT + 2 * lane) = (unsigned)rb; SMW(wbL + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
@@ -1233,24 +1234,26 @@ restart:;
             }
             const int nw_data = nw;
             if (p.ring_pad > nw) nw = p.ring_pad;
-            float *rg = o_ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
-            for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < nw; cc += 32) {
-                if (cc < 0) continue;
-                const float v = cc >= nw_data ? 0.f : __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wbL + L::SNAP + cc) : SMW(wbL + L::ACT + cc - CDA_SNAPSHOT_DIM));
-                rg[cc] = v;
-                if (o_ring_mirror && cc < CDA_SNAPSHOT_DIM) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
+            float *rg0 = o_ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
+#pragma unroll 1
+            for (int g = 0; g < o_rep_n; ++g) {   // (fused all-gather: the same cell of every rank's window, over NVLink)
+                float *rg = reinterpret_cast<float *>(reinterpret_cast<char *>(rg0) + (g ? p.rep_delta[g] : 0LL));
+                for (int cc = lane - (int)((reinterpret_cast<size_t>(rg) >> 2) & 31); cc < nw; cc += 32) {
+                    if (cc < 0) continue;
+                    const float v = cc >= nw_data ? 0.f : __uint_as_float(cc < CDA_SNAPSHOT_DIM ? SMW(wbL + L::SNAP + cc) : SMW(wbL + L::ACT + cc - CDA_SNAPSHOT_DIM));
+                    rg[cc] = v;
+                    if (o_ring_mirror && cc < CDA_SNAPSHOT_DIM) rg[cfg.n_hist * CDA_SNAPSHOT_DIM + cc] = v;
+                }
             }
         }
         if (lane == 0 && last_it) {
             const unsigned char f_term = (done_mask & all) == all, f_trunc = (t_step + 1 >= (unsigned)cfg.max_step);
-            if (o_gather_world > 0) {
-                const size_t off = (size_t)p.gather_rows * ((size_t)cfg.W * 4 + (size_t)A * 8) + (size_t)(p.gather_row0 + m);
-                for (int g = 0; g < o_gather_world; ++g) { p.gather_peer[g][off] = f_term; p.gather_peer[g][off + p.gather_rows] = f_trunc; }
-            } else {
-                if (o_flag_pack) *reinterpret_cast<unsigned short *>(p.term + (size_t)m * o_flag_stride) = (unsigned short)(f_term | (f_trunc << 8));   // adjacent bytes: one store
+            for (int g = 0; g < o_rep_n; ++g) {
+                const long long dl = g ? p.rep_delta[g] : 0LL;
+                if (o_flag_pack) *reinterpret_cast<unsigned short *>(p.term + (size_t)m * o_flag_stride + dl) = (unsigned short)(f_term | (f_trunc << 8));   // adjacent bytes: one store
                 else {
-                    if (p.term) p.term[(size_t)m * o_flag_stride] = f_term;
-                    if (p.trunc) p.trunc[(size_t)m * o_flag_stride] = f_trunc;
+                    if (p.term) p.term[(size_t)m * o_flag_stride + dl] = f_term;
+                    if (p.trunc) p.trunc[(size_t)m * o_flag_stride + dl] = f_trunc;
                 }
             }
             if (p.fill_counts) p.fill_counts[m] = k.n_fills;
@@ -1317,6 +1320,8 @@ restart:;
             *p.done_ctr = 0u;          // (every other warp has counted itself: the next launch starts from zero)
             __threadfence_system();
             *reinterpret_cast<volatile unsigned *>(p.done_flag) = p.done_seq;
+            for (int g = 1; g < o_rep_n; ++g)    // fused all-gather: this rank's "step done" word in every peer's flag array
+                *reinterpret_cast<volatile unsigned *>(reinterpret_cast<char *>(p.done_flag) + p.rep_delta[g]) = p.done_seq;
         }
     }
     CDA_TICK(9);   // state stored
@@ -1432,6 +1437,19 @@ __global__ void cda_ring_fill_kernel(CdaDevCfg cfg, const unsigned char *state, 
     if (mask && !mask[m]) return;
     const float *g_hist = reinterpret_cast<const float *>(state + (size_t)m * cfg.stride + cfg.off_hist);
     ring[i] = g_hist[e % CDA_SNAPSHOT_DIM];   // slot 0 (all slots are equal right after a reset)
+}
+
+// fused all-gather: wait (on the consumer's stream) until every rank has published step `seq` into this rank's flag array.  A rank may be
+// one step ahead (flag == seq + 1): compare as signed distance.  Gives up after ~2 s (a dead peer must not hang the GPU): *err = 1.
+__global__ void cda_gather_wait_kernel(const volatile unsigned *flags, int world, unsigned seq, unsigned *err) {
+    if ((int)threadIdx.x < world) {
+        const long long t0 = clock64();
+        while ((int)(flags[threadIdx.x] - seq) < 0) {
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000000LL) { *err = 1u; break; }
+        }
+    }
+    __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -447,46 +447,65 @@ class VecCDAEnv:
         return self._ensure_pinned()
 
     # ------------------------------------------------------------------ fused step + all-gather (multi-GPU)
+    GATHER_SLOTS = 32
+
     def enable_peer_gather(self, group=None):
-        """Set up the NVLink peer-memory gather (one process per GPU, torch.distributed initialised).
-        Returns (obs f32[G*M,W], reward f64[G*M,A], terminated u8[G*M], truncated u8[G*M]) — CUDA tensors
-        viewing THIS rank's gather buffer, which every rank's step kernel fills directly."""
+        """Set up the NVLink peer-memory gather (one process per GPU, torch.distributed initialised; call after reset(), on every rank).
+        Every rank gets a gather WINDOW (G*M rows of 32 snapshot slots + two result records) that all ranks' step kernels fill directly.  Returns the stacked
+        observations of all G*M markets (see step_gather)."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         handle = (ctypes.c_ubyte * 64)()
         ptr, nbytes = ctypes.c_void_p(), ctypes.c_uint64()
-        _native.check(self._L.cda_gather_create(self._h, world, rank, handle, ctypes.byref(ptr), ctypes.byref(nbytes)))
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
-        _native.check(self._L.cda_gather_connect(self._h, blob))
+        with torch.cuda.device(self.device):
+            _native.check(self._L.cda_gather_create(self._h, world, rank, handle, ctypes.byref(ptr), ctypes.byref(nbytes)))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+            _native.check(self._L.cda_gather_connect(self._h, blob))
         rows = world * self.M
 
         class _Raw:   # expose the cudaMalloc'ed buffer to torch without copying
             def __init__(s, p, n):
                 s.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
         raw = torch.as_tensor(_Raw(ptr.value, nbytes.value), device=self.device)
-        o_b, r_b, half = rows * self.W * 4, rows * self.A * 8, nbytes.value // 2
-        # two halves written alternately (cda_b200.h): a faster rank's step t+1 lands in the other half while this rank reads step t
-        self._gather_halves = [
-            (raw[k:k + o_b].view(torch.float32).view(rows, self.W), raw[k + o_b:k + o_b + r_b].view(torch.float64).view(rows, self.A),
-             raw[k + o_b + r_b:k + o_b + r_b + rows], raw[k + o_b + r_b + rows:k + o_b + r_b + 2 * rows]) for k in (0, half)]
-        self._gather = self._gather_halves[0]
+        self._gather_row = self._L.cda_gather_row_words(self._h)        # 32 snapshot slots + two result records, in 4-byte words
+        wbytes = rows * self._gather_row * 4
         self._gather_raw = raw
-        dist.barrier(group=group)
-        return self._gather
+        self._gather_f32 = raw[:wbytes].view(torch.float32)
+        self._gather_f64 = raw[:wbytes].view(torch.float64)
+        self._gather_u8 = raw[:wbytes]
+        self._gather_rows = rows
+        dist.barrier(group=group)               # every window exists and is mapped everywhere
+        return self.publish_gather()
 
-    def step_gather(self, category, size_mean, size_sigma, price, price_offset):
-        """cda_step whose epilogue writes this rank's rows into every rank's gather buffer (P2P stores over NVLink).
-        Returns (obs f32[G*M,W], reward f64[G*M,A], terminated u8[G*M], truncated u8[G*M]) views of the half of THIS rank's
-        double-buffered gather region that this step fills.  Make ONE cross-rank barrier (e.g. a 1-element all-reduce on the
-        same stream) after the call before consuming them; they stay valid until the call after next (the other half takes the
-        next step), so no second "consumers are done" barrier is needed."""
+    def publish_gather(self):
+        """Send every local market's current stack to all ranks' windows (after reset() / a masked reset; every rank calls it)."""
+        _native.check(self._L.cda_gather_publish(self._h, self._stream()))
+        _native.check(self._L.cda_gather_wait(self._h, self._stream()))
+        return self._gather_views()[0]
+
+    def _gather_views(self):
+        pos, S, H, A, rows = self._L.cda_gather_pos(self._h), self.GATHER_SLOTS, self.n_hist, self.A, self._gather_rows
+        row_f = self._gather_row
+        obs = torch.as_strided(self._gather_f32, (rows, self.W), (row_f, 1), (pos - H + 1) * SNAPSHOT_DIM)
+        rec_b = (S * SNAPSHOT_DIM + self._L.cda_gather_record_parity(self._h) * (2 * A + 2)) * 4     # byte offset of this step's record inside a row
+        rew = torch.as_strided(self._gather_f64, (rows, A), (row_f // 2, 1), rec_b // 8)
+        term = torch.as_strided(self._gather_u8, (rows,), (row_f * 4,), rec_b + 8 * A)
+        trunc = torch.as_strided(self._gather_u8, (rows,), (row_f * 4,), rec_b + 8 * A + 1)
+        return obs, rew, term, trunc
+
+    def step_gather(self, category, size_mean, size_sigma, price, price_offset, wait=True):
+        """cda_step whose epilogue writes this rank's newest snapshots + result records into EVERY rank's gather window (P2P stores
+        over NVLink) and publishes a completion flag to every rank; with wait=True a one-warp kernel on the current stream then waits
+        for all ranks' flags (no NCCL call).  Returns (obs f32[G*M, W], reward f64[G*M, A], terminated u8[G*M], truncated u8[G*M]):
+        strided CUDA views of THIS rank's window (rows contiguous), valid until the next step_gather."""
         with torch.cuda.device(self.device):
             _native.check(self._L.cda_step_gather(self._h, _ptr(category), _ptr(size_mean), _ptr(size_sigma), _ptr(price),
                                                   _ptr(price_offset), self._stream()))
-        self._gather = self._gather_halves[self._L.cda_gather_parity(self._h)]
-        return self._gather
+            if wait:
+                _native.check(self._L.cda_gather_wait(self._h, self._stream()))
+        return self._gather_views()
 
     # ------------------------------------------------------------------ fused random rollout
     def rollout_random(self, num_steps, policy_seed=0):

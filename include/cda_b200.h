@@ -203,23 +203,35 @@ int cda_rollout_random(CdaEnv *env, int32_t num_steps, uint64_t policy_seed, flo
                        uint8_t *d_terminated, uint8_t *d_truncated, void *stream);
 
 /* ---- fused step + all-gather over NVLink peer memory (one policy batch spanning G GPUs) ----
- * Each rank owns M markets (global rows [rank*M, (rank+1)*M)).  cda_gather_create allocates this rank's
- * gather buffer  obs f32[G*M][W] | reward f64[G*M][A] | terminated u8[G*M] | truncated u8[G*M]  and
- * returns its 64-byte CUDA IPC handle; after the ranks exchange handles (any transport),
- * cda_gather_connect maps every peer's buffer.  cda_step_gather is cda_step whose epilogue stores each
- * market's outputs straight into ALL G buffers (P2P stores over NVLink/NVSwitch), so the transfer overlaps
- * the matching work of other warps and no separate collective moves the data.  The caller orders the
- * consumers with any tiny cross-rank barrier (e.g. a 1-element NCCL all-reduce) after the call.
- * The buffer is DOUBLE-BUFFERED: it holds two such blocks (each rounded up to 256 B; *bytes covers both) and consecutive
- * cda_step_gather calls write them alternately, so a rank that is one step ahead never overwrites rows a slower rank is still
- * reading (the per-step barrier keeps the ranks within one step of each other: no second, consumer-done barrier is needed).
- * cda_gather_parity() = index (0/1) of the block the LAST cda_step_gather wrote; block k starts at byte k * (*bytes / 2). */
+ * Each rank owns M markets (global rows [rank*M, (rank+1)*M)).  cda_gather_create allocates this rank's GATHER WINDOW: G*M rows of
+ *     f32 snapshot[CDA_GATHER_SLOTS][42], then two result records { double reward[A]; uint8_t terminated, truncated; pad to 8 }
+ * (row = cda_gather_row_words() 4-byte words), followed by u32 flags[64]; it returns the window's 64-byte CUDA IPC handle.  After the
+ * ranks exchange handles (any transport), cda_gather_connect maps every peer's window and cda_gather_publish sends every local
+ * market's current stack to slots 0..n_hist-1 of its row in EVERY rank's window (call it after a reset, on all ranks).
+ * cda_step_gather is then cda_step whose epilogue stores, for every local market, the newest 42-float snapshot into the next slot of
+ * that market's row, and the result record into record slot (step parity), in ALL G windows — plain stores to peer-mapped addresses
+ * that travel over NVLink / NVSwitch while other warps are still matching.  Of the 168-float observation only those 42 floats are new
+ * each step, so this moves 3.5x fewer bytes than an all-gather of the stacked observations (what NCCL would be given), and the
+ * stacked observation of global row r stays ONE contiguous run of its window row:
+ *     obs(r)    = row(r).snapshot[pos-n_hist+1 .. pos][0..41]     (pos = cda_gather_pos(); a strided [G*M, 168] view, oldest first)
+ *     record(r) = row(r).record[cda_gather_record_parity()]
+ * When the row is full the whole stack is re-sent into slots 0..n_hist-1 (once per CDA_GATHER_SLOTS - n_hist + 1 steps).
+ * Ordering is fused too: every warp fences its peer stores and counts itself; the last one writes this rank's step number into every
+ * rank's flag array.  cda_gather_wait enqueues a one-warp kernel on `stream` that returns once all G ranks have published the current
+ * step — no NCCL call anywhere on the path.  A rank may run at most one step ahead of its peers' consumers: the step it writes lands
+ * in a different snapshot slot and the other record slot than the ones being read, and it cannot start a second step before every
+ * peer has published the first (the flag wait): no second, consumer-done barrier.  Needs CDA_GATHER_SLOTS >= 2*n_hist + 2. */
 #define CDA_MAX_PEERS 8
+#define CDA_GATHER_SLOTS 32
 int cda_gather_create(CdaEnv *env, int32_t world, int32_t rank, void *ipc_handle_out64, void **d_local_buf, uint64_t *bytes);
 int cda_gather_connect(CdaEnv *env, const void *all_ipc_handles /* [world][64] */);
+int cda_gather_publish(CdaEnv *env, void *stream);
 int cda_step_gather(CdaEnv *env, const int32_t *d_category, const float *d_size_mean, const float *d_size_sigma,
                     const int32_t *d_price, const int32_t *d_price_offset, void *stream);
-int32_t cda_gather_parity(const CdaEnv *env);
+int cda_gather_wait(CdaEnv *env, void *stream);
+int32_t cda_gather_pos(const CdaEnv *env);
+int32_t cda_gather_row_words(const CdaEnv *env);
+int32_t cda_gather_record_parity(const CdaEnv *env);
 
 /* Lazy info (info_helper.py:30-116): gathers one field for all markets into d_out. */
 int cda_get_info(CdaEnv *env, int32_t field, int64_t *d_out, void *stream);
