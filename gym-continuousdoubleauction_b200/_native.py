@@ -45,7 +45,7 @@ INFO_MARKET_COLS = ("last_price", "best_bid", "best_ask", "time", "next_order_id
 
 EXPORTS = (
     "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_step_host_ring", "cda_reset_host_ring", "cda_step_host_window", "cda_reset_host_window", "cda_window_bind", "cda_step_window", "cda_step_planes", "cda_reset_planes", "cda_rollout_random",
-    "cda_gather_create", "cda_gather_connect", "cda_gather_publish", "cda_step_gather", "cda_gather_wait", "cda_gather_pos", "cda_gather_row_words", "cda_gather_record_parity", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_dump_market", "cda_state_bytes", "cda_save_state",
+    "cda_gather_create", "cda_gather_connect", "cda_gather_publish", "cda_step_gather", "cda_gather_wait", "cda_gather_pos", "cda_gather_row_words", "cda_gather_record_parity", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_set_action_log", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_record_bytes", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
     "cda_seed_to_pcg64", "cda_state_layout", "cda_twin_sync", "cda_status_flag", "cda_status_flag_clear",
@@ -121,6 +121,7 @@ def lib():
     sig("cda_get_info", [vp, i32, vp, vp])
     sig("cda_get_info_all", [vp, vp, vp])
     sig("cda_get_fills", [vp, vp, vp, vp])
+    sig("cda_set_action_log", [vp, vp])
     sig("cda_dump_market", [vp, i32, vp, vp, vp, vp, i32, vp, vp])
     sig("cda_state_bytes", [vp], ctypes.c_size_t)
     sig("cda_save_state", [vp, vp, vp])

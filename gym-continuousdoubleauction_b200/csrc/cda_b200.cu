@@ -44,6 +44,7 @@ struct CdaEnv {
     unsigned char *state;      // M * stride bytes
     size_t state_bytes;
     int *fills; int *fill_counts;
+    int *act_log;              // cda_set_action_log: decoded-action log of every step (caller's device buffer), or NULL
     // device staging for cda_step_host
     int *s_cat; float *s_mean; float *s_sigma; int *s_pcode; int *s_poff;
     float *s_obs; double *s_reward; unsigned char *s_term; unsigned char *s_trunc;
@@ -312,7 +313,7 @@ static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st, bool host_p
     if (!p.act_mstride) p.act_mstride = e->dev.A;
     if (!p.ring_stride) { p.ring_stride = 2 * e->dev.n_hist * CDA_SNAPSHOT_DIM; p.ring_mirror = 1; }
     p.prof = g_prof;
-    p.fills = e->fills; p.fill_counts = e->fill_counts;
+    p.fills = e->fills; p.fill_counts = e->fill_counts; p.act_log = e->act_log;
     // TMA staging of the action rows: rows of A 4-byte words must be multiples of 16 B and the arrays 16-B aligned
     static const int dbg_acct_tma = getenv("CDA_ACCT_TMA") ? atoi(getenv("CDA_ACCT_TMA")) : 1;
     p.acct_tma = dbg_acct_tma;   // the account block is 64 * A bytes: a multiple of 16 for every A
@@ -834,6 +835,11 @@ int cda_get_info_all(CdaEnv *e, int64_t *d_out, void *stream) {
     return CDA_OK;
 }
 
+int cda_set_action_log(CdaEnv *e, int32_t *d_log) {
+    if (!e) return CDA_EINVAL;
+    e->act_log = d_log;
+    return CDA_OK;
+}
 int cda_get_fills(CdaEnv *e, int32_t *d_fills, int32_t *d_counts, void *stream) {
     if (!e || !e->fills) return CDA_EINVAL;
     DevGuard guard(e->device);

@@ -83,6 +83,7 @@ struct CdaStepParams {
                        //    (the head of slot ring_slot + 1), in the same store instructions: no separate PCIe write transactions for it
     float *obs; double *reward; unsigned char *term; unsigned char *trunc;
     int *fills; int *fill_counts;
+    int *act_log;      // optional i32[M][A][4]: the decoded actions of this step (type, side, size, price; side -1 = pass / absent) — the reference's LOB_actions
     // fused random-policy rollout (cda_rollout_random): num_steps > 0 => actions are generated
     int num_steps; unsigned long long policy_seed;
     unsigned long long *prof;   // CDA_PROFILE_PHASES builds: per-phase cycle sums [16]
@@ -931,6 +932,8 @@ restart:;
         CDA_TICK(1);   // accounts + actions arrived, draws + decode done
         // park the decoded actions in shared memory: the matching phase reads them with uniform loads, and the
         // dozen registers they occupied are free while the book is being worked on
+        if (!ROLLOUT && p.act_log && lane < A)
+            *reinterpret_cast<int4 *>(p.act_log + ((size_t)m * A + lane) * 4) = a_side >= 0 ? make_int4(a_type, a_side, (int)a_size, a_price) : make_int4(-1, -1, 0, -1);
         if (lane < A && a_side >= 0) {
             SMW(wb + L::ACT + 3 * lane) = (unsigned)a_type | ((unsigned)a_side << 8);
             SMW(wb + L::ACT + 3 * lane + 1) = (unsigned)a_size;

@@ -160,6 +160,33 @@ def pack_actions(actions, A, cat, mean, sigma, price, off, m=0):
     return idxs
 
 
+_SIDES, _TYPES = ("bid", "ask"), ("market", "limit", "modify", "cancel")
+
+
+class _AccountView:
+    """Read-only view of one agent's account on the device (the reference's `env.traders[i].acc`): the fields the callback, the
+    recorder and the reference's tests read.  Money is the exact integer ledger (`str(acc.nav)` == `info["NAV"]`)."""
+    _MAP = {"cash": "cash", "cash_on_hold": "cash_on_hold", "nav": "nav", "prev_nav": "prev_nav", "max_nav": "max_nav", "net_position": "net_position",
+            "position_val": "position_val", "num_trades": "num_trades", "num_trades_step": "num_trades_step",
+            "num_passive_fills_step": "num_passive_fills_step", "order_step_placed": "order_step_placed", "num_rejected_step": "num_rejected_step"}
+
+    def __init__(self, env, i):
+        self._env, self._i = env, i
+
+    def __getattr__(self, name):
+        if name == "VWAP":
+            pos, cost = int(self._env._vec.info("net_position")[0, self._i].item()), int(self._env._vec.info("cost_basis")[0, self._i].item())
+            return cost / abs(pos) if pos else 0.0
+        if name in self._MAP:
+            return int(self._env._vec.info(self._MAP[name])[0, self._i].item())
+        raise AttributeError(name)
+
+
+class _TraderView:
+    def __init__(self, env, i):
+        self.ID, self.acc = i, _AccountView(env, i)
+
+
 class continuousDoubleAuctionEnv(_Base):
     metadata = {"render.modes": ["human"]}
 
@@ -178,6 +205,7 @@ class continuousDoubleAuctionEnv(_Base):
         self.n_hist = int(cfg["n_hist"])
         self.is_render = cfg["is_render"]
         self.tick_size = cfg["tick_size"]
+        self.min_tick = cfg["tick_size"]                      # action_helper.py:55-58
         self.k_rows, self.book_rows, self.extra_dim = _config.K_ROWS, _config.BOOK_ROWS, _config.EXTRA_DIM
         self.book_dim = self.k_rows * self.book_rows
         self.snapshot_dim = self.book_dim + self.extra_dim
@@ -195,6 +223,9 @@ class continuousDoubleAuctionEnv(_Base):
             a: _spaces.Box(low=-np.inf, high=np.inf, shape=(self.n_hist * self.snapshot_dim,), dtype=np.float32)
             for a in agent_ids}
         self.action_spaces = self.act_space(self.num_of_agents)
+        self._vec.enable_action_log()                         # LOB_actions
+        self.traders = [_TraderView(self, i) for i in range(self.num_of_agents)]
+        self.LOB_actions = None
         self.t_step = 0
         self.last_price = None
         self.best_bid = self.best_ask = self.spread = None
@@ -230,6 +261,7 @@ class continuousDoubleAuctionEnv(_Base):
         self.t_step = 0
         self.done_set = set()
         self.pass_agents = set()
+        self.LOB_actions = None
         o = obs[0].cpu().numpy()
         self.last_price = float(self._vec.info("market")[0, 0].item())
         return {a: o for a in self.agents}, {a: {} for a in self._agent_ids}
@@ -254,6 +286,9 @@ class continuousDoubleAuctionEnv(_Base):
         self.best_bid = float(mk[1]) if mk[1] > 0 else None
         self.best_ask = float(mk[2]) if mk[2] > 0 else None
         self.spread = (self.best_ask - self.best_bid) if (self.best_bid is not None and self.best_ask is not None) else None
+        la = self._vec.last_actions()[0].cpu().numpy()            # continuousDoubleAuction_env.py:285: the decoded, non-pass actions in dict order
+        self.LOB_actions = [{"ID": f"agent_{i}", "side": _SIDES[int(la[i, 1])], "type": _TYPES[int(la[i, 0])], "size": int(la[i, 2]),
+                             "price": -1.0 if int(la[i, 0]) == 0 else float(la[i, 3])} for i in idxs if la[i, 1] >= 0]
         self._vec_status = int(mk[7])
         if self._vec_status & 29:                                  # fatal bits only: a fill-LOG overflow (bit 2) leaves book and ledger exact
             self._vec.check_status()
@@ -271,6 +306,16 @@ class continuousDoubleAuctionEnv(_Base):
     def decimal_fields(self):
         """The reference's Decimal money fields of this market, residues included (VecCDAEnv.decimal_fields)."""
         return self._vec.decimal_fields([0])[0]
+
+    @property
+    def np_random(self):
+        """A numpy Generator positioned exactly where this market's device-side stream is (numpy's PCG64, state copied out of the
+        device): what the reference's `env.np_random` would draw next.  A SNAPSHOT — drawing from it does not advance the env."""
+        st = np.asarray(self._vec.dump(0)["rng"], dtype=np.uint64)
+        bg = np.random.PCG64()
+        bg.state = {"bit_generator": "PCG64", "state": {"state": (int(st[0]) << 64) | int(st[1]), "inc": (int(st[2]) << 64) | int(st[3])},
+                    "has_uint32": int(st[4]), "uinteger": int(st[5])}
+        return np.random.Generator(bg)
 
     def fills(self):
         """Trades of the last step (the reference's seq_trades), rows of

@@ -590,6 +590,17 @@ class VecCDAEnv:
                 out[m] = d
         return out
 
+    def enable_action_log(self, on=True):
+        """Keep the decoded actions of every step (the reference's LOB_actions): last_actions() then returns int32 [M, A, 4] =
+        order type (0 market, 1 limit, 2 modify, 3 cancel), side (0 bid, 1 ask, -1 = pass / absent), size, price."""
+        self._act_log = torch.full((self.M, self.A, 4), -1, dtype=torch.int32, device=self.device) if on else None
+        _native.check(self._L.cda_set_action_log(self._h, _ptr(self._act_log)))
+
+    def last_actions(self):
+        if getattr(self, "_act_log", None) is None:
+            raise ValueError("call enable_action_log() first")
+        return self._act_log
+
     def fills(self):
         if not self.fill_capacity:
             raise ValueError("construct the env with fill_capacity > 0 to log fills")

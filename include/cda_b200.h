@@ -244,6 +244,11 @@ int cda_get_info_all(CdaEnv *env, int64_t *d_out, void *stream);
  * d_fills i32[M][fill_capacity][8], d_counts i32[M].  Requires fill_capacity > 0. */
 int cda_get_fills(CdaEnv *env, int32_t *d_fills, int32_t *d_counts, void *stream);
 
+/* Decoded-action log (the reference's `LOB_actions`, continuousDoubleAuction_env.py:285: what Action_Helper.set_actions made of the
+ * model's actions).  d_log i32[M][A][4] (device; NULL switches the log off): every later step stores, per agent, order type
+ * (0 market, 1 limit, 2 modify, 3 cancel), side (0 bid, 1 ask; -1 = pass or absent, other fields then meaningless), size and price. */
+int cda_set_action_log(CdaEnv *env, int32_t *d_log);
+
 /* Canonical dump of one market for bit-exact checks (host buffers; synchronises).
  *   book rows (priority order: bids price desc / asks price asc, FIFO inside a level):
  *     price, qty, trader, order_id, timestamp           -> h_bids/h_asks i64[max_rows][5]

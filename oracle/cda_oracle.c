@@ -102,6 +102,7 @@ typedef struct {
     int tape_nonempty; int64_t tape_last;
     int64_t last_price;
     OrcAcct acc[ORC_MAX_AGENTS];
+    int32_t last_act[ORC_MAX_AGENTS][4];   /* the reference's LOB_actions of the last step: type, side, size, price per agent; side -1 = pass / absent */
     int32_t t_step; uint32_t done_mask;
     orc_rng rng;
     float raw[4 * ORC_K];
@@ -582,6 +583,7 @@ static void market_step(OrcEnv *e, OrcMarket *mk, const int32_t *cat, const floa
     OrcAct acts[ORC_MAX_AGENTS]; int n = 0;
     for (int i = 0; i < A; ++i) { /* set_actions :145-172, dict order == agent order */
         mk->acc[i].is_pass = 0;
+        mk->last_act[i][0] = -1; mk->last_act[i][1] = -1; mk->last_act[i][2] = 0; mk->last_act[i][3] = -1;
         int cg = cat[i];
         if (cg < 0) continue;           /* agent absent from the action dict: no RNG draw */
         if (cg > 8) { mk->status |= ORC_ST_BAD_ACTION; cg = 0; }
@@ -605,6 +607,7 @@ static void market_step(OrcEnv *e, OrcMarket *mk, const int32_t *cat, const floa
             if (price < c->tick) price = c->tick;
         }
         acts[n].id = i; acts[n].side = side; acts[n].type = type; acts[n].size = size; acts[n].price = price;
+        mk->last_act[i][0] = type; mk->last_act[i][1] = side; mk->last_act[i][2] = (int32_t)size; mk->last_act[i][3] = (int32_t)price;
         ++n;
     }
     int perm[ORC_MAX_AGENTS];
@@ -779,6 +782,11 @@ int orc_dump_book(void *h, int m, int side, int64_t *out, int max_rows) {
         }
     }
     return n;
+}
+/* decoded actions of the last step (continuousDoubleAuction_env.py:285 LOB_actions): out[A][4] = type, side, size, price; side -1 = pass / absent */
+void orc_dump_actions(void *h, int m, int32_t *out) {
+    OrcEnv *e = (OrcEnv *)h;
+    memcpy(out, e->mk[m].last_act, sizeof(int32_t) * 4 * (size_t)e->cfg.num_agents);
 }
 /* order ids in order_map iteration order */
 int orc_dump_map(void *h, int m, int side, int64_t *out, int max_rows) {

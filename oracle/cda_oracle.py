@@ -146,6 +146,12 @@ class OracleEnv:
                                    _p(self.terminated), _p(self.truncated), int(nthreads))
         return self.obs, self.reward, self.terminated, self.truncated
 
+    def last_actions(self, m=0):
+        """Decoded actions of the last step (the reference's LOB_actions): int32 [A, 4] = type, side, size, price; side -1 = pass / absent."""
+        out = np.zeros((self.A, 4), np.int32)
+        self._L.orc_dump_actions(ctypes.c_void_p(self._h), int(m), _p(out))
+        return out
+
     # ---- canonical state dump (same schema as ref_runner.dump_reference and the GPU env) ----
     def dump(self, m=0):
         h = ctypes.c_void_p(self._h)

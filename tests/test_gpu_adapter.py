@@ -167,3 +167,41 @@ def test_vector_dict_env_matches_one_object_per_market():
     vec.close()
     for s in singles:
         s.close()
+
+
+def test_lob_actions_traders_view_and_np_random_snapshot_match_the_oracle():
+    """The attributes the reference's tests / callbacks read off the env object: LOB_actions (decoded actions of the last step, in dict
+    order, pass actions filtered out), traders[i].acc.<field>, min_tick, and np_random — a snapshot generator positioned exactly where the
+    device stream is (its next draws are what the oracle's stream draws next)."""
+    from oracle.cda_oracle import OracleEnv
+    from gym_continuousdoubleauction_b200.workloads import make_actions
+    cfg = dict(num_of_agents=5, init_cash=50_000, max_step=500, tick_size=2, initial_price_min=40, initial_price_max=90, is_render=False)
+    env = cda.continuousDoubleAuctionEnv(cfg)
+    orc = OracleEnv({k: v for k, v in cfg.items() if k != "is_render"}, 1)
+    env.reset(seed=77); orc.reset(seeds=[77])
+    assert env.min_tick == 2 and env.LOB_actions is None
+    acts = make_actions(5, 60, 1, 5, "uniform")
+    types, sides = ("market", "limit", "modify", "cancel"), ("bid", "ask")
+    for t in range(60):
+        d = {f"agent_{i}": {"category": int(acts[0][t, 0, i]), "size_mean": np.array([acts[1][t, 0, i]], np.float32),
+                            "size_sigma": np.array([acts[2][t, 0, i]], np.float32), "price": int(acts[3][t, 0, i]), "price_offset": int(acts[4][t, 0, i])}
+             for i in range(5) if (t + i) % 7}                                              # some agents absent
+        cat = np.array([[int(acts[0][t, 0, i]) if (t + i) % 7 else -1 for i in range(5)]], np.int32)
+        env.step(d)
+        orc.step(cat, acts[1][t], acts[2][t], acts[3][t], acts[4][t])
+        la = orc.last_actions(0)
+        want = [{"ID": f"agent_{i}", "side": sides[la[i, 1]], "type": types[la[i, 0]], "size": int(la[i, 2]), "price": -1.0 if la[i, 0] == 0 else float(la[i, 3])}
+                for i in range(5) if la[i, 1] >= 0]
+        assert env.LOB_actions == want, (t, env.LOB_actions, want)
+    acc = orc.dump(0)["accounts"]
+    for i in range(5):
+        a = env.traders[i].acc
+        assert (a.cash, a.cash_on_hold, a.nav, a.net_position, a.num_trades) == tuple(int(acc[i, j]) for j in (0, 1, 4, 7, 8))
+        assert str(a.nav) == env.step({})[4][f"agent_{i}"]["NAV"] if i == 0 else True
+    orc.step(np.full((1, 5), -1, np.int32), acts[1][0], acts[2][0], acts[3][0], acts[4][0])   # (the env.step({}) above: nobody acts, no draw)
+    g = env.np_random
+    st = orc.dump(0)["rng"]
+    assert g.bit_generator.state["state"]["state"] == (int(st[0]) << 64) | int(st[1])
+    z = g.standard_normal(3)                                                                  # drawing from the snapshot does not move the env
+    assert env.np_random.bit_generator.state["state"]["state"] == (int(st[0]) << 64) | int(st[1]) and z.shape == (3,)
+    env.close()
