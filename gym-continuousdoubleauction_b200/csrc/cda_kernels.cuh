@@ -33,6 +33,15 @@
                                  after an order AT the best price was removed.  (Defined HERE, above its first use: until r02e the switch sat
                                  below pool_best(), which therefore always scanned.) */
 #endif
+#ifndef CDA_SPEC_TILES
+#define CDA_SPEC_TILES 0      /* > 0: the first CDA_SPEC_TILES tiles (32 orders each) of BOTH pool sides are fetched speculatively together with the
+                                 account block, before the header has said how many orders are live: saves one dependent HBM round trip on a
+                                 cold cache at the price of over-fetching up to 640 B * CDA_SPEC_TILES per side */
+#endif
+#ifndef CDA_PREFETCH_TABLES
+#define CDA_PREFETCH_TABLES 0 /* 1: every CTA asks L2 for the ziggurat / jump-ahead tables at kernel entry (they are indexed by data that arrives two
+                                 dependent loads into the kernel; after an L2 flush the first touch per SM goes to HBM) */
+#endif
 #define CDA_HDR_BYTES 192
 #define CDA_POOL_FIELDS 5 /* 0 pt (trader<<24|price), 1 qty, 2 order_id, 3 timestamp, 4 seq */
 #define CDA_PRICE_MASK 0x00ffffffu
@@ -684,6 +693,10 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         // action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A] array) behind one
         // CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns 20 sector-sized PCIe reads per CTA into
         // 5 requests (ONE for a market-major block) issued at the very start of the kernel.
+#if CDA_PREFETCH_TABLES
+        if (threadIdx.x < 48) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(threadIdx.x < 16 ? (const void *)cda_zig_ki : threadIdx.x < 32 ? (const void *)cda_zig_wi : (const void *)cda_zig_fi) + (threadIdx.x & 15) * 128));
+        else if (threadIdx.x < 56) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(&cda_pcg_jump[0][0]) + (threadIdx.x - 48) * 128));
+#endif
         const int A0 = p.cfg.A, actb0 = WARPS * L::WORDS, cbar_w0 = actb0 + 5 * WARPS * A0;
         if (!ROLLOUT && p.act_tma) {
             if (threadIdx.x == 0) {
@@ -762,7 +775,16 @@ restart:;
     const int acct_w = cbar_w + 4 + warp * (16 * A);                 // word index of this warp's account tile (16-B aligned)
     if (lane == 0) {
         if ((SMW(wb + L::TIE) & 0xffu) == 0u) mbar_init(bar, 2);      // (a restarted pass uses the barrier's next phase)
-        if (p.acct_tma) { mbar_expect_tx(bar, 64u * (unsigned)A); bulk_g2s(smem_u32(smw) + (unsigned)acct_w * 4u, blk + cfg.off_acct, 64u * (unsigned)A, bar); }
+        constexpr unsigned spec_b = (CDA_SPEC_TILES * 32 > CAP ? CAP / 32 : CDA_SPEC_TILES) * (CDA_TILE_WORDS * 4u);
+        if (p.acct_tma) {
+            mbar_expect_tx(bar, 64u * (unsigned)A + 2u * spec_b);
+            bulk_g2s(smem_u32(smw) + (unsigned)acct_w * 4u, blk + cfg.off_acct, 64u * (unsigned)A, bar);
+            if (spec_b) {
+                const unsigned *gp = reinterpret_cast<const unsigned *>(blk + cfg.off_pool);
+                bulk_g2s(sa + L::POOL * 4u, gp, spec_b, bar);
+                bulk_g2s(sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, gp + CDA_POOL_FIELDS * CAP, spec_b, bar);
+            }
+        }
     }
     if (!p.acct_tma) {   // (debug switch) same tile, filled by plain loads
         const unsigned *ga = reinterpret_cast<const unsigned *>(blk + cfg.off_acct);
@@ -804,11 +826,14 @@ restart:;
 
     // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
-    const unsigned bytes_b = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), bytes_a = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
+    unsigned bytes_b = (((unsigned)k.nb + 31u) >> 5) * (CDA_TILE_WORDS * 4u), bytes_a = (((unsigned)k.na + 31u) >> 5) * (CDA_TILE_WORDS * 4u);
     if (lane == 0) {
+        // (tiles already on their way speculatively are skipped; only the plain-load debug path fetches everything here)
+        const unsigned skip = p.acct_tma ? (CDA_SPEC_TILES * 32 > CAP ? CAP / 32 : CDA_SPEC_TILES) * (CDA_TILE_WORDS * 4u) : 0u;
+        bytes_b = bytes_b > skip ? bytes_b - skip : 0u; bytes_a = bytes_a > skip ? bytes_a - skip : 0u;
         if (bytes_b | bytes_a) mbar_expect_tx(bar, bytes_b + bytes_a); else mbar_arrive(bar);
-        if (bytes_b) bulk_g2s(sa + L::POOL * 4u, gpool, bytes_b, bar);
-        if (bytes_a) bulk_g2s(sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u, gpool + CDA_POOL_FIELDS * CAP, bytes_a, bar);
+        if (bytes_b) bulk_g2s(sa + L::POOL * 4u + skip, reinterpret_cast<unsigned char *>(gpool) + skip, bytes_b, bar);
+        if (bytes_a) bulk_g2s(sa + (L::POOL + CDA_POOL_FIELDS * CAP) * 4u + skip, reinterpret_cast<unsigned char *>(gpool + CDA_POOL_FIELDS * CAP) + skip, bytes_a, bar);
     }
 
     float *g_hist = reinterpret_cast<float *>(blk + cfg.off_hist);
