@@ -75,13 +75,13 @@ static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 // reserved per CTA).  Used by the host paths: with fewer resident warps the grid runs as a stream of short CTAs instead
 // of ONE wave in which every market finishes at the same moment, so the outputs of early markets cross PCIe while later
 // markets are still being matched (and the action reads of later CTAs overlap the matching of earlier ones).
-template <int CAP>
+template <int CAP, bool DEC>
 static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st, int ctas_per_sm) {
     const int grid = (e->M + CDA_WARPS_PER_CTA - 1) / CDA_WARPS_PER_CTA;
     // per-warp tiles, then the CTA's action tile u32[5][WARPS][A] and its mbarrier
-    //     then one 16-B aligned account tile (60*A bytes) per warp
-    size_t smem = (size_t)CdaSmemLayout<CAP>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
-                  (size_t)CDA_WARPS_PER_CTA * (16 * e->dev.A * 4);
+    //     then one 16-B aligned account tile per warp
+    size_t smem = (size_t)CdaSmemLayout<CAP, DEC>::BYTES * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
+                  (size_t)CDA_WARPS_PER_CTA * (CDA_ACCT_TILE_WORDS(DEC, e->dev.A) * 4);
     if (ctas_per_sm > 0) {
         const size_t per_sm = 233472, pad = per_sm / (size_t)(ctas_per_sm + 1) - 1024 + 256;   // ctas_per_sm + 1 CTAs no longer fit
         if (pad > smem && pad <= 232448 - 1024) smem = pad;
@@ -92,30 +92,34 @@ static cudaError_t launch_step(const CdaEnv *e, const CdaStepParams &p, cudaStre
             cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         };
-        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, false>);
-        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, true>);
-        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true, false>);
+        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, false, DEC>);
+        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, true, DEC>);
+        set((const void *)cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true, false, DEC>);
         attr_set[e->device & 15] = smem;
     }
-    // routed outputs (host window / ring, packed or strided records, split rows, fused all-gather) take the full kernel; the plain
-    // device step and the fused rollout take the body without that code
+    // routed outputs (host window / ring / planes, packed or strided records, split rows, fused all-gather, completion doorbell) take the full
+    // kernel; the plain device step and the fused rollout take the body without that code
     const bool routed = p.rep_n > 1 || p.done_flag || p.ring_out || p.rec_inline || p.flag_pack || p.obs_hi || p.obs_split != e->M ||
                         p.obs_stride != e->dev.W || p.reward_stride != e->dev.A || p.flag_stride != 1;
     if (p.num_steps > 0) {
         if (routed) return cudaErrorInvalidValue;   // the rollout writes dense device arrays only
-        cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
-    } else if (routed) cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, true><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
-    else cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, false><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+        cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true, false, DEC><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    } else if (routed) cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, true, DEC><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
+    else cda_step_kernel<CAP, CDA_WARPS_PER_CTA, false, false, DEC><<<grid, CDA_WARPS_PER_CTA * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
-static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st, int ctas_per_sm) {
+template <bool DEC>
+static cudaError_t launch_step_cap(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st, int ctas_per_sm) {
     switch (e->dev.cap) {
-        case 64: return launch_step<64>(e, p, st, ctas_per_sm);
-        case 128: return launch_step<128>(e, p, st, ctas_per_sm);
-        case 160: return launch_step<160>(e, p, st, ctas_per_sm);
-        case 192: return launch_step<192>(e, p, st, ctas_per_sm);
-        default: return launch_step<256>(e, p, st, ctas_per_sm);
+        case 64: return launch_step<64, DEC>(e, p, st, ctas_per_sm);
+        case 128: return launch_step<128, DEC>(e, p, st, ctas_per_sm);
+        case 160: return launch_step<160, DEC>(e, p, st, ctas_per_sm);
+        case 192: return launch_step<192, DEC>(e, p, st, ctas_per_sm);
+        default: return launch_step<256, DEC>(e, p, st, ctas_per_sm);
     }
+}
+static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cudaStream_t st, int ctas_per_sm) {
+    return e->dev.dec ? launch_step_cap<true>(e, p, st, ctas_per_sm) : launch_step_cap<false>(e, p, st, ctas_per_sm);
 }
 
 extern "C" {
@@ -316,7 +320,7 @@ static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st, bool host_p
     p.fills = e->fills; p.fill_counts = e->fill_counts; p.act_log = e->act_log;
     // TMA staging of the action rows: rows of A 4-byte words must be multiples of 16 B and the arrays 16-B aligned
     static const int dbg_acct_tma = getenv("CDA_ACCT_TMA") ? atoi(getenv("CDA_ACCT_TMA")) : 1;
-    p.acct_tma = dbg_acct_tma;   // the account block is 64 * A bytes: a multiple of 16 for every A
+    p.acct_tma = dbg_acct_tma && (e->dev.dec || (e->dev.A % 4) == 0);   // bulk copies move multiples of 16 B: 64*A with the twin flags, else 60*A
     p.act_tma = e->act_tma && p.num_steps == 0 && (e->dev.A % 4) == 0 &&
                 (((uintptr_t)p.cat | (uintptr_t)p.mean | (uintptr_t)p.sigma | (uintptr_t)p.pcode | (uintptr_t)p.poff) & 15) == 0;
     CUDA_TRY(launch_step_any(e, p, st, host_path ? e->host_ctas : e->dev_ctas));

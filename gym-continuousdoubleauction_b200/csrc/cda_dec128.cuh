@@ -25,7 +25,8 @@ struct CdaDec { cda_u128 c; int exp; int sign; };   // c == 0 <=> zero (sign 0)
 #define CDA_DEC_P 28
 #if defined(__CUDACC__)
 #define CDA_HD __host__ __device__ __forceinline__
-#define CDA_HDN __host__ __device__ __noinline__ inline   /* the arithmetic proper: real calls, or one replay is 50 k instructions */
+#define CDA_HDN __host__ __device__ __noinline__ inline   /* add / mul / div (each with its rounding inlined) are real calls: with everything
+                                                              inlined one replay is 50 k instructions and every step kernel carries a copy */
 #else
 #define CDA_HD inline
 #define CDA_HDN inline
@@ -141,7 +142,7 @@ CDA_HD unsigned cda_div64_32(unsigned long long n, unsigned d, unsigned *rem) {
 #endif
 }
 // x / d, remainder in *rem, for 0 < d < 2^32
-CDA_HDN cda_u128 cda_u128_divmod_small(cda_u128 x, unsigned d, unsigned *rem) {
+CDA_HD cda_u128 cda_u128_divmod_small(cda_u128 x, unsigned d, unsigned *rem) {
     const unsigned long long hi = (unsigned long long)(x >> 64), lo = (unsigned long long)x;
     unsigned r = 0;
     const unsigned q3 = cda_div64_32(hi >> 32, d, &r);
@@ -171,7 +172,7 @@ CDA_HD unsigned long long cda_div2by1(unsigned long long u1, unsigned long long 
     return q1;
 }
 // x / 10^k for 0 <= k <= 38; the remainder is x - q * 10^k (the caller multiplies back: exact and cheap)
-CDA_HDN cda_u128 cda_u128_div_pow10(cda_u128 x, int k) {
+CDA_HD cda_u128 cda_u128_div_pow10(cda_u128 x, int k) {
     while (k > 0) {
         const int j = k > 19 ? 19 : k;
         k -= j;
@@ -192,7 +193,7 @@ CDA_HDN cda_u128 cda_u128_div_pow10(cda_u128 x, int k) {
 CDA_HD CdaDec cda_dec_zero() { CdaDec r; r.c = 0; r.exp = 0; r.sign = 0; return r; }
 
 // x * 10^exp (+ sticky: something non-zero beyond x) -> 28 significant digits, half to even
-CDA_HDN CdaDec cda_dec_round(int sign, cda_u128 x, int exp, int sticky) {
+CDA_HD CdaDec cda_dec_round(int sign, cda_u128 x, int exp, int sticky) {
     CdaDec r = cda_dec_zero();
     if (x == 0) return r;
     const int nd = cda_dec_ndigits(x);

@@ -348,7 +348,7 @@ __device__ __forceinline__ void acct_fill(CdaAcct &a, int party, int side /*0 bi
 #define SMW(i) smw[(i)]
 
 // Per-warp shared-memory tile, in 32-bit words.
-template <int CAP>
+template <int CAP, bool DEC = false>
 struct CdaSmemLayout {
     static constexpr int POOL = 0;                                   // u32[2 sides][CAP/32 tiles][5 fields][32]
     static constexpr int SNAP = 2 * CDA_POOL_FIELDS * CAP;           // f32[44] newest snapshot
@@ -359,7 +359,7 @@ struct CdaSmemLayout {
     static constexpr int ACT = ORDER + 32;                           // u32[32][3] decoded actions: type|side<<8, size, price
     static constexpr int PARK = ACT + 96;                            // 10 words: parked PCG64 state (+2 pad)
     static constexpr int TIE = PARK + 12;                            // u32[8] decimal_ledger: restart count | answers << 8, then up to 7 parked tie answers
-    static constexpr int BAR = TIE + 8;                              // mbarrier (8-B aligned)
+    static constexpr int BAR = TIE + (DEC ? 8 : 0);                  // mbarrier (8-B aligned)
     static constexpr int WORDS = ((BAR + 2 + 3) / 4) * 4;            // keep 16-B alignment of the next tile
     static constexpr int BYTES = WORDS * 4;
     static_assert(BAR % 2 == 0, "mbarrier must be 8-B aligned");
@@ -410,6 +410,9 @@ template <int CAP> __device__ __forceinline__ void twin_log(const CdaMkt<CAP> &k
 // (step, agent).  Cost: one extra pass for that one market, about once per 10^5..10^6 agent-steps on low-cash configurations.
 __device__ unsigned long long cda_debug_restarts = 0ULL;   // tie-resolution passes made by all step kernels so far (cda_debug_restart_count)
 #define CDA_TIE_SLOTS 7
+// words of a warp's account tile in shared memory: the whole 64*A-byte account block with the Decimal twin (its flags word is the 16th
+// array), else the 60*A bytes of r1 rounded up to 16 B (32 B less per warp and agent quadruple: what lets 7 CTAs of 8-agent markets fit an SM)
+#define CDA_ACCT_TILE_WORDS(DEC, A) ((DEC) ? 16 * (A) : ((15 * (A) + 3) & ~3))
 #define CDA_TIE_KEY_GATE(it, q) (0x10000u | ((unsigned)(it) << 8) | (unsigned)(q))
 #define CDA_TIE_KEY_NAV(it, a) (0x20000u | ((unsigned)(it) << 8) | (unsigned)(a))
 // answer for `key` (2 bits) or -1; tie_w[0] = restarts | n << 8, tie_w[1..] = key << 2 | answer
@@ -532,7 +535,7 @@ template <int CAP> __device__ __forceinline__ bool pool_append(CdaMkt<CAP> &k, i
 // Returns true when the gate hit an exact-equality tie that only the Decimal twin can decide and no answer is parked for it yet
 // (decimal_ledger; nothing has been changed): the trader's lane has parked the gated value in req_w, the caller leaves the step body.
 // tie_w: the warp's answer table; tie_key: this action's key; req_w: two scratch words for the value.
-template <int CAP>
+template <int CAP, bool DEC>
 __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams &p, CdaAcct &ac, int t, int type, int side, long long size, int price,
                                             int tie_w, unsigned tie_key, int req_w) {
     const int opp = side ^ 1;
@@ -541,7 +544,7 @@ __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams 
     int best_opp = -1;
     if (type == 0) best_opp = pool_best(k, opp);
     int ok_l = 0;
-    if (is_t && nav_positive(k, ac.nav)) {
+    if (is_t && (DEC ? nav_positive(k, ac.nav) : ac.nav > 0)) {
         long long opening;
         if ((side == 0 && ac.pos >= 0) || (side == 1 && ac.pos <= 0)) opening = size;
         else { const long long ap = ac.pos < 0 ? -ac.pos : ac.pos; opening = size - ap; if (opening < 0) opening = 0; }
@@ -549,7 +552,7 @@ __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams 
         else {
             const long long est = type == 0 ? (best_opp > 0 ? best_opp : (k.tape_nonempty ? k.tape_px : 1)) : price;
             ok_l = ac.cash >= opening * est;
-            if ((ac.ctr & CDA_TRACKED_BIT) && ac.cash == opening * est) {   // the Decimal residue decides (about 1 agent-step in 10^5 at low cash)
+            if (DEC && (ac.ctr & CDA_TRACKED_BIT) && ac.cash == opening * est) {   // the Decimal residue decides (about 1 agent-step in 10^5 at low cash)
                 const int ans = tie_lookup(tie_w, tie_key);
                 if (ans >= 0) ok_l = ans != 3;             // cash >= value unless the Decimal cash is smaller
                 else { const long long v = opening * est; SMW(req_w) = (unsigned)v; SMW(req_w + 1) = (unsigned)((unsigned long long)v >> 32); ok_l = 2; }
@@ -557,7 +560,7 @@ __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams 
         }
     }
     ok_l = __shfl_sync(CDA_FULL, ok_l, t);
-    if (ok_l == 2) return true;
+    if (DEC && ok_l == 2) return true;
     if (!ok_l) { if (is_t) ac.ctr |= 1u << 25; return false; }
     if (type <= 1 && is_t) ac.ctr |= 1u << 24;                          // trader.py:75-76
     if (size <= 0 && type <= 1) { k.raise(CDA_ST_BAD_SIZE); return false; }  // reference: sys.exit in process_order
@@ -580,7 +583,7 @@ __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams 
         oid = SMW(pl + 64);
         if (is_t) {
             const long long ov = (long long)op * oq; ac.hold -= ov; ac.cash += ov;
-            if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, ov));
+            if (DEC && (ac.ctr & CDA_TRACKED_BIT)) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, ov));
         }
         k.time++;                                                        // orderbook.py:196-200, :212-215
         if (type == 3) { pool_remove(k, side, idx); return false; }
@@ -591,7 +594,7 @@ __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams 
             __syncwarp();
             if (is_t) {
                 const long long v = (long long)price * size; ac.cash -= v; ac.hold += v;
-                if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, -v));
+                if (DEC && (ac.ctr & CDA_TRACKED_BIT)) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, -v));
             }
             return false;
         }
@@ -642,20 +645,20 @@ __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams 
         k.n_fills++;
         if (maker != t) {                     // trader.py:311-322: counter party, then initiator (disjoint lanes)
             if (k.lane == maker || is_t) {
-                if (k.twf_w >= 0) twin_log_fill(k, p, ac, is_t ? 0 : 1, is_t ? side : opp, traded, P);
+                if (DEC) twin_log_fill(k, p, ac, is_t ? 0 : 1, is_t ? side : opp, traded, P);
                 acct_fill(ac, is_t ? 0 : 1, is_t ? side : opp, traded, P);
             }
         } else if (is_t) {                    // cash_processor.py:55-62 self-trade: escrow back to cash
             const long long tv = (long long)traded * P;
             ac.hold -= tv; ac.cash += tv;
-            if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, tv));
+            if (DEC && (ac.ctr & CDA_TRACKED_BIT)) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, tv));
         }
     }
     // ---- residue rests (orderbook.py:174-191) and is escrowed (cash_processor.py:15-29); market remainder dropped
     if (type != 0 && qty > 0 && pool_append(k, side, (unsigned)price, qty, t, oid, k.time)) {
         if (is_t) {
             const long long v = (long long)price * qty; ac.cash -= v; ac.hold += v;
-            if (ac.ctr & CDA_TRACKED_BIT) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, -v));
+            if (DEC && (ac.ctr & CDA_TRACKED_BIT)) twin_log(k, p, cda_ev_value(CDA_EV_ESCROW, -v));
         }
     }
     return false;
@@ -686,9 +689,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
    boundaries of its destination (routed outputs: PCIe / NVLink write transactions), four when chunk 0 starts at the row start */
 #define CDA_HIST_PREFETCH (ROUTED ? 5 : 4)
 
-template <int CAP, int WARPS, bool ROLLOUT, bool ROUTED>
+template <int CAP, int WARPS, bool ROLLOUT, bool ROUTED, bool DEC>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
-    using L = CdaSmemLayout<CAP>;
+    using L = CdaSmemLayout<CAP, DEC>;
     {   // ---- CTA prologue (its values die here: nothing defined above `restart` may be live across the resolve block's call) ----
         // action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A] array) behind one
         // CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns 20 sector-sized PCIe reads per CTA into
@@ -719,14 +722,17 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         }
         __syncthreads();                                   // mbarrier initialised before any warp goes on
         if ((int)(blockIdx.x * WARPS + (threadIdx.x >> 5)) >= p.M) return;
-        if ((threadIdx.x & 31) == 0) smw[(threadIdx.x >> 5) * L::WORDS + L::TIE] = 0u;  // decimal_ledger: no restart yet, no parked answers
-        __syncwarp();
+        if (DEC) {
+            if ((threadIdx.x & 31) == 0) smw[(threadIdx.x >> 5) * L::WORDS + L::TIE] = 0u;  // decimal_ledger: no restart yet, no parked answers
+            __syncwarp();
+        }
     }
     // decimal_ledger: a tie only the Decimal twin can decide makes the warp leave the step body (`goto resolve`, nothing committed),
     // answer it at the bottom of the kernel and come back HERE to run this launch's steps for its market again (see tie_lookup)
 restart:;
   {
-    const int warp = (int)(fresh_tid_x() >> 5), lane = (int)(fresh_tid_x() & 31u);   // (fresh reads: not the prologue's copies kept alive across `resolve`)
+    // (decimal_ledger: fresh reads, not the prologue's copies kept alive across `resolve`)
+    const int warp = DEC ? (int)(fresh_tid_x() >> 5) : (int)(threadIdx.x >> 5), lane = DEC ? (int)(fresh_tid_x() & 31u) : (int)(threadIdx.x & 31);
     const int m = blockIdx.x * WARPS + warp;
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
@@ -772,13 +778,14 @@ restart:;
     //      lanes pick their fields out of shared memory when do_actions / mark-to-market need them, so no register
     //      holds an account value across the decode / RNG phases and no global-load latency is exposed later.
     //      The warp's mbarrier counts two arrivals: this copy and the order-pool copy issued once the header is here.
-    const int acct_w = cbar_w + 4 + warp * (16 * A);                 // word index of this warp's account tile (16-B aligned)
+    const int acct_w = cbar_w + 4 + warp * CDA_ACCT_TILE_WORDS(DEC, A);   // word index of this warp's account tile (16-B aligned)
+    const unsigned acct_b = DEC ? 64u * (unsigned)A : 60u * (unsigned)A;   // bytes staged: the twin-flags array only with the Decimal twin
     if (lane == 0) {
-        if ((SMW(wb + L::TIE) & 0xffu) == 0u) mbar_init(bar, 2);      // (a restarted pass uses the barrier's next phase)
+        if (!DEC || (SMW(wb + L::TIE) & 0xffu) == 0u) mbar_init(bar, 2);      // (a restarted pass uses the barrier's next phase)
         constexpr unsigned spec_b = (CDA_SPEC_TILES * 32 > CAP ? CAP / 32 : CDA_SPEC_TILES) * (CDA_TILE_WORDS * 4u);
         if (p.acct_tma) {
-            mbar_expect_tx(bar, 64u * (unsigned)A + 2u * spec_b);
-            bulk_g2s(smem_u32(smw) + (unsigned)acct_w * 4u, blk + cfg.off_acct, 64u * (unsigned)A, bar);
+            mbar_expect_tx(bar, acct_b + 2u * spec_b);
+            bulk_g2s(smem_u32(smw) + (unsigned)acct_w * 4u, blk + cfg.off_acct, acct_b, bar);
             if (spec_b) {
                 const unsigned *gp = reinterpret_cast<const unsigned *>(blk + cfg.off_pool);
                 bulk_g2s(sa + L::POOL * 4u, gp, spec_b, bar);
@@ -788,7 +795,7 @@ restart:;
     }
     if (!p.acct_tma) {   // (debug switch) same tile, filled by plain loads
         const unsigned *ga = reinterpret_cast<const unsigned *>(blk + cfg.off_acct);
-        for (int i = lane; i < 16 * A; i += 32) SMW(acct_w + i) = ga[i];
+        for (int i = lane; i < (int)(acct_b >> 2); i += 32) SMW(acct_w + i) = ga[i];
         __syncwarp();
         if (lane == 0) mbar_arrive(bar);
     }
@@ -822,7 +829,7 @@ restart:;
     k.fills_base = p.fills; k.mkt = m;
     k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
     k.bestb = -2; k.besta = -2;
-    k.twf_w = (cfg.dec && lane < A) ? acct_w + 15 * A + lane : -1;
+    k.twf_w = (DEC && lane < A) ? acct_w + 15 * A + lane : -1;
 
     // ---- order pool: ONE TMA bulk copy per side of the live tiles (640 B per 32 orders)
     unsigned *gpool = reinterpret_cast<unsigned *>(blk + cfg.off_pool);
@@ -984,7 +991,7 @@ restart:;
         __syncwarp();
 
         CDA_TICK(2);   // shuffle done
-        if (!waited) { mbar_wait(bar, SMW(wb + L::TIE) & 1u); waited = true; }
+        if (!waited) { mbar_wait(bar, DEC ? (SMW(wb + L::TIE) & 1u) : 0u); waited = true; }
         {   // this lane's account, out of the account tile.  In a multi-step rollout the tile is also where the
                                              // accounts live BETWEEN steps (written back at the end of every step): nothing account-related is
                                              // carried in registers across the decode / RNG phases of the next step.  Unconditional loads (lanes
@@ -993,7 +1000,7 @@ restart:;
             const long long *sq = reinterpret_cast<const long long *>(&smw[acct_w]);
             ac.cash = sq[al]; ac.hold = sq[A + al]; ac.cost = sq[2 * A + al]; ac.nav = sq[3 * A + al];
             ac.pos = (int)SMW(acct_w + 12 * A + al); ac.ntr = SMW(acct_w + 13 * A + al);
-            if (k.twf_w >= 0 && (SMW(k.twf_w) & CDA_TWF_TRACKED)) ac.ctr |= CDA_TRACKED_BIT;
+            if (DEC && k.twf_w >= 0 && (SMW(k.twf_w) & CDA_TWF_TRACKED)) ac.ctr |= CDA_TRACKED_BIT;
         }
         CDA_TICK(3);   // pool + account tiles landed
 
@@ -1008,7 +1015,7 @@ restart:;
             const unsigned ts_ = SMW(wb + L::ACT + 3 * t);
             const long long size = (long long)SMW(wb + L::ACT + 3 * t + 1);
             const int price = (int)SMW(wb + L::ACT + 3 * t + 2);
-            if (place_order(k, p, ac, t, (int)(ts_ & 0xffu), (int)(ts_ >> 8), size, price, wb + L::TIE, CDA_TIE_KEY_GATE(it, q), wb + L::SNAP)) {
+            if (place_order<CAP, DEC>(k, p, ac, t, (int)(ts_ & 0xffu), (int)(ts_ >> 8), size, price, wb + L::TIE, CDA_TIE_KEY_GATE(it, q), wb + L::SNAP) && DEC) {
                 // gate tie without an answer (decimal_ledger, rare): request = {mode 1, value, -, -, key} in this lane's slot of the pool tile
                 // (the pool is reloaded by the next pass), then leave
                 const int rq = wb + L::POOL + 8 * lane;
@@ -1032,7 +1039,7 @@ restart:;
             }
             // decimal_ledger: an integer NAV of exactly 0 — the Decimal NAV's sign decides bankruptcy and the next gate (done_helper.py,
             // trader.py:112).  Answer parked by an earlier pass -> record it in the twin flags; none yet -> park the request and leave.
-            if (cfg.dec && __any_sync(CDA_FULL, lane < A && ac.nav == 0)) {
+            if (DEC && __any_sync(CDA_FULL, lane < A && ac.nav == 0)) {
                 int code = -2;                                   // -2: no tie on this lane
                 if (lane < A && ac.nav == 0) code = tie_lookup(wb + L::TIE, CDA_TIE_KEY_NAV(it, lane));
                 if (__any_sync(CDA_FULL, code == -1)) {
@@ -1245,7 +1252,7 @@ restart:;
                 *rp = r;
                 for (int g = 1; g < o_rep_n; ++g) *reinterpret_cast<double *>(reinterpret_cast<char *>(rp) + p.rep_delta[g]) = r;
             }
-            broke = !nav_positive(k, ac.nav);
+            broke = DEC ? !nav_positive(k, ac.nav) : ac.nav <= 0;
             if (o_rec_inline) { const unsigned long long rb = (unsigned long long)__double_as_longlong(r); SMW(wbL + L::ACT + 2 * lane) = (unsigned)rb; SMW(wbL + L::ACT + 2 * lane + 1) = (unsigned)(rb >> 32); }
         }
         const unsigned done_mask = SMW(wbL + L::PARK + 10) | __ballot_sync(CDA_FULL, broke);
@@ -1305,7 +1312,7 @@ restart:;
     CDA_TICK(8);   // reward/done
     const int wbL = (int)(fresh_tid_x() >> 5) * L::WORDS;   // (as inside the loop: not the entry-time copy)
     // ---- store: header, accounts, pool prefix
-    if (cfg.dec) {   // a Decimal operation left the 128-bit domain (sizes / prices far beyond the reference's ranges): sticky status
+    if (DEC) {   // a Decimal operation left the 128-bit domain (sizes / prices far beyond the reference's ranges): sticky status
         const bool re = k.twf_w >= 0 && (SMW(k.twf_w) & CDA_TWF_RANGE);
         if (__any_sync(CDA_FULL, re)) k.raise(CDA_ST_DEC_RANGE);
         __syncwarp();
@@ -1325,7 +1332,7 @@ restart:;
         g_cash[lane] = ac.cash; g_hold[lane] = ac.hold; g_cost[lane] = ac.cost; g_nav[lane] = ac.nav;
         g_prev[lane] = nav_prev_carry; g_max[lane] = nav_max_carry; g_pos[lane] = (int)ac.pos; g_ntr[lane] = ac.ntr;
         g_ctr[lane] = ac.ctr;
-        if (k.twf_w >= 0) {
+        if (DEC && k.twf_w >= 0) {
             const unsigned twf = SMW(k.twf_w);
             g_twf[lane] = twf & ~CDA_TWF_RANGE;
         }
@@ -1359,6 +1366,7 @@ restart:;
     return;
   }
 resolve:
+    if (!DEC) return;        // (unreachable without the Decimal twin: nothing jumps here)
     // ---- decimal_ledger, rare: answer the parked tie requests with the Decimal twin (the ONLY place the step kernel calls the 128-bit
     //      arithmetic: top level, nothing live), park the answers, run the launch's steps for this market again
     {

@@ -103,12 +103,14 @@ def test_single_step_kernels_stay_spill_free_and_within_the_one_wave_register_bu
     txt = subprocess.run([tool, "--dump-resource-usage", _native.SO_PATH], capture_output=True, text=True).stdout
     usage = dict(re.findall(r"Function (\S+):\s*\n\s*(REG:\d+ STACK:\d+)", txt))
     step = {k: v for k, v in usage.items() if "cda_step_kernel" in k}
-    assert len(step) == 15                                         # 5 capacities x {device step, routed step, rollout}
+    assert len(step) == 30                                         # 5 capacities x {device step, routed step, rollout} x {ledger off, Decimal twin}
     for name, res in step.items():
         reg, stack = (int(x) for x in re.findall(r"\d+", res))
         assert reg <= 72, (name, res)
+        if "ILi160ELi4ELb0E" in name and name.endswith("ELb0EEv13CdaStepParams"):   # single-step bodies of the default capacity, ledger off: not one byte of stack
+            assert stack == 0, (name, res)
     sass = subprocess.run([tool, "-sass", _native.SO_PATH], capture_output=True, text=True).stdout
-    for fn in ("_Z15cda_step_kernelILi160ELi4ELb0ELb0EEv13CdaStepParams", "_Z15cda_step_kernelILi160ELi4ELb0ELb1EEv13CdaStepParams"):
+    for fn in ("_Z15cda_step_kernelILi160ELi4ELb0ELb0ELb1EEv13CdaStepParams", "_Z15cda_step_kernelILi160ELi4ELb0ELb1ELb1EEv13CdaStepParams"):   # with the Decimal twin
         body = sass.split("Function : " + fn)[1].split("Function : ")[0]
         ins = [m.group(1).strip() for m in re.finditer(r"/\*[0-9a-f]{4,6}\*/\s+(.*?);", body)]
         end = max(i for i, x in enumerate(ins) if re.search(r"\bEXIT\b", x)) + 1        # the kernel proper ends at its last EXIT; its callees follow
