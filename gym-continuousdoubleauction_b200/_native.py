@@ -31,7 +31,7 @@ class CdaConfig(ctypes.Structure):
         ("order_capacity", ctypes.c_int32), ("fill_capacity", ctypes.c_int32),
         ("order_penalty", ctypes.c_double), ("trade_penalty", ctypes.c_double),
         ("drawdown_penalty", ctypes.c_double), ("passive_bonus", ctypes.c_double),
-        ("loss_multiplier", ctypes.c_double), ("decimal_ledger", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("loss_multiplier", ctypes.c_double), ("decimal_ledger", ctypes.c_int32), ("fill_tape", ctypes.c_int32),
     ]
 
 

@@ -182,7 +182,7 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     d.mkt_mul = (float)((cfg->mkt_max_size - cfg->min_size) / 2.0);
     d.lim_mul = (float)(((double)cfg->mkt_max_size * cfg->limit_size_multiple - cfg->min_size) / 2.0);
     d.price_lo = cfg->initial_price_min; d.price_hi = cfg->initial_price_max;
-    d.cap = cap; d.fill_cap = cfg->fill_capacity;
+    d.cap = cap; d.fill_cap = cfg->fill_capacity; d.fill_tape = cfg->fill_tape && cfg->fill_capacity > 0 ? 1 : 0;
     d.c_order = cfg->order_penalty; d.c_trade = cfg->trade_penalty; d.c_dd = cfg->drawdown_penalty;
     d.c_passive = cfg->passive_bonus; d.c_loss = cfg->loss_multiplier;
     d.W = cfg->n_hist * CDA_SNAPSHOT_DIM;

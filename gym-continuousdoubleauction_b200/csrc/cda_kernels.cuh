@@ -72,6 +72,8 @@ struct CdaDevCfg {
     float mkt_mul, lim_mul;   // action_helper.py:46-47 (cast to f32 like numpy's weak python float)
     int price_lo, price_hi;
     int cap, fill_cap;
+    int fill_tape;            // 1: the fill log is a TAPE — a ring of the last fill_cap fills of the market across steps and launches (header word 42 counts
+                              //    all fills since the reset; the reference's unbounded LOB.tape, orderbook.py:20,140), instead of one step's fills
     double c_order, c_trade, c_dd, c_passive, c_loss;
     unsigned off_acct, off_hist, off_pool, stride;
     int W;                    // n_hist * 42
@@ -633,12 +635,12 @@ __device__ __forceinline__ bool place_order(CdaMkt<CAP> &k, const CdaStepParams 
         }
         k.tape_nonempty = 1; k.tape_px = P;   // :140 tape.append (trade price = resting price)
         if (k.fills_base) {
-            if (k.n_fills < k.fill_cap) {
+            if (k.n_fills < k.fill_cap || p.cfg.fill_tape) {
                 if (k.lane < CDA_FILL_WORDS) {
                     int *frow = k.fills_base + (size_t)k.mkt * k.fill_cap * CDA_FILL_WORDS;
                     const int v = k.lane == 0 ? (int)k.time : k.lane == 1 ? P : k.lane == 2 ? (int)traded : k.lane == 3 ? maker
                                 : k.lane == 4 ? (int)moid : k.lane == 5 ? left : k.lane == 6 ? t : side;
-                    frow[k.n_fills * CDA_FILL_WORDS + k.lane] = v;
+                    frow[(p.cfg.fill_tape ? k.n_fills % k.fill_cap : k.n_fills) * CDA_FILL_WORDS + k.lane] = v;
                 }
             } else k.raise(CDA_ST_FILL_OVERFLOW);
         }
@@ -827,7 +829,7 @@ restart:;
     rng.has32 = h2.z; rng.u32 = h2.w;
     k.tape_px = (int)h1.x;
     k.fills_base = p.fills; k.mkt = m;
-    k.fill_cap = cfg.fill_cap; k.n_fills = 0; k.dirty = 0;
+    k.fill_cap = cfg.fill_cap; k.n_fills = (cfg.fill_tape && p.fills) ? (int)hdr[42] : 0; k.dirty = 0;
     k.bestb = -2; k.besta = -2;
     k.twf_w = (DEC && lane < A) ? acct_w + 15 * A + lane : -1;
 
@@ -882,7 +884,7 @@ restart:;
             const ulonglong2 r1 = *reinterpret_cast<const ulonglong2 *>(hdr + 16);
             rng.shi = r0.x; rng.slo = r0.y; rng.ihi = r1.x; rng.ilo = r1.y;
         }
-        k.n_fills = 0;
+        if (!cfg.fill_tape) k.n_fills = 0;
         ac.ctr = 0;
         const bool bad = lane < A && (a_cat > 8 || (a_cat > 0 && ((a_cat - 1) & 3) != 0 && (a_pcode < 0 || a_pcode >= CDA_K_ROWS || a_poff < 0 || a_poff > 2)));
         if (__any_sync(CDA_FULL, bad)) k.raise(CDA_ST_BAD_ACTION);
@@ -1319,6 +1321,7 @@ restart:;
     }
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(hdr + 0) = make_uint4(k.time, k.next_id, k.seqctr, t_step);
+        if (cfg.fill_tape && p.fills) hdr[42] = (unsigned)k.n_fills;
         const unsigned stv = SMW(wbL + L::PARK + 11);
         if (stv) *p.status_flag = 1u;   // (rare) lets the host notice a sticky status without a gather
         *reinterpret_cast<uint4 *>(hdr + 4) = make_uint4((unsigned)k.tape_px, k.tape_nonempty ? CDA_FLAG_TAPE : 0u, SMW(wbL + L::PARK + 10), stv);

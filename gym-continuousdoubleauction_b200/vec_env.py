@@ -55,8 +55,10 @@ class StackedPlanes:
 
 
 class VecCDAEnv:
-    def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0, status_policy="raise", decimal_ledger=False):
-        """decimal_ledger: besides the exact int64 ledger the env carries the reference's Decimal(prec 28) residues (VWAP and cash,
+    def __init__(self, config=None, num_markets=1, device=0, order_capacity=0, fill_capacity=0, status_policy="raise", decimal_ledger=False, fill_tape=False):
+        """fill_tape: with fill_capacity > 0 the fill log becomes a tape — the last fill_capacity fills of every market across steps and
+        fused-rollout launches (the reference's LOB.tape, bounded) instead of the last step's fills; see tape().
+        decimal_ledger: besides the exact int64 ledger the env carries the reference's Decimal(prec 28) residues (VWAP and cash,
         csrc/cda_twin.cuh: event journal + deferred replay, off the step's critical path), so that a cash gate or bankruptcy test that
         lands on EXACT integer equality is decided like the reference's Decimal compare (agent/trader.py:108-151) — results are then
         identical to the reference's unconditionally.  It costs a journal replay kernel every few steps (measured in DESIGN.md §4.3),
@@ -89,7 +91,8 @@ class VecCDAEnv:
             int(cfg["min_size"]), int(cfg["mkt_max_size"]), int(cfg["limit_size_multiple"]),
             int(cfg["initial_price_min"]), int(cfg["initial_price_max"]), int(order_capacity),
             int(fill_capacity), float(cfg["order_penalty"]), float(cfg["trade_penalty"]),
-            float(cfg["drawdown_penalty"]), float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]), 1 if decimal_ledger else 0, 0)
+            float(cfg["drawdown_penalty"]), float(cfg["passive_bonus"]), float(cfg["loss_multiplier"]), 1 if decimal_ledger else 0, 1 if fill_tape else 0)
+        self.fill_tape = bool(fill_tape) and int(fill_capacity) > 0
         self.decimal_ledger = bool(decimal_ledger)
         h = ctypes.c_void_p()
         _native.check(self._L.cda_create(ctypes.byref(c), self.M, self.device.index, ctypes.byref(h)))
@@ -589,6 +592,19 @@ class VecCDAEnv:
                     d["nav"].append((cash + hold) + pv)
                 out[m] = d
         return out
+
+    def tape(self, m=0):
+        """fill_tape mode: (rows, total) — the most recent min(total, fill_capacity) fills of market m in execution order, oldest first
+        (rows of time, price, qty, maker, maker_order_id, maker_left, taker, taker_side), and the number of fills since the reset."""
+        if not self.fill_tape:
+            raise ValueError("construct the env with fill_capacity > 0 and fill_tape=True")
+        f, n = self.fills()
+        total, cap = int(n[m].item()), self.fill_capacity
+        rows = f[m].cpu().numpy()
+        if total <= cap:
+            return rows[:total], total
+        k = total % cap
+        return np.concatenate([rows[k:], rows[:k]]), total
 
     def enable_action_log(self, on=True):
         """Keep the decoded actions of every step (the reference's LOB_actions): last_actions() then returns int32 [M, A, 4] =

@@ -66,7 +66,9 @@ typedef struct CdaConfig {
     int32_t decimal_ledger;      /* 1: keep the reference's Decimal(prec 28) residues (deferred twin, csrc/cda_twin.cuh) so that a cash gate or a
                                     bankruptcy test at EXACT integer equality is decided like the reference's Decimal compare
                                     (agent/trader.py:108-151); 0: exact int64 ledger only (identical except at such ties) */
-    int32_t reserved_;
+    int32_t fill_tape;           /* 1: the fill log is a tape — a ring holding the last fill_capacity fills of each market ACROSS steps and launches
+                                    (the reference's LOB.tape, orderbook.py:20,140, bounded), row of fill number n at n % fill_capacity, and the count
+                                    cda_get_fills returns is the number of fills since the reset; 0: one step's fills, overwritten by the next step */
 } CdaConfig;
 
 typedef struct CdaEnv CdaEnv; /* opaque handle */
@@ -241,7 +243,8 @@ int cda_get_info(CdaEnv *env, int32_t field, int64_t *d_out, void *stream);
 int cda_get_info_all(CdaEnv *env, int64_t *d_out, void *stream);
 
 /* Fill log of the last step (the reference's per-step `seq_trades`, action_helper.py:201-239):
- * d_fills i32[M][fill_capacity][8], d_counts i32[M].  Requires fill_capacity > 0. */
+ * d_fills i32[M][fill_capacity][8], d_counts i32[M].  Requires fill_capacity > 0.  With CdaConfig.fill_tape the same buffer is a tape:
+ * the last fill_capacity fills of every market across steps (and across the steps of a fused rollout), d_counts = fills since the reset. */
 int cda_get_fills(CdaEnv *env, int32_t *d_fills, int32_t *d_counts, void *stream);
 
 /* Decoded-action log (the reference's `LOB_actions`, continuousDoubleAuction_env.py:285: what Action_Helper.set_actions made of the

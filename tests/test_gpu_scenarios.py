@@ -95,6 +95,38 @@ def test_fill_log_overflow_is_not_fatal_in_the_dict_adapter():
     env.close()
 
 
+def test_fill_tape_keeps_the_fills_of_every_step_of_a_fused_rollout():
+    """only the last step's fills survived a launch.  With fill_tape the log is a ring across steps: after a fused 40-step
+    rollout (ONE launch) plus 10 single steps it holds the market's most recent fills, equal to the oracle's per-step fills concatenated."""
+    from oracle.cda_oracle import OracleEnv
+    cfg = dict(num_of_agents=4, max_step=100000)
+    M, cap = 32, 64
+    env = cda.VecCDAEnv(cfg, num_markets=M, fill_capacity=cap, fill_tape=True)
+    orc = OracleEnv(cfg, M)
+    seeds = np.arange(M, dtype=np.uint64) + np.uint64(17)
+    env.reset(seed=seeds); orc.reset(seeds=seeds)
+    hist = [[] for _ in range(M)]
+    def orc_steps(n):
+        for _ in range(n):
+            orc.rollout_random(1, policy_seed=3)
+            for m in range(M):
+                d = orc.dump(m)
+                hist[m] += [tuple(r) for r in d["fills"][:d["n_fills"]]]
+    env.rollout_random(40, policy_seed=3); orc_steps(40)
+    for _ in range(10):
+        env.rollout_random(1, policy_seed=3)
+    orc_steps(10)
+    some = 0
+    for m in range(M):
+        rows, total = env.tape(m)
+        assert total == len(hist[m]) and [tuple(r) for r in rows.tolist()] == [tuple(int(x) for x in r) for r in hist[m][-cap:]], m
+        some += total > cap
+    assert some > 0                                      # the ring did wrap for some markets
+    env.reset(seed=seeds)
+    assert env.tape(0)[1] == 0
+    env.close()
+
+
 def test_rollout_random_conserves_nav_and_matches_stepwise_rng_state():
     """The fused T-step rollout is the same state machine: NAV is conserved exactly and the env RNG stream
     advances exactly as a step-by-step run with the same (device-generated) policy would."""
