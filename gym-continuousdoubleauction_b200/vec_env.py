@@ -391,13 +391,16 @@ class VecCDAEnv:
             self._plane_out = [(np.ndarray((M, A), np.float64, pn, (s * M * cell + SNAPSHOT_DIM) * 4, (cb, 8)),
                                 np.ndarray((M,), np.uint8, pn, (s * M * cell + SNAPSHOT_DIM) * 4 + 8 * A, (cb,)),
                                 np.ndarray((M,), np.uint8, pn, (s * M * cell + SNAPSHOT_DIM) * 4 + 8 * A + 1, (cb,))) for s in range(S)]
+            H = self.n_hist
+            # one precomputed result tuple per ring position (the per-step call then only indexes a list)
+            self._plane_results = [(StackedPlanes([self._plane_snap[(s - H + 1 + j) % S] for j in range(H)]),) + self._plane_out[s] for s in range(S)]
+            self._plane_step = self._L.cda_step_planes
             self._plane_pos = None
         return self._planes
 
     def _plane_stack(self):
         """The stacked observation as n_hist [M, 42] views, oldest snapshot first."""
-        S, H = self.PLANE_SLOTS, self.n_hist
-        return StackedPlanes([self._plane_snap[(self._plane_pos - H + 1 + j) % S] for j in range(H)])
+        return self._plane_results[self._plane_pos][0]
 
     def reset_host_planes(self, seed=None, mask=None):
         """reset() for the dense-plane host path (see include/cda_b200.h cda_step_planes): returns a StackedPlanes."""
@@ -425,14 +428,14 @@ class VecCDAEnv:
         if pos is None:
             raise RuntimeError("call reset_host_planes() before step_host_planes()")
         pos = (pos + 1) % self.PLANE_SLOTS
-        rc = self._L.cda_step_planes(self._h, action_block.data_ptr(), self._plane_ptrs[pos], self._plane_cell,
-                                     (1 if sync else 0) | (2 if market_major else 0), self._plane_stream)
+        rc = self._plane_step(self._h, action_block.data_ptr(), self._plane_ptrs[pos], self._plane_cell,
+                              (1 if sync else 0) | (2 if market_major else 0), self._plane_stream)
         if rc:
             _native.check(rc)
         self._plane_pos = pos
         if self._status_flag[0]:
             self._poll_status()
-        return (self._plane_stack(),) + self._plane_out[pos]
+        return self._plane_results[pos]
 
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""
