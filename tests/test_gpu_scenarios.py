@@ -100,7 +100,7 @@ def test_fill_tape_keeps_the_fills_of_every_step_of_a_fused_rollout():
     rollout (ONE launch) plus 10 single steps it holds the market's most recent fills, equal to the oracle's per-step fills concatenated."""
     from oracle.cda_oracle import OracleEnv
     cfg = dict(num_of_agents=4, max_step=100000)
-    M, cap = 32, 64
+    M, cap = 32, 16
     env = cda.VecCDAEnv(cfg, num_markets=M, fill_capacity=cap, fill_tape=True)
     orc = OracleEnv(cfg, M)
     seeds = np.arange(M, dtype=np.uint64) + np.uint64(17)

@@ -15,7 +15,7 @@ from gym_continuousdoubleauction_b200.workloads import make_actions
 M, A = 4096, 4
 slots = int(os.environ.get("WSLOTS", "64"))
 cda.VecCDAEnv.WINDOW_SLOTS = slots
-env = cda.VecCDAEnv(dict(num_of_agents=A, max_step=1 << 30), num_markets=M)
+env = cda.VecCDAEnv(dict(num_of_agents=A, max_step=1 << 30), num_markets=M, status_policy="ignore")   # (the no-input mode replays one action block: books overflow)
 env.reset(seed=1000)
 acts = make_actions(7, 300, M, A, "limit_market")
 dev = [torch.from_numpy(a).cuda() for a in acts]
