@@ -277,7 +277,7 @@ int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *
     DevGuard guard(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 128, grid = (e->M + threads - 1) / threads;
-    cda_reset_kernel<<<grid, threads, 0, st>>>(e->dev, e->state, e->M, (const unsigned long long *)d_seeds, d_mask, d_obs);
+    cda_reset_kernel<<<grid, threads, 0, st>>>(e->dev, e->state, e->M, (const unsigned long long *)d_seeds, d_mask, d_obs, e->fill_counts);
     CUDA_TRY(cudaGetLastError());
     e->launches++;
     if (!d_mask) e->was_reset = true;

@@ -1398,10 +1398,11 @@ resolve:
 // reset: continuousDoubleAuction_env.py:175-231 — one thread per market (cold path).
 // ------------------------------------------------------------------------------------------
 __global__ void cda_reset_kernel(CdaDevCfg cfg, unsigned char *state, int M, const unsigned long long *seeds,
-                                 const unsigned char *mask, float *obs) {
+                                 const unsigned char *mask, float *obs, int *fill_counts) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     if (mask && !mask[m]) return;
+    if (fill_counts) fill_counts[m] = 0;      // the fill log / tape of a reset market is empty
     unsigned char *blk = state + (size_t)m * cfg.stride;
     unsigned *hdr = reinterpret_cast<unsigned *>(blk);
     CdaRng rng;
