@@ -367,48 +367,51 @@ def main():
     # ------------------------------------------------------------------ obs all-gather (BASELINE config 5: one policy batch spans the GPUs)
     ag = None
     if world > 1 and not args.no_allgather:
-        # (a) baseline: step, then ONE NCCL all-gather of the packed obs|reward|flags block (what a caller of torch.distributed does)
-        blk_bytes = M * env.W * 4 + M * A * 8 + 2 * M
-        loc = torch.empty(blk_bytes, dtype=torch.uint8, device=dev)
-        outs = (loc[:M * env.W * 4].view(torch.float32).view(M, env.W), loc[M * env.W * 4:M * env.W * 4 + M * A * 8].view(torch.float64).view(M, A),
-                loc[M * env.W * 4 + M * A * 8:M * env.W * 4 + M * A * 8 + M], loc[M * env.W * 4 + M * A * 8 + M:])
-        allb = torch.empty(world * blk_bytes, dtype=torch.uint8, device=dev)
+        try:
+            # (a) baseline: step, then ONE NCCL all-gather of the packed obs|reward|flags block (what a caller of torch.distributed does)
+            blk_bytes = M * env.W * 4 + M * A * 8 + 2 * M
+            loc = torch.empty(blk_bytes, dtype=torch.uint8, device=dev)
+            outs = (loc[:M * env.W * 4].view(torch.float32).view(M, env.W), loc[M * env.W * 4:M * env.W * 4 + M * A * 8].view(torch.float64).view(M, A),
+                    loc[M * env.W * 4 + M * A * 8:M * env.W * 4 + M * A * 8 + M], loc[M * env.W * 4 + M * A * 8 + M:])
+            allb = torch.empty(world * blk_bytes, dtype=torch.uint8, device=dev)
 
-        def nccl_step():
-            k = step_ctr[0] % P; step_ctr[0] += 1
-            env.step(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k], out=outs)
-            dist.all_gather_into_tensor(allb, loc)
+            def nccl_step():
+                k = step_ctr[0] % P; step_ctr[0] += 1
+                env.step(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k], out=outs)
+                dist.all_gather_into_tensor(allb, loc)
 
-        def timed_dev(fn):
-            for i in range(5):
-                fn()
-            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-            e0.record()
-            for i in range(args.steps):
-                fn()
-            e1.record(); torch.cuda.synchronize()
-            tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return float(tt.item())
-        tg = timed_dev(nccl_step)
-        # (b) fused: the step kernel's epilogue stores the newest snapshot + result record of every local market into EVERY rank's gather
-        #     window over NVLink and publishes a completion flag; a one-warp kernel waits for all ranks' flags: no NCCL call per step
-        env.enable_peer_gather()
+            def timed_dev(fn):
+                for i in range(5):
+                    fn()
+                torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+                e0.record()
+                for i in range(args.steps):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return float(tt.item())
+            tg = timed_dev(nccl_step)
+            # (b) fused: the step kernel's epilogue stores the newest snapshot + result record of every local market into EVERY rank's gather
+            #     window over NVLink and publishes a completion flag; a one-warp kernel waits for all ranks' flags: no NCCL call per step
+            env.enable_peer_gather()
 
-        def fused_step():
-            k = step_ctr[0] % P; step_ctr[0] += 1
-            env.step_gather(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k])
-        tf = timed_dev(fused_step)
-        cell = 4 * 42 + 8 * A + 2
-        ag = {"nccl_allgather": {"value": world * M * args.steps / (tg * 1e-3), "unit": UNIT, "ms_per_step": tg / args.steps,
-                                 "bytes_received_per_gpu_per_step": int((world - 1) * blk_bytes),
-                                 "note": "VecCDAEnv.step + one NCCL all_gather_into_tensor of the packed obs|reward|flags block per step, L2-hot"},
-              "fused_peer_gather": {"value": world * M * args.steps / (tf * 1e-3), "unit": UNIT, "ms_per_step": tf / args.steps,
-                                    "nvlink_bytes_sent_per_gpu_per_step": int((world - 1) * M * cell),
-                                    "note": "VecCDAEnv.step_gather: the kernel's epilogue stores the newest snapshot + record into every rank's gather window "
-                                            "(peer-mapped, NVLink) and publishes a completion flag; cda_gather_wait (one warp) orders the consumers; "
-                                            "obs = strided [G*M,168] view of the window; L2-hot"},
-              "fused_over_nccl": tg / tf}
+            def fused_step():
+                k = step_ctr[0] % P; step_ctr[0] += 1
+                env.step_gather(acts_dev[0][k], acts_dev[1][k], acts_dev[2][k], acts_dev[3][k], acts_dev[4][k])
+            tf = timed_dev(fused_step)
+            cell = 4 * 42 + 8 * A + 2
+            ag = {"nccl_allgather": {"value": world * M * args.steps / (tg * 1e-3), "unit": UNIT, "ms_per_step": tg / args.steps,
+                                     "bytes_received_per_gpu_per_step": int((world - 1) * blk_bytes),
+                                     "note": "VecCDAEnv.step + one NCCL all_gather_into_tensor of the packed obs|reward|flags block per step, L2-hot"},
+                  "fused_peer_gather": {"value": world * M * args.steps / (tf * 1e-3), "unit": UNIT, "ms_per_step": tf / args.steps,
+                                        "nvlink_bytes_sent_per_gpu_per_step": int((world - 1) * M * cell),
+                                        "note": "VecCDAEnv.step_gather: the kernel's epilogue stores the newest snapshot + record into every rank's gather window "
+                                                "(peer-mapped, NVLink) and publishes a completion flag; cda_gather_wait (one warp) orders the consumers; "
+                                                "obs = strided [G*M,168] view of the window; L2-hot"},
+                  "fused_over_nccl": tg / tf}
+        except Exception as exc:   # (e.g. no CUDA IPC / peer access between the GPUs of this box): the headline line must still be printed
+            ag = {"error": repr(exc)[:300]}
 
     if rank != 0:
         if world > 1:
