@@ -2,10 +2,10 @@
 """Wide fuzz of the device Decimal twin (decimal_ledger) against the oracle's decimal_ledger mode (which reproduces the reference's Decimal
 fields exactly, tests/test_oracle_vs_reference.py): N seeded low- and mid-cash configurations x M markets x T steps; integer state compared
 every `every` steps and at the end, the twins' Decimal cash / VWAP / nav at the end.  Prints one line per configuration and a summary.
-usage (under gpurun): python tools/decimal_fuzz.py [N=120] [M=12] [T=160]"""
+usage (under gpurun): python tests/decimal_fuzz.py [N=120] [M=12] [T=160]   (a script, not a pytest module; lives under tests/ because it drives the oracle)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))   # (ROOT = repo root)
 import numpy as np, torch
 import gym_continuousdoubleauction_b200 as cda
 from oracle.cda_oracle import OracleEnv
