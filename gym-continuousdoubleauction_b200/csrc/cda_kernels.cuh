@@ -38,6 +38,11 @@
                                  account block, before the header has said how many orders are live: saves one dependent HBM round trip on a
                                  cold cache at the price of over-fetching up to 640 B * CDA_SPEC_TILES per side */
 #endif
+#ifndef CDA_WARP_ACT_TMA
+#define CDA_WARP_ACT_TMA 0    /* 1: on the plain device step every WARP stages its own market's action rows behind its own mbarrier (five 4*A-byte bulk
+                                 copies), so the kernel starts without a __syncthreads; the routed (host) bodies keep ONE set of copies per CTA:
+                                 reads from host memory are bound by the number of requests */
+#endif
 #ifndef CDA_PREFETCH_TABLES
 #define CDA_PREFETCH_TABLES 0 /* 1: every CTA asks L2 for the ziggurat / jump-ahead tables at kernel entry (they are indexed by data that arrives two
                                  dependent loads into the kernel; after an L2 flush the first touch per SM goes to HBM) */
@@ -362,7 +367,7 @@ struct CdaSmemLayout {
     static constexpr int PARK = ACT + 96;                            // 10 words: parked PCG64 state (+2 pad)
     static constexpr int TIE = PARK + 12;                            // u32[8] decimal_ledger: restart count | answers << 8, then up to 7 parked tie answers
     static constexpr int BAR = TIE + (DEC ? 8 : 0);                  // mbarrier (8-B aligned)
-    static constexpr int WORDS = ((BAR + 2 + 3) / 4) * 4;            // keep 16-B alignment of the next tile
+    static constexpr int WORDS = ((BAR + 4 + 3) / 4) * 4;            // (BAR + 2: a second mbarrier, the warp's own action copies) keep 16-B alignment of the next tile
     static constexpr int BYTES = WORDS * 4;
     static_assert(BAR % 2 == 0, "mbarrier must be 8-B aligned");
 };
@@ -703,7 +708,26 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
         else if (threadIdx.x < 56) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(&cda_pcg_jump[0][0]) + (threadIdx.x - 48) * 128));
 #endif
         const int A0 = p.cfg.A, actb0 = WARPS * L::WORDS, cbar_w0 = actb0 + 5 * WARPS * A0;
-        if (!ROLLOUT && p.act_tma) {
+        constexpr bool WARP_ACT0 = CDA_WARP_ACT_TMA && !ROUTED;
+        if (!ROLLOUT && p.act_tma && WARP_ACT0) {
+            const int w = threadIdx.x >> 5, m0 = blockIdx.x * WARPS + w;
+            if ((threadIdx.x & 31) == 0 && m0 < p.M) {
+                const unsigned abar = smem_u32(smw) + (unsigned)(w * L::WORDS + L::BAR + 2) * 4u, fb = (unsigned)A0 * 4u;
+                mbar_init(abar, 1);
+                mbar_expect_tx(abar, 5u * fb);
+                const size_t so = (size_t)m0 * p.act_mstride;
+                if (p.act_packed) bulk_g2s(smem_u32(smw) + (unsigned)(actb0 + w * 5 * A0) * 4u, p.cat + so, 5u * fb, abar);
+                else {
+                    const unsigned dst = smem_u32(smw) + (unsigned)(actb0 + w * A0) * 4u, fs = (unsigned)(WARPS * A0) * 4u;
+                    bulk_g2s(dst, p.cat + so, fb, abar);
+                    bulk_g2s(dst + fs, p.mean + so, fb, abar);
+                    bulk_g2s(dst + 2u * fs, p.sigma + so, fb, abar);
+                    bulk_g2s(dst + 3u * fs, p.pcode + so, fb, abar);
+                    bulk_g2s(dst + 4u * fs, p.poff + so, fb, abar);
+                }
+            }
+        }
+        if (!ROLLOUT && p.act_tma && !WARP_ACT0) {
             if (threadIdx.x == 0) {
                 const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w0 * 4u;
                 const int m0 = blockIdx.x * WARPS, nm = min(WARPS, p.M - m0);
@@ -722,7 +746,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
                 }
             }
         }
-        __syncthreads();                                   // mbarrier initialised before any warp goes on
+        if (!ROLLOUT && p.act_tma && !WARP_ACT0) __syncthreads();   // the CTA's mbarrier is initialised before any warp goes on
         if ((int)(blockIdx.x * WARPS + (threadIdx.x >> 5)) >= p.M) return;
         if (DEC) {
             if ((threadIdx.x & 31) == 0) smw[(threadIdx.x >> 5) * L::WORDS + L::TIE] = 0u;  // decimal_ledger: no restart yet, no parked answers
@@ -872,7 +896,7 @@ restart:;
             }
         }
         if (!ROLLOUT && p.act_tma) {
-            mbar_wait(smem_u32(smw) + (unsigned)cbar_w * 4u, 0);
+            mbar_wait((CDA_WARP_ACT_TMA && !ROUTED) ? smem_u32(smw) + (unsigned)(wb + L::BAR + 2) * 4u : smem_u32(smw) + (unsigned)cbar_w * 4u, 0);
             if (lane < A) {
                 const int o = actb + (p.act_packed ? warp * 5 * A : warp * A) + lane, fs = p.act_packed ? A : WARPS * A;
                 a_cat = (int)SMW(o); a_mean = __uint_as_float(SMW(o + fs)); a_sigma = __uint_as_float(SMW(o + 2 * fs));
