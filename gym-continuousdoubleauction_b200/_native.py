@@ -44,7 +44,7 @@ INFO_MARKET_COLS = ("last_price", "best_bid", "best_ask", "time", "next_order_id
                     "done_mask", "status")
 
 EXPORTS = (
-    "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_step_host_ring", "cda_reset_host_ring", "cda_step_host_window", "cda_reset_host_window", "cda_window_bind", "cda_step_window", "cda_step_planes", "cda_reset_planes", "cda_rollout_random",
+    "cda_create", "cda_destroy", "cda_reset", "cda_step", "cda_step_host", "cda_step_host_ring", "cda_reset_host_ring", "cda_step_host_window", "cda_reset_host_window", "cda_window_bind", "cda_step_window", "cda_step_planes", "cda_reset_planes", "cda_serve_bind", "cda_serve_step", "cda_serve_stop", "cda_serve_launches", "cda_rollout_random",
     "cda_gather_create", "cda_gather_connect", "cda_gather_publish", "cda_step_gather", "cda_gather_wait", "cda_gather_pos", "cda_gather_row_words", "cda_gather_record_parity", "cda_get_info", "cda_get_info_all", "cda_get_fills", "cda_set_action_log", "cda_dump_market", "cda_state_bytes", "cda_save_state",
     "cda_load_state", "cda_num_markets", "cda_record_bytes", "cda_obs_dim", "cda_order_capacity",
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
@@ -114,6 +114,10 @@ def lib():
     sig("cda_step_window", [vp, vp, i32, i32])
     sig("cda_step_planes", [vp, vp, vp, i32, i32, vp])
     sig("cda_reset_planes", [vp, vp, vp, vp, i32, i32, i32, vp])
+    sig("cda_serve_bind", [vp, vp, i32, i32])
+    sig("cda_serve_step", [vp, vp, i32, vp])
+    sig("cda_serve_stop", [vp])
+    sig("cda_serve_launches", [vp], i64)
     sig("cda_rollout_random", [vp, i32, u64, vp, vp, vp, vp, vp])
     sig("cda_gather_create", [vp, i32, i32, vp, ctypes.POINTER(vp), ctypes.POINTER(u64)])
     sig("cda_gather_connect", [vp, vp])

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <time.h>
 
 #include "cda_kernels.cuh"
 #include "cda_b200_testing.h"
@@ -66,6 +67,14 @@ struct CdaEnv {
     int twin_steps, twin_every;            // decimal_ledger: steps since the last journal flush; flush cadence (CDA_TWIN_FLUSH_STEPS, $CDA_TWIN_FLUSH overrides: measurements)
     int g_pos; unsigned g_seq;             // fused all-gather: slot of the newest snapshot in the gather windows; steps published so far
     size_t smem_bytes;
+    // resident step server (cda_serve_*): status_host word 16/17 = the message word the host rings, word 32 = watchdog flag
+    cudaStream_t srv_stream; cudaEvent_t srv_event;
+    unsigned long long *srv_go_dev; unsigned *srv_done_dev;
+    float *srv_planes_host, *srv_planes_dev; int srv_slots, srv_cell;
+    const char *srv_act_host0; const unsigned char *srv_act_dev0;     // first action block seen: the base the messages' offsets count from
+    const void *srv_ptr_cache_h[64]; const unsigned char *srv_ptr_cache_d[64];   // host pointer -> device alias of recent action blocks
+    bool srv_bound, srv_running; unsigned srv_seq; long long srv_launches;
+    unsigned long long srv_lease_ns, srv_last_ns;   // lease; host clock (CLOCK_MONOTONIC) at the end of the last served step
     int host_ctas, dev_ctas;   // resident CTAs per SM for the host paths / the device path (0 = as many as fit)
 };
 
@@ -122,6 +131,86 @@ static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cuda
     return e->dev.dec ? launch_step_cap<true>(e, p, st, ctas_per_sm) : launch_step_cap<false>(e, p, st, ctas_per_sm);
 }
 
+
+// ---- resident step server: host side (device side: "Resident step server" in cda_kernels.cuh; contract: include/cda_b200.h) ----------
+#define CDA_SRV_GO_WORD 16      /* status_host word index of the 64-bit message the host rings (its own 64-B line) */
+#define CDA_SRV_DONE_WORD 10    /* completion word the kernel's last warp writes (NOT word 8: the launch paths' doorbell counts differently) */
+#define CDA_SRV_ERR_WORD 32     /* a worker's watchdog fired */
+static unsigned long long host_now_ns() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (unsigned long long)ts.tv_sec * 1000000000ULL + (unsigned long long)ts.tv_nsec; }
+static size_t srv_smem_bytes(const CdaEnv *e, int cap_words_bytes) {
+    return (size_t)cap_words_bytes * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
+           (size_t)CDA_WARPS_PER_CTA * (CDA_ACCT_TILE_WORDS(false, e->dev.A) * 4);
+}
+// check_only: can every CTA of the grid (one poller + one per four markets) be resident at once?  cudaErrorLaunchOutOfResources if not.
+template <int CAP>
+static cudaError_t launch_serve(CdaEnv *e, const CdaStepParams &p, bool check_only) {
+    auto kern = cda_step_kernel<CAP, CDA_WARPS_PER_CTA, true, true, false>;
+    const int grid = (e->M + CDA_WARPS_PER_CTA - 1) / CDA_WARPS_PER_CTA + 1;
+    const size_t smem = srv_smem_bytes(e, CdaSmemLayout<CAP, false>::BYTES);
+    cudaError_t err = cudaSuccess;
+    static size_t attr_set[16] = {0};
+    if (attr_set[e->device & 15] < smem) {
+        err = cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute((const void *)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
+        attr_set[e->device & 15] = smem;
+    }
+    if (check_only) {
+        int per_sm = 0, sms = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, CDA_WARPS_PER_CTA * 32, smem);
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        if (err != cudaSuccess) return err;
+        return (long long)per_sm * sms >= grid ? cudaSuccess : cudaErrorLaunchOutOfResources;
+    }
+    kern<<<grid, CDA_WARPS_PER_CTA * 32, smem, e->srv_stream>>>(p);
+    return cudaGetLastError();
+}
+static cudaError_t launch_serve_cap(CdaEnv *e, const CdaStepParams &p, bool check_only) {
+    switch (e->dev.cap) {
+        case 64: return launch_serve<64>(e, p, check_only);
+        case 128: return launch_serve<128>(e, p, check_only);
+        case 160: return launch_serve<160>(e, p, check_only);
+        case 192: return launch_serve<192>(e, p, check_only);
+        default: return launch_serve<256>(e, p, check_only);
+    }
+}
+// (re)launch the resident kernel for step srv_seq + 1, behind whatever the caller has queued on `st`
+static int srv_launch(CdaEnv *e, cudaStream_t st) {
+    CdaStepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cfg = e->dev; p.state = e->state; p.M = e->M; p.status_flag = e->status_dev;
+    p.obs_split = e->M; p.obs_stride = e->dev.W; p.reward_stride = e->dev.A; p.flag_stride = 1;
+    p.act_mstride = 5 * e->dev.A; p.act_packed = 1; p.num_steps = 1;
+    p.ring_out = e->srv_planes_dev; p.ring_stride = e->srv_cell; p.ring_pad = e->srv_cell; p.rec_inline = 1;
+    p.fills = e->fills; p.fill_counts = e->fill_counts; p.act_log = e->act_log;
+    p.acct_tma = (e->dev.A % 4) == 0;
+    p.done_ctr = e->done_ctr; p.done_flag = e->status_dev + CDA_SRV_DONE_WORD;
+    p.srv_go_host = reinterpret_cast<const unsigned long long *>(e->status_dev + CDA_SRV_GO_WORD);
+    p.srv_go_dev = e->srv_go_dev; p.srv_done_dev = e->srv_done_dev; p.srv_err = e->status_dev + CDA_SRV_ERR_WORD;
+    p.srv_act_base = e->srv_act_dev0; p.srv_next = e->srv_seq + 1u;
+    p.srv_lease_ns = e->srv_lease_ns; p.srv_watchdog_ns = 1000000000ULL + 4ULL * e->srv_lease_ns;
+    static const int dbg_mode = getenv("CDA_SERVE_ACT_MODE") ? atoi(getenv("CDA_SERVE_ACT_MODE")) : 0;
+    p.srv_act_mode = ((e->dev.A % 4) == 0 && dbg_mode == 0) ? 0 : 1;   // bulk copies move multiples of 16 B from 16-B aligned addresses
+    CUDA_TRY(cudaEventRecord(e->srv_event, st));
+    CUDA_TRY(cudaStreamWaitEvent(e->srv_stream, e->srv_event, 0));
+    CUDA_TRY(cudaMemsetAsync(e->srv_go_dev, 0, (size_t)CDA_SRV_COPIES * 128, e->srv_stream));   // (a message left by an earlier launch must not match)
+    CUDA_TRY(launch_serve_cap(e, p, false));
+    e->launches++; e->srv_launches++;
+    e->srv_running = true;
+    return CDA_OK;
+}
+// retire the resident kernel (state back in HBM) before anything else touches the handle's state
+static int srv_quiesce(CdaEnv *e) {
+    if (!e->srv_running) return CDA_OK;
+    __atomic_store_n(reinterpret_cast<unsigned long long *>(e->status_host + CDA_SRV_GO_WORD),
+                     (unsigned long long)cda_srv_seq24(e->srv_seq + 1u) | ((unsigned long long)CDA_SRV_STOP << 24), __ATOMIC_RELEASE);
+    e->srv_running = false;
+    CUDA_TRY(cudaStreamSynchronize(e->srv_stream));
+    if (e->status_host[CDA_SRV_ERR_WORD]) { snprintf(g_cuda_err, sizeof(g_cuda_err), "resident step server: worker watchdog fired"); return CDA_ECUDA; }
+    return CDA_OK;
+}
+#define SRV_QUIESCE(e) do { if ((e)->srv_running) { DevGuard g__((e)->device); int rc__ = srv_quiesce(e); if (rc__) return rc__; } } while (0)
+
 extern "C" {
 
 const char *cda_strerror(int code) {
@@ -131,6 +220,7 @@ const char *cda_strerror(int code) {
         case CDA_ECUDA: return "CUDA runtime error (see cda_last_cuda_error)";
         case CDA_ENOMEM: return "out of memory";
         case CDA_ESTATE: return "environment used before reset";
+        case CDA_EUNSUPPORTED: return "mode not available for this handle (see the header for the fallback)";
         default: return "unknown error";
     }
 }
@@ -209,8 +299,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
     // caller's host buffers are laid out the same way)
     if (err == cudaSuccess) err = cudaMalloc(&e->s_obs, (size_t)num_markets * d.W * 4 + MA * 8 + (size_t)num_markets * 2);
     if (err == cudaSuccess) err = cudaMalloc(&e->s_rec, (size_t)num_markets * (((size_t)d.A * 8 + 8 + 63) / 64 * 64));
-    if (err == cudaSuccess) err = cudaHostAlloc(reinterpret_cast<void **>(&e->status_host), 64, cudaHostAllocMapped | cudaHostAllocPortable);
-    if (err == cudaSuccess) { memset(e->status_host, 0, 64); err = cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->status_dev), e->status_host, 0); }
+    if (err == cudaSuccess) err = cudaHostAlloc(reinterpret_cast<void **>(&e->status_host), 256, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess) { memset(e->status_host, 0, 256); err = cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->status_dev), e->status_host, 0); }
     if (err == cudaSuccess) err = cudaMalloc(&e->done_ctr, 64);
     if (err == cudaSuccess) err = cudaMemset(e->done_ctr, 0, 64);
     if (err != cudaSuccess) {
@@ -262,6 +352,8 @@ int cda_create(const CdaConfig *cfg, int32_t num_markets, int32_t device, CdaEnv
 int cda_destroy(CdaEnv *e) {
     if (!e) return CDA_OK;
     DevGuard guard(e->device);
+    if (e->srv_running) srv_quiesce(e);
+    if (e->srv_stream) { cudaStreamDestroy(e->srv_stream); cudaEventDestroy(e->srv_event); cudaFree(e->srv_go_dev); }
     if (e->status_host) cudaFreeHost(e->status_host);
     if (e->g_connected) for (int g = 0; g < e->g_world; ++g) if (g != e->g_rank && e->g_peer[g]) cudaIpcCloseMemHandle(e->g_peer[g]);
     cudaFree(e->g_local);
@@ -275,6 +367,7 @@ int cda_reset(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *
     if (!e) return CDA_EINVAL;
     if (!d_seeds && !e->was_reset) return CDA_ESTATE;   // reset(seed=None) needs an existing stream
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 128, grid = (e->M + threads - 1) / threads;
     cda_reset_kernel<<<grid, threads, 0, st>>>(e->dev, e->state, e->M, (const unsigned long long *)d_seeds, d_mask, d_obs, e->fill_counts);
@@ -308,6 +401,7 @@ static int twin_flush(CdaEnv *e, cudaStream_t st) {
 }
 static unsigned long long *g_prof = nullptr;
 static int step_common(CdaEnv *e, CdaStepParams &p, cudaStream_t st, bool host_path = false) {
+    SRV_QUIESCE(e);   // (a resident step server holds the state in shared memory: retire it first)
     p.cfg = e->dev; p.state = e->state; p.M = e->M;
     p.status_flag = e->status_dev;
     if (!p.obs_hi) p.obs_split = e->M;   // no split: every row goes to p.obs
@@ -663,6 +757,106 @@ int cda_reset_planes(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, 
     return CDA_OK;
 }
 
+
+int cda_serve_bind(CdaEnv *e, float *h_planes, int32_t slots, int32_t cell_words) {
+    if (!e || !h_planes || slots < e->dev.n_hist + 1 || slots >= (int)CDA_SRV_STOP) return CDA_EINVAL;
+    if (cell_words < CDA_SNAPSHOT_DIM + 2 * e->dev.A + 2 || (cell_words & 1)) return CDA_EINVAL;
+    DevGuard guard(e->device);
+    SRV_QUIESCE(e);
+    e->srv_bound = false;
+    static const int enabled = getenv("CDA_SERVE") ? atoi(getenv("CDA_SERVE")) : 1;
+    if (!enabled || e->dev.dec || !e->zerocopy || !e->zerocopy_in) return CDA_EUNSUPPORTED;
+    float *zp = reinterpret_cast<float *>(mapped_alias(h_planes));
+    if (!zp) return CDA_EUNSUPPORTED;
+    if (!e->srv_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->srv_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->srv_event, cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&e->srv_go_dev, (size_t)CDA_SRV_COPIES * 128 + 128));
+        CUDA_TRY(cudaMemset(e->srv_go_dev, 0, (size_t)CDA_SRV_COPIES * 128 + 128));
+        e->srv_done_dev = reinterpret_cast<unsigned *>(e->srv_go_dev + CDA_SRV_COPIES * 16);
+        const char *ls = getenv("CDA_SERVE_LEASE_US");
+        e->srv_lease_ns = (unsigned long long)(ls && atoi(ls) > 0 ? atoi(ls) : 2000) * 1000ULL;
+    }
+    CdaStepParams none;
+    memset(&none, 0, sizeof(none));
+    const cudaError_t fit = launch_serve_cap(e, none, true);
+    if (fit == cudaErrorLaunchOutOfResources) return CDA_EUNSUPPORTED;   // more markets than one resident wave holds
+    CUDA_TRY(fit);
+    e->srv_planes_host = h_planes; e->srv_planes_dev = zp; e->srv_slots = slots; e->srv_cell = cell_words;
+    e->srv_bound = true;
+    return CDA_OK;
+}
+
+int cda_serve_step(CdaEnv *e, const int32_t *h_action_block, int32_t slot, void *stream) {
+    if (!e || !e->srv_bound || !h_action_block || slot < 0 || slot >= e->srv_slots) return CDA_EINVAL;
+    if (!e->was_reset) return CDA_ESTATE;
+    // device alias of this step's action block (recent blocks cached: cudaPointerGetAttributes costs about a microsecond)
+    const unsigned ci = (unsigned)((reinterpret_cast<uintptr_t>(h_action_block) >> 6) * 0x9E3779B1u >> 26) & 63u;
+    if (e->srv_ptr_cache_h[ci] != h_action_block) {
+        DevGuard guard(e->device);
+        const unsigned char *d = reinterpret_cast<const unsigned char *>(mapped_alias(h_action_block));
+        if (!d) return CDA_EINVAL;            // the action block must be pinned + mapped
+        e->srv_ptr_cache_h[ci] = h_action_block; e->srv_ptr_cache_d[ci] = d;
+    }
+    const unsigned char *dblk = e->srv_ptr_cache_d[ci];
+    if (!e->srv_act_dev0) {
+        if (e->srv_running) SRV_QUIESCE(e);
+        e->srv_act_dev0 = dblk;
+    }
+    long long off = dblk - e->srv_act_dev0;
+    if ((off & 15) || off < -(1LL << 34) || off >= (1LL << 34)) {   // out of a message's reach (or misaligned against the base): move the base
+        if (reinterpret_cast<uintptr_t>(dblk) & 15) return CDA_EINVAL;
+        SRV_QUIESCE(e);
+        e->srv_act_dev0 = dblk; off = 0;
+    }
+    const unsigned seq = e->srv_seq + 1u;
+    const unsigned long long msg = (unsigned long long)cda_srv_seq24(seq) | ((unsigned long long)(unsigned)slot << 24) |
+                                   ((unsigned long long)(unsigned)(int)(off >> 4) << 32);
+    volatile unsigned *done = e->status_host + CDA_SRV_DONE_WORD;
+    __atomic_store_n(reinterpret_cast<unsigned long long *>(e->status_host + CDA_SRV_GO_WORD), msg, __ATOMIC_RELEASE);   // (the caller's action writes come first: TSO + release)
+    if (e->srv_running && host_now_ns() - e->srv_last_ns > e->srv_lease_ns / 2) {   // idle for a while: the kernel may have given the SMs back
+        DevGuard guard(e->device);
+        if (cudaStreamQuery(e->srv_stream) == cudaSuccess) e->srv_running = false; else cudaGetLastError();
+    }
+    if (!e->srv_running) {
+        DevGuard guard(e->device);
+        int rc = srv_launch(e, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    for (unsigned spins = 1;; ++spins) {
+        if (*done == seq) break;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0x3ffu) == 0) {          // every ~50 us: did the kernel retire (lease ran out just before the message) without serving this step?
+            DevGuard guard(e->device);
+            const cudaError_t q = cudaStreamQuery(e->srv_stream);
+            if (q == cudaSuccess) {
+                if (*done == seq) break;
+                e->srv_running = false;
+                if (e->status_host[CDA_SRV_ERR_WORD]) { snprintf(g_cuda_err, sizeof(g_cuda_err), "resident step server: worker watchdog fired"); return CDA_ECUDA; }
+                int rc = srv_launch(e, (cudaStream_t)stream);
+                if (rc) return rc;
+            } else if (q != cudaErrorNotReady) {
+                snprintf(g_cuda_err, sizeof(g_cuda_err), "resident step server: %s", cudaGetErrorString(q));
+                e->srv_running = false;
+                return CDA_ECUDA;
+            } else cudaGetLastError();
+            if (spins > 200000000u) { snprintf(g_cuda_err, sizeof(g_cuda_err), "resident step server: no completion"); return CDA_ECUDA; }
+        }
+    }
+    e->srv_seq = seq;
+    e->srv_last_ns = host_now_ns();
+    return CDA_OK;
+}
+
+int cda_serve_stop(CdaEnv *e) {
+    if (!e) return CDA_EINVAL;
+    SRV_QUIESCE(e);
+    return CDA_OK;
+}
+int64_t cda_serve_launches(const CdaEnv *e) { return e ? e->srv_launches : 0; }
+
 int cda_reset_host_window(CdaEnv *e, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_window, int32_t slots, void *stream) {
     if (!e || !h_window || slots < e->dev.n_hist) return CDA_EINVAL;
     DevGuard guard(e->device);
@@ -757,6 +951,7 @@ int cda_gather_publish(CdaEnv *e, void *stream) {
     if (!e) return CDA_EINVAL;
     if (!e->was_reset || !e->g_connected) return CDA_ESTATE;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     cudaStream_t st = (cudaStream_t)stream;
     const int n = e->M * e->dev.W, threads = 256, wstride = gather_row_words(e);
     for (int g = 0; g < e->g_world; ++g) {   // every market's current stack into slots 0..n_hist-1 of its row of every rank's window (cold path)
@@ -820,6 +1015,7 @@ int32_t cda_gather_record_parity(const CdaEnv *e) { return e ? (int32_t)(e->g_se
 int cda_get_info(CdaEnv *e, int32_t field, int64_t *d_out, void *stream) {
     if (!e || !d_out || field < 0 || field >= CDA_INFO__COUNT) return CDA_EINVAL;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     const int n = field == CDA_INFO_MARKET ? e->M : e->M * e->dev.A;
     const int threads = 256, grid = (n + threads - 1) / threads;
     cda_info_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, field, (long long *)d_out);
@@ -831,6 +1027,7 @@ int cda_get_info(CdaEnv *e, int32_t field, int64_t *d_out, void *stream) {
 int cda_get_info_all(CdaEnv *e, int64_t *d_out, void *stream) {
     if (!e || !d_out) return CDA_EINVAL;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     const int n = CDA_INFO_MARKET * e->M * e->dev.A + e->M;
     const int threads = 256, grid = (n + threads - 1) / threads;
     cda_info_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(e->dev, e->state, e->M, -1, (long long *)d_out);
@@ -841,12 +1038,14 @@ int cda_get_info_all(CdaEnv *e, int64_t *d_out, void *stream) {
 
 int cda_set_action_log(CdaEnv *e, int32_t *d_log) {
     if (!e) return CDA_EINVAL;
+    SRV_QUIESCE(e);
     e->act_log = d_log;
     return CDA_OK;
 }
 int cda_get_fills(CdaEnv *e, int32_t *d_fills, int32_t *d_counts, void *stream) {
     if (!e || !e->fills) return CDA_EINVAL;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_fills) CUDA_TRY(cudaMemcpyAsync(d_fills, e->fills, (size_t)e->M * e->dev.fill_cap * CDA_FILL_WORDS * 4, cudaMemcpyDeviceToDevice, st));
     if (d_counts) CUDA_TRY(cudaMemcpyAsync(d_counts, e->fill_counts, (size_t)e->M * 4, cudaMemcpyDeviceToDevice, st));
@@ -857,6 +1056,7 @@ int cda_dump_market(CdaEnv *e, int32_t market, int64_t *h_bids, int64_t *h_asks,
                     int64_t *h_asks_map, int32_t max_rows, int32_t *h_counts, uint64_t *h_rng6) {
     if (!e || market < 0 || market >= e->M || !h_counts) return CDA_EINVAL;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     std::vector<unsigned char> blk(e->dev.stride);
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(blk.data(), e->state + (size_t)market * e->dev.stride, e->dev.stride, cudaMemcpyDeviceToHost));
@@ -910,6 +1110,7 @@ int cda_twin_sync(CdaEnv *e, int64_t *d_out, void *stream) {
     if (!e) return CDA_EINVAL;
     if (!e->dev.dec) return d_out ? CDA_EINVAL : CDA_OK;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = twin_flush(e, st);
     if (rc || !d_out) return rc;
@@ -930,12 +1131,14 @@ int cda_state_layout(const CdaEnv *e, int32_t out[12]) {
 int cda_save_state(CdaEnv *e, void *h_dst, void *stream) {
     if (!e || !h_dst) return CDA_EINVAL;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     CUDA_TRY(cudaMemcpyAsync(h_dst, e->state, e->state_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return CDA_OK;
 }
 int cda_load_state(CdaEnv *e, const void *h_src, void *stream) {
     if (!e || !h_src) return CDA_EINVAL;
     DevGuard guard(e->device);
+    SRV_QUIESCE(e);
     CUDA_TRY(cudaMemcpyAsync(e->state, h_src, e->state_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     e->was_reset = true;
     return CDA_OK;

@@ -122,6 +122,16 @@ struct CdaStepParams {
     // stream: it sees the results a few microseconds before the driver sees the kernel retire
     unsigned *done_ctr; unsigned *done_flag; unsigned done_seq;
     unsigned *status_flag;            // mapped pinned host word: set to 1 by any market that ends the step with a non-zero sticky status
+    // resident step server (cda_serve_*; the <ROLLOUT = 1, ROUTED = 1> body): the kernel stays on the SMs between steps with every market's
+    // book and ledger in shared memory; the host rings a message word per step instead of launching (see "resident step server" below)
+    const unsigned long long *srv_go_host;   // mapped pinned message word written by the host
+    unsigned long long *srv_go_dev;          // CDA_SRV_COPIES copies of the newest message, 128 B apart (device memory), republished by the poller CTA
+    unsigned *srv_done_dev;                  // device copy of the completion word (the poller's idle clock starts when a step has completed)
+    unsigned *srv_err;                       // mapped pinned word: a worker's watchdog fired (the poller never answered)
+    const unsigned char *srv_act_base;       // device alias of the pinned action area; a message carries the step's block as an offset from it
+    unsigned srv_next;                       // number of the first step this launch serves
+    unsigned long long srv_lease_ns, srv_watchdog_ns;
+    int srv_act_mode;                        // 0: one cp.async.bulk per market and step from mapped host memory; 1: volatile loads
 };
 
 // ------------------------------------ numpy-exact RNG --------------------------------------
@@ -680,6 +690,72 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Resident step server (the <ROLLOUT = 1, ROUTED = 1> body; cda_serve_step in include/cda_b200.h).
+// The end-to-end host path costs a launch, a completion hand-shake and a state load / store per step on top of the step itself.  In this
+// mode the kernel is launched ONCE and stays resident: every warp keeps its market's order pool and accounts in shared memory between
+// steps (like the fused rollout), and a step is triggered by a 64-bit MESSAGE the host writes to a mapped pinned word:
+//     bits [0,24)  step number, as (seq mod (2^24 - 1)) + 1 (never 0: a cleared word matches nothing)
+//     bits [24,32) slot of the plane ring that receives this step's outputs; 0xff = STOP (store the state and exit)
+//     bits [32,64) signed offset of the step's pinned action block from srv_act_base, in 16-byte units
+// CTA 0 is the POLLER: thread 0 reads the host word over PCIe (no other thread of the grid does), and the CTA republishes a new message into
+// CDA_SRV_COPIES device words in different 128-B lines, which the worker warps poll in L2.  A worker that sees its next step number
+// stages the market's action record (one bulk copy from host memory per warp), runs the step, stores the newest snapshot + result record
+// into the plane, fences, and counts itself; the last one rings the completion word the host spins on.
+// Nothing can wait forever: the poller gives the SMs back (publishes STOP itself) when no message has arrived for srv_lease_ns after the
+// last step completed — the host notices that the kernel has retired and launches it again with the next step — and a worker that has
+// not heard from the poller for srv_watchdog_ns (which cannot happen while the poller is resident) raises srv_err and exits.
+// ------------------------------------------------------------------------------------------
+#define CDA_SRV_COPIES 128
+#define CDA_SRV_STOP 0xffu
+__host__ __device__ __forceinline__ unsigned cda_srv_seq24(unsigned seq) { return seq % 0xffffffu + 1u; }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+    unsigned v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// the poller CTA (all its threads; smw[0..1] is the mailbox between thread 0 and the others)
+// (arguments by value: taking the address of the kernel's parameter block would copy it to every thread's stack)
+__device__ __noinline__ void cda_serve_poller(const unsigned long long *go_host, unsigned long long *go_dev, const unsigned *done_dev, unsigned next, unsigned long long lease_ns) {
+    bool idle = true;                      // no step in flight
+    unsigned long long t_idle = globaltimer_ns();
+    for (;;) {
+        if (threadIdx.x == 0) {
+            unsigned long long v;
+            for (;;) {
+                v = ld_volatile_u64(go_host);
+                if (((unsigned)v & 0xffffffu) == cda_srv_seq24(next)) break;
+                const unsigned long long now = globaltimer_ns();
+                if (!idle) { if (ld_volatile_u32(done_dev) == next - 1u) { idle = true; t_idle = now; } }
+                else if (now - t_idle > lease_ns) { v = (unsigned long long)cda_srv_seq24(next) | ((unsigned long long)CDA_SRV_STOP << 24); break; }
+            }
+            *reinterpret_cast<volatile unsigned long long *>(smw) = v;
+        }
+        __syncthreads();
+        const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(smw);
+        if (threadIdx.x < CDA_SRV_COPIES) *reinterpret_cast<volatile unsigned long long *>(go_dev + threadIdx.x * 16) = v;
+        if ((((unsigned)v >> 24) & 0xffu) == CDA_SRV_STOP) return;
+        __syncthreads();
+        next++; idle = false;
+    }
+}
+// a worker warp's lane 0 waits for the message of step `seq` (or STOP)
+__device__ __forceinline__ unsigned long long cda_serve_wait(const CdaStepParams &p, unsigned seq, int cta) {   // (inlined: p stays in the constant bank)
+    const unsigned long long *w = p.srv_go_dev + (cta & (CDA_SRV_COPIES - 1)) * 16;
+    const unsigned want = cda_srv_seq24(seq);
+    unsigned long long v = ld_volatile_u64(w);
+    if (((unsigned)v & 0xffffffu) == want) return v;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        __nanosleep(100);
+        v = ld_volatile_u64(w);
+        if (((unsigned)v & 0xffffffu) == want) return v;
+        if (globaltimer_ns() - t0 > p.srv_watchdog_ns) { *reinterpret_cast<volatile unsigned *>(p.srv_err) = 1u; return (unsigned long long)want | ((unsigned long long)CDA_SRV_STOP << 24); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // The fused step kernel: load -> decode -> shuffle -> match/settle -> MTM -> snapshot -> reward
 // -> store, one warp per market.  WARPS warps per CTA share nothing but the CTA's shared memory
 // carve-up, so there is no __syncthreads anywhere.
@@ -699,6 +775,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 template <int CAP, int WARPS, bool ROLLOUT, bool ROUTED, bool DEC>
 __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(const CdaStepParams p) {
     using L = CdaSmemLayout<CAP, DEC>;
+    constexpr bool SERVE = ROLLOUT && ROUTED;   // resident step server: CTA 0 polls the host, CTA b > 0 steps markets 4(b-1) .. 4(b-1)+3 whenever a message arrives
+    static_assert(!(SERVE && DEC), "the resident step server runs the integer ledger only");
+    if (SERVE && blockIdx.x == 0) { cda_serve_poller(p.srv_go_host, p.srv_go_dev, p.srv_done_dev, p.srv_next, p.srv_lease_ns); return; }
     {   // ---- CTA prologue (its values die here: nothing defined above `restart` may be live across the resolve block's call) ----
         // action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A] array) behind one
         // CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns 20 sector-sized PCIe reads per CTA into
@@ -747,7 +826,8 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             }
         }
         if (!ROLLOUT && p.act_tma && !WARP_ACT0) __syncthreads();   // the CTA's mbarrier is initialised before any warp goes on
-        if ((int)(blockIdx.x * WARPS + (threadIdx.x >> 5)) >= p.M) return;
+        if ((int)((SERVE ? blockIdx.x - 1u : blockIdx.x) * WARPS + (threadIdx.x >> 5)) >= p.M) return;
+        if (SERVE && (threadIdx.x & 31) == 0) mbar_init(smem_u32(smw) + (unsigned)((threadIdx.x >> 5) * L::WORDS + L::BAR + 2) * 4u, 1);   // the warp's action mbarrier
         if (DEC) {
             if ((threadIdx.x & 31) == 0) smw[(threadIdx.x >> 5) * L::WORDS + L::TIE] = 0u;  // decimal_ledger: no restart yet, no parked answers
             __syncwarp();
@@ -759,7 +839,7 @@ restart:;
   {
     // (decimal_ledger: fresh reads, not the prologue's copies kept alive across `resolve`)
     const int warp = DEC ? (int)(fresh_tid_x() >> 5) : (int)(threadIdx.x >> 5), lane = DEC ? (int)(fresh_tid_x() & 31u) : (int)(threadIdx.x & 31);
-    const int m = blockIdx.x * WARPS + warp;
+    const int m = (SERVE ? blockIdx.x - 1u : blockIdx.x) * WARPS + warp;
     const CdaDevCfg &cfg = p.cfg;
     const int A = cfg.A;
     // Output routing.  ROUTED = false is the plain device step (dense obs / reward / flag arrays): everything only the host window /
@@ -875,14 +955,32 @@ restart:;
     bool waited = false;
     long long nav_max_carry = 0, nav_prev_carry = 0;   // multi-step rollout: carry max_nav / prev_nav between steps
     const int n_iter = ROLLOUT ? p.num_steps : 1;
-    for (int it = 0; it < n_iter; ++it) {
-        const bool last_it = !ROLLOUT || it == n_iter - 1;
+    int it = 0;
+    for (; SERVE || it < n_iter; ++it) {
+        const bool last_it = SERVE || !ROLLOUT || it == n_iter - 1;   // this step's outputs leave the SM (resident server: every step's do)
         float hv[CDA_HIST_PREFETCH];
         int slot_new = 0;
+        if (SERVE) {   // wait for the host's message for step srv_next + it; STOP (or the poller's idle lease running out) ends the launch
+            unsigned long long msg = 0ULL;
+            if (lane == 0) msg = cda_serve_wait(p, p.srv_next + (unsigned)it, (int)blockIdx.x - 1);
+            msg = __shfl_sync(CDA_FULL, msg, 0);
+            const unsigned pslot = ((unsigned)msg >> 24) & 0xffu;
+            if (pslot == CDA_SRV_STOP) break;
+            const unsigned char *ab = p.srv_act_base + (long long)(int)(msg >> 32) * 16LL + (size_t)m * (size_t)(20 * A);   // i32[5][A] of this market
+            if (lane == 0) SMW(wb + L::SNAP + 42) = pslot;                         // (parked: needed again when the outputs are stored)
+            if (p.srv_act_mode == 0) {
+                if (lane == 0) {
+                    const unsigned abar = sa + (L::BAR + 2) * 4u;
+                    mbar_expect_tx(abar, 20u * (unsigned)A);
+                    bulk_g2s(smem_u32(smw) + (unsigned)(actb + warp * 5 * A) * 4u, ab, 20u * (unsigned)A, abar);
+                }
+            } else for (int i = lane; i < 5 * A; i += 32) SMW(actb + warp * 5 * A + i) = ld_volatile_u32(reinterpret_cast<const unsigned *>(ab) + i);
+            __syncwarp();
+        }
         // ================= set_actions: action_helper.py:145-172, :241-397 =================
         int a_cat = -1, a_pcode = 0, a_poff = 1; float a_mean = 0.f, a_sigma = 0.f;
         if (lane < A) {
-            if (ROLLOUT) {   // fused uniform random policy (model_handler.py:38-78)
+            if (ROLLOUT && !SERVE) {   // fused uniform random policy (model_handler.py:38-78)
                 const unsigned long long h = splitmix64(p.policy_seed ^ splitmix64(((unsigned long long)m << 32) ^ ((unsigned long long)(t_step) * 64ULL + lane)));
                 a_cat = (int)(((h & 0xffffu) * 9u) >> 16);
                 a_pcode = (int)((((h >> 16) & 0xffffu) * 10u) >> 16);
@@ -890,9 +988,17 @@ restart:;
                 const unsigned long long h2 = splitmix64(h);
                 a_mean = (float)((double)(h2 & 0xffffffu) * (2.0 / 16777216.0) - 1.0);
                 a_sigma = (float)((double)((h2 >> 24) & 0xffffffu) * (1.0 / 16777216.0));
-            } else if (!p.act_tma) {
+            } else if (!SERVE && !p.act_tma) {
                 const size_t o = (size_t)m * p.act_mstride + lane;
                 a_cat = p.cat[o]; a_mean = p.mean[o]; a_sigma = p.sigma[o]; a_pcode = p.pcode[o]; a_poff = p.poff[o];
+            }
+        }
+        if (SERVE) {   // this market's action record i32[5][A], staged above
+            if (p.srv_act_mode == 0) mbar_wait(sa + (L::BAR + 2) * 4u, (unsigned)it & 1u);
+            if (lane < A) {
+                const int o = actb + warp * 5 * A + lane;
+                a_cat = (int)SMW(o); a_mean = __uint_as_float(SMW(o + A)); a_sigma = __uint_as_float(SMW(o + 2 * A));
+                a_pcode = (int)SMW(o + 3 * A); a_poff = (int)SMW(o + 4 * A);
             }
         }
         if (!ROLLOUT && p.act_tma) {
@@ -990,7 +1096,7 @@ restart:;
         CDA_TICK(1);   // accounts + actions arrived, draws + decode done
         // park the decoded actions in shared memory: the matching phase reads them with uniform loads, and the
         // dozen registers they occupied are free while the book is being worked on
-        if (!ROLLOUT && p.act_log && lane < A)
+        if ((!ROLLOUT || SERVE) && p.act_log && lane < A)
             *reinterpret_cast<int4 *>(p.act_log + ((size_t)m * A + lane) * 4) = a_side >= 0 ? make_int4(a_type, a_side, (int)a_size, a_price) : make_int4(-1, -1, 0, -1);
         if (lane < A && a_side >= 0) {
             SMW(wb + L::ACT + 3 * lane) = (unsigned)a_type | ((unsigned)a_side << 8);
@@ -1295,7 +1401,9 @@ restart:;
             }
             const int nw_data = nw;
             if (p.ring_pad > nw) nw = p.ring_pad;
-            float *rg0 = o_ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
+            // (resident server: cell m of the plane the message named; planes are M * ring_stride floats apart)
+            float *rg0 = SERVE ? o_ring_out + ((size_t)SMW(wbL + L::SNAP + 42) * (size_t)p.M + (size_t)m) * (size_t)p.ring_stride
+                               : o_ring_out + (size_t)m * p.ring_stride + p.ring_slot * CDA_SNAPSHOT_DIM;
 #pragma unroll 1
             for (int g = 0; g < o_rep_n; ++g) {   // (fused all-gather: the same cell of every rank's window, over NVLink)
                 float *rg = reinterpret_cast<float *>(reinterpret_cast<char *>(rg0) + (g ? p.rep_delta[g] : 0LL));
@@ -1322,7 +1430,19 @@ restart:;
         }
         t_step++;
         __syncwarp();
-        if (ROLLOUT && !last_it) {    // multi-step rollout: the accounts go back to their tile, the generator comes back for the next step's draws
+        if (SERVE) {   // this step's completion: outputs fenced, every warp counts itself, the last one rings the host (and tells the poller)
+            if (lane == 0 && SMW(wbL + L::PARK + 11)) *p.status_flag = 1u;
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0 && atomicAdd(p.done_ctr, 1u) == (unsigned)p.M - 1u) {
+                *p.done_ctr = 0u;          // (every other warp has counted itself, and none starts the next step before the host has seen this one)
+                __threadfence_system();
+                const unsigned sq = p.srv_next + (unsigned)it;
+                *reinterpret_cast<volatile unsigned *>(p.done_flag) = sq;
+                *reinterpret_cast<volatile unsigned *>(p.srv_done_dev) = sq;
+            }
+        }
+        if (ROLLOUT && (SERVE || !last_it)) {    // multi-step rollout: the accounts go back to their tile, the generator comes back for the next step's draws
             if (lane < A) {
                 long long *sq = reinterpret_cast<long long *>(&smw[acct_w]);
                 sq[lane] = ac.cash; sq[A + lane] = ac.hold; sq[2 * A + lane] = ac.cost; sq[3 * A + lane] = ac.nav;
@@ -1335,6 +1455,10 @@ restart:;
         }
     }
 
+    if (SERVE && it == 0) {   // stopped before the first step: nothing has changed (the staged copies must have landed before the CTA may go)
+        if (!waited) mbar_wait(bar, 0u);
+        return;
+    }
     CDA_TICK(8);   // reward/done
     const int wbL = (int)(fresh_tid_x() >> 5) * L::WORDS;   // (as inside the loop: not the entry-time copy)
     // ---- store: header, accounts, pool prefix
@@ -1375,7 +1499,7 @@ restart:;
             bulk_wait_read0();
         }
     }
-    if (ROUTED && p.done_flag) {
+    if (ROUTED && !SERVE && p.done_flag) {
         __threadfence_system();        // this warp's stores to host memory are visible before it counts itself
         __syncwarp();
         if (lane == 0 && atomicAdd(p.done_ctr, 1u) == (unsigned)p.M - 1u) {

@@ -423,19 +423,58 @@ class VecCDAEnv:
         """Dense-plane host path.  `action_block`: ONE pinned int32 tensor, [M, 5, A] (market_major) or [5, M, A], read in place by
         the kernel.  Returns (StackedPlanes obs, reward f64[M, A], terminated u8[M], truncated u8[M]) — views of the pinned plane
         ring, valid until PLANE_SLOTS - n_hist further steps have been made.  `np.asarray(obs)` / `obs.stacked()` materialises the
-        contiguous f32[M, n_hist*42] array (one host copy); `obs.planes` are the n_hist zero-copy [M, 42] views, oldest first."""
+        contiguous f32[M, n_hist*42] array (one host copy); `obs.planes` are the n_hist zero-copy [M, 42] views, oldest first.
+        With `host_resident = True` (see serve()) the market-major synchronous form goes through the resident step server."""
         pos = self._plane_pos
         if pos is None:
             raise RuntimeError("call reset_host_planes() before step_host_planes()")
         pos = (pos + 1) % self.PLANE_SLOTS
-        rc = self._plane_step(self._h, action_block.data_ptr(), self._plane_ptrs[pos], self._plane_cell,
-                              (1 if sync else 0) | (2 if market_major else 0), self._plane_stream)
+        if self._serve_on and sync and market_major:
+            rc = self._serve_step(self._h, action_block.data_ptr(), pos, self._plane_stream)
+        else:
+            rc = self._plane_step(self._h, action_block.data_ptr(), self._plane_ptrs[pos], self._plane_cell,
+                                  (1 if sync else 0) | (2 if market_major else 0), self._plane_stream)
         if rc:
             _native.check(rc)
         self._plane_pos = pos
         if self._status_flag[0]:
             self._poll_status()
         return self._plane_results[pos]
+
+    # ---- resident step server (include/cda_b200.h, cda_serve_*): the plane path without a launch per step
+    _serve_on = False
+
+    def serve(self, on=True):
+        """Switch the RESIDENT STEP SERVER on / off for step_host_planes(market_major=True): the step kernel is launched once and stays
+        on the SMs with every market's book and ledger in shared memory; a step is then one doorbell write by the host (no launch, no
+        stream hand-shake, no state round trip through HBM) and the same outputs in the same planes.  For HOST-side policies: while
+        the server is resident (until 2 ms after the last step, or any other call on this env) it occupies the whole GPU.
+        Returns True when the mode is active, False when this env cannot use it (decimal_ledger, more markets than one resident
+        wave holds, unmapped buffers) and step_host_planes keeps launching per step."""
+        if not on:
+            if self._serve_on:
+                _native.check(self._L.cda_serve_stop(self._h))
+            self._serve_on = False
+            return False
+        self._ensure_planes()
+        rc = self._L.cda_serve_bind(self._h, ctypes.c_void_p(self._plane_ptrs[0]), self.PLANE_SLOTS, self._plane_cell)
+        if rc == -5:     # CDA_EUNSUPPORTED
+            self._serve_on = False
+            return False
+        _native.check(rc)
+        self._serve_step = self._L.cda_serve_step
+        self._serve_on = True
+        return True
+
+    host_resident = property(lambda self: self._serve_on, lambda self, v: self.serve(bool(v)))
+
+    def serve_stop(self):
+        """Retire the resident kernel now (state back in HBM, SMs free); the next step_host_planes launches it again."""
+        _native.check(self._L.cda_serve_stop(self._h))
+
+    @property
+    def serve_launches(self):
+        return int(self._L.cda_serve_launches(self._h))
 
     def step_pinned(self, sync=True):
         """Like step_host but the caller has already written the actions into `pinned_buffers()`."""

@@ -196,6 +196,33 @@ int cda_step_window(CdaEnv *env, const int32_t *h_action_block, int32_t pos, int
 int cda_step_planes(CdaEnv *env, const int32_t *h_action_block, float *h_plane, int32_t cell_words, int32_t flags, void *stream);
 int cda_reset_planes(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask, float *h_planes, int32_t slots, int32_t cell_words, int32_t pos, void *stream);
 
+/* ---- RESIDENT STEP SERVER: the plane path without a launch, a stream hand-shake or a state load / store per step ----
+ * For a policy that lives on the HOST (the reference's: RLlib workers call env.step from Python, train/train.py:509-518) the per-step
+ * cost of cda_step_planes is a kernel launch, the completion hand-shake and the market state's round trip through HBM — more than the
+ * matching itself.  cda_serve_step removes all three: the step kernel is launched once and STAYS RESIDENT (one warp per market; books
+ * and ledgers kept in shared memory between steps, as in the fused rollout), and a step is one 8-byte message the host writes into a
+ * mapped pinned word: a poller CTA reads it over PCIe and republishes it in L2, every warp fetches its market's 20*A-byte action record
+ * from the caller's pinned block, steps, stores snapshot + result record into cell m of plane `slot` (same layout and bytes as
+ * cda_step_planes) and counts itself; the last warp rings a pinned completion word the call spins on.  Results are identical to
+ * cda_step_planes' (tests/test_gpu_serve.py compares them step by step, and the state afterwards).
+ *   cda_serve_bind   registers the plane ring (pinned + mapped, as above).  Returns CDA_EUNSUPPORTED when the mode cannot be used and
+ *                    the caller should stay on cda_step_planes: decimal_ledger handles, more markets than one resident wave holds
+ *                    (7 CTAs x 4 markets per SM: 4140 markets of <= 4 agents on a B200), buffers that are not mapped.
+ *   cda_serve_step   h_action_block: pinned i32[M][5][A] (market-major) for THIS step — any block within +-32 GB of the first one
+ *                    seen; slot: plane that receives the outputs (the caller advances it modulo slots).  Returns when the outputs
+ *                    are in host memory.  `stream`: the caller's stream; a (re)launch is ordered behind the work already queued there.
+ *   cda_serve_stop   stores the state back and retires the kernel.  Every other entry point that touches the handle's state
+ *                    (reset, step*, rollout, info, fills, dump, save / load) does this implicitly, so the modes can be mixed freely.
+ * The kernel also retires by itself when no step has been requested for the lease (2 ms; $CDA_SERVE_LEASE_US) — a host that went away
+ * cannot pin the GPU — and the next cda_serve_step launches it again: an idle server costs one launch, not a hang.  While it is resident
+ * it occupies every SM: other kernels on the device wait for the lease to run out, so this mode is for host-side policies (GPU-side
+ * policies use cda_step / cda_step_gather, which never leave the device). */
+#define CDA_EUNSUPPORTED (-5)   /* the requested mode cannot serve this handle; use the fallback the header names */
+int cda_serve_bind(CdaEnv *env, float *h_planes, int32_t slots, int32_t cell_words);
+int cda_serve_step(CdaEnv *env, const int32_t *h_action_block, int32_t slot, void *stream);
+int cda_serve_stop(CdaEnv *env);
+int64_t cda_serve_launches(const CdaEnv *env);   /* how many times the resident kernel has been (re)launched so far */
+
 /* Fused T-step rollout with the on-device uniform random policy (the RandomRLModule /
  * CDA_rand.py workload: category U{0..8}, price U{0..9}, offset U{0..2}, mean U(-1,1), sigma U(0,1),
  * gym_continuousDoubleAuction/train/model/model_handler.py:38-78).  Policy draws come from a
