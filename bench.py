@@ -244,16 +244,26 @@ def main():
     pin_mm.copy_(pin_blk.permute(0, 2, 1, 3))
     pin_mm_steps = [pin_mm[i] for i in range(PH)]
 
+    # The e2e legs hand the env ONE pinned action block that the host REWRITES before every step (outside the timer: producing the
+    # actions is the policy's job) — what a host-side policy does, and the only way to time the input leg reproducibly: blocks that were
+    # built long before and have left the CPU's caches are read by the GPU at a rate that collapses for a few steps every ~6 MB of
+    # host memory on this box (tools/serve_timeline.py, profiles/r04a_serve_timeline.txt: 35 us becomes 90 us in one step out of ten).
+    stage_mm = torch.empty((M, 5, A), dtype=torch.int32, pin_memory=True)
+    stage_fm = torch.empty((5, M, A), dtype=torch.int32, pin_memory=True)
+
+    def produce(i):
+        stage_mm.copy_(pin_mm_steps[i % PH]); stage_fm.copy_(pin_steps[i % PH])
+
     def host_step(i):
         # actions read in place from the pinned block; newest snapshot + result record written straight to pinned memory
-        return env.step_host_window(pin_mm_steps[i % PH], market_major=True)
+        return env.step_host_window(stage_mm, market_major=True)
 
     def host_step_planes(i):
         # dense plane ring: this step's snapshot + result record of every market land in ONE contiguous region of pinned memory
-        return env.step_host_planes(pin_mm_steps[i % PH], market_major=True)
+        return env.step_host_planes(stage_mm, market_major=True)
 
     def host_step_full(i):
-        return env.step_host_block(pin_steps[i % PH])     # same, but the whole 168-float stack of every market crosses PCIe
+        return env.step_host_block(stage_fm)     # same, but the whole 168-float stack of every market crosses PCIe
 
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     step_ctr = [0]
@@ -309,9 +319,17 @@ def main():
     # ------------------------------------------------------------------ e2e (host buffers in/out)
     e2e = None
     if not args.no_e2e:
-        def timed_host(fn):
+        def timed_host(fn, attach=None):
+            # every leg starts from the same book depth as the device-timed region: fresh books, the same prewarm + warm-up steps
+            # (a run that just kept stepping through four legs would time each leg on deeper books than the one before)
+            env.reset(seed=gseeds)
+            step_ctr[0] = 0
+            for i in range(args.prewarm + args.warmup):
+                dev_step(i)
+            if attach is not None:
+                attach()
             for i in range(max(3, args.warmup // 2)):
-                fn(i)
+                produce(i); fn(i)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -322,6 +340,7 @@ def main():
                     # (the flush is waited for on ITS stream: a device-wide synchronisation would also wait for the resident step server,
                     # which holds its SMs until its idle lease runs out; the fill runs beside it on the SMs that are not full)
                     flush_buf.fill_(i & 0xff); cur.synchronize()
+                produce(i + args.warmup)
                 t0 = time.perf_counter()
                 o, r, te, tr = fn(i + args.warmup)
                 _ = float(r[0, 0]) + float(o[M - 1, env.W - 1])   # the host reads the step's result
@@ -331,16 +350,13 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt.item())
         t_full = timed_host(host_step_full)
-        env.attach_host_window()   # hand every market's current stack to the host window (no market is reset)
-        t_win = timed_host(host_step)
-        env.attach_host_planes()
-        t_pl = timed_host(host_step_planes)
+        t_win = timed_host(host_step, env.attach_host_window)   # (attach: hand every market's current stack to the host window, no market is reset)
+        t_pl = timed_host(host_step_planes, env.attach_host_planes)
         # the same call with the RESIDENT STEP SERVER switched on (VecCDAEnv.serve): the kernel stays on the SMs, a step is a doorbell write
         t_srv, srv_launches = None, 0
         if env.serve(True):
-            srv0 = env.serve_launches
-            t_srv = timed_host(host_step_planes)
-            srv_launches = env.serve_launches - srv0
+            t_srv = timed_host(host_step_planes, env.attach_host_planes)
+            srv_launches = env.serve_launches       # (of the whole leg: warm-up included; the timed loop needs none when the lease holds)
             env.serve(False)
         S, H = env.WINDOW_SLOTS - 1, env.n_hist                     # the last slot only ever carries a record
         rec = M * 8 * (A + 1)
@@ -363,7 +379,8 @@ def main():
                       "terminated, truncated) into cell m of the pinned plane ring and counts itself; the last warp rings the pinned completion word the call "
                       "spins on.  Same inputs, outputs and bytes as cda_step_planes (tests/test_gpu_serve.py: identical planes, records and state), no "
                       "launch, no stream hand-shake, no state round trip through HBM per step",
-               "resident_kernel_launches_in_timed_loop": int(srv_launches),
+               "resident_kernel_launches": int(srv_launches),
+               "inputs": "one pinned i32[M,5,A] block, rewritten by the host before every step (outside the timer), read by the kernel over PCIe inside it",
                "launch_per_step_variant": {"value": world * M * args.steps / t_pl, "ms_per_step": 1e3 * t_pl / args.steps,
                                            "d2h_bytes_per_step": int(M * env._plane_cell * 4), "api": planes_api},
                "window_variant": {"value": world * M * args.steps / t_win, "ms_per_step": 1e3 * t_win / args.steps, "d2h_bytes_per_step": int(d2h_win),

@@ -50,7 +50,7 @@ EXPORTS = (
     "cda_kernel_launches", "cda_strerror", "cda_last_cuda_error", "cda_build_info",
     "cda_seed_to_pcg64", "cda_state_layout", "cda_twin_sync", "cda_status_flag", "cda_status_flag_clear",
 )
-TESTING_EXPORTS = ("cda_debug_phase_buffer", "cda_debug_dec_op", "cda_debug_dec_op_device", "cda_debug_set_window_mode", "cda_debug_restart_count")
+TESTING_EXPORTS = ("cda_debug_phase_buffer", "cda_debug_dec_op", "cda_debug_dec_op_device", "cda_debug_set_window_mode", "cda_debug_restart_count", "cda_debug_serve_timeline")
 
 
 def needs_build():
@@ -149,6 +149,7 @@ def lib():
     sig("cda_debug_set_window_mode", [i32], None)
     sig("cda_debug_restart_count", None, i64)
     sig("cda_debug_phase_buffer", None, ctypes.c_void_p)
+    sig("cda_debug_serve_timeline", [i32], ctypes.c_void_p)
     sig("cda_debug_dec_op", [i32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, ctypes.POINTER(i32)])
     sig("cda_debug_dec_op_device", [i32, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, i32, ctypes.POINTER(i32)])
     _lib = L

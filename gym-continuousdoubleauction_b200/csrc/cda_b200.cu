@@ -136,6 +136,8 @@ static cudaError_t launch_step_any(const CdaEnv *e, const CdaStepParams &p, cuda
 #define CDA_SRV_GO_WORD 16      /* status_host word index of the 64-bit message the host rings (its own 64-B line) */
 #define CDA_SRV_DONE_WORD 10    /* completion word the kernel's last warp writes (NOT word 8: the launch paths' doorbell counts differently) */
 #define CDA_SRV_ERR_WORD 32     /* a worker's watchdog fired */
+static unsigned long long *g_srv_prof = nullptr;   // cda_debug_serve_timeline: u64[(M + 1)][16] milestone times of the last served step
+static int g_srv_dbg = getenv("CDA_SERVE_DEBUG") ? atoi(getenv("CDA_SERVE_DEBUG")) : 0;
 static unsigned long long host_now_ns() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (unsigned long long)ts.tv_sec * 1000000000ULL + (unsigned long long)ts.tv_nsec; }
 static size_t srv_smem_bytes(const CdaEnv *e, int cap_words_bytes) {
     return (size_t)cap_words_bytes * CDA_WARPS_PER_CTA + (size_t)5 * CDA_WARPS_PER_CTA * e->dev.A * 4 + 16 +
@@ -190,7 +192,17 @@ static int srv_launch(CdaEnv *e, cudaStream_t st) {
     p.srv_act_base = e->srv_act_dev0; p.srv_next = e->srv_seq + 1u;
     p.srv_lease_ns = e->srv_lease_ns; p.srv_watchdog_ns = 1000000000ULL + 4ULL * e->srv_lease_ns;
     static const int dbg_mode = getenv("CDA_SERVE_ACT_MODE") ? atoi(getenv("CDA_SERVE_ACT_MODE")) : 0;
-    p.srv_act_mode = ((e->dev.A % 4) == 0 && dbg_mode == 0) ? 0 : 1;   // bulk copies move multiples of 16 B from 16-B aligned addresses
+    p.srv_act_mode = ((e->dev.A % 4) == 0 && dbg_mode == 0) ? 0 : 1;
+    p.prof = g_srv_prof;
+    if (g_srv_dbg & 1) {   // timing experiments (tools/serve_timeline.py): actions read from a device copy of the first block (no input transfer)
+        CUDA_TRY(cudaMemcpyAsync(e->s_cat, e->srv_act_dev0, (size_t)e->M * e->dev.A * 20, cudaMemcpyDefault, e->srv_stream));
+        p.srv_act_base = reinterpret_cast<const unsigned char *>(e->s_cat);
+    }
+    if (g_srv_dbg & 2) {   // ... outputs kept on the device (no output transfer)
+        static float *dbg_planes = nullptr;   // (one env per process in the tool)
+        if (!dbg_planes) CUDA_TRY(cudaMalloc(&dbg_planes, (size_t)e->srv_slots * e->M * e->srv_cell * 4));
+        p.ring_out = dbg_planes;
+    }   // bulk copies move multiples of 16 B from 16-B aligned addresses
     CUDA_TRY(cudaEventRecord(e->srv_event, st));
     CUDA_TRY(cudaStreamWaitEvent(e->srv_stream, e->srv_event, 0));
     CUDA_TRY(cudaMemsetAsync(e->srv_go_dev, 0, (size_t)CDA_SRV_COPIES * 128, e->srv_stream));   // (a message left by an earlier launch must not match)
@@ -809,6 +821,7 @@ int cda_serve_step(CdaEnv *e, const int32_t *h_action_block, int32_t slot, void 
         SRV_QUIESCE(e);
         e->srv_act_dev0 = dblk; off = 0;
     }
+    if (g_srv_dbg & 1) off = 0;
     const unsigned seq = e->srv_seq + 1u;
     const unsigned long long msg = (unsigned long long)cda_srv_seq24(seq) | ((unsigned long long)(unsigned)slot << 24) |
                                    ((unsigned long long)(unsigned)(int)(off >> 4) << 32);
@@ -1213,4 +1226,14 @@ int cda_debug_dec_op_device(int32_t op, int32_t n, const char *const *a, const c
     return CDA_OK;
 }
 
+// measurement only: the resident step server leaves per-market milestone times (globaltimer ns) of the LAST served step in rows of 16 u64
+// (0 message seen, 1 actions here, 2 step computed, 3 outputs fenced); row M: 0 completion rung, 1 poller read the message.  NULL = off.
+unsigned long long *cda_debug_serve_timeline(int32_t markets) {
+    if (markets <= 0) { g_srv_prof = nullptr; return nullptr; }
+    unsigned long long *b = nullptr;
+    if (cudaMalloc(&b, (size_t)(markets + 1) * 16 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(b, 0, (size_t)(markets + 1) * 16 * sizeof(unsigned long long));
+    g_srv_prof = b;
+    return b;
+}
 }  // extern "C"

@@ -706,6 +706,8 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 // not heard from the poller for srv_watchdog_ns (which cannot happen while the poller is resident) raises srv_err and exits.
 // ------------------------------------------------------------------------------------------
 #define CDA_SRV_COPIES 128
+/* measurement only (cda_debug_serve_timeline, tools/serve_timeline.py): lane 0 of every warp leaves the time of the step's milestones */
+#define CDA_SRV_STAMP(i) do { if (p.prof && lane == 0) p.prof[(size_t)m * 16 + (i)] = globaltimer_ns(); } while (0)
 #define CDA_SRV_STOP 0xffu
 __host__ __device__ __forceinline__ unsigned cda_srv_seq24(unsigned seq) { return seq % 0xffffffu + 1u; }
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
@@ -717,7 +719,8 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // the poller CTA (all its threads; smw[0..1] is the mailbox between thread 0 and the others)
 // (arguments by value: taking the address of the kernel's parameter block would copy it to every thread's stack)
-__device__ __noinline__ void cda_serve_poller(const unsigned long long *go_host, unsigned long long *go_dev, const unsigned *done_dev, unsigned next, unsigned long long lease_ns) {
+__device__ __noinline__ void cda_serve_poller(const unsigned long long *go_host, unsigned long long *go_dev, const unsigned *done_dev, unsigned next, unsigned long long lease_ns,
+                                              unsigned long long *prof_row) {
     bool idle = true;                      // no step in flight
     unsigned long long t_idle = globaltimer_ns();
     for (;;) {
@@ -731,6 +734,7 @@ __device__ __noinline__ void cda_serve_poller(const unsigned long long *go_host,
                 else if (now - t_idle > lease_ns) { v = (unsigned long long)cda_srv_seq24(next) | ((unsigned long long)CDA_SRV_STOP << 24); break; }
             }
             *reinterpret_cast<volatile unsigned long long *>(smw) = v;
+            if (prof_row && (((unsigned)v >> 24) & 0xffu) != CDA_SRV_STOP) prof_row[1] = globaltimer_ns();   // (timeline tool) step message read from host memory
         }
         __syncthreads();
         const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(smw);
@@ -777,7 +781,7 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
     using L = CdaSmemLayout<CAP, DEC>;
     constexpr bool SERVE = ROLLOUT && ROUTED;   // resident step server: CTA 0 polls the host, CTA b > 0 steps markets 4(b-1) .. 4(b-1)+3 whenever a message arrives
     static_assert(!(SERVE && DEC), "the resident step server runs the integer ledger only");
-    if (SERVE && blockIdx.x == 0) { cda_serve_poller(p.srv_go_host, p.srv_go_dev, p.srv_done_dev, p.srv_next, p.srv_lease_ns); return; }
+    if (SERVE && blockIdx.x == 0) { cda_serve_poller(p.srv_go_host, p.srv_go_dev, p.srv_done_dev, p.srv_next, p.srv_lease_ns, p.prof ? p.prof + (size_t)p.M * 16 : nullptr); return; }
     {   // ---- CTA prologue (its values die here: nothing defined above `restart` may be live across the resolve block's call) ----
         // action tile of this CTA: five bulk copies (one per field, the CTA's markets are adjacent rows of every [M][A] array) behind one
         // CTA mbarrier.  When the arrays live in pinned host memory (end-to-end path) this turns 20 sector-sized PCIe reads per CTA into
@@ -826,8 +830,11 @@ __global__ void __launch_bounds__(WARPS * 32, CDA_MIN_CTAS) cda_step_kernel(cons
             }
         }
         if (!ROLLOUT && p.act_tma && !WARP_ACT0) __syncthreads();   // the CTA's mbarrier is initialised before any warp goes on
+        if (SERVE) {   // the CTA's action mbarrier (one bulk copy per CTA and step, issued by whichever warp sees the message first) and its claim word
+            if (threadIdx.x == 0) { mbar_init(smem_u32(smw) + (unsigned)cbar_w0 * 4u, 1); smw[cbar_w0 + 2] = 0u; }
+            __syncthreads();
+        }
         if ((int)((SERVE ? blockIdx.x - 1u : blockIdx.x) * WARPS + (threadIdx.x >> 5)) >= p.M) return;
-        if (SERVE && (threadIdx.x & 31) == 0) mbar_init(smem_u32(smw) + (unsigned)((threadIdx.x >> 5) * L::WORDS + L::BAR + 2) * 4u, 1);   // the warp's action mbarrier
         if (DEC) {
             if ((threadIdx.x & 31) == 0) smw[(threadIdx.x >> 5) * L::WORDS + L::TIE] = 0u;  // decimal_ledger: no restart yet, no parked answers
             __syncwarp();
@@ -966,15 +973,23 @@ restart:;
             msg = __shfl_sync(CDA_FULL, msg, 0);
             const unsigned pslot = ((unsigned)msg >> 24) & 0xffu;
             if (pslot == CDA_SRV_STOP) break;
-            const unsigned char *ab = p.srv_act_base + (long long)(int)(msg >> 32) * 16LL + (size_t)m * (size_t)(20 * A);   // i32[5][A] of this market
+            CDA_SRV_STAMP(0);   // message seen
+            // the step's action records i32[markets][5][A] of this CTA's markets are ONE contiguous run of the caller's block: one bulk copy per
+            // CTA (reads from host memory are bound by the number of requests: 4096 copies of 80 B took 17 us, 1024 of 320 B take 7), issued by
+            // the first of the CTA's warps to see the message
+            const unsigned char *ab = p.srv_act_base + (long long)(int)(msg >> 32) * 16LL;
             if (lane == 0) SMW(wb + L::SNAP + 42) = pslot;                         // (parked: needed again when the outputs are stored)
             if (p.srv_act_mode == 0) {
-                if (lane == 0) {
-                    const unsigned abar = sa + (L::BAR + 2) * 4u;
-                    mbar_expect_tx(abar, 20u * (unsigned)A);
-                    bulk_g2s(smem_u32(smw) + (unsigned)(actb + warp * 5 * A) * 4u, ab, 20u * (unsigned)A, abar);
+                if (lane == 0 && atomicMax(&smw[cbar_w + 2], (unsigned)it + 1u) <= (unsigned)it) {
+                    const int m0 = m - warp, nm = min(WARPS, p.M - m0);
+                    const unsigned cbar = smem_u32(smw) + (unsigned)cbar_w * 4u, nb = (unsigned)(nm * 20 * A);
+                    mbar_expect_tx(cbar, nb);
+                    bulk_g2s(smem_u32(smw) + (unsigned)actb * 4u, ab + (size_t)m0 * (size_t)(20 * A), nb, cbar);
                 }
-            } else for (int i = lane; i < 5 * A; i += 32) SMW(actb + warp * 5 * A + i) = ld_volatile_u32(reinterpret_cast<const unsigned *>(ab) + i);
+            } else {
+                const unsigned *aw = reinterpret_cast<const unsigned *>(ab + (size_t)m * (size_t)(20 * A));
+                for (int i = lane; i < 5 * A; i += 32) SMW(actb + warp * 5 * A + i) = ld_volatile_u32(aw + i);
+            }
             __syncwarp();
         }
         // ================= set_actions: action_helper.py:145-172, :241-397 =================
@@ -994,7 +1009,8 @@ restart:;
             }
         }
         if (SERVE) {   // this market's action record i32[5][A], staged above
-            if (p.srv_act_mode == 0) mbar_wait(sa + (L::BAR + 2) * 4u, (unsigned)it & 1u);
+            if (p.srv_act_mode == 0) mbar_wait(smem_u32(smw) + (unsigned)cbar_w * 4u, (unsigned)it & 1u);
+            CDA_SRV_STAMP(1);   // actions here
             if (lane < A) {
                 const int o = actb + warp * 5 * A + lane;
                 a_cat = (int)SMW(o); a_mean = __uint_as_float(SMW(o + A)); a_sigma = __uint_as_float(SMW(o + 2 * A));
@@ -1391,6 +1407,7 @@ restart:;
         __syncwarp();
         if (lane == 0) SMW(wbL + L::PARK + 10) = done_mask;
         const unsigned all = A >= 32 ? 0xffffffffu : ((1u << A) - 1u);
+        if (SERVE) CDA_SRV_STAMP(2);   // step computed, outputs about to leave
         if (o_ring_out && last_it) {   // host ring / sliding window: only the newest 42 floats leave the GPU (128-B aligned chunks, like the stack)
             int nw = CDA_SNAPSHOT_DIM;
             if (o_rec_inline) {        // ... followed by the result record, which then shares the snapshot's last write transaction (the
@@ -1432,14 +1449,19 @@ restart:;
         __syncwarp();
         if (SERVE) {   // this step's completion: outputs fenced, every warp counts itself, the last one rings the host (and tells the poller)
             if (lane == 0 && SMW(wbL + L::PARK + 11)) *p.status_flag = 1u;
-            __threadfence_system();
+            // every warp orders its stores before its count at GPU scope (cheap); the LAST warp's system-scope fence, made after it has
+            // observed all the counts, is cumulative: everything the others stored is visible to the host before the completion word.
+            // (4096 system-scope fences in flight at once cost every warp 4 - 14 us, profiles/r04a_serve_timeline.txt.)
+            __threadfence();
             __syncwarp();
+            CDA_SRV_STAMP(3);   // outputs issued and ordered
             if (lane == 0 && atomicAdd(p.done_ctr, 1u) == (unsigned)p.M - 1u) {
                 *p.done_ctr = 0u;          // (every other warp has counted itself, and none starts the next step before the host has seen this one)
                 __threadfence_system();
                 const unsigned sq = p.srv_next + (unsigned)it;
                 *reinterpret_cast<volatile unsigned *>(p.done_flag) = sq;
                 *reinterpret_cast<volatile unsigned *>(p.srv_done_dev) = sq;
+                if (p.prof) p.prof[(size_t)p.M * 16 + 0] = globaltimer_ns();   // (timeline tool) completion rung
             }
         }
         if (ROLLOUT && (SERVE || !last_it)) {    // multi-step rollout: the accounts go back to their tile, the generator comes back for the next step's draws

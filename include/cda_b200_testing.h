@@ -30,6 +30,11 @@ void cda_debug_set_window_mode(int32_t mode);
  * kernels of this process have made so far on the current device; -1 on error.  Synchronises. */
 int64_t cda_debug_restart_count(void);
 
+/* Resident step server (cda_serve_*): device buffer u64[markets + 1][16] in which every warp leaves the globaltimer (ns) of the milestones
+ * of the LAST served step — 0 message seen, 1 actions here, 2 step computed, 3 outputs fenced; row `markets`: 0 completion rung, 1 poller read
+ * the host's message.  Applies to launches made after the call; markets <= 0 switches it off.  tools/serve_timeline.py. */
+unsigned long long *cda_debug_serve_timeline(int32_t markets);
+
 #ifdef __cplusplus
 }
 #endif

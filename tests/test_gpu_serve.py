@@ -83,12 +83,16 @@ def test_resident_server_equals_oracle():
     assert np.array_equal(np.asarray(o), oc)
     acts = make_actions(3, T, M, A, "limit_market")
     pin = torch.from_numpy(mm_blocks(acts, T, M, A)).pin_memory()
-    for t in range(T):
+    outs = []
+    for t in range(T):                # back to back (the oracle runs afterwards: a pause longer than the lease would retire the kernel)
         og, rg, teg, trg = env.step_host_planes(pin[t])
-        oc, rc, tec, trc = orc.step(*[a[t] for a in acts], nthreads=4)
-        assert np.abs(np.asarray(og).astype(np.float64) - oc).max() <= 1e-6 and np.abs(rg - rc).max() <= 1e-6, t
-        assert np.array_equal(teg, tec) and np.array_equal(trg, trc), t
+        outs.append((np.asarray(og), rg.copy(), teg.copy(), trg.copy()))
     assert env.serve_launches == 1, "96 back-to-back steps are served by ONE launch"
+    for t in range(T):
+        og, rg, teg, trg = outs[t]
+        oc, rc, tec, trc = orc.step(*[a[t] for a in acts], nthreads=4)
+        assert np.abs(og.astype(np.float64) - oc).max() <= 1e-6 and np.abs(rg - rc).max() <= 1e-6, t
+        assert np.array_equal(teg, tec) and np.array_equal(trg, trc), t
     dumps = env.dump_all()
     for m in range(M):
         assert_dump_equal(dumps[m], orc.dump(m), ctx=f"m={m}", fills=False)
