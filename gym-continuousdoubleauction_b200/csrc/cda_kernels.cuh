@@ -1522,7 +1522,10 @@ restart:;
         }
     }
     if (ROUTED && !SERVE && p.done_flag) {
-        __threadfence_system();        // this warp's stores to host memory are visible before it counts itself
+        // this warp's stores are ordered before its count; host memory only: at GPU scope — the last warp's system-scope fence below is
+        // cumulative over everything it has observed (thousands of system-scope fences in flight at once cost each warp microseconds,
+        // profiles/r04a_serve_timeline.txt); peer windows over NVLink keep the system-scope fence per warp
+        if (p.rep_n > 1) __threadfence_system(); else __threadfence();
         __syncwarp();
         if (lane == 0 && atomicAdd(p.done_ctr, 1u) == (unsigned)p.M - 1u) {
             *p.done_ctr = 0u;          // (every other warp has counted itself: the next launch starts from zero)

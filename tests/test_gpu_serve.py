@@ -117,3 +117,30 @@ def test_resident_server_declines_what_it_cannot_serve():
     ok.step_host_planes(torch.zeros((4096, 5, 4), dtype=torch.int32, pin_memory=True))
     assert ok.serve(False) is False
     ok.close()
+
+
+def test_resident_server_full_size_every_step_matches_the_device_path():
+    """BASELINE cfg3 shape (4 x 4096: the one-wave grid the server is built for): 400 served steps, every market's planes and records
+    compared with the plain device step's outputs at every step (a completion word that overtook a late output store would show here)."""
+    cfg = base_cfg(max_step=150)
+    M, A, T = 4096, 4, 400
+    e1 = cda.VecCDAEnv(cfg, num_markets=M); e2 = cda.VecCDAEnv(cfg, num_markets=M)
+    e1.reset(seed=5); e2.reset_host_planes(seed=5)
+    assert e2.serve(True)
+    acts = make_actions(12, T, M, A, "limit_market")
+    dev = [torch.from_numpy(a).cuda() for a in acts]
+    pin = torch.from_numpy(mm_blocks(acts, T, M, A)).pin_memory()
+    one = torch.empty((M, 5, A), dtype=torch.int32, pin_memory=True)
+    for t in range(T):
+        if t % 150 == 149:      # episodes end by truncation: reset everything (retires and relaunches the server)
+            o1, r1, te1, tr1 = e1.step(*[a[t] for a in dev]); one.copy_(pin[t]); o2, r2, te2, tr2 = e2.step_host_planes(one)
+            assert tr2.all() and np.array_equal(o1.cpu().numpy(), np.asarray(o2))
+            e1.reset(seed=None); e2.reset_host_planes(seed=None)
+            continue
+        one.copy_(pin[t])
+        o1, r1, te1, tr1 = e1.step(*[a[t] for a in dev])
+        o2, r2, te2, tr2 = e2.step_host_planes(one)
+        assert np.array_equal(o1.cpu().numpy(), np.asarray(o2)), t
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2), t
+    assert e2.serve_launches >= 3, e2.serve_launches      # (more when the host was held up for longer than the lease between two steps)
+    e1.close(); e2.close()
