@@ -343,7 +343,8 @@ def main():
                 produce(i + args.warmup)
                 t0 = time.perf_counter()
                 o, r, te, tr = fn(i + args.warmup)
-                _ = float(r[0, 0]) + float(o[M - 1, env.W - 1])   # the host reads the step's result
+                newest = o.planes[-1] if hasattr(o, "planes") else o      # (StackedPlanes: the newest [M,42] plane; else the [M,W] stack)
+                _ = float(r[0, 0]) + float(newest[M - 1, newest.shape[1] - 1])   # the host reads the step's result: first reward, last observation element
                 tot += time.perf_counter() - t0
             tt = torch.tensor([tot], dtype=torch.float64, device=dev)
             if world > 1:
