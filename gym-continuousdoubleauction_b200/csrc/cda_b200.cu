@@ -815,16 +815,17 @@ int cda_serve_step(CdaEnv *e, const int32_t *h_action_block, int32_t slot, void 
         if (e->srv_running) SRV_QUIESCE(e);
         e->srv_act_dev0 = dblk;
     }
+    // (bulk copies need 16-B aligned sources: blocks of 4k-agent markets from cudaHostAlloc / torch pin_memory are; the volatile-load path takes any int32 block)
+    if ((reinterpret_cast<uintptr_t>(dblk) & 3) || ((e->dev.A % 4) == 0 && (reinterpret_cast<uintptr_t>(dblk) & 15))) return CDA_EINVAL;
     long long off = dblk - e->srv_act_dev0;
-    if ((off & 15) || off < -(1LL << 34) || off >= (1LL << 34)) {   // out of a message's reach (or misaligned against the base): move the base
-        if (reinterpret_cast<uintptr_t>(dblk) & 15) return CDA_EINVAL;
+    if (off < -(1LL << 32) || off >= (1LL << 32)) {   // out of a message's reach: move the base (retires the kernel once)
         SRV_QUIESCE(e);
         e->srv_act_dev0 = dblk; off = 0;
     }
     if (g_srv_dbg & 1) off = 0;
     const unsigned seq = e->srv_seq + 1u;
     const unsigned long long msg = (unsigned long long)cda_srv_seq24(seq) | ((unsigned long long)(unsigned)slot << 24) |
-                                   ((unsigned long long)(unsigned)(int)(off >> 4) << 32);
+                                   ((unsigned long long)(unsigned)(int)(off >> 2) << 32);
     volatile unsigned *done = e->status_host + CDA_SRV_DONE_WORD;
     __atomic_store_n(reinterpret_cast<unsigned long long *>(e->status_host + CDA_SRV_GO_WORD), msg, __ATOMIC_RELEASE);   // (the caller's action writes come first: TSO + release)
     if (e->srv_running && host_now_ns() - e->srv_last_ns > e->srv_lease_ns / 2) {   // idle for a while: the kernel may have given the SMs back

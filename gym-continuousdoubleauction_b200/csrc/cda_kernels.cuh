@@ -696,7 +696,7 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 // steps (like the fused rollout), and a step is triggered by a 64-bit MESSAGE the host writes to a mapped pinned word:
 //     bits [0,24)  step number, as (seq mod (2^24 - 1)) + 1 (never 0: a cleared word matches nothing)
 //     bits [24,32) slot of the plane ring that receives this step's outputs; 0xff = STOP (store the state and exit)
-//     bits [32,64) signed offset of the step's pinned action block from srv_act_base, in 16-byte units
+//     bits [32,64) signed offset of the step's pinned action block from srv_act_base, in 4-byte words
 // CTA 0 is the POLLER: thread 0 reads the host word over PCIe (no other thread of the grid does), and the CTA republishes a new message into
 // CDA_SRV_COPIES device words in different 128-B lines, which the worker warps poll in L2.  A worker that sees its next step number
 // stages the market's action record (one bulk copy from host memory per warp), runs the step, stores the newest snapshot + result record
@@ -977,7 +977,7 @@ restart:;
             // the step's action records i32[markets][5][A] of this CTA's markets are ONE contiguous run of the caller's block: one bulk copy per
             // CTA (reads from host memory are bound by the number of requests: 4096 copies of 80 B took 17 us, 1024 of 320 B take 7), issued by
             // the first of the CTA's warps to see the message
-            const unsigned char *ab = p.srv_act_base + (long long)(int)(msg >> 32) * 16LL;
+            const unsigned char *ab = p.srv_act_base + (long long)(int)(msg >> 32) * 4LL;
             if (lane == 0) SMW(wb + L::SNAP + 42) = pslot;                         // (parked: needed again when the outputs are stored)
             if (p.srv_act_mode == 0) {
                 if (lane == 0 && atomicMax(&smw[cbar_w + 2], (unsigned)it + 1u) <= (unsigned)it) {
@@ -1474,6 +1474,15 @@ restart:;
             const unsigned long long *pk = reinterpret_cast<const unsigned long long *>(&smw[wbL + L::PARK]);
             rng.shi = pk[0]; rng.slo = pk[1]; rng.ihi = pk[2]; rng.ilo = pk[3];
             rng.has32 = SMW(wbL + L::PARK + 8); rng.u32 = SMW(wbL + L::PARK + 9);
+        }
+        if (SERVE) {
+            // The CTA's warps meet before the next step: the next step's action copy (issued by whichever warp sees the message first)
+            // overwrites the tile the others read THIS step's actions from.  That is already ordered through the completion count, the
+            // host and the next message; the barrier makes it explicit inside the CTA (and visible to racecheck) at no cost — a warp
+            // that is done has nothing to do before every warp of the grid is done.  (Named barrier with the live warps' thread count:
+            // warps beyond the last market have left the kernel.)
+            const int live = min(WARPS, p.M - (int)(blockIdx.x - 1u) * WARPS);
+            asm volatile("bar.sync 1, %0;" ::"r"(live * 32) : "memory");
         }
     }
 

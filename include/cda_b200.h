@@ -208,7 +208,7 @@ int cda_reset_planes(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask
  *   cda_serve_bind   registers the plane ring (pinned + mapped, as above).  Returns CDA_EUNSUPPORTED when the mode cannot be used and
  *                    the caller should stay on cda_step_planes: decimal_ledger handles, more markets than one resident wave holds
  *                    (7 CTAs x 4 markets per SM: 4140 markets of <= 4 agents on a B200), buffers that are not mapped.
- *   cda_serve_step   h_action_block: pinned i32[M][5][A] (market-major) for THIS step — any block within +-32 GB of the first one
+ *   cda_serve_step   h_action_block: pinned i32[M][5][A] (market-major) for THIS step — any block within +-4 GB of the first one
  *                    seen; slot: plane that receives the outputs (the caller advances it modulo slots).  Returns when the outputs
  *                    are in host memory.  `stream`: the caller's stream; a (re)launch is ordered behind the work already queued there.
  *   cda_serve_stop   stores the state back and retires the kernel.  Every other entry point that touches the handle's state
