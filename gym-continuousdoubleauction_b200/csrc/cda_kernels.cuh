@@ -47,6 +47,11 @@
 #define CDA_PREFETCH_TABLES 0 /* 1: every CTA asks L2 for the ziggurat / jump-ahead tables at kernel entry (they are indexed by data that arrives two
                                  dependent loads into the kernel; after an L2 flush the first touch per SM goes to HBM) */
 #endif
+#ifndef CDA_SCAN_UNROLL
+#define CDA_SCAN_UNROLL 0     /* 1: the pool scans (best price, a trader's order, head of a level) read ALL tiles of a side first (CAP/32 predicated loads in
+                                 flight at once) and compare afterwards, instead of one dependent load -> compare round per tile: the kernel is bound by
+                                 dependent-issue latency, not by issue slots */
+#endif
 #define CDA_HDR_BYTES 192
 #define CDA_POOL_FIELDS 5 /* 0 pt (trader<<24|price), 1 qty, 2 order_id, 3 timestamp, 4 seq */
 #define CDA_PRICE_MASK 0x00ffffffu
@@ -474,11 +479,21 @@ template <int CAP> __device__ __forceinline__ int pool_best_scan(const CdaMkt<CA
     const int n = k.count(side);
     if (n == 0) return -1;
     unsigned loc = side == 0 ? 0u : 0xffffffffu;
+#if CDA_SCAN_UNROLL
+    {
+        unsigned v[CAP / 32];
+#pragma unroll
+        for (int t = 0; t < CAP / 32; ++t) v[t] = k.lane + 32 * t < n ? SMW(pt + t * CDA_TILE_WORDS) & CDA_PRICE_MASK : loc;
+#pragma unroll
+        for (int t = 0; t < CAP / 32; ++t) loc = side == 0 ? max(loc, v[t]) : min(loc, v[t]);
+    }
+#else
     CDA_SCAN_PRAGMA
     for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
         const unsigned p = SMW(pt) & CDA_PRICE_MASK;
         loc = side == 0 ? max(loc, p) : min(loc, p);
     }
+#endif
     return (int)(side == 0 ? __reduce_max_sync(CDA_FULL, loc) : __reduce_min_sync(CDA_FULL, loc));
 }
 // best price of a side through the cache (a scan only after an order AT the best price was removed)
@@ -496,10 +511,21 @@ template <int CAP> __device__ __forceinline__ int pool_argmin(const CdaMkt<CAP> 
     int pt = k.side_w(side) + k.lane;
     const int n = k.count(side);
     unsigned bk = 0xffffffffu; int bi = -1;
+#if CDA_SCAN_UNROLL
+    {
+        unsigned hit = 0u;          // bit t: this lane's order in tile t matches
+#pragma unroll
+        for (int t = 0; t < CAP / 32; ++t) hit |= (k.lane + 32 * t < n && (SMW(pt + t * CDA_TILE_WORDS) & mask) == want) ? 1u << t : 0u;
+#pragma unroll
+        for (int t = 0; t < CAP / 32; ++t)
+            if ((hit >> t) & 1u) { const unsigned kk = SMW(pt + t * CDA_TILE_WORDS + field * 32); if (kk < bk) { bk = kk; bi = k.lane + 32 * t; } }
+    }
+#else
     CDA_SCAN_PRAGMA
     for (int i = k.lane; i < n; i += 32, pt += CDA_TILE_WORDS) {
         if ((SMW(pt) & mask) == want) { const unsigned kk = SMW(pt + field * 32); if (kk < bk) { bk = kk; bi = i; } }
     }
+#endif
     const unsigned mk = __reduce_min_sync(CDA_FULL, bk);
     if (mk == 0xffffffffu) return -1;
     const unsigned b = __ballot_sync(CDA_FULL, bk == mk);

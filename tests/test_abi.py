@@ -84,6 +84,8 @@ def test_create_rejects_bad_configurations_before_touching_cuda():
     assert L.cda_create(ctypes.byref(c), 7_000_000, 0, ctypes.byref(h)) == -1         # beyond the 32-bit indexing limit of the cold paths
     assert L.cda_create(None, 16, 0, ctypes.byref(h)) == -1
     assert L.cda_step(None, *([None] * 10)) == -1 and L.cda_step_window(None, None, 3, 1) == -1
+    assert L.cda_serve_bind(None, None, 8, 52) == -1 and L.cda_serve_step(None, None, 0, None) == -1 and L.cda_serve_stop(None) == -1
+    assert L.cda_serve_launches(None) == 0 and b"mode not available" in L.cda_strerror(-5)
 
 
 def test_single_step_kernels_stay_spill_free_and_within_the_one_wave_register_budget():
