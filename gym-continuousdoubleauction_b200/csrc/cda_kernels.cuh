@@ -52,6 +52,9 @@
                                  flight at once) and compare afterwards, instead of one dependent load -> compare round per tile: the kernel is bound by
                                  dependent-issue latency, not by issue slots */
 #endif
+#ifndef CDA_TOPK_UNROLL
+#define CDA_TOPK_UNROLL 0     /* 1: the same for the first sweep of the top-K snapshot (occupancy masks of both sides) */
+#endif
 #define CDA_HDR_BYTES 192
 #define CDA_POOL_FIELDS 5 /* 0 pt (trader<<24|price), 1 qty, 2 order_id, 3 timestamp, 4 seq */
 #define CDA_PRICE_MASK 0x00ffffffu
@@ -1251,6 +1254,22 @@ restart:;
             bestB = k.nb ? (unsigned)pool_best(k, 0) : 0u;      // usually cached by the matching phase
             bestA = k.na ? (unsigned)pool_best(k, 1) : 0u;
             unsigned bl = 0, bh = 0, al = 0, ah = 0; bool fB = false, fA = false;
+#if CDA_TOPK_UNROLL
+            {   // all tiles' prices in flight at once (predicated), masks afterwards
+                unsigned vb[CAP / 32], va[CAP / 32];
+#pragma unroll
+                for (int t = 0; t < CAP / 32; ++t) {
+                    vb[t] = t < ntB ? bestB - (SMW(ptB + t * CDA_TILE_WORDS) & CDA_PRICE_MASK) : 0xffffffffu;
+                    va[t] = t < ntA ? (SMW(ptA + t * CDA_TILE_WORDS) & CDA_PRICE_MASK) - bestA : 0xffffffffu;
+                }
+#pragma unroll
+                for (int t = 0; t < CAP / 32; ++t) {
+                    const unsigned db = vb[t], da = va[t];
+                    bl |= db < 32u ? 1u << db : 0u; bh |= (db - 32u) < 32u ? 1u << (db - 32u) : 0u; fB |= (db - 64u) < 0xffffffbfu;
+                    al |= da < 32u ? 1u << da : 0u; ah |= (da - 32u) < 32u ? 1u << (da - 32u) : 0u; fA |= (da - 64u) < 0xffffffbfu;
+                }
+            }
+#else
             CDA_SCAN_PRAGMA
             for (int it = 0; it < ntm; ++it) {
                 const unsigned db = it < ntB ? bestB - (SMW(ptB + it * CDA_TILE_WORDS) & CDA_PRICE_MASK) : 0xffffffffu;
@@ -1258,6 +1277,7 @@ restart:;
                 bl |= db < 32u ? 1u << db : 0u; bh |= (db - 32u) < 32u ? 1u << (db - 32u) : 0u; fB |= (db - 64u) < 0xffffffbfu;   // 64 <= db < 2^32-1
                 al |= da < 32u ? 1u << da : 0u; ah |= (da - 32u) < 32u ? 1u << (da - 32u) : 0u; fA |= (da - 64u) < 0xffffffbfu;
             }
+#endif
             bl = __reduce_or_sync(CDA_FULL, bl); bh = __reduce_or_sync(CDA_FULL, bh);
             al = __reduce_or_sync(CDA_FULL, al); ah = __reduce_or_sync(CDA_FULL, ah);
             const unsigned farb = __ballot_sync(CDA_FULL, fB), fara = __ballot_sync(CDA_FULL, fA);
