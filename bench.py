@@ -354,11 +354,17 @@ def main():
         t_win = timed_host(host_step, env.attach_host_window)   # (attach: hand every market's current stack to the host window, no market is reset)
         t_pl = timed_host(host_step_planes, env.attach_host_planes)
         # the same call with the RESIDENT STEP SERVER switched on (VecCDAEnv.serve): the kernel stays on the SMs, a step is a doorbell write
-        t_srv, srv_launches = None, 0
-        if env.serve(True):
-            t_srv = timed_host(host_step_planes, env.attach_host_planes)
-            srv_launches = env.serve_launches       # (of the whole leg: warm-up included; the timed loop needs none when the lease holds)
+        t_srv, srv_launches, srv_error = None, 0, None
+        try:
+            if env.serve(True):
+                t_srv = timed_host(host_step_planes, env.attach_host_planes)
+                srv_launches = env.serve_launches       # (of the whole leg: warm-up included; the timed loop needs none when the lease holds)
+        except Exception as exc:   # the headline line must be printed whatever happens to this leg: fall back to the launch-per-step number
+            t_srv, srv_error = None, repr(exc)[:300]
+        try:
             env.serve(False)
+        except Exception as exc:
+            srv_error = (srv_error or "") + " | " + repr(exc)[:200]
         S, H = env.WINDOW_SLOTS - 1, env.n_hist                     # the last slot only ever carries a record
         rec = M * 8 * (A + 1)
         d2h_win = rec + M * 4 * 42 * ((S - H) + H) / (S - H + 1)     # per window cycle: S-H newest-only steps + one whole-stack step
@@ -380,7 +386,7 @@ def main():
                       "terminated, truncated) into cell m of the pinned plane ring and counts itself; the last warp rings the pinned completion word the call "
                       "spins on.  Same inputs, outputs and bytes as cda_step_planes (tests/test_gpu_serve.py: identical planes, records and state), no "
                       "launch, no stream hand-shake, no state round trip through HBM per step",
-               "resident_kernel_launches": int(srv_launches),
+               "resident_kernel_launches": int(srv_launches), "resident_server_error": srv_error,
                "inputs": "one pinned i32[M,5,A] block, rewritten by the host before every step (outside the timer), read by the kernel over PCIe inside it",
                "launch_per_step_variant": {"value": world * M * args.steps / t_pl, "ms_per_step": 1e3 * t_pl / args.steps,
                                            "d2h_bytes_per_step": int(M * env._plane_cell * 4), "api": planes_api},

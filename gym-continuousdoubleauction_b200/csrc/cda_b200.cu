@@ -837,6 +837,7 @@ int cda_serve_step(CdaEnv *e, const int32_t *h_action_block, int32_t slot, void 
         int rc = srv_launch(e, (cudaStream_t)stream);
         if (rc) return rc;
     }
+    const unsigned long long t_start = host_now_ns();
     for (unsigned spins = 1;; ++spins) {
         if (*done == seq) break;
 #if defined(__x86_64__)
@@ -856,7 +857,11 @@ int cda_serve_step(CdaEnv *e, const int32_t *h_action_block, int32_t slot, void 
                 e->srv_running = false;
                 return CDA_ECUDA;
             } else cudaGetLastError();
-            if (spins > 200000000u) { snprintf(g_cuda_err, sizeof(g_cuda_err), "resident step server: no completion"); return CDA_ECUDA; }
+            if (host_now_ns() - t_start > 3000000000ULL) {   // 3 s without a completion (a step takes tens of microseconds): give up, retire the kernel
+                snprintf(g_cuda_err, sizeof(g_cuda_err), "resident step server: step %u not completed within 3 s", seq);
+                srv_quiesce(e);
+                return CDA_ECUDA;
+            }
         }
     }
     e->srv_seq = seq;
