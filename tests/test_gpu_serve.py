@@ -73,7 +73,8 @@ def test_resident_server_equals_launch_per_step_planes(A, n_hist, M, reuse_block
     e1.close(); e2.close()
 
 
-def test_resident_server_equals_oracle():
+def test_resident_server_equals_oracle(monkeypatch):
+    monkeypatch.setenv("CDA_SERVE_LEASE_US", "500000")   # (read when the env binds its server) a busy test box must not retire the kernel mid-loop
     cfg = base_cfg(max_step=10_000)
     M, T, A = 128, 96, 4
     env = cda.VecCDAEnv(cfg, num_markets=M); orc = OracleEnv(cfg, M)
