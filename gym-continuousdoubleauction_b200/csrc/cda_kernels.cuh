@@ -734,6 +734,16 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 // last step completed — the host notices that the kernel has retired and launches it again with the next step — and a worker that has
 // not heard from the poller for srv_watchdog_ns (which cannot happen while the poller is resident) raises srv_err and exits.
 // ------------------------------------------------------------------------------------------
+#ifndef CDA_SRV_FENCE_ACQREL
+#define CDA_SRV_FENCE_ACQREL 0   /* 1: the last warp's system-scope fence is fence.acq_rel.sys instead of the sequentially consistent __threadfence_system() */
+#endif
+#if CDA_SRV_FENCE_ACQREL
+#define CDA_FINAL_SYS_FENCE() asm volatile("fence.acq_rel.sys;" ::: "memory")
+#define CDA_WARP_GPU_FENCE() asm volatile("fence.acq_rel.gpu;" ::: "memory")
+#else
+#define CDA_FINAL_SYS_FENCE() __threadfence_system()
+#define CDA_WARP_GPU_FENCE() __threadfence()
+#endif
 #define CDA_SRV_COPIES 128
 /* measurement only (cda_debug_serve_timeline, tools/serve_timeline.py): lane 0 of every warp leaves the time of the step's milestones */
 #define CDA_SRV_STAMP(i) do { if (p.prof && lane == 0) p.prof[(size_t)m * 16 + (i)] = globaltimer_ns(); } while (0)
@@ -1498,12 +1508,12 @@ restart:;
             // every warp orders its stores before its count at GPU scope (cheap); the LAST warp's system-scope fence, made after it has
             // observed all the counts, is cumulative: everything the others stored is visible to the host before the completion word.
             // (4096 system-scope fences in flight at once cost every warp 4 - 14 us, profiles/r04a_serve_timeline.txt.)
-            __threadfence();
+            CDA_WARP_GPU_FENCE();
             __syncwarp();
             CDA_SRV_STAMP(3);   // outputs issued and ordered
             if (lane == 0 && atomicAdd(p.done_ctr, 1u) == (unsigned)p.M - 1u) {
                 *p.done_ctr = 0u;          // (every other warp has counted itself, and none starts the next step before the host has seen this one)
-                __threadfence_system();
+                CDA_FINAL_SYS_FENCE();
                 const unsigned sq = p.srv_next + (unsigned)it;
                 *reinterpret_cast<volatile unsigned *>(p.done_flag) = sq;
                 *reinterpret_cast<volatile unsigned *>(p.srv_done_dev) = sq;
