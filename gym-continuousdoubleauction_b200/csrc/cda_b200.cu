@@ -74,6 +74,7 @@ struct CdaEnv {
     const char *srv_act_host0; const unsigned char *srv_act_dev0;     // first action block seen: the base the messages' offsets count from
     const void *srv_ptr_cache_h[64]; const unsigned char *srv_ptr_cache_d[64];   // host pointer -> device alias of recent action blocks
     bool srv_bound, srv_running; unsigned srv_seq; long long srv_launches;
+    int srv_win_steps, srv_win_launches;   // relaunches over the current window of 64 served steps (a server that is relaunched for most steps is no server)
     unsigned long long srv_lease_ns, srv_last_ns;   // lease; host clock (CLOCK_MONOTONIC) at the end of the last served step
     int host_ctas, dev_ctas;   // resident CTAs per SM for the host paths / the device path (0 = as many as fit)
 };
@@ -795,6 +796,7 @@ int cda_serve_bind(CdaEnv *e, float *h_planes, int32_t slots, int32_t cell_words
     if (fit == cudaErrorLaunchOutOfResources) return CDA_EUNSUPPORTED;   // more markets than one resident wave holds
     CUDA_TRY(fit);
     e->srv_planes_host = h_planes; e->srv_planes_dev = zp; e->srv_slots = slots; e->srv_cell = cell_words;
+    e->srv_win_steps = e->srv_win_launches = 0;
     e->srv_bound = true;
     return CDA_OK;
 }
@@ -823,6 +825,14 @@ int cda_serve_step(CdaEnv *e, const int32_t *h_action_block, int32_t slot, void 
         e->srv_act_dev0 = dblk; off = 0;
     }
     if (g_srv_dbg & 1) off = 0;
+    // A server that has to be relaunched for most steps — the host takes longer than the lease between steps, or other work keeps claiming the
+    // GPU — only adds its (larger) launch to every step: decline from here on, the caller goes back to cda_step_planes.
+    if (e->srv_win_steps >= 64) {
+        const bool thrash = e->srv_win_launches >= 48;
+        e->srv_win_steps = e->srv_win_launches = 0;
+        if (thrash) { SRV_QUIESCE(e); e->srv_bound = false; return CDA_EUNSUPPORTED; }
+    }
+    const long long launches0 = e->srv_launches;
     const unsigned seq = e->srv_seq + 1u;
     const unsigned long long msg = (unsigned long long)cda_srv_seq24(seq) | ((unsigned long long)(unsigned)slot << 24) |
                                    ((unsigned long long)(unsigned)(int)(off >> 2) << 32);
@@ -866,6 +876,7 @@ int cda_serve_step(CdaEnv *e, const int32_t *h_action_block, int32_t slot, void 
     }
     e->srv_seq = seq;
     e->srv_last_ns = host_now_ns();
+    e->srv_win_steps++; e->srv_win_launches += (int)(e->srv_launches - launches0);
     return CDA_OK;
 }
 

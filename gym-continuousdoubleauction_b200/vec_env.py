@@ -429,9 +429,12 @@ class VecCDAEnv:
         if pos is None:
             raise RuntimeError("call reset_host_planes() before step_host_planes()")
         pos = (pos + 1) % self.PLANE_SLOTS
+        rc = -5
         if self._serve_on and sync and market_major:
             rc = self._serve_step(self._h, action_block.data_ptr(), pos, self._plane_stream)
-        else:
+            if rc == -5:       # CDA_EUNSUPPORTED: the server was being relaunched for most steps (slow policy / shared GPU) and has switched itself off
+                self._serve_on = False
+        if rc == -5:
             rc = self._plane_step(self._h, action_block.data_ptr(), self._plane_ptrs[pos], self._plane_cell,
                                   (1 if sync else 0) | (2 if market_major else 0), self._plane_stream)
         if rc:

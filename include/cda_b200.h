@@ -216,7 +216,9 @@ int cda_reset_planes(CdaEnv *env, const uint64_t *d_seeds, const uint8_t *d_mask
  * The kernel also retires by itself when no step has been requested for the lease (2 ms; $CDA_SERVE_LEASE_US) — a host that went away
  * cannot pin the GPU — and the next cda_serve_step launches it again: an idle server costs one launch, not a hang.  While it is resident
  * it occupies every SM: other kernels on the device wait for the lease to run out, so this mode is for host-side policies (GPU-side
- * policies use cda_step / cda_step_gather, which never leave the device). */
+ * policies use cda_step / cda_step_gather, which never leave the device).  A server that had to be relaunched for 48 of the last 64 steps
+ * (the host needs longer than the lease between steps, or other work keeps claiming the GPU) switches itself off: cda_serve_step returns
+ * CDA_EUNSUPPORTED without having stepped, and the caller continues with cda_step_planes (cda_serve_bind switches it on again). */
 #define CDA_EUNSUPPORTED (-5)   /* the requested mode cannot serve this handle; use the fallback the header names */
 int cda_serve_bind(CdaEnv *env, float *h_planes, int32_t slots, int32_t cell_words);
 int cda_serve_step(CdaEnv *env, const int32_t *h_action_block, int32_t slot, void *stream);

@@ -145,3 +145,22 @@ def test_resident_server_full_size_every_step_matches_the_device_path():
         assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2), t
     assert e2.serve_launches >= 3, e2.serve_launches      # (more when the host was held up for longer than the lease between two steps)
     e1.close(); e2.close()
+
+
+def test_resident_server_switches_itself_off_when_it_is_relaunched_for_most_steps(monkeypatch):
+    """A lease shorter than the host's time between two steps: every step needs a relaunch.  After a window of 64 such steps the server
+    declines (CDA_EUNSUPPORTED, nothing stepped), step_host_planes continues on the launch path, and the results stay those of the
+    launch path throughout."""
+    monkeypatch.setenv("CDA_SERVE_LEASE_US", "1")
+    cfg = base_cfg()
+    M, A, T = 64, 4, 90
+    e1 = cda.VecCDAEnv(cfg, num_markets=M); e2 = cda.VecCDAEnv(cfg, num_markets=M)
+    e1.reset_host_planes(seed=9); e2.reset_host_planes(seed=9)
+    assert e2.serve(True)
+    pin = torch.from_numpy(mm_blocks(make_actions(4, T, M, A, "uniform"), T, M, A)).pin_memory()
+    for t in range(T):
+        time.sleep(0.0005)
+        r1 = e1.step_host_planes(pin[t]); r2 = e2.step_host_planes(pin[t])
+        assert np.array_equal(np.asarray(r1[0]), np.asarray(r2[0])) and np.array_equal(r1[1], r2[1]), t
+    assert e2.host_resident is False and 48 <= e2.serve_launches <= 64, e2.serve_launches
+    e1.close(); e2.close()
