@@ -54,6 +54,9 @@ def test_committed_gpu_bench_line_has_the_contract_keys():
     e = line["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 * 4 * 20 and e["d2h_bytes_per_step"] > 4096 * 168
     assert e["value"] < line["value"]                                   # measured through the host API, not a copy of `value`
+    if "launch_per_step_variant" in e:                                   # lines since the resident step server: the headline e2e is the better of the two forms
+        assert e["resident_kernel_launches"] >= 1 and not e.get("resident_server_error")
+        assert e["value"] >= e["launch_per_step_variant"]["value"] > 0 and "rewritten by the host" in e["inputs"]
     r = line["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert abs(r["achieved"] - 2738 * 4096 / (r["kernel_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"] and r["traffic"]
